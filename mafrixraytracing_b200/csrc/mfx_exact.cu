@@ -1,0 +1,536 @@
+// mfx_exact.cu -- MFX_EXACT_F64 kernels.  COMPILED WITH --fmad=false.
+//
+// f64 arithmetic in the operation order of the F# reference, IEEE
+// divide and sqrt, no FMA contraction: primitive ids, hit distances and radiance are
+// bit-identical to the reference algorithm (as restated by oracle/).  Only the traversal
+// ORDER differs from Bvh.CheckHit (BvhNode.fs:62-82): near child first with a conservative
+// t-shrink cull, and the reference's tie rules applied explicitly -- DESIGN.md "Exact traversal"
+// argues the equivalence.
+#include "mfx_device.cuh"
+
+typedef V3<double> D3;
+
+struct HitX {
+    int    slot;   // leaf-order primitive slot or -1
+    int    sub;    // which triangle of a Rect
+    double t;
+};
+
+// AABB.hit (Interfaces/IHitable.fs:18-54): divides by dir, `>= 0.` select (true for -0.0).
+__device__ __forceinline__ bool aabb_hit_x(const NodeX &n, D3 o, D3 dir, double tMin, double tMax, double &entry)
+{
+    double tmin, tmax, tymin, tymax, tzmin, tzmax;
+    if (dir.x >= 0.) { tmin = (n.pmin[0] - o.x) / dir.x; tmax = (n.pmax[0] - o.x) / dir.x; }
+    else             { tmin = (n.pmax[0] - o.x) / dir.x; tmax = (n.pmin[0] - o.x) / dir.x; }
+    if (dir.y >= 0.) { tymin = (n.pmin[1] - o.y) / dir.y; tymax = (n.pmax[1] - o.y) / dir.y; }
+    else             { tymin = (n.pmax[1] - o.y) / dir.y; tymax = (n.pmin[1] - o.y) / dir.y; }
+    if (tmin > tymax || tymin > tmax) return false;
+    tmin = (tymin > tmin) ? tymin : tmin;
+    tmax = (tymax < tmax) ? tymax : tmax;
+    if (dir.z >= 0.) { tzmin = (n.pmin[2] - o.z) / dir.z; tzmax = (n.pmax[2] - o.z) / dir.z; }
+    else             { tzmin = (n.pmax[2] - o.z) / dir.z; tzmax = (n.pmin[2] - o.z) / dir.z; }
+    if (tmin > tzmax || tzmin > tmax) return false;
+    tmin = (tzmin > tmin) ? tzmin : tmin;
+    tmax = (tzmax < tmax) ? tzmax : tmax;
+    entry = tmin;
+    return tmin < tMax && tmax > tMin;
+}
+
+// Triangle.PreCalcu + Hit (Shape/Trangle.fs:120-155); tMax ignored (quirk Q2).
+__device__ __forceinline__ bool tri_hit_x(D3 v0, D3 e1, D3 e2, D3 o, D3 dir, double tMin, double &t_out)
+{
+    const D3 s1 = cross(dir, e2);
+    const double divisor = dot(s1, e1);
+    if (fabs(divisor) < 1e-6) return false;
+    const double inv = 1. / divisor;
+    const D3 d = o - v0;
+    const double b1 = dot(d, s1) * inv;
+    if (b1 < 0. || b1 > 1.) return false;
+    const D3 s2 = cross(d, e1);
+    const double b2 = dot(dir, s2) * inv;
+    if (b2 < 0. || (b1 + b2) >= 1.) return false;
+    const double t = dot(e2, s2) * inv;
+    if (t > tMin) { t_out = t; return true; }
+    return false;
+}
+
+// Sphere.Hit (Shape/Sphere.fs:21-43)
+__device__ __forceinline__ bool sphere_hit_x(D3 center, double radius, D3 o, D3 dir, double tMin, double tMax, double &t_out)
+{
+    const D3 oc = o - center;
+    const double a = 1.;
+    const double b = 2.0 * dot(oc, dir);
+    const double c = dot(oc, oc) - radius * radius;
+    const double disc = b * b - 4.0 * a * c;
+    if (disc > 0) {
+        const double root = sqrt(disc);
+        const double q = (b < 0.) ? -0.5 * (b - root) : -0.5 * (b + root);
+        const double t0 = q, t1 = c / q;
+        const double lo = (t0 < t1) ? t0 : t1, hi = (t0 > t1) ? t0 : t1;
+        if (lo >= tMin && lo < tMax) { t_out = lo; return true; }
+        else if (hi > tMin && hi < tMax) { t_out = hi; return true; }
+    }
+    return false;
+}
+
+// IHitable.Hit on one leaf-order slot; Rect.Hit: tri1 if it hits ELSE tri2 (Rect.fs:26-31, quirk Q3).
+__device__ __forceinline__ bool prim_hit_x(const PrimX &p, D3 o, D3 dir, double tMin, double tMax, double &t, int &sub)
+{
+    sub = 0;
+    if (p.kind == 0) return tri_hit_x(ld3(p.v0), ld3(p.e1), ld3(p.e2), o, dir, tMin, t);
+    if (p.kind == 1) {
+        if (tri_hit_x(ld3(p.v0), ld3(p.e1), ld3(p.e2), o, dir, tMin, t)) return true;
+        sub = 1;
+        return tri_hit_x(ld3(p.v0), ld3(p.e2), ld3(p.e3), o, dir, tMin, t);
+    }
+    return sphere_hit_x(ld3(p.v0), p.e1[0], o, dir, tMin, tMax, t);
+}
+
+// Bvh.Hit (BvhNode.fs:62-83).  ANY: shadow query -- returns as soon as a leaf yields a hit record.
+// COUNT: add visited node/primitive records to ctr (instrumented runs).
+template <bool ANY, bool COUNT>
+__device__ HitX bvh_hit_x(const SceneX &sc, D3 o, D3 dir, double tMin, double tMax, unsigned long long *ctr)
+{
+    HitX best; best.slot = -1; best.sub = 0; best.t = 0.;
+    int bestFirst = -1;
+    int stack[40];
+    int sp = 0;
+    double e;
+    NodeX node = sc.nodes[0];
+    if (COUNT) ctr[0]++;
+    if (!aabb_hit_x(node, o, dir, tMin, tMax, e)) return best;
+    int cur = 0;
+    for (;;) {
+        if (node.count > MFX_LEAF_NODE_COUNT) {
+            const int li = 2 * cur + 1, ri = 2 * cur + 2;
+            const NodeX L = sc.nodes[li];
+            const NodeX R = sc.nodes[ri];
+            if (COUNT) ctr[0] += 2;
+            double el, er;
+            bool hl = aabb_hit_x(L, o, dir, tMin, tMax, el);
+            bool hr = aabb_hit_x(R, o, dir, tMin, tMax, er);
+            if (!ANY && best.slot >= 0) {
+                // conservative t-shrink: a box whose entry is beyond the best hit by more than
+                // rounding noise cannot hold a hit with t <= best.t (ties must survive, quirk Q1)
+                const double lim = best.t + best.t * 1e-9;
+                if (el > lim) hl = false;
+                if (er > lim) hr = false;
+            }
+            if (hl && hr) {
+                const bool rightNear = er < el;
+                stack[sp++] = rightNear ? li : ri;
+                cur = rightNear ? ri : li;
+                node = rightNear ? R : L;
+                continue;
+            } else if (hl) { cur = li; node = L; continue; }
+            else if (hr) { cur = ri; node = R; continue; }
+        } else {
+            // leaf: Array.map Hit |> Array.minBy (hit ? t : tMax) -- FIRST minimal key (BvhNode.fs:76-80)
+            bool have = false, recHit = false; double bestKey = 0., recT = 0.; int recSlot = -1, recSub = 0;
+            for (int k = 0; k < node.count; k++) {
+                const PrimX p = sc.prims[node.first + k];
+                if (COUNT) { if (p.kind == 2) ctr[2]++; else ctr[1] += (p.kind == 1) ? 2 : 1; }
+                double t; int sub;
+                const bool h = prim_hit_x(p, o, dir, tMin, tMax, t, sub);
+                const double key = h ? t : tMax;
+                if (!have || key < bestKey) { have = true; bestKey = key; recHit = h; recT = t; recSlot = node.first + k; recSub = sub; }
+            }
+            if (recHit) {
+                if (ANY) { best.slot = recSlot; best.sub = recSub; best.t = recT; return best; }
+                // interior combine `if l.t < r.t then l else r` (BvhNode.fs:69-70): on equal t the
+                // record later in depth-first order wins == the leaf with the larger `first`
+                if (best.slot < 0 || recT < best.t || (recT == best.t && node.first > bestFirst)) {
+                    best.slot = recSlot; best.sub = recSub; best.t = recT; bestFirst = node.first;
+                }
+            }
+        }
+        if (sp == 0) break;
+        cur = stack[--sp];
+        node = sc.nodes[cur];
+        if (COUNT) ctr[0]++;   // re-fetch of a deferred node (its box was already tested)
+    }
+    return best;
+}
+
+// ---------------------------------------------------------------- RNG-driven samplers
+struct RngX { uint32_t pixel, sample, k0, k1; };
+
+__device__ __forceinline__ void rng_draw_x(const RngX &g, uint32_t dim, uint32_t iter, double (&u)[4])
+{
+    uint32_t o[4];
+    philox4x32_10(g.pixel, g.sample, dim, iter, g.k0, g.k1, o);
+#pragma unroll
+    for (int i = 0; i < 4; i++) u[i] = u32_to_unit_f64(o[i]);
+}
+
+// GetRandomInUnitSphere (Materials/Material.fs:9-14), capped like the oracle.
+__device__ D3 random_in_unit_sphere_x(D3 nm, const RngX &g, uint32_t dim)
+{
+    D3 p = mk3<double>(20., 20., 20.);
+    uint32_t it = 0;
+    while (dot(p, p) >= 1.0 || dot(nm, p) <= 0.) {
+        if (it >= MFX_REJECTION_CAP) return nm;
+        double u[4];
+        rng_draw_x(g, dim, it++, u);
+        p = mk3<double>(u[0], u[1], u[2]) * 2.0 - mk3<double>(1., 1., 1.);
+    }
+    return p;
+}
+
+__device__ __forceinline__ D3 normalize_x(D3 a)     // Vector.Normalize, Point.fs:52-56
+{
+    const double l = sqrt(len2(a));
+    if (l == 0.0) return mk3<double>(0., 0., 0.);
+    return mk3<double>(a.x / l, a.y / l, a.z / l);
+}
+
+__device__ __forceinline__ D3 reflect_x(D3 v, D3 n) { return v - n * (2.0 * dot(v, n)); }   // Material.fs:16
+
+__device__ __forceinline__ double fmax_fs(double a, double b) { return a > b ? a : (b > a ? b : (a != a ? a : b)); }
+
+// FresnelDielectric.Evaluate (Material.fs:74-96)
+__device__ double fresnel_x(double eta_i, double eta_t, double cosi)
+{
+    double ei, et;
+    if (cosi > 0.) { ei = eta_i; et = eta_t; } else { ei = eta_t; et = eta_i; }
+    const double sint = ei / et * sqrt(fmax_fs(0., 1. - cosi * cosi));
+    if (sint >= 1.) return 1.0;
+    const double cost = sqrt(fmax_fs(0., 1. - sint * sint));
+    const double ci = fabs(cosi);
+    const double rparl = ((et * ci) - (ei * cost)) / ((et * ci) + (ei * cost));
+    const double rperp = ((ei * ci) - (et * cost)) / ((ei * ci) + (et * cost));
+    return (rparl * rparl + rperp * rperp) / 2.;
+}
+
+// Triangle.SamplePoint (Trangle.fs:157-169)
+__device__ __forceinline__ D3 tri_sample_x(const TriSampleX &t, double tu, double tv)
+{
+    double u, v;
+    if (tu + tv > 1.) { u = 1. - tu; v = 1. - tv; } else { u = tu; v = tv; }
+    const double sq = sqrt(1. - u);
+    const double s1 = 1. - sq;
+    const double s2 = v * sq;
+    return (ld3(t.v0) + ld3(t.e1) * s1) + ld3(t.e2) * s2;
+}
+
+// Triangle ctor normal (Trangle.fs:108-112): (e1 x e2) / |e1 x e2|
+__device__ __forceinline__ D3 tri_normal_x(D3 e1, D3 e2)
+{
+    const D3 a = cross(e1, e2);
+    const double al = sqrt(len2(a));
+    return a / al;
+}
+
+__device__ __forceinline__ D3 camera_ray_dir_x(const CamX &c, double u, double v)   // Camera.fs:134-139
+{
+    const D3 target = (ld3(c.topleft) + ld3(c.right) * u) + ld3(c.down) * v;
+    return normalize_x(target - ld3(c.pos));
+}
+
+// ---------------------------------------------------------------- kernels
+#define GRID_STRIDE_WARP(i, n) \
+    for (long long i##_base = (long long)blockIdx.x * blockDim.x; i##_base < (n); i##_base += (long long)gridDim.x * blockDim.x)
+
+__global__ void __launch_bounds__(128) k_x_raygen(SceneX sc, WaveX w, TileMap tm, int pix0, int npix, int s0, int S, uint64_t seed)
+{
+    const long long total = (long long)npix * S;
+    for (long long pid = (long long)blockIdx.x * blockDim.x + threadIdx.x; pid < total; pid += (long long)gridDim.x * blockDim.x) {
+        const int sl = (int)(pid / npix), pl = (int)(pid - (long long)sl * npix);
+        int pix, px, py;
+        pixel_of(tm, sc.width, pix0 + pl, pix, px, py);
+        RngX g; g.pixel = (uint32_t)pix; g.sample = (uint32_t)(s0 + sl); g.k0 = (uint32_t)seed; g.k1 = (uint32_t)(seed >> 32);
+        double u4[4];
+        rng_draw_x(g, MFX_DIM_CAMERA, 0, u4);
+        const double u = ((double)px + u4[0]) / (double)sc.width;      // Integrators.fs:167
+        const double v = ((double)py + u4[1]) / (double)sc.height;     // Integrators.fs:168
+        const D3 d = camera_ray_dir_x(sc.cam, u, v);
+        const size_t P = (size_t)w.P;
+        w.ray_o[pid] = sc.cam.pos[0]; w.ray_o[P + pid] = sc.cam.pos[1]; w.ray_o[2 * P + pid] = sc.cam.pos[2];
+        w.ray_d[pid] = d.x; w.ray_d[P + pid] = d.y; w.ray_d[2 * P + pid] = d.z;
+        w.nv[pid] = 0;
+        w.queue[0][pid] = (int)pid;
+        if (pid == 0) w.counts[0] = (int)total;
+    }
+}
+
+template <bool COUNT>
+__global__ void __launch_bounds__(128) k_x_extend(SceneX sc, WaveX w, int bounce, TravCounters *ctr)
+{
+    const int n = w.counts[bounce];
+    const int *q = w.queue[bounce & 1];
+    const size_t P = (size_t)w.P;
+    unsigned long long local[3] = { 0, 0, 0 };
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int pid = q[i];
+        const D3 o = mk3<double>(w.ray_o[pid], w.ray_o[P + pid], w.ray_o[2 * P + pid]);
+        const D3 d = mk3<double>(w.ray_d[pid], w.ray_d[P + pid], w.ray_d[2 * P + pid]);
+        const HitX h = bvh_hit_x<false, COUNT>(sc, o, d, 1e-6, 99999999., local);   // Integrators.fs:108
+        w.hit_t[pid] = h.t;
+        w.hit_slot[pid] = (h.slot < 0) ? -1 : (h.slot | (h.sub << 30));
+    }
+    if (COUNT) { for (int k = 0; k < 3; k++) if (local[k]) atomicAdd(&ctr->v[0][k], local[k]); }
+}
+
+// One path vertex: PathIntegrator.TraceRay body (Integrators.fs:109-136, mode 0) or
+// NewPathTracer.TraceRay body (PathTracer.fs:25-41, mode 1), minus the two bvh.Hit calls.
+__global__ void __launch_bounds__(128) k_x_shade(SceneX sc, WaveX w, TileMap tm, int pix0, int npix, int s0, int bounce, uint64_t seed)
+{
+    const int n = w.counts[bounce];
+    const int *qin = w.queue[bounce & 1];
+    int *qout = w.queue[(bounce + 1) & 1];
+    const size_t P = (size_t)w.P;
+    const int nwarp_iters = (n + 31) / 32;
+    const int k = bounce;
+    for (int it = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); it < nwarp_iters; it += gridDim.x * (blockDim.x >> 5)) {
+        const int i = it * 32 + (threadIdx.x & 31);
+        bool alive = false;
+        int pid = -1;
+        if (i < n) {
+            pid = qin[i];
+            const int hs = w.hit_slot[pid];
+            if (hs >= 0) {
+                alive = true;
+                const int slot = hs & 0x3fffffff, sub = hs >> 30;
+                const double t = w.hit_t[pid];
+                const D3 o = mk3<double>(w.ray_o[pid], w.ray_o[P + pid], w.ray_o[2 * P + pid]);
+                const D3 d = mk3<double>(w.ray_d[pid], w.ray_d[P + pid], w.ray_d[2 * P + pid]);
+                const PrimX p = sc.prims[slot];
+                const D3 point = o + d * t;                                   // Ray.PointAtParameter, Ray.fs:8-10
+                D3 normal;
+                if (p.kind == 2) normal = normalize_x(point - ld3(p.v0));     // Sphere.fs:33
+                else if (sub == 0) normal = tri_normal_x(ld3(p.e1), ld3(p.e2));
+                else normal = tri_normal_x(ld3(p.e2), ld3(p.e3));
+                const MatX m = sc.mats[p.material];
+                const int sl = pid / npix, pl = pid - sl * npix;
+                int pix, px, py;
+                pixel_of(tm, sc.width, pix0 + pl, pix, px, py);
+                RngX g; g.pixel = (uint32_t)pix; g.sample = (uint32_t)(s0 + sl); g.k0 = (uint32_t)seed; g.k1 = (uint32_t)(seed >> 32);
+
+                const double INVPI = 1. / 3.14159265358979323846, TWOPI = 2. * 3.14159265358979323846;
+                D3 wi; double cr, cg, cb; double ei_shade = 0.;
+                if (sc.mode == 0) {
+                    // GetBxdf(): LambertianBrdf(a) for Lambertian/Metal, LambertianBrdf(Color()) for
+                    // SpecularTransmission (Material.fs:52,68,121); SampleF (Material.fs:33-36)
+                    const double ar = (m.kind == 2) ? 0. : m.albedo[0], ag = (m.kind == 2) ? 0. : m.albedo[1], ab = (m.kind == 2) ? 0. : m.albedo[2];
+                    wi = normalize_x(random_in_unit_sphere_x(normal, g, MFX_DIM_BSDF(k)));
+                    const double ei = dot(normal, wi);
+                    cr = TWOPI * (ei * (INVPI * ar)); cg = TWOPI * (ei * (INVPI * ag)); cb = TWOPI * (ei * (INVPI * ab));
+                } else if (m.kind == 0) {                                      // Lambertian.Scatter, Material.fs:41-46
+                    wi = normalize_x(random_in_unit_sphere_x(normal, g, MFX_DIM_BSDF(k)));
+                    cr = INVPI * m.albedo[0]; cg = INVPI * m.albedo[1]; cb = INVPI * m.albedo[2];
+                    ei_shade = dot(normal, wi);                                // Lambertian.Shade, Material.fs:48
+                } else if (m.kind == 1) {                                      // Metal.Scatter, Material.fs:61-65
+                    const double fuzz = (m.fuzz < 1.0) ? m.fuzz : 1.0;
+                    const D3 reflected = reflect_x(d, normal);
+                    const D3 rnd = random_in_unit_sphere_x(normal, g, MFX_DIM_BSDF(k));
+                    wi = normalize_x(reflected + rnd * fuzz);
+                    cr = m.albedo[0]; cg = m.albedo[1]; cb = m.albedo[2];
+                } else {                                                       // SpecularTransmission.Scatter, Material.fs:103-118
+                    const D3 dir = -d;
+                    const double cosi = dot(dir, normal);
+                    double ei, et;
+                    if (cosi > 0.) { ei = m.ei; et = m.et; } else { ei = m.et; et = m.ei; }
+                    // Refract (Material.fs:17-24)
+                    const double r = ei / et;
+                    const D3 uv = normalize_x(dir);
+                    const double dt = dot(uv, normal);
+                    const double disc = 1.0 - r * r * (1.0 - dt * dt);
+                    if (disc > 0) {
+                        wi = (dir - normal * dt) * r - normal * sqrt(disc);
+                        const double F = fresnel_x(m.ei, m.et, cosi);
+                        const double f = (et * et) / (ei * ei);
+                        const double den = fabs(dot(wi, normal));
+                        cr = ((f * (1. - F)) * m.albedo[0]) / den;
+                        cg = ((f * (1. - F)) * m.albedo[1]) / den;
+                        cb = ((f * (1. - F)) * m.albedo[2]) / den;
+                    } else {
+                        wi = reflect_x(dir, normal);
+                        cr = cg = cb = 0.;
+                    }
+                }
+                // light sample: Rect.SamplePoint (Rect.fs:33-38) -> NewAreaLight.GetDirection (Light.fs:42-47)
+                double u[4];
+                rng_draw_x(g, MFX_DIM_LIGHT(k), 0, u);
+                const D3 lp = (u[0] < 0.5) ? tri_sample_x(sc.light.t1, u[1], u[2]) : tri_sample_x(sc.light.t2, u[1], u[2]);
+                const D3 toLight = lp - point;
+                const double dist = sqrt(len2(toLight));
+                const D3 unit = toLight / dist;
+                // NewAreaLight.L (Light.fs:48-56) and `unitToLight.Dot(hit.normal) * l` (Integrators.fs:52)
+                double lr = 0., lg = 0., lb = 0.;
+                const double cos_o = dot(toLight, ld3(sc.light.normal));
+                if (cos_o < 0.) {
+                    const double solid = fabs(cos_o) * sc.light.area / len2(toLight);
+                    lr = solid * sc.light.color[0]; lg = solid * sc.light.color[1]; lb = solid * sc.light.color[2];
+                }
+                const double dn = dot(unit, normal);
+                lr = dn * lr; lg = dn * lg; lb = dn * lb;
+
+                const size_t vb = (size_t)k * 3 * P;
+                w.v_l[vb + pid] = lr; w.v_l[vb + P + pid] = lg; w.v_l[vb + 2 * P + pid] = lb;
+                w.v_col[vb + pid] = cr; w.v_col[vb + P + pid] = cg; w.v_col[vb + 2 * P + pid] = cb;
+                w.v_ei[(size_t)k * P + pid] = ei_shade;
+                w.v_kind[(size_t)k * P + pid] = m.kind;
+                w.nv[pid] = k + 1;
+                w.sh_d[pid] = unit.x; w.sh_d[P + pid] = unit.y; w.sh_d[2 * P + pid] = unit.z;
+                w.sh_dist[pid] = dist;
+                w.ray_o[pid] = point.x; w.ray_o[P + pid] = point.y; w.ray_o[2 * P + pid] = point.z;
+                w.ray_d[pid] = wi.x; w.ray_d[P + pid] = wi.y; w.ray_d[2 * P + pid] = wi.z;
+            }
+        }
+        const int pos = warp_append(alive, &w.counts[bounce + 1]);
+        if (alive) qout[pos] = pid;
+    }
+}
+
+// Shadow query of SingleDirectLightIntegrator (Integrators.fs:44): occluded -> Color().
+template <bool COUNT>
+__global__ void __launch_bounds__(128) k_x_shadow(SceneX sc, WaveX w, int bounce, TravCounters *ctr)
+{
+    // runs over the paths that were shaded at vertex `bounce` = queue[bounce+1]
+    const int n = w.counts[bounce + 1];
+    const int *q = w.queue[(bounce + 1) & 1];
+    const size_t P = (size_t)w.P;
+    unsigned long long local[3] = { 0, 0, 0 };
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int pid = q[i];
+        const D3 o = mk3<double>(w.ray_o[pid], w.ray_o[P + pid], w.ray_o[2 * P + pid]);   // hit.point
+        const D3 d = mk3<double>(w.sh_d[pid], w.sh_d[P + pid], w.sh_d[2 * P + pid]);
+        const double dist = w.sh_dist[pid];
+        const HitX h = bvh_hit_x<true, COUNT>(sc, o, d, 1e-6, dist - 1e-6, local);
+        if (h.slot >= 0) {
+            const size_t vb = (size_t)bounce * 3 * P;
+            w.v_l[vb + pid] = 0.; w.v_l[vb + P + pid] = 0.; w.v_l[vb + 2 * P + pid] = 0.;
+        }
+    }
+    if (COUNT) { for (int k = 0; k < 3; k++) if (local[k]) atomicAdd(&ctr->v[1][k], local[k]); }
+}
+
+// Unwinds the recursion inside-out so the rounding sequence equals the reference's:
+//   mode 0: L_k = ((l_k / pdf_li + L_{k+1}) * col_k) / pdf          (Integrators.fs:136)
+//   mode 1: L_k = l_k * col_k + col_k * Shade(L_{k+1})              (PathTracer.fs:40-41)
+// then color <- color + L_0 per sample in sample order                (Integrators.fs:170).
+__global__ void __launch_bounds__(128) k_x_resolve(SceneX sc, WaveX w, TileMap tm, int pix0, int npix, int S, double *pixsum)
+{
+    const size_t P = (size_t)w.P;
+    const double pdf_li = 1. / sc.light.area;      // Light.fs:59
+    const double PI = 3.14159265358979323846;
+    for (int pl = blockIdx.x * blockDim.x + threadIdx.x; pl < npix; pl += gridDim.x * blockDim.x) {
+        int pix, px, py;
+        pixel_of(tm, sc.width, pix0 + pl, pix, px, py);
+        double cr = pixsum[4 * (size_t)pix], cg = pixsum[4 * (size_t)pix + 1], cb = pixsum[4 * (size_t)pix + 2];
+        for (int sl = 0; sl < S; sl++) {
+            const size_t pid = (size_t)sl * npix + pl;
+            const int nv = w.nv[pid];
+            double Lr = 0., Lg = 0., Lb = 0.;
+            for (int k = nv - 1; k >= 0; k--) {
+                const size_t vb = (size_t)k * 3 * P;
+                const double lr = w.v_l[vb + pid], lg = w.v_l[vb + P + pid], lb = w.v_l[vb + 2 * P + pid];
+                const double kr = w.v_col[vb + pid], kg = w.v_col[vb + P + pid], kb = w.v_col[vb + 2 * P + pid];
+                if (sc.mode == 0) {
+                    Lr = ((lr / pdf_li + Lr) * kr) / 1.;
+                    Lg = ((lg / pdf_li + Lg) * kg) / 1.;
+                    Lb = ((lb / pdf_li + Lb) * kb) / 1.;
+                } else {
+                    double sr = Lr, sg = Lg, sb = Lb;
+                    if (w.v_kind[(size_t)k * P + pid] == 0) {                  // Lambertian.Shade, Material.fs:47-50
+                        const double ei = w.v_ei[(size_t)k * P + pid];
+                        sr = ei * (PI * (2. * Lr)); sg = ei * (PI * (2. * Lg)); sb = ei * (PI * (2. * Lb));
+                    }
+                    Lr = lr * kr + kr * sr;
+                    Lg = lg * kg + kg * sg;
+                    Lb = lb * kb + kb * sb;
+                }
+            }
+            cr = cr + Lr; cg = cg + Lg; cb = cb + Lb;
+        }
+        pixsum[4 * (size_t)pix] = cr; pixsum[4 * (size_t)pix + 1] = cg; pixsum[4 * (size_t)pix + 2] = cb;
+        pixsum[4 * (size_t)pix + 3] = 1.0;
+    }
+}
+
+__global__ void __launch_bounds__(128) k_x_bvh_hit(SceneX sc, int any_hit, long long n, const double *o, const double *d,
+                                                   double tmin, double tmax, int *prim, int *sub, double *t)
+{
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const D3 oo = mk3<double>(o[3 * i], o[3 * i + 1], o[3 * i + 2]);
+        const D3 dd = mk3<double>(d[3 * i], d[3 * i + 1], d[3 * i + 2]);
+        const HitX h = any_hit ? bvh_hit_x<true, false>(sc, oo, dd, tmin, tmax, nullptr)
+                               : bvh_hit_x<false, false>(sc, oo, dd, tmin, tmax, nullptr);
+        prim[i] = (h.slot < 0) ? -1 : sc.ref_id[h.slot];
+        if (sub) sub[i] = (h.slot < 0) ? 0 : h.sub;
+        t[i] = (h.slot < 0) ? 0. : h.t;
+    }
+}
+
+__global__ void __launch_bounds__(128) k_x_primary(SceneX sc, long long n, const double *uv, int *prim, double *t)
+{
+    for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += (long long)gridDim.x * blockDim.x) {
+        double u, v;
+        if (uv) { u = uv[2 * r]; v = uv[2 * r + 1]; }
+        else {
+            const int j = (int)(r / sc.width), i = (int)(r - (long long)j * sc.width);
+            u = ((double)i + 0.5) / (double)sc.width;
+            v = ((double)j + 0.5) / (double)sc.height;
+        }
+        const D3 d = camera_ray_dir_x(sc.cam, u, v);
+        const HitX h = bvh_hit_x<false, false>(sc, ld3(sc.cam.pos), d, 1e-6, 99999999., nullptr);
+        prim[r] = (h.slot < 0) ? -1 : sc.ref_id[h.slot];
+        t[r] = (h.slot < 0) ? 0. : h.t;
+    }
+}
+
+// texture[i,j] <- color / float n (Integrators.fs:171); also the f32 row-major view.
+__global__ void __launch_bounds__(256) k_finalize(const double *pixsum, int width, int height, int spp, TileMap tm,
+                                                  double *color_wh, float4 *rgba_f32)
+{
+    const int n = tm.pix ? tm.n_pix : width * height;
+    const double dn = (double)spp;
+    for (int pl = blockIdx.x * blockDim.x + threadIdx.x; pl < n; pl += gridDim.x * blockDim.x) {
+        int pix, px, py;
+        pixel_of(tm, width, pl, pix, px, py);
+        const double r = pixsum[4 * (size_t)pix] / dn, g = pixsum[4 * (size_t)pix + 1] / dn, b = pixsum[4 * (size_t)pix + 2] / dn;
+        if (color_wh) {
+            double *o = color_wh + ((size_t)px * height + py) * 4;
+            o[0] = r; o[1] = g; o[2] = b; o[3] = 1.0;
+        }
+        if (rgba_f32) rgba_f32[pix] = make_float4((float)r, (float)g, (float)b, 1.0f);
+    }
+}
+
+// ---------------------------------------------------------------- launchers
+void mfx_x_raygen(const LaunchCfg &c, const SceneX &sc, const WaveX &w, TileMap tm, int pix0, int npix, int s0, int S, uint64_t seed)
+{
+    k_x_raygen<<<persistent_blocks(k_x_raygen, c.threads, c.blocks), c.threads, 0, c.stream>>>(sc, w, tm, pix0, npix, s0, S, seed);
+}
+void mfx_x_extend(const LaunchCfg &c, const SceneX &sc, const WaveX &w, int bounce, TravCounters *ctr)
+{
+    if (ctr) k_x_extend<true><<<persistent_blocks(k_x_extend<true>, c.threads, c.blocks), c.threads, 0, c.stream>>>(sc, w, bounce, ctr);
+    else k_x_extend<false><<<persistent_blocks(k_x_extend<false>, c.threads, c.blocks), c.threads, 0, c.stream>>>(sc, w, bounce, ctr);
+}
+void mfx_x_shade(const LaunchCfg &c, const SceneX &sc, const WaveX &w, TileMap tm, int pix0, int npix, int s0, int bounce, uint64_t seed)
+{
+    k_x_shade<<<persistent_blocks(k_x_shade, c.threads, c.blocks), c.threads, 0, c.stream>>>(sc, w, tm, pix0, npix, s0, bounce, seed);
+}
+void mfx_x_shadow(const LaunchCfg &c, const SceneX &sc, const WaveX &w, int bounce, TravCounters *ctr)
+{
+    if (ctr) k_x_shadow<true><<<persistent_blocks(k_x_shadow<true>, c.threads, c.blocks), c.threads, 0, c.stream>>>(sc, w, bounce, ctr);
+    else k_x_shadow<false><<<persistent_blocks(k_x_shadow<false>, c.threads, c.blocks), c.threads, 0, c.stream>>>(sc, w, bounce, ctr);
+}
+void mfx_x_resolve(const LaunchCfg &c, const SceneX &sc, const WaveX &w, TileMap tm, int pix0, int npix, int S, double *pixsum)
+{
+    k_x_resolve<<<persistent_blocks(k_x_resolve, c.threads, c.blocks), c.threads, 0, c.stream>>>(sc, w, tm, pix0, npix, S, pixsum);
+}
+void mfx_x_bvh_hit(const LaunchCfg &c, const SceneX &sc, int any_hit, long long n, const double *o, const double *d,
+                   double tmin, double tmax, int *prim, int *sub, double *t)
+{
+    k_x_bvh_hit<<<persistent_blocks(k_x_bvh_hit, c.threads, c.blocks), c.threads, 0, c.stream>>>(sc, any_hit, n, o, d, tmin, tmax, prim, sub, t);
+}
+void mfx_x_primary(const LaunchCfg &c, const SceneX &sc, long long n, const double *uv, int *prim, double *t)
+{
+    k_x_primary<<<persistent_blocks(k_x_primary, c.threads, c.blocks), c.threads, 0, c.stream>>>(sc, n, uv, prim, t);
+}
+void mfx_x_finalize(const LaunchCfg &c, const double *pixsum, int width, int height, double, int spp, TileMap tm,
+                    double *color_wh, float4 *rgba_f32)
+{
+    k_finalize<<<persistent_blocks(k_finalize, 256, c.blocks), 256, 0, c.stream>>>(pixsum, width, height, spp, tm, color_wh, rgba_f32);
+}

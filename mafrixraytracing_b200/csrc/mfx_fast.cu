@@ -1,0 +1,546 @@
+// mfx_fast.cu -- MFX_FAST_F32 wavefront kernels (the throughput path) + small utility kernels.
+//
+// Layout (mfx_internal.h): children-pair records of 64 B (4 x float4, one per interior heap
+// node, boxes rounded outward), 48 B primitive slots in leaf order (3 x float4), geometric
+// normals + material in a 16 B side array touched only by the shading kernel.
+// Traversal: one ray per thread, ordered descent (near child first), t-shrink, STACKLESS --
+// the reference tree is heap-indexed (BvhNode.fs:40-41), so the deferred far children are a
+// 32-bit trail register (one bit per level) and the only per-level state kept is the far
+// child's entry distance, in shared memory (conflict-free: column = thread).
+#include "mfx_device.cuh"
+
+typedef V3<float> F3;
+
+#define FAST_BLOCK 128
+#define FAST_LEVELS 30
+
+__device__ __forceinline__ F3 f3(float x, float y, float z) { return mk3<float>(x, y, z); }
+__device__ __forceinline__ float4 ldg4(const float4 *p) { return __ldg(p); }
+
+struct RayF {
+    F3 o, d, idir, ood;
+    float tmin;
+    int src;    // leaf-order primitive the ray starts on (never re-hit a planar source), -1 none
+};
+
+__device__ __forceinline__ float safe_rcp(float d)
+{
+    const float eps = 1e-30f;
+    return 1.0f / (fabsf(d) > eps ? d : copysignf(eps, d));
+}
+
+__device__ __forceinline__ RayF make_ray(F3 o, F3 d, float tmin, int src)
+{
+    RayF r; r.o = o; r.d = d; r.tmin = tmin; r.src = src;
+    r.idir = f3(safe_rcp(d.x), safe_rcp(d.y), safe_rcp(d.z));
+    r.ood = f3(o.x * r.idir.x, o.y * r.idir.y, o.z * r.idir.z);
+    return r;
+}
+
+// slab test; returns entry distance, hit iff entry <= exit
+__device__ __forceinline__ bool box_f(const RayF &r, float lx, float ly, float lz, float hx, float hy, float hz,
+                                      float tmax, float &entry)
+{
+    const float x0 = fmaf(lx, r.idir.x, -r.ood.x), x1 = fmaf(hx, r.idir.x, -r.ood.x);
+    const float y0 = fmaf(ly, r.idir.y, -r.ood.y), y1 = fmaf(hy, r.idir.y, -r.ood.y);
+    const float z0 = fmaf(lz, r.idir.z, -r.ood.z), z1 = fmaf(hz, r.idir.z, -r.ood.z);
+    const float tn = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fmaxf(fminf(z0, z1), r.tmin));
+    const float tf = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fminf(fmaxf(z0, z1), tmax));
+    entry = tn;
+    return tn <= tf;
+}
+
+// Intersects the `cnt` slots of one leaf.  Moller-Trumbore with the reference's rejection rules
+// (Trangle.fs:120-148: |div| < 1e-6, b1 in [0,1], b2 >= 0, b1+b2 < 1, t > tMin) and the stable
+// quadratic of Sphere.fs:21-43.  Closest: keeps t < best_t.  Returns true if anything was hit.
+template <bool COUNT>
+__device__ __forceinline__ bool leaf_f(const SceneF &sc, const RayF &r, int meta, float &best_t, int &best_slot,
+                                       unsigned long long *ctr)
+{
+    const int first = meta >> 3, cnt = meta & 7;
+    bool any = false;
+    for (int k = 0; k < cnt; k++) {
+        const SlotF *sp = sc.slots + first + k;
+        const float4 a = ldg4(&sp->a);
+        const float4 b = ldg4(&sp->b);
+        const int prim = __float_as_int(b.w) & 0x3fffffff;
+        if (__float_as_int(a.w) != 2) {
+            const float4 c = ldg4(&sp->c);
+            if (COUNT) ctr[1]++;
+            if (prim == r.src) continue;
+            const F3 e1 = f3(b.x, b.y, b.z), e2 = f3(c.x, c.y, c.z);
+            const F3 s1 = cross(r.d, e2);
+            const float div = dot(s1, e1);
+            if (fabsf(div) < 1e-6f) continue;
+            const float inv = 1.0f / div;
+            const F3 dd = r.o - f3(a.x, a.y, a.z);
+            const float b1 = dot(dd, s1) * inv;
+            if (b1 < 0.f || b1 > 1.f) continue;
+            const F3 s2 = cross(dd, e1);
+            const float b2 = dot(r.d, s2) * inv;
+            if (b2 < 0.f || (b1 + b2) >= 1.f) continue;
+            const float t = dot(e2, s2) * inv;
+            if (t > r.tmin && t < best_t) { best_t = t; best_slot = first + k; any = true; }
+        } else {
+            if (COUNT) ctr[2]++;
+            const F3 oc = r.o - f3(a.x, a.y, a.z);
+            const float hb = dot(oc, r.d);                   // b/2
+            // discriminant/4 via the residual of oc against the ray: robust in f32 when
+            // |oc| >> radius (Haines et al., "Precision improvements for ray/sphere intersection")
+            const F3 perp = oc - r.d * hb;
+            const float disc = b.y - dot(perp, perp);        // r^2 - |perp|^2
+            if (disc > 0.f) {
+                const float root = sqrtf(disc);
+                const float q = (hb < 0.f) ? -(hb - root) : -(hb + root);
+                const float cc = dot(oc, oc) - b.y;
+                float t0 = q, t1 = (q != 0.f) ? cc / q : q;
+                float lo = fminf(t0, t1), hi = fmaxf(t0, t1);
+                if (prim == r.src) {
+                    // leaving a convex surface outward cannot re-hit it; entering takes the far root
+                    if (hb >= 0.f) continue;
+                    lo = -1.f;
+                }
+                float t = -1.f;
+                if (lo >= r.tmin && lo < best_t) t = lo;
+                else if (hi > r.tmin && hi < best_t) t = hi;
+                if (t > 0.f) { best_t = t; best_slot = first + k; any = true; }
+            }
+        }
+    }
+    return any;
+}
+
+// Closest hit (ANY=false) or occlusion (ANY=true) for one ray.
+template <bool ANY, bool COUNT>
+__device__ __forceinline__ void trace_f(const SceneF &sc, const RayF &r, float tmax, float &best_t, int &best_slot,
+                                        float *lvl_entry /* shared: [level*FAST_BLOCK] column of this thread */,
+                                        unsigned long long *ctr)
+{
+    best_t = tmax; best_slot = -1;
+    float e;
+    if (COUNT) ctr[0]++;
+    if (!box_f(r, sc.root_min[0], sc.root_min[1], sc.root_min[2], sc.root_max[0], sc.root_max[1], sc.root_max[2], best_t, e)) return;
+    if (sc.root_meta >= 0) { leaf_f<COUNT>(sc, r, sc.root_meta, best_t, best_slot, ctr); return; }
+    unsigned h = 1u;        // 1-based heap index of the current interior node
+    unsigned pend = 0u;     // bit L set: the sibling of our ancestor at depth L is still to be visited
+    for (;;) {
+        const PairF *pp = sc.pairs + (h - 1u);
+        const float4 q0 = ldg4(&pp->q0), q1 = ldg4(&pp->q1), q2 = ldg4(&pp->q2), q3 = ldg4(&pp->q3);
+        if (COUNT) ctr[0] += 2;
+        const int metaL = __float_as_int(q3.x), metaR = __float_as_int(q3.y);
+        float eL, eR;
+        bool hitL = box_f(r, q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, best_t, eL);
+        bool hitR = box_f(r, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, best_t, eR);
+        // leaf children are intersected at once, nearer leaf first
+        const bool lfL = hitL && metaL >= 0, lfR = hitR && metaR >= 0;
+        if (lfL || lfR) {
+            bool found = false;
+            if (lfL && lfR) {
+                const bool rFirst = eR < eL;
+                found |= leaf_f<COUNT>(sc, r, rFirst ? metaR : metaL, best_t, best_slot, ctr);
+                if (!(ANY && found) && (rFirst ? eL : eR) <= best_t)
+                    found |= leaf_f<COUNT>(sc, r, rFirst ? metaL : metaR, best_t, best_slot, ctr);
+            } else found = leaf_f<COUNT>(sc, r, lfL ? metaL : metaR, best_t, best_slot, ctr);
+            if (ANY && found) return;
+        }
+        const bool goL = hitL && metaL < 0 && eL <= best_t;
+        const bool goR = hitR && metaR < 0 && eR <= best_t;
+        if (goL || goR) {
+            const bool rNear = goR && (!goL || eR < eL);
+            if (goL && goR) {
+                const unsigned lvl = 32u - __clz(h);       // depth of the children
+                pend |= 1u << lvl;
+                if (!ANY) lvl_entry[lvl * FAST_BLOCK] = rNear ? eL : eR;
+            }
+            h = 2u * h + (rNear ? 1u : 0u);
+            continue;
+        }
+        // pop the deepest deferred sibling that can still beat the best hit
+        for (;;) {
+            if (pend == 0u) return;
+            const unsigned b = 31u - __clz(pend);
+            pend ^= 1u << b;
+            const unsigned dc = 31u - __clz(h);
+            h = (h >> (dc - b)) ^ 1u;
+            if (ANY || lvl_entry[b * FAST_BLOCK] <= best_t) break;
+        }
+    }
+}
+
+// ---------------------------------------------------------------- kernels
+__device__ __forceinline__ F3 normalize_f(F3 a)
+{
+    const float l2 = len2(a);
+    const float inv = (l2 > 0.f) ? rsqrtf(l2) : 0.f;
+    return a * inv;
+}
+
+__device__ __forceinline__ F3 camera_dir_f64(const CamX &c, double u, double v)
+{
+    // generated in f64 with the reference's operation order (Camera.fs:134-139), rounded once
+    const double tx = (c.topleft[0] + c.right[0] * u) + c.down[0] * v - c.pos[0];
+    const double ty = (c.topleft[1] + c.right[1] * u) + c.down[1] * v - c.pos[1];
+    const double tz = (c.topleft[2] + c.right[2] * u) + c.down[2] * v - c.pos[2];
+    const double l = sqrt(tx * tx + ty * ty + tz * tz);
+    return f3((float)(tx / l), (float)(ty / l), (float)(tz / l));
+}
+
+__global__ void __launch_bounds__(256) k_f_raygen(SceneF sc, WaveF w, TileMap tm, int pix0, int npix, int s0, int S, uint64_t seed)
+{
+    const long long total = (long long)npix * S;
+    for (long long pid = (long long)blockIdx.x * blockDim.x + threadIdx.x; pid < total; pid += (long long)gridDim.x * blockDim.x) {
+        const int sl = (int)(pid / npix), pl = (int)(pid - (long long)sl * npix);
+        int pix, px, py;
+        pixel_of(tm, sc.width, pix0 + pl, pix, px, py);
+        uint32_t o4[4];
+        philox4x32_10((uint32_t)pix, (uint32_t)(s0 + sl), MFX_DIM_CAMERA, 0, (uint32_t)seed, (uint32_t)(seed >> 32), o4);
+        const double u = ((double)px + u32_to_unit_f64(o4[0])) / (double)sc.width;
+        const double v = ((double)py + u32_to_unit_f64(o4[1])) / (double)sc.height;
+        const F3 d = camera_dir_f64(sc.camx, u, v);
+        w.ray_o[pid] = make_float4(sc.cam.pos[0], sc.cam.pos[1], sc.cam.pos[2], __int_as_float(-1));
+        w.ray_d[pid] = make_float4(d.x, d.y, d.z, 0.f);
+        w.thr[pid] = make_float4(1.f, 1.f, 1.f, 0.f);
+        w.rad[pid] = make_float4(0.f, 0.f, 0.f, 0.f);
+        w.q_ext[0][pid] = (int)pid;
+        if (pid == 0) w.counts[0] = (int)total;
+    }
+}
+
+template <bool COUNT>
+__global__ void __launch_bounds__(FAST_BLOCK) k_f_extend(SceneF sc, WaveF w, int bounce, TravCounters *ctr)
+{
+    __shared__ float s_entry[FAST_LEVELS * FAST_BLOCK];
+    const int n = w.counts[bounce];
+    const int *q = w.q_ext[bounce & 1];
+    unsigned long long local[3] = { 0, 0, 0 };
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int pid = q[i];
+        const float4 o = w.ray_o[pid], d = w.ray_d[pid];
+        const RayF r = make_ray(f3(o.x, o.y, o.z), f3(d.x, d.y, d.z), 1e-6f, __float_as_int(o.w));
+        float t; int slot;
+        trace_f<false, COUNT>(sc, r, 99999999.f, t, slot, s_entry + threadIdx.x, local);
+        w.hit[pid] = make_float2(t, __int_as_float(slot));
+    }
+    if (COUNT) { for (int k = 0; k < 3; k++) if (local[k]) atomicAdd(&ctr->v[0][k], local[k]); }
+}
+
+template <bool COUNT>
+__global__ void __launch_bounds__(FAST_BLOCK) k_f_shadow(SceneF sc, WaveF w, int bounce, TravCounters *ctr)
+{
+    const int n = w.counts[MFX_MAX_VERTS + 2 + bounce];
+    const int *q = w.q_sh;
+    unsigned long long local[3] = { 0, 0, 0 };
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int pid = q[i];
+        const float4 o = w.ray_o[pid], d = w.sh_d[pid];
+        const RayF r = make_ray(f3(o.x, o.y, o.z), f3(d.x, d.y, d.z), 1e-6f, __float_as_int(o.w));
+        float t; int slot;
+        trace_f<true, COUNT>(sc, r, d.w - 1e-6f, t, slot, nullptr, local);      // Integrators.fs:44
+        if (slot < 0) {
+            const float4 c = w.sh_c[pid];
+            float4 a = w.rad[pid];
+            a.x += c.x; a.y += c.y; a.z += c.z;
+            w.rad[pid] = a;
+        }
+    }
+    if (COUNT) { for (int k = 0; k < 3; k++) if (local[k]) atomicAdd(&ctr->v[1][k], local[k]); }
+}
+
+struct RngF { uint32_t pixel, sample, k0, k1; };
+
+// GetRandomInUnitSphere (Material.fs:9-14) on the f32 view of the same Philox stream.
+__device__ __forceinline__ F3 random_in_unit_sphere_f(F3 nm, const RngF &g, uint32_t dim)
+{
+    for (uint32_t it = 0; it < MFX_REJECTION_CAP; it++) {
+        uint32_t o[4];
+        philox4x32_10(g.pixel, g.sample, dim, it, g.k0, g.k1, o);
+        const F3 p = f3(2.f * u32_to_unit_f32(o[0]) - 1.f, 2.f * u32_to_unit_f32(o[1]) - 1.f, 2.f * u32_to_unit_f32(o[2]) - 1.f);
+        if (dot(p, p) < 1.0f && dot(nm, p) > 0.f) return p;
+    }
+    return nm;
+}
+
+__device__ __forceinline__ F3 tri_sample_f(const float *v0, const float *e1, const float *e2, float tu, float tv)
+{
+    float u = tu, v = tv;
+    if (tu + tv > 1.f) { u = 1.f - tu; v = 1.f - tv; }
+    const float sq = sqrtf(1.f - u);
+    const float s1 = 1.f - sq, s2 = v * sq;
+    return f3(v0[0] + e1[0] * s1 + e2[0] * s2, v0[1] + e1[1] * s1 + e2[1] * s2, v0[2] + e1[2] * s1 + e2[2] * s2);
+}
+
+__device__ __forceinline__ float fresnel_f(float eta_i, float eta_t, float cosi)    // Material.fs:74-96
+{
+    const float ei = cosi > 0.f ? eta_i : eta_t, et = cosi > 0.f ? eta_t : eta_i;
+    const float sint = ei / et * sqrtf(fmaxf(0.f, 1.f - cosi * cosi));
+    if (sint >= 1.f) return 1.f;
+    const float cost = sqrtf(fmaxf(0.f, 1.f - sint * sint));
+    const float ci = fabsf(cosi);
+    const float rparl = ((et * ci) - (ei * cost)) / ((et * ci) + (ei * cost));
+    const float rperp = ((ei * ci) - (et * cost)) / ((ei * ci) + (et * cost));
+    return (rparl * rparl + rperp * rperp) * 0.5f;
+}
+
+// Shades vertex `bounce` of every path in the extend queue: BSDF/scatter sample, light sample,
+// throughput update; compacts survivors into the next extend queue and the shadow queue with
+// warp-aggregated appends.  Radiance bookkeeping (both integrators unrolled):
+//   mode 0 (Integrators.fs:136):  L += T * (l/pdf_li) * col ;  T *= col/pdf
+//   mode 1 (PathTracer.fs:40-41): L += T * l * col          ;  T *= col * shadeFactor
+__global__ void __launch_bounds__(FAST_BLOCK) k_f_shade(SceneF sc, WaveF w, TileMap tm, int pix0, int npix, int s0, int bounce, uint64_t seed)
+{
+    const int n = w.counts[bounce];
+    const int *qin = w.q_ext[bounce & 1];
+    int *qout = w.q_ext[(bounce + 1) & 1];
+    const int k = bounce;
+    const bool last = (bounce >= sc.max_depth);
+    const int nwarp_iters = (n + 31) / 32;
+    for (int it = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); it < nwarp_iters; it += gridDim.x * (blockDim.x >> 5)) {
+        const int i = it * 32 + (threadIdx.x & 31);
+        bool cont = false, shadow = false;
+        int pid = -1;
+        if (i < n) {
+            pid = qin[i];
+            const float2 hr = w.hit[pid];
+            const int fs = __float_as_int(hr.y);
+            if (fs >= 0) {
+                const float t = hr.x;
+                const float4 o4 = w.ray_o[pid], d4 = w.ray_d[pid];
+                const F3 o = f3(o4.x, o4.y, o4.z), d = f3(d4.x, d4.y, d4.z);
+                const F3 point = o + d * t;
+                const float4 sa = ldg4(&sc.slots[fs].a);
+                const float4 sb = ldg4(&sc.slots[fs].b);
+                const float4 nm4 = ldg4(&sc.slot_nrm[fs]);
+                const int prim = __float_as_int(sb.w) & 0x3fffffff;
+                F3 normal = f3(nm4.x, nm4.y, nm4.z);
+                if (__float_as_int(sa.w) == 2) normal = normalize_f(point - f3(sa.x, sa.y, sa.z));
+                const MatF m = sc.mats[__float_as_int(nm4.w)];
+                const int sl = pid / npix, pl = pid - sl * npix;
+                int pix, px, py;
+                pixel_of(tm, sc.width, pix0 + pl, pix, px, py);
+                RngF g; g.pixel = (uint32_t)pix; g.sample = (uint32_t)(s0 + sl); g.k0 = (uint32_t)seed; g.k1 = (uint32_t)(seed >> 32);
+
+                F3 wi; float cr, cg, cb; float sf = 1.f;   // col and the Shade factor applied to the continuation
+                if (sc.mode == 0) {
+                    const float z = (m.kind == 2) ? 0.f : 1.f;
+                    wi = normalize_f(random_in_unit_sphere_f(normal, g, MFX_DIM_BSDF(k)));
+                    const float ei2 = 2.f * dot(normal, wi);                 // INVPI * a * ei * TwoPi
+                    cr = z * m.albedo[0] * ei2; cg = z * m.albedo[1] * ei2; cb = z * m.albedo[2] * ei2;
+                } else if (m.kind == 0) {
+                    wi = normalize_f(random_in_unit_sphere_f(normal, g, MFX_DIM_BSDF(k)));
+                    const float ip = 0.318309886183790672f;
+                    cr = m.albedo[0] * ip; cg = m.albedo[1] * ip; cb = m.albedo[2] * ip;
+                    sf = 6.283185307179586477f * dot(normal, wi);            // Lambertian.Shade
+                } else if (m.kind == 1) {
+                    const float fuzz = fminf(m.fuzz, 1.f);
+                    const F3 refl = d - normal * (2.f * dot(d, normal));
+                    wi = normalize_f(refl + random_in_unit_sphere_f(normal, g, MFX_DIM_BSDF(k)) * fuzz);
+                    cr = m.albedo[0]; cg = m.albedo[1]; cb = m.albedo[2];
+                } else {
+                    const F3 dir = -d;
+                    const float cosi = dot(dir, normal);
+                    const float ei = cosi > 0.f ? m.ei : m.et, et = cosi > 0.f ? m.et : m.ei;
+                    const float r = ei / et;
+                    const float dt = dot(normalize_f(dir), normal);
+                    const float disc = 1.f - r * r * (1.f - dt * dt);
+                    if (disc > 0.f) {
+                        wi = (dir - normal * dt) * r - normal * sqrtf(disc);
+                        const float F = fresnel_f(m.ei, m.et, cosi);
+                        const float f = (et * et) / (ei * ei) * (1.f - F) / fabsf(dot(wi, normal));
+                        cr = f * m.albedo[0]; cg = f * m.albedo[1]; cb = f * m.albedo[2];
+                    } else {
+                        wi = dir - normal * (2.f * dot(dir, normal));
+                        cr = cg = cb = 0.f;
+                    }
+                }
+                // light sample (Rect.fs:33-38, Trangle.fs:157-169, Light.fs:42-59)
+                uint32_t lo4[4];
+                philox4x32_10(g.pixel, g.sample, MFX_DIM_LIGHT(k), 0, g.k0, g.k1, lo4);
+                const float us = u32_to_unit_f32(lo4[0]), tu = u32_to_unit_f32(lo4[1]), tv = u32_to_unit_f32(lo4[2]);
+                // the coin uses the full 32-bit value so it matches the f64 stream's `s < 0.5`
+                const F3 lp = (lo4[0] < 0x80000000u) ? tri_sample_f(sc.light.v0a, sc.light.e1a, sc.light.e2a, tu, tv)
+                                                     : tri_sample_f(sc.light.v0b, sc.light.e1b, sc.light.e2b, tu, tv);
+                (void)us;
+                const F3 toLight = lp - point;
+                const float d2 = len2(toLight);
+                const float dist = sqrtf(d2);
+                const F3 unit = toLight * (1.f / dist);
+                const float cos_o = dot(toLight, f3(sc.light.normal[0], sc.light.normal[1], sc.light.normal[2]));
+                float4 thr = w.thr[pid];
+                float lscale = 0.f;
+                if (cos_o < 0.f) lscale = dot(unit, normal) * (fabsf(cos_o) * sc.light.area / d2);
+                if (sc.mode == 0) lscale *= sc.light.inv_pdf;                // l / pdf_li
+                const float4 c = make_float4(thr.x * cr * lscale * sc.light.color[0], thr.y * cg * lscale * sc.light.color[1],
+                                             thr.z * cb * lscale * sc.light.color[2], 0.f);
+                shadow = (c.x != 0.f) || (c.y != 0.f) || (c.z != 0.f);
+                thr.x *= cr * sf; thr.y *= cg * sf; thr.z *= cb * sf;
+                cont = !last && ((thr.x != 0.f) || (thr.y != 0.f) || (thr.z != 0.f));
+                if (shadow) { w.sh_d[pid] = make_float4(unit.x, unit.y, unit.z, dist); w.sh_c[pid] = c; }
+                if (shadow || cont) {
+                    // planar sources are never re-hit; spheres keep themselves as source (far root / none)
+                    w.ray_o[pid] = make_float4(point.x, point.y, point.z, __int_as_float(prim));
+                }
+                if (cont) { w.ray_d[pid] = make_float4(wi.x, wi.y, wi.z, 0.f); w.thr[pid] = thr; }
+            }
+        }
+        const int pe = warp_append(cont, &w.counts[bounce + 1]);
+        if (cont) qout[pe] = pid;
+        const int ps = warp_append(shadow, &w.counts[MFX_MAX_VERTS + 2 + bounce]);
+        if (shadow) w.q_sh[ps] = pid;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_f_resolve(SceneF sc, WaveF w, TileMap tm, int pix0, int npix, int S, double *pixsum)
+{
+    for (int pl = blockIdx.x * blockDim.x + threadIdx.x; pl < npix; pl += gridDim.x * blockDim.x) {
+        int pix, px, py;
+        pixel_of(tm, sc.width, pix0 + pl, pix, px, py);
+        float r = 0.f, g = 0.f, b = 0.f;
+        for (int sl = 0; sl < S; sl++) {
+            const float4 a = w.rad[(size_t)sl * npix + pl];
+            r += a.x; g += a.y; b += a.z;
+        }
+        double *p = pixsum + 4 * (size_t)pix;
+        p[0] += (double)r; p[1] += (double)g; p[2] += (double)b; p[3] = 1.0;
+    }
+}
+
+__global__ void __launch_bounds__(FAST_BLOCK) k_f_bvh_hit(SceneF sc, int any_hit, long long n, const double *o, const double *d,
+                                                          double tmin, double tmax, int *prim, int *sub, double *t)
+{
+    __shared__ float s_entry[FAST_LEVELS * FAST_BLOCK];
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const RayF r = make_ray(f3((float)o[3 * i], (float)o[3 * i + 1], (float)o[3 * i + 2]),
+                                f3((float)d[3 * i], (float)d[3 * i + 1], (float)d[3 * i + 2]), (float)tmin, -1);
+        float bt; int slot;
+        if (any_hit) trace_f<true, false>(sc, r, (float)tmax, bt, slot, nullptr, nullptr);
+        else trace_f<false, false>(sc, r, (float)tmax, bt, slot, s_entry + threadIdx.x, nullptr);
+        if (slot < 0) { prim[i] = -1; if (sub) sub[i] = 0; t[i] = 0.; }
+        else {
+            const int ps = __float_as_int(sc.slots[slot].b.w);
+            prim[i] = sc.ref_id[ps & 0x3fffffff];
+            if (sub) sub[i] = (ps >> 30) & 1;
+            t[i] = (double)bt;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(FAST_BLOCK) k_f_primary(SceneF sc, long long n, const double *uv, int *prim, double *t)
+{
+    __shared__ float s_entry[FAST_LEVELS * FAST_BLOCK];
+    for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += (long long)gridDim.x * blockDim.x) {
+        double u, v;
+        if (uv) { u = uv[2 * r]; v = uv[2 * r + 1]; }
+        else {
+            const int j = (int)(r / sc.width), i = (int)(r - (long long)j * sc.width);
+            u = ((double)i + 0.5) / (double)sc.width;
+            v = ((double)j + 0.5) / (double)sc.height;
+        }
+        const F3 d = camera_dir_f64(sc.camx, u, v);
+        const RayF ray = make_ray(f3(sc.cam.pos[0], sc.cam.pos[1], sc.cam.pos[2]), d, 1e-6f, -1);
+        float bt; int slot;
+        trace_f<false, false>(sc, ray, 99999999.f, bt, slot, s_entry + threadIdx.x, nullptr);
+        if (slot < 0) { prim[r] = -1; t[r] = 0.; }
+        else { prim[r] = sc.ref_id[__float_as_int(sc.slots[slot].b.w) & 0x3fffffff]; t[r] = (double)bt; }
+    }
+}
+
+// ---------------------------------------------------------------- utility kernels
+__global__ void k_accum_totals(const int *counts, int ext_lo, int ext_n, int sh_lo, int sh_n, unsigned long long *totals)
+{
+    unsigned long long e = 0, s = 0;
+    for (int i = 0; i < ext_n; i++) e += (unsigned)counts[ext_lo + i];
+    for (int i = 0; i < sh_n; i++) s += (unsigned)counts[sh_lo + i];
+    totals[0] += e; totals[1] += s; totals[2] += (unsigned)counts[0];
+}
+
+// Film.AddSample (Film.fs:18-23): c = sum + frame; sum <- c; target <- c / frameCount
+__global__ void __launch_bounds__(256) k_film_add(double *sum, const double *frame, double *target, long long n_pixels, double fc)
+{
+    for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < n_pixels; p += (long long)gridDim.x * blockDim.x) {
+        for (int c = 0; c < 3; c++) {
+            const double v = sum[4 * p + c] + frame[4 * p + c];
+            sum[4 * p + c] = v;
+            target[4 * p + c] = v / fc;
+        }
+        const double a = sum[4 * p + 3] + frame[4 * p + 3];
+        sum[4 * p + 3] = a < 1.0 ? a : 1.0;
+        target[4 * p + 3] = 1.0;
+    }
+}
+
+__device__ __forceinline__ double clamp01(double x) { return x < 0. ? 0. : (x > 1. ? 1. : x); }
+
+// ACESFilmToneMapping + sqrt + int(255.99 c) (Scene.fs:273-289,315-330).  target is Color[w,h]
+// x-major; out is RGBA8 at x*4 + y*width*4.  f64 with explicit non-fused operations.
+__global__ void __launch_bounds__(256) k_film_tonemap(const double *target, int width, int height, uint8_t *rgba8)
+{
+    const long long n = (long long)width * height;
+    for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += (long long)gridDim.x * blockDim.x) {
+        const int y = (int)(p / width), x = (int)(p - (long long)y * width);
+        const double *px = target + ((size_t)x * height + y) * 4;
+        uint8_t out[4];
+        for (int c = 0; c < 3; c++) {
+            const double v = px[c];
+            const double num = __dmul_rn(v, __dadd_rn(__dmul_rn(2.51, v), 0.03));
+            const double den = __dadd_rn(__dmul_rn(v, __dadd_rn(__dmul_rn(2.43, v), 0.59)), 0.14);
+            const double q = sqrt(clamp01(num / den));
+            out[c] = (uint8_t)(int)__dmul_rn(255.99, q);
+        }
+        out[3] = 255;
+        *reinterpret_cast<uchar4 *>(rgba8 + 4 * p) = make_uchar4(out[0], out[1], out[2], out[3]);
+    }
+}
+
+__global__ void __launch_bounds__(256) k_fill_zero(double *p, long long n)
+{
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) p[i] = 0.;
+}
+
+// ---------------------------------------------------------------- launchers
+void mfx_f_raygen(const LaunchCfg &c, const SceneF &sc, const WaveF &w, TileMap tm, int pix0, int npix, int s0, int S, uint64_t seed)
+{
+    k_f_raygen<<<persistent_blocks(k_f_raygen, 256, c.blocks), 256, 0, c.stream>>>(sc, w, tm, pix0, npix, s0, S, seed);
+}
+void mfx_f_extend(const LaunchCfg &c, const SceneF &sc, const WaveF &w, int bounce, TravCounters *ctr)
+{
+    if (ctr) k_f_extend<true><<<persistent_blocks(k_f_extend<true>, FAST_BLOCK, c.blocks), FAST_BLOCK, 0, c.stream>>>(sc, w, bounce, ctr);
+    else k_f_extend<false><<<persistent_blocks(k_f_extend<false>, FAST_BLOCK, c.blocks), FAST_BLOCK, 0, c.stream>>>(sc, w, bounce, ctr);
+}
+void mfx_f_shade(const LaunchCfg &c, const SceneF &sc, const WaveF &w, TileMap tm, int pix0, int npix, int s0, int bounce, uint64_t seed)
+{
+    k_f_shade<<<persistent_blocks(k_f_shade, FAST_BLOCK, c.blocks), FAST_BLOCK, 0, c.stream>>>(sc, w, tm, pix0, npix, s0, bounce, seed);
+}
+void mfx_f_shadow(const LaunchCfg &c, const SceneF &sc, const WaveF &w, int bounce, TravCounters *ctr)
+{
+    if (ctr) k_f_shadow<true><<<persistent_blocks(k_f_shadow<true>, FAST_BLOCK, c.blocks), FAST_BLOCK, 0, c.stream>>>(sc, w, bounce, ctr);
+    else k_f_shadow<false><<<persistent_blocks(k_f_shadow<false>, FAST_BLOCK, c.blocks), FAST_BLOCK, 0, c.stream>>>(sc, w, bounce, ctr);
+}
+void mfx_f_resolve(const LaunchCfg &c, const SceneF &sc, const WaveF &w, TileMap tm, int pix0, int npix, int S, double *pixsum)
+{
+    k_f_resolve<<<persistent_blocks(k_f_resolve, 256, c.blocks), 256, 0, c.stream>>>(sc, w, tm, pix0, npix, S, pixsum);
+}
+void mfx_f_bvh_hit(const LaunchCfg &c, const SceneF &sc, int any_hit, long long n, const double *o, const double *d,
+                   double tmin, double tmax, int *prim, int *sub, double *t)
+{
+    k_f_bvh_hit<<<persistent_blocks(k_f_bvh_hit, FAST_BLOCK, c.blocks), FAST_BLOCK, 0, c.stream>>>(sc, any_hit, n, o, d, tmin, tmax, prim, sub, t);
+}
+void mfx_f_primary(const LaunchCfg &c, const SceneF &sc, long long n, const double *uv, int *prim, double *t)
+{
+    k_f_primary<<<persistent_blocks(k_f_primary, FAST_BLOCK, c.blocks), FAST_BLOCK, 0, c.stream>>>(sc, n, uv, prim, t);
+}
+void mfx_accum_ray_totals(cudaStream_t s, const int *counts, int ext_lo, int ext_n, int sh_lo, int sh_n, unsigned long long *totals)
+{
+    k_accum_totals<<<1, 1, 0, s>>>(counts, ext_lo, ext_n, sh_lo, sh_n, totals);
+}
+void mfx_film_add(cudaStream_t s, double *sum, const double *frame, double *target, long long n_pixels, double fc)
+{
+    k_film_add<<<592, 256, 0, s>>>(sum, frame, target, n_pixels, fc);
+}
+void mfx_film_tonemap(cudaStream_t s, const double *target_wh, int width, int height, uint8_t *rgba8)
+{
+    k_film_tonemap<<<592, 256, 0, s>>>(target_wh, width, height, rgba8);
+}
+void mfx_fill_zero_f64(cudaStream_t s, double *p, long long n)
+{
+    k_fill_zero<<<592, 256, 0, s>>>(p, n);
+}

@@ -1,0 +1,908 @@
+// mfx_host.cpp -- host side of libmafrix_cuda: the C ABI (include/mafrix_cuda.h), the host
+// reproductions of PinholeCamera and Bvh.Build, scene flattening into the two HBM layouts and
+// the wavefront driver that sequences the kernels of mfx_exact.cu / mfx_fast.cu.
+//
+// Compiled with -ffp-contract=off: the flattening arithmetic (edge vectors, areas, camera
+// basis) must round exactly like the reference's f64 expressions.
+#include "../../include/mafrix_cuda.h"
+#include "mfx_internal.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <string>
+#include <tuple>
+#include <vector>
+
+// ------------------------------------------------------------------ errors
+static thread_local std::string g_err;
+
+static int fail(int code, const char *fmt, ...)
+{
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CUDA_TRY(x)                                                                              \
+    do {                                                                                         \
+        cudaError_t e_ = (x);                                                                    \
+        if (e_ != cudaSuccess)                                                                   \
+            return fail(e_ == cudaErrorMemoryAllocation ? MFX_ERR_OUT_OF_MEMORY : MFX_ERR_CUDA,  \
+                        "%s failed: %s (%s:%d)", #x, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+#define MFX_TRY(x)               \
+    do {                         \
+        int r_ = (x);            \
+        if (r_ != MFX_OK) return r_; \
+    } while (0)
+
+extern "C" const char *mfx_version(void) { return "mafrix_cuda 0.1 (sm_100a)"; }
+extern "C" const char *mfx_last_error(void) { return g_err.c_str(); }
+
+extern "C" int mfx_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+static thread_local int g_device = -1;
+
+extern "C" int mfx_init(int device)
+{
+    int n = mfx_device_count();
+    if (n <= 0) return fail(MFX_ERR_NO_DEVICE, "no CUDA device visible: libmafrix_cuda has no CPU fallback");
+    if (device < 0 || device >= n) return fail(MFX_ERR_INVALID_ARGUMENT, "device %d out of range (0..%d)", device, n - 1);
+    CUDA_TRY(cudaSetDevice(device));
+    g_device = device;
+    return MFX_OK;
+}
+
+static int ensure_device()
+{
+    if (g_device >= 0) { CUDA_TRY(cudaSetDevice(g_device)); return MFX_OK; }
+    return mfx_init(0);
+}
+
+// ------------------------------------------------------------------ host math (f64, reference order)
+struct H3 { double x, y, z; };
+static inline H3 h3(double x, double y, double z) { return H3{ x, y, z }; }
+static inline H3 hsub(H3 a, H3 b) { return h3(a.x - b.x, a.y - b.y, a.z - b.z); }
+static inline H3 hadd(H3 a, H3 b) { return h3(a.x + b.x, a.y + b.y, a.z + b.z); }
+static inline H3 hmul(H3 a, double s) { return h3(a.x * s, a.y * s, a.z * s); }
+static inline H3 hcross(H3 a, H3 b) { return h3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
+static inline double hlen(H3 a) { return std::sqrt(a.x * a.x + a.y * a.y + a.z * a.z); }
+static inline H3 hnorm(H3 a)
+{
+    double l = hlen(a);
+    if (l == 0.0) return h3(0, 0, 0);
+    return h3(a.x / l, a.y / l, a.z / l);
+}
+static inline H3 hld(const double *p) { return h3(p[0], p[1], p[2]); }
+static inline void hst(double *p, H3 v) { p[0] = v.x; p[1] = v.y; p[2] = v.z; }
+
+// PinholeCamera(pos, dir, fov, aspect): Camera.fs:96-133
+extern "C" int mfx_camera_pinhole(const double pos[3], const double dir[3], double fov, double aspect, MfxCamera *out)
+{
+    if (!pos || !dir || !out) return fail(MFX_ERR_INVALID_ARGUMENT, "mfx_camera_pinhole: null argument");
+    const double PI = 3.14159265358979323846;
+    H3 fwd = hnorm(hld(dir));                                   // CameraCoordinate(dir), Camera.fs:96-104
+    H3 up0 = hnorm(h3(0, 1, 0));
+    H3 hori = hcross(fwd, hnorm(up0));                          // not re-normalised (quirk Q5)
+    H3 vert = hcross(hori, fwd);
+    double hs = std::tan(0.5 * fov * PI / 360.);                // Camera.fs:125: effective FOV = fov/2
+    double vs = hs / aspect;
+    H3 up = hmul(vert, vs), right = hmul(hori, hs);
+    H3 down = h3(-up.x, -up.y, -up.z);
+    H3 p = hld(pos);
+    // TopLeft(pos, 0.5) = pos + dist*forward - 0.5*right + 0.5*up, Camera.fs:110-111
+    H3 tl = hadd(hsub(hadd(p, hmul(fwd, 0.5)), hmul(right, 0.5)), hmul(up, 0.5));
+    hst(out->pos, p); hst(out->topleft, tl); hst(out->right, right); hst(out->down, down);
+    return MFX_OK;
+}
+
+// ------------------------------------------------------------------ Bvh.Build reproduction
+struct HBound { double lo[3], hi[3]; };
+
+static HBound prim_bound(const MfxPrim &p)
+{
+    HBound b;
+    if (p.kind == MFX_SPHERE) {                                 // Sphere.fs:17-20: Bound(c - v, c + v)
+        for (int a = 0; a < 3; a++) {
+            double m0 = p.v[a] - p.v[3], m1 = p.v[a] + p.v[3];
+            b.lo[a] = std::min(m0, m1); b.hi[a] = std::max(m0, m1);
+        }
+        return b;
+    }
+    const int nv = (p.kind == MFX_RECT) ? 4 : 3;                // Trangle.fs:113, Rect.fs:23
+    for (int a = 0; a < 3; a++) {
+        double lo = p.v[a], hi = p.v[a];
+        for (int k = 1; k < nv; k++) { lo = std::min(lo, p.v[3 * k + a]); hi = std::max(hi, p.v[3 * k + a]); }
+        b.lo[a] = lo; b.hi[a] = hi;
+    }
+    return b;
+}
+
+struct BuildCtx {
+    const std::vector<HBound> *pb;
+    MfxBvhNode *nodes;
+    int32_t *indices;
+    int32_t n_slots;
+    std::vector<std::pair<double, int32_t>> scratch;
+};
+
+static MfxBvhNode init_node(const BuildCtx &c, int start, int count)    // BvhNode.fs:32-37
+{
+    MfxBvhNode n;
+    const HBound &b0 = (*c.pb)[c.indices[start]];
+    for (int a = 0; a < 3; a++) { n.pmin[a] = b0.lo[a]; n.pmax[a] = b0.hi[a]; }
+    for (int i = 1; i < count; i++) {
+        const HBound &b = (*c.pb)[c.indices[start + i]];
+        for (int a = 0; a < 3; a++) { n.pmin[a] = std::min(n.pmin[a], b.lo[a]); n.pmax[a] = std::max(n.pmax[a], b.hi[a]); }
+    }
+    n.first = start; n.count = count;
+    return n;
+}
+
+static int subdivide(BuildCtx &c, int root)                              // BvhNode.fs:42-61
+{
+    std::vector<int> todo{ root };
+    while (!todo.empty()) {
+        const int i = todo.back(); todo.pop_back();
+        const MfxBvhNode node = c.nodes[i];
+        if (node.count <= MFX_LEAF_NODE_COUNT) continue;
+        // Bound.MaximumExtent, Aggregate.fs:29-36
+        const double dx = node.pmax[0] - node.pmin[0], dy = node.pmax[1] - node.pmin[1], dz = node.pmax[2] - node.pmin[2];
+        const int axis = (dx > dy && dx > dz) ? 0 : (dy > dz ? 1 : 2);
+        c.scratch.resize(node.count);
+        for (int k = 0; k < node.count; k++) {
+            const int32_t id = c.indices[node.first + k];
+            const HBound &b = (*c.pb)[id];
+            const double dig = (b.hi[axis] - b.lo[axis]) * 0.5;           // b.Diagnal() * 0.5
+            c.scratch[k] = { b.lo[axis] + dig, id };                      // b.pMin + dig
+        }
+        // Array.sortInPlaceBy is an unstable introsort in .NET (quirk Q9); ties are fixed to "stable"
+        std::stable_sort(c.scratch.begin(), c.scratch.end(),
+                         [](const std::pair<double, int32_t> &a, const std::pair<double, int32_t> &b) { return a.first < b.first; });
+        for (int k = 0; k < node.count; k++) c.indices[node.first + k] = c.scratch[k].second;
+        const int leftcount = node.count / 2;
+        const int li = i * 2 + 1, ri = i * 2 + 2;
+        if (ri >= c.n_slots) return fail(MFX_ERR_INVALID_ARGUMENT, "mfx_bvh_build: heap index %d exceeds %d slots", ri, c.n_slots);
+        c.nodes[li] = init_node(c, node.first, leftcount);
+        c.nodes[ri] = init_node(c, node.first + leftcount, node.count - leftcount);
+        todo.push_back(ri);
+        todo.push_back(li);
+    }
+    return MFX_OK;
+}
+
+extern "C" int mfx_bvh_build(const MfxPrim *prims, int32_t n, MfxBvhNode *nodes_out, int32_t n_slots, int32_t *indices_out)
+{
+    if (!prims || !nodes_out || !indices_out || n <= 0) return fail(MFX_ERR_INVALID_ARGUMENT, "mfx_bvh_build: null/empty input");
+    if (n_slots != 2 * n - 1) return fail(MFX_ERR_INVALID_ARGUMENT, "mfx_bvh_build: n_slots must be 2n-1 = %d, got %d", 2 * n - 1, n_slots);
+    std::vector<HBound> pb(n);
+    for (int i = 0; i < n; i++) {
+        if (prims[i].kind < 0 || prims[i].kind > 2) return fail(MFX_ERR_INVALID_ARGUMENT, "primitive %d: unknown kind %d", i, prims[i].kind);
+        pb[i] = prim_bound(prims[i]);
+    }
+    for (int i = 0; i < n; i++) indices_out[i] = i;
+    memset(nodes_out, 0, sizeof(MfxBvhNode) * (size_t)n_slots);
+    BuildCtx c{ &pb, nodes_out, indices_out, n_slots, {} };
+    nodes_out[0] = init_node(c, 0, n);
+    return subdivide(c, 0);
+}
+
+// ------------------------------------------------------------------ scene
+struct MfxScene {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;
+    std::vector<MfxPrim> prims;
+    std::vector<MfxMaterial> mats;
+    std::vector<MfxBvhNode> nodes;
+    std::vector<int32_t> indices;
+    MfxAreaLight light;
+    MfxCamera camera;
+    int width = 0, height = 0, max_depth = 0, integrator = 0;
+
+    std::vector<void *> allocs;          // every cudaMalloc of this scene
+    bool x_ready = false, f_ready = false, wx_ready = false, wf_ready = false;
+    SceneX sx; SceneF sf; WaveX wx; WaveF wf;
+    uint64_t x_bytes = 0, f_bytes = 0;
+    double *d_pixsum = nullptr;          // [w*h][4] row-major sums
+    double *d_color_wh = nullptr;        // Color[w,h]
+    float4 *d_rgba = nullptr;            // row-major float4 (internal, when the caller gives none)
+    unsigned long long *d_totals = nullptr;   // [3]
+    TravCounters *d_ctr = nullptr;
+    void *h_pinned = nullptr; size_t h_pinned_bytes = 0;
+    std::map<std::tuple<int, int, int>, std::pair<int *, int>> tilemaps;
+    std::vector<cudaEvent_t> events;
+    MfxStats stats;
+};
+
+static int dev_alloc(MfxScene *s, void **p, size_t bytes)
+{
+    CUDA_TRY(cudaMalloc(p, bytes ? bytes : 16));
+    s->allocs.push_back(*p);
+    return MFX_OK;
+}
+template <typename T> static int dev_alloc_t(MfxScene *s, T **p, size_t count) { return dev_alloc(s, (void **)p, count * sizeof(T)); }
+
+template <typename T> static int upload(MfxScene *s, T **dp, const std::vector<T> &h)
+{
+    MFX_TRY(dev_alloc_t(s, dp, h.size()));
+    if (!h.empty()) CUDA_TRY(cudaMemcpyAsync(*dp, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice, s->stream));
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    return MFX_OK;
+}
+
+static long env_long(const char *name, long dflt)
+{
+    const char *v = getenv(name);
+    if (!v || !*v) return dflt;
+    return atol(v);
+}
+
+extern "C" int mfx_scene_create(const MfxSceneDesc *d, MfxScene **out)
+{
+    if (!d || !out) return fail(MFX_ERR_INVALID_ARGUMENT, "mfx_scene_create: null argument");
+    *out = nullptr;
+    if (!d->prims || d->n_prims <= 0) return fail(MFX_ERR_INVALID_ARGUMENT, "scene has no primitives");
+    if (d->n_prims >= (1 << 27)) return fail(MFX_ERR_UNSUPPORTED, "more than 2^27 primitives");
+    if (!d->materials || d->n_materials <= 0) return fail(MFX_ERR_INVALID_ARGUMENT, "scene has no materials");
+    if (d->width <= 0 || d->height <= 0) return fail(MFX_ERR_INVALID_ARGUMENT, "bad film size %dx%d", d->width, d->height);
+    if (d->max_depth < 0 || d->max_depth >= MFX_MAX_VERTS) return fail(MFX_ERR_UNSUPPORTED, "max_depth %d outside 0..%d", d->max_depth, MFX_MAX_VERTS - 1);
+    if (d->integrator != MFX_PATH_INTEGRATOR && d->integrator != MFX_NEW_PATH_TRACER) return fail(MFX_ERR_INVALID_ARGUMENT, "unknown integrator %d", d->integrator);
+    for (int i = 0; i < d->n_prims; i++) {
+        if (d->prims[i].kind < 0 || d->prims[i].kind > 2) return fail(MFX_ERR_INVALID_ARGUMENT, "primitive %d: unknown kind %d", i, d->prims[i].kind);
+        if (d->prims[i].material < 0 || d->prims[i].material >= d->n_materials)
+            return fail(MFX_ERR_INVALID_ARGUMENT, "primitive %d: material %d outside the table of %d", i, d->prims[i].material, d->n_materials);
+    }
+    MFX_TRY(ensure_device());
+    MfxScene *s = new MfxScene();
+    s->device = g_device;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, s->device) == cudaSuccess) s->sm_count = prop.multiProcessorCount;
+    s->prims.assign(d->prims, d->prims + d->n_prims);
+    s->mats.assign(d->materials, d->materials + d->n_materials);
+    s->light = d->light; s->camera = d->camera;
+    s->width = d->width; s->height = d->height; s->max_depth = d->max_depth; s->integrator = d->integrator;
+    const int n_slots = 2 * d->n_prims - 1;
+    s->nodes.resize(n_slots); s->indices.resize(d->n_prims);
+    int rc = MFX_OK;
+    if (d->nodes) {
+        if (d->n_node_slots != n_slots || !d->indices) { delete s; return fail(MFX_ERR_INVALID_ARGUMENT, "supplied tree needs 2n-1 = %d node slots and an index array", n_slots); }
+        memcpy(s->nodes.data(), d->nodes, sizeof(MfxBvhNode) * (size_t)n_slots);
+        memcpy(s->indices.data(), d->indices, sizeof(int32_t) * (size_t)d->n_prims);
+    } else rc = mfx_bvh_build(s->prims.data(), d->n_prims, s->nodes.data(), n_slots, s->indices.data());
+    if (rc != MFX_OK) { delete s; return rc; }
+    if (cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking) != cudaSuccess) { delete s; return fail(MFX_ERR_CUDA, "cudaStreamCreate failed"); }
+    memset(&s->stats, 0, sizeof(s->stats));
+    *out = s;
+    return MFX_OK;
+}
+
+extern "C" int mfx_scene_destroy(MfxScene *s)
+{
+    if (!s) return MFX_OK;
+    cudaSetDevice(s->device);
+    if (s->stream) cudaStreamSynchronize(s->stream);
+    for (void *p : s->allocs) cudaFree(p);
+    for (cudaEvent_t e : s->events) cudaEventDestroy(e);
+    if (s->h_pinned) cudaFreeHost(s->h_pinned);
+    if (s->stream) cudaStreamDestroy(s->stream);
+    delete s;
+    return MFX_OK;
+}
+
+extern "C" int mfx_scene_get_bvh(const MfxScene *s, MfxBvhNode *nodes_out, int32_t *indices_out)
+{
+    if (!s || !nodes_out || !indices_out) return fail(MFX_ERR_INVALID_ARGUMENT, "mfx_scene_get_bvh: null argument");
+    memcpy(nodes_out, s->nodes.data(), sizeof(MfxBvhNode) * s->nodes.size());
+    memcpy(indices_out, s->indices.data(), sizeof(int32_t) * s->indices.size());
+    return MFX_OK;
+}
+
+// ---- flatten: exact layout
+static void tri_sample_x(TriSampleX &t, H3 v0, H3 v1, H3 v2)
+{
+    hst(t.v0, v0); hst(t.e1, hsub(v1, v0)); hst(t.e2, hsub(v2, v0));
+}
+static double tri_area(H3 v0, H3 v1, H3 v2)      // Trangle.fs:108-116: |e1 x e2| * 0.5
+{
+    return hlen(hcross(hsub(v1, v0), hsub(v2, v0))) * 0.5;
+}
+
+static int flatten_exact(MfxScene *s)
+{
+    if (s->x_ready) return MFX_OK;
+    const int n = (int)s->prims.size();
+    std::vector<NodeX> nodes(s->nodes.size());
+    for (size_t i = 0; i < nodes.size(); i++) {
+        memset(&nodes[i], 0, sizeof(NodeX));
+        for (int a = 0; a < 3; a++) { nodes[i].pmin[a] = s->nodes[i].pmin[a]; nodes[i].pmax[a] = s->nodes[i].pmax[a]; }
+        nodes[i].first = s->nodes[i].first; nodes[i].count = s->nodes[i].count;
+    }
+    std::vector<PrimX> prims(n);
+    std::vector<int> ref(n);
+    for (int slot = 0; slot < n; slot++) {
+        const MfxPrim &p = s->prims[s->indices[slot]];
+        PrimX &x = prims[slot];
+        memset(&x, 0, sizeof(PrimX));
+        x.kind = p.kind; x.material = p.material; ref[slot] = s->indices[slot];
+        if (p.kind == MFX_SPHERE) { hst(x.v0, hld(p.v)); x.e1[0] = p.v[3]; }
+        else {
+            H3 v0 = hld(p.v), v1 = hld(p.v + 3), v2 = hld(p.v + 6);
+            hst(x.v0, v0); hst(x.e1, hsub(v1, v0)); hst(x.e2, hsub(v2, v0));
+            if (p.kind == MFX_RECT) hst(x.e3, hsub(hld(p.v + 9), v0));
+        }
+    }
+    std::vector<MatX> mats(s->mats.size());
+    for (size_t i = 0; i < mats.size(); i++) {
+        mats[i].kind = s->mats[i].kind; mats[i].pad = 0;
+        for (int a = 0; a < 3; a++) mats[i].albedo[a] = s->mats[i].albedo[a];
+        mats[i].fuzz = s->mats[i].fuzz; mats[i].ei = s->mats[i].ei; mats[i].et = s->mats[i].et;
+    }
+    NodeX *dn; PrimX *dp; int *dr; MatX *dm;
+    MFX_TRY(upload(s, &dn, nodes)); MFX_TRY(upload(s, &dp, prims)); MFX_TRY(upload(s, &dr, ref)); MFX_TRY(upload(s, &dm, mats));
+    s->x_bytes = nodes.size() * sizeof(NodeX) + prims.size() * sizeof(PrimX) + ref.size() * 4 + mats.size() * sizeof(MatX);
+    SceneX &sx = s->sx;
+    memset(&sx, 0, sizeof(sx));
+    sx.nodes = dn; sx.prims = dp; sx.ref_id = dr; sx.mats = dm;
+    const double *lp = s->light.p;
+    H3 p0 = hld(lp), p1 = hld(lp + 3), p2 = hld(lp + 6), p3 = hld(lp + 9);
+    tri_sample_x(sx.light.t1, p0, p1, p2);                      // Rect(p0,p1,p2,p3,0), Light.fs:38 / Rect.fs:17-19
+    tri_sample_x(sx.light.t2, p0, p2, p3);
+    sx.light.area = tri_area(p0, p1, p2) + tri_area(p0, p2, p3);   // Rect.fs:24
+    for (int a = 0; a < 3; a++) { sx.light.normal[a] = s->light.normal[a]; sx.light.color[a] = s->light.color[a]; }
+    memcpy(sx.cam.pos, s->camera.pos, 24); memcpy(sx.cam.topleft, s->camera.topleft, 24);
+    memcpy(sx.cam.right, s->camera.right, 24); memcpy(sx.cam.down, s->camera.down, 24);
+    sx.width = s->width; sx.height = s->height; sx.max_depth = s->max_depth; sx.mode = s->integrator; sx.n_prims = n;
+    s->x_ready = true;
+    return MFX_OK;
+}
+
+// ---- flatten: fast layout
+static float round_down(double x)
+{
+    float f = (float)x;
+    if ((double)f > x) f = std::nextafterf(f, -INFINITY);
+    return f;
+}
+static float round_up(double x)
+{
+    float f = (float)x;
+    if ((double)f < x) f = std::nextafterf(f, INFINITY);
+    return f;
+}
+static float int_bits(int v) { float f; memcpy(&f, &v, 4); return f; }
+
+static int flatten_fast(MfxScene *s)
+{
+    if (s->f_ready) return MFX_OK;
+    const int n = (int)s->prims.size();
+    // fast slots in leaf order; a Rect becomes its two triangles (Rect.fs:17-19)
+    std::vector<SlotF> slots; std::vector<float4> nrm; std::vector<int> ffirst(n + 1), ref(n);
+    slots.reserve(n); nrm.reserve(n);
+    for (int slot = 0; slot < n; slot++) {
+        const MfxPrim &p = s->prims[s->indices[slot]];
+        ref[slot] = s->indices[slot];
+        ffirst[slot] = (int)slots.size();
+        if (p.kind == MFX_SPHERE) {
+            SlotF f; memset(&f, 0, sizeof(f));
+            f.a = make_float4((float)p.v[0], (float)p.v[1], (float)p.v[2], int_bits(2));
+            f.b = make_float4((float)p.v[3], (float)(p.v[3] * p.v[3]), 0.f, int_bits(slot));
+            slots.push_back(f);
+            nrm.push_back(make_float4(0.f, 0.f, 0.f, int_bits(p.material)));
+        } else {
+            const int ntri = (p.kind == MFX_RECT) ? 2 : 1;
+            for (int k = 0; k < ntri; k++) {
+                H3 v0 = hld(p.v), v1 = hld(p.v + 3 * (1 + k)), v2 = hld(p.v + 3 * (2 + k));
+                H3 e1 = hsub(v1, v0), e2 = hsub(v2, v0);
+                H3 a = hcross(e1, e2);
+                double al = hlen(a);
+                H3 nm = h3(a.x / al, a.y / al, a.z / al);       // Trangle.fs:110-112
+                SlotF f; memset(&f, 0, sizeof(f));
+                f.a = make_float4((float)v0.x, (float)v0.y, (float)v0.z, int_bits(0));
+                f.b = make_float4((float)e1.x, (float)e1.y, (float)e1.z, int_bits(slot | (k << 30)));
+                f.c = make_float4((float)e2.x, (float)e2.y, (float)e2.z, 0.f);
+                slots.push_back(f);
+                nrm.push_back(make_float4((float)nm.x, (float)nm.y, (float)nm.z, int_bits(p.material)));
+            }
+        }
+    }
+    ffirst[n] = (int)slots.size();
+    auto leaf_meta = [&](const MfxBvhNode &nd) {
+        const int f0 = ffirst[nd.first], f1 = ffirst[nd.first + nd.count];
+        return (f0 << 3) | (f1 - f0);
+    };
+    // children pairs, indexed by the interior node's heap index
+    std::vector<PairF> pairs;
+    SceneF &sf = s->sf;
+    memset(&sf, 0, sizeof(sf));
+    const MfxBvhNode &root = s->nodes[0];
+    for (int a = 0; a < 3; a++) { sf.root_min[a] = round_down(root.pmin[a]); sf.root_max[a] = round_up(root.pmax[a]); }
+    sf.root_meta = -1;
+    if (root.count <= MFX_LEAF_NODE_COUNT) sf.root_meta = leaf_meta(root);
+    else {
+        std::vector<int> todo{ 0 };
+        while (!todo.empty()) {
+            const int i = todo.back(); todo.pop_back();
+            if ((size_t)i >= pairs.size()) { PairF z; memset(&z, 0, sizeof(z)); z.q3 = make_float4(int_bits(0), int_bits(0), 0.f, 0.f); pairs.resize(i + 1, z); }
+            const MfxBvhNode &L = s->nodes[2 * i + 1], &R = s->nodes[2 * i + 2];
+            const bool li = L.count > MFX_LEAF_NODE_COUNT, ri = R.count > MFX_LEAF_NODE_COUNT;
+            PairF &pr = pairs[i];
+            pr.q0 = make_float4(round_down(L.pmin[0]), round_down(L.pmin[1]), round_down(L.pmin[2]), round_up(L.pmax[0]));
+            pr.q1 = make_float4(round_up(L.pmax[1]), round_up(L.pmax[2]), round_down(R.pmin[0]), round_down(R.pmin[1]));
+            pr.q2 = make_float4(round_down(R.pmin[2]), round_up(R.pmax[0]), round_up(R.pmax[1]), round_up(R.pmax[2]));
+            pr.q3 = make_float4(int_bits(li ? -1 : leaf_meta(L)), int_bits(ri ? -1 : leaf_meta(R)), 0.f, 0.f);
+            if (li) todo.push_back(2 * i + 1);
+            if (ri) todo.push_back(2 * i + 2);
+        }
+    }
+    std::vector<MatF> mats(s->mats.size());
+    for (size_t i = 0; i < mats.size(); i++) {
+        for (int a = 0; a < 3; a++) mats[i].albedo[a] = (float)s->mats[i].albedo[a];
+        mats[i].kind = s->mats[i].kind; mats[i].fuzz = (float)s->mats[i].fuzz;
+        mats[i].ei = (float)s->mats[i].ei; mats[i].et = (float)s->mats[i].et; mats[i].pad = 0.f;
+    }
+    PairF *dpairs; SlotF *dslots; float4 *dnrm; int *dref; MatF *dm;
+    MFX_TRY(upload(s, &dpairs, pairs)); MFX_TRY(upload(s, &dslots, slots)); MFX_TRY(upload(s, &dnrm, nrm));
+    MFX_TRY(upload(s, &dref, ref)); MFX_TRY(upload(s, &dm, mats));
+    s->f_bytes = pairs.size() * sizeof(PairF) + slots.size() * sizeof(SlotF) + nrm.size() * 16 + ref.size() * 4 + mats.size() * sizeof(MatF);
+    sf.pairs = dpairs; sf.slots = dslots; sf.slot_nrm = dnrm; sf.ref_id = dref; sf.slot_prim = nullptr; sf.mats = dm;
+    const double *lp = s->light.p;
+    H3 p0 = hld(lp), p1 = hld(lp + 3), p2 = hld(lp + 6), p3 = hld(lp + 9);
+    H3 e;
+    for (int a = 0; a < 3; a++) { sf.light.v0a[a] = (float)lp[a]; sf.light.v0b[a] = (float)lp[a]; }
+    e = hsub(p1, p0); sf.light.e1a[0] = (float)e.x; sf.light.e1a[1] = (float)e.y; sf.light.e1a[2] = (float)e.z;
+    e = hsub(p2, p0); sf.light.e2a[0] = (float)e.x; sf.light.e2a[1] = (float)e.y; sf.light.e2a[2] = (float)e.z;
+    sf.light.e1b[0] = (float)e.x; sf.light.e1b[1] = (float)e.y; sf.light.e1b[2] = (float)e.z;
+    e = hsub(p3, p0); sf.light.e2b[0] = (float)e.x; sf.light.e2b[1] = (float)e.y; sf.light.e2b[2] = (float)e.z;
+    const double area = tri_area(p0, p1, p2) + tri_area(p0, p2, p3);
+    sf.light.area = (float)area; sf.light.inv_pdf = (float)area;
+    for (int a = 0; a < 3; a++) { sf.light.normal[a] = (float)s->light.normal[a]; sf.light.color[a] = (float)s->light.color[a]; }
+    for (int a = 0; a < 3; a++) {
+        sf.cam.pos[a] = (float)s->camera.pos[a]; sf.cam.topleft[a] = (float)s->camera.topleft[a];
+        sf.cam.right[a] = (float)s->camera.right[a]; sf.cam.down[a] = (float)s->camera.down[a];
+    }
+    memcpy(sf.camx.pos, s->camera.pos, 24); memcpy(sf.camx.topleft, s->camera.topleft, 24);
+    memcpy(sf.camx.right, s->camera.right, 24); memcpy(sf.camx.down, s->camera.down, 24);
+    sf.width = s->width; sf.height = s->height; sf.max_depth = s->max_depth; sf.mode = s->integrator;
+    sf.n_slots = (int)slots.size();
+    s->f_ready = true;
+    return MFX_OK;
+}
+
+extern "C" int mfx_scene_device_bytes(const MfxScene *sc, uint64_t *exact_bytes, uint64_t *fast_bytes)
+{
+    if (!sc) return fail(MFX_ERR_INVALID_ARGUMENT, "null scene");
+    MfxScene *s = const_cast<MfxScene *>(sc);
+    MFX_TRY(ensure_device());
+    MFX_TRY(flatten_exact(s)); MFX_TRY(flatten_fast(s));
+    if (exact_bytes) *exact_bytes = s->x_bytes;
+    if (fast_bytes) *fast_bytes = s->f_bytes;
+    return MFX_OK;
+}
+
+// ---- per-wave path state
+static int ensure_wave_exact(MfxScene *s)
+{
+    if (s->wx_ready) return MFX_OK;
+    const size_t P = (size_t)env_long("MFX_WAVE_PATHS_EXACT", 1 << 20);
+    const size_t V = (size_t)s->max_depth + 1;
+    WaveX &w = s->wx;
+    memset(&w, 0, sizeof(w));
+    w.P = (int)P;
+    MFX_TRY(dev_alloc_t(s, &w.ray_o, 3 * P)); MFX_TRY(dev_alloc_t(s, &w.ray_d, 3 * P));
+    MFX_TRY(dev_alloc_t(s, &w.hit_t, P)); MFX_TRY(dev_alloc_t(s, &w.hit_slot, P));
+    MFX_TRY(dev_alloc_t(s, &w.sh_d, 3 * P)); MFX_TRY(dev_alloc_t(s, &w.sh_dist, P));
+    MFX_TRY(dev_alloc_t(s, &w.v_l, V * 3 * P)); MFX_TRY(dev_alloc_t(s, &w.v_col, V * 3 * P));
+    MFX_TRY(dev_alloc_t(s, &w.v_ei, V * P)); MFX_TRY(dev_alloc_t(s, &w.v_kind, V * P));
+    MFX_TRY(dev_alloc_t(s, &w.nv, P));
+    MFX_TRY(dev_alloc_t(s, &w.queue[0], P)); MFX_TRY(dev_alloc_t(s, &w.queue[1], P));
+    MFX_TRY(dev_alloc_t(s, &w.counts, MFX_COUNTS_LEN));
+    s->wx_ready = true;
+    return MFX_OK;
+}
+
+static int ensure_wave_fast(MfxScene *s)
+{
+    if (s->wf_ready) return MFX_OK;
+    const size_t P = (size_t)env_long("MFX_WAVE_PATHS", 1 << 22);
+    WaveF &w = s->wf;
+    memset(&w, 0, sizeof(w));
+    w.P = (int)P;
+    MFX_TRY(dev_alloc_t(s, &w.ray_o, P)); MFX_TRY(dev_alloc_t(s, &w.ray_d, P));
+    MFX_TRY(dev_alloc_t(s, &w.hit, P)); MFX_TRY(dev_alloc_t(s, &w.thr, P)); MFX_TRY(dev_alloc_t(s, &w.rad, P));
+    MFX_TRY(dev_alloc_t(s, &w.sh_d, P)); MFX_TRY(dev_alloc_t(s, &w.sh_c, P));
+    MFX_TRY(dev_alloc_t(s, &w.q_ext[0], P)); MFX_TRY(dev_alloc_t(s, &w.q_ext[1], P)); MFX_TRY(dev_alloc_t(s, &w.q_sh, P));
+    MFX_TRY(dev_alloc_t(s, &w.counts, MFX_COUNTS_LEN));
+    s->wf_ready = true;
+    return MFX_OK;
+}
+
+static int ensure_frame_buffers(MfxScene *s)
+{
+    const size_t npx = (size_t)s->width * s->height;
+    if (!s->d_pixsum) MFX_TRY(dev_alloc_t(s, &s->d_pixsum, 4 * npx));
+    if (!s->d_color_wh) MFX_TRY(dev_alloc_t(s, &s->d_color_wh, 4 * npx));
+    if (!s->d_rgba) MFX_TRY(dev_alloc_t(s, &s->d_rgba, npx));
+    if (!s->d_totals) MFX_TRY(dev_alloc_t(s, &s->d_totals, 4));
+    if (!s->d_ctr) MFX_TRY(dev_alloc_t(s, &s->d_ctr, 1));
+    return MFX_OK;
+}
+
+// Interleaved square tiles: tile k (row-major over the tile grid) belongs to rank k % world.
+static int get_tilemap(MfxScene *s, int tile, int rank, int world, TileMap *tm)
+{
+    if (world <= 1 || tile <= 0) { tm->pix = nullptr; tm->n_pix = s->width * s->height; return MFX_OK; }
+    auto key = std::make_tuple(tile, rank, world);
+    auto it = s->tilemaps.find(key);
+    if (it == s->tilemaps.end()) {
+        std::vector<int> pix;
+        const int tx = (s->width + tile - 1) / tile, ty = (s->height + tile - 1) / tile;
+        for (int t = rank; t < tx * ty; t += world) {
+            const int x0 = (t % tx) * tile, y0 = (t / tx) * tile;
+            for (int y = y0; y < std::min(y0 + tile, s->height); y++)
+                for (int x = x0; x < std::min(x0 + tile, s->width); x++) pix.push_back(y * s->width + x);
+        }
+        int *d = nullptr;
+        MFX_TRY(upload(s, &d, pix));
+        it = s->tilemaps.emplace(key, std::make_pair(d, (int)pix.size())).first;
+    }
+    tm->pix = it->second.first; tm->n_pix = it->second.second;
+    return MFX_OK;
+}
+
+static int get_event(MfxScene *s, size_t idx, cudaEvent_t *e)
+{
+    while (s->events.size() <= idx) {
+        cudaEvent_t ev;
+        CUDA_TRY(cudaEventCreate(&ev));
+        s->events.push_back(ev);
+    }
+    *e = s->events[idx];
+    return MFX_OK;
+}
+
+// ------------------------------------------------------------------ the wavefront driver
+// One IPixelIntegrator.Sample(n) call (Integrators.fs:160-172): every (pixel, sample) of this
+// rank's tiles becomes one path; paths advance one vertex per bounce through
+//   extend (closest hit) -> shade (BSDF + light sample, queue compaction) -> shadow (occlusion)
+// and are resolved into per-pixel sums.  No host synchronisation inside: queue sizes stay on
+// the device and every kernel is a persistent grid-stride loop over `counts[bounce]`.
+static int run_sample(MfxScene *s, const MfxSampleParams *p, double *d_color_wh, float4 *d_rgba)
+{
+    if (!s || !p) return fail(MFX_ERR_INVALID_ARGUMENT, "null scene/params");
+    if (p->spp <= 0) return fail(MFX_ERR_INVALID_ARGUMENT, "spp must be positive, got %d", p->spp);
+    if (p->precision != MFX_EXACT_F64 && p->precision != MFX_FAST_F32) return fail(MFX_ERR_INVALID_ARGUMENT, "unknown precision %d", p->precision);
+    if (p->world > 1 && (p->rank < 0 || p->rank >= p->world)) return fail(MFX_ERR_INVALID_ARGUMENT, "rank %d outside world %d", p->rank, p->world);
+    if (p->world > 1 && p->tile_size <= 0) return fail(MFX_ERR_INVALID_ARGUMENT, "world > 1 needs a positive tile_size");
+    MFX_TRY(ensure_device());
+    const bool exact = (p->precision == MFX_EXACT_F64);
+    if (exact) { MFX_TRY(flatten_exact(s)); MFX_TRY(ensure_wave_exact(s)); }
+    else { MFX_TRY(flatten_fast(s)); MFX_TRY(ensure_wave_fast(s)); }
+    MFX_TRY(ensure_frame_buffers(s));
+    TileMap tm;
+    MFX_TRY(get_tilemap(s, p->tile_size, p->rank, p->world, &tm));
+    const bool counting = (p->flags & MFX_SAMPLE_COUNT_TRAVERSAL) != 0;
+    TravCounters *ctr = counting ? s->d_ctr : nullptr;
+    const size_t npx = (size_t)s->width * s->height;
+    cudaStream_t st = s->stream;
+    LaunchCfg cfg{ s->sm_count, 128, st };
+
+    CUDA_TRY(cudaMemsetAsync(s->d_pixsum, 0, 4 * npx * sizeof(double), st));
+    CUDA_TRY(cudaMemsetAsync(s->d_totals, 0, 4 * sizeof(unsigned long long), st));
+    CUDA_TRY(cudaMemsetAsync(s->d_ctr, 0, sizeof(TravCounters), st));
+    if (tm.pix) {   // pixels of other ranks must read as zero
+        if (d_color_wh) CUDA_TRY(cudaMemsetAsync(d_color_wh, 0, 4 * npx * sizeof(double), st));
+        if (d_rgba) CUDA_TRY(cudaMemsetAsync(d_rgba, 0, npx * sizeof(float4), st));
+    }
+    size_t ev = 0;
+    cudaEvent_t e_begin, e_end;
+    MFX_TRY(get_event(s, ev++, &e_begin)); MFX_TRY(get_event(s, ev++, &e_end));
+    CUDA_TRY(cudaEventRecord(e_begin, st));
+    struct Span { size_t a, b; int cls; };
+    std::vector<Span> spans;
+    auto timed = [&](int cls) -> int {      // returns via spans the event pair bracketing the next launch
+        cudaEvent_t a, b;
+        MFX_TRY(get_event(s, ev, &a)); MFX_TRY(get_event(s, ev + 1, &b));
+        spans.push_back(Span{ ev, ev + 1, cls });
+        ev += 2;
+        CUDA_TRY(cudaEventRecord(a, st));
+        return MFX_OK;
+    };
+    auto timed_end = [&]() -> int { CUDA_TRY(cudaEventRecord(s->events[spans.back().b], st)); return MFX_OK; };
+
+    const int P = exact ? s->wx.P : s->wf.P;
+    const int D = s->max_depth;
+    const int npix_total = tm.n_pix;
+    const int pix_chunk = std::min(npix_total, P);
+    const int S_wave = std::max(1, std::min(p->spp, P / std::max(1, pix_chunk)));
+    uint32_t launches = 0, l_ext = 0, l_sh = 0;
+    int *counts = exact ? s->wx.counts : s->wf.counts;
+    for (int pix0 = 0; pix0 < npix_total; pix0 += pix_chunk) {
+        const int np = std::min(pix_chunk, npix_total - pix0);
+        for (int s0 = 0; s0 < p->spp; s0 += S_wave) {
+            const int S = std::min(S_wave, p->spp - s0);
+            const int sabs = p->first_sample + s0;
+            CUDA_TRY(cudaMemsetAsync(counts, 0, MFX_COUNTS_LEN * sizeof(int), st));
+            if (exact) mfx_x_raygen(cfg, s->sx, s->wx, tm, pix0, np, sabs, S, p->seed);
+            else mfx_f_raygen(cfg, s->sf, s->wf, tm, pix0, np, sabs, S, p->seed);
+            launches++;
+            for (int b = 0; b <= D; b++) {
+                MFX_TRY(timed(0));
+                if (exact) mfx_x_extend(cfg, s->sx, s->wx, b, ctr); else mfx_f_extend(cfg, s->sf, s->wf, b, ctr);
+                MFX_TRY(timed_end());
+                if (exact) mfx_x_shade(cfg, s->sx, s->wx, tm, pix0, np, sabs, b, p->seed);
+                else mfx_f_shade(cfg, s->sf, s->wf, tm, pix0, np, sabs, b, p->seed);
+                MFX_TRY(timed(1));
+                if (exact) mfx_x_shadow(cfg, s->sx, s->wx, b, ctr); else mfx_f_shadow(cfg, s->sf, s->wf, b, ctr);
+                MFX_TRY(timed_end());
+                launches += 3; l_ext++; l_sh++;
+            }
+            if (exact) mfx_x_resolve(cfg, s->sx, s->wx, tm, pix0, np, S, s->d_pixsum);
+            else mfx_f_resolve(cfg, s->sf, s->wf, tm, pix0, np, S, s->d_pixsum);
+            // rays traced: exact: closest = counts[0..D], shadow = counts[1..D+1];
+            //              fast : closest = counts[0..D], shadow = counts[V+2 .. V+2+D]
+            if (exact) mfx_accum_ray_totals(st, counts, 0, D + 1, 1, D + 1, s->d_totals);
+            else mfx_accum_ray_totals(st, counts, 0, D + 1, MFX_MAX_VERTS + 2, D + 1, s->d_totals);
+            launches += 2;
+        }
+    }
+    mfx_x_finalize(cfg, s->d_pixsum, s->width, s->height, 0.0, p->spp, tm, d_color_wh, d_rgba);
+    launches++;
+    CUDA_TRY(cudaEventRecord(e_end, st));
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaStreamSynchronize(st));
+
+    unsigned long long totals[4];
+    TravCounters hc;
+    CUDA_TRY(cudaMemcpy(totals, s->d_totals, sizeof(totals), cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(&hc, s->d_ctr, sizeof(hc), cudaMemcpyDeviceToHost));
+    MfxStats &stt = s->stats;
+    memset(&stt, 0, sizeof(stt));
+    stt.closest_rays = totals[0]; stt.shadow_rays = totals[1]; stt.paths = totals[2];
+    for (int c = 0; c < 2; c++) { stt.nodes[c] = hc.v[c][0]; stt.tris[c] = hc.v[c][1]; stt.spheres[c] = hc.v[c][2]; }
+    float ms = 0.f;
+    CUDA_TRY(cudaEventElapsedTime(&ms, e_begin, e_end));
+    stt.ms_total = ms;
+    double m_ext = 0., m_sh = 0.;
+    for (const Span &sp : spans) {
+        CUDA_TRY(cudaEventElapsedTime(&ms, s->events[sp.a], s->events[sp.b]));
+        if (sp.cls == 0) m_ext += ms; else m_sh += ms;
+    }
+    stt.ms_extend = m_ext; stt.ms_shadow = m_sh; stt.ms_shade = stt.ms_total - m_ext - m_sh;
+    stt.launches = launches; stt.launches_extend = l_ext; stt.launches_shadow = l_sh;
+    return MFX_OK;
+}
+
+static int ensure_pinned(MfxScene *s, size_t bytes)
+{
+    if (s->h_pinned_bytes >= bytes) return MFX_OK;
+    if (s->h_pinned) { cudaFreeHost(s->h_pinned); s->h_pinned = nullptr; s->h_pinned_bytes = 0; }
+    CUDA_TRY(cudaMallocHost(&s->h_pinned, bytes));
+    s->h_pinned_bytes = bytes;
+    return MFX_OK;
+}
+
+// D2H into a caller buffer: direct when the caller registered it (mfx_host_register), else
+// through the scene's pinned staging buffer.
+static int copy_out(MfxScene *s, void *host, const void *dev, size_t bytes)
+{
+    cudaPointerAttributes attr;
+    bool pinned = (cudaPointerGetAttributes(&attr, host) == cudaSuccess) && (attr.type == cudaMemoryTypeHost);
+    cudaGetLastError();
+    if (pinned) {
+        CUDA_TRY(cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, s->stream));
+        CUDA_TRY(cudaStreamSynchronize(s->stream));
+    } else {
+        MFX_TRY(ensure_pinned(s, bytes));
+        CUDA_TRY(cudaMemcpyAsync(s->h_pinned, dev, bytes, cudaMemcpyDeviceToHost, s->stream));
+        CUDA_TRY(cudaStreamSynchronize(s->stream));
+        memcpy(host, s->h_pinned, bytes);
+    }
+    return MFX_OK;
+}
+
+extern "C" int mfx_pixel_integrator_sample(MfxScene *s, const MfxSampleParams *p, double *texture)
+{
+    if (!texture) return fail(MFX_ERR_INVALID_ARGUMENT, "null texture");
+    if (!s) return fail(MFX_ERR_INVALID_ARGUMENT, "null scene");
+    MFX_TRY(ensure_device()); MFX_TRY(ensure_frame_buffers(s));
+    MFX_TRY(run_sample(s, p, s->d_color_wh, nullptr));
+    return copy_out(s, texture, s->d_color_wh, (size_t)s->width * s->height * 4 * sizeof(double));
+}
+
+extern "C" int mfx_pixel_integrator_sample_device(MfxScene *s, const MfxSampleParams *p, void *d_rgba_f32)
+{
+    if (!d_rgba_f32) return fail(MFX_ERR_INVALID_ARGUMENT, "null device buffer");
+    if (!s) return fail(MFX_ERR_INVALID_ARGUMENT, "null scene");
+    return run_sample(s, p, nullptr, (float4 *)d_rgba_f32);
+}
+
+extern "C" int mfx_pixel_integrator_sample_f32(MfxScene *s, const MfxSampleParams *p, float *rgba)
+{
+    if (!rgba) return fail(MFX_ERR_INVALID_ARGUMENT, "null output");
+    if (!s) return fail(MFX_ERR_INVALID_ARGUMENT, "null scene");
+    MFX_TRY(ensure_device()); MFX_TRY(ensure_frame_buffers(s));
+    MFX_TRY(run_sample(s, p, nullptr, s->d_rgba));
+    return copy_out(s, rgba, s->d_rgba, (size_t)s->width * s->height * sizeof(float4));
+}
+
+extern "C" int mfx_get_stats(const MfxScene *s, MfxStats *out)
+{
+    if (!s || !out) return fail(MFX_ERR_INVALID_ARGUMENT, "null argument");
+    *out = s->stats;
+    return MFX_OK;
+}
+
+extern "C" int mfx_host_register(void *ptr, uint64_t bytes)
+{
+    if (!ptr || !bytes) return fail(MFX_ERR_INVALID_ARGUMENT, "null buffer");
+    MFX_TRY(ensure_device());
+    CUDA_TRY(cudaHostRegister(ptr, bytes, cudaHostRegisterDefault));
+    return MFX_OK;
+}
+extern "C" int mfx_host_unregister(void *ptr)
+{
+    if (!ptr) return fail(MFX_ERR_INVALID_ARGUMENT, "null buffer");
+    MFX_TRY(ensure_device());
+    CUDA_TRY(cudaHostUnregister(ptr));
+    return MFX_OK;
+}
+
+// ------------------------------------------------------------------ finer seams
+template <typename F>
+static int with_ray_buffers(MfxScene *s, int64_t n, const double *a, size_t a_per, const double *b, size_t b_per,
+                            int32_t *prim, int32_t *sub, double *t, F launch)
+{
+    double *da = nullptr, *db = nullptr, *dt = nullptr; int *dp = nullptr, *ds = nullptr;
+    int rc = MFX_OK;
+    auto cleanup = [&]() { cudaFree(da); cudaFree(db); cudaFree(dt); cudaFree(dp); cudaFree(ds); };
+#define WRB_TRY(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { cleanup(); return fail(MFX_ERR_CUDA, "%s failed: %s", #x, cudaGetErrorString(e_)); } } while (0)
+    if (a) { WRB_TRY(cudaMalloc(&da, n * a_per * sizeof(double))); WRB_TRY(cudaMemcpy(da, a, n * a_per * sizeof(double), cudaMemcpyHostToDevice)); }
+    if (b) { WRB_TRY(cudaMalloc(&db, n * b_per * sizeof(double))); WRB_TRY(cudaMemcpy(db, b, n * b_per * sizeof(double), cudaMemcpyHostToDevice)); }
+    WRB_TRY(cudaMalloc(&dt, n * sizeof(double))); WRB_TRY(cudaMalloc(&dp, n * sizeof(int)));
+    if (sub) WRB_TRY(cudaMalloc(&ds, n * sizeof(int)));
+    launch(da, db, dp, ds, dt);
+    WRB_TRY(cudaGetLastError());
+    WRB_TRY(cudaStreamSynchronize(s->stream));
+    WRB_TRY(cudaMemcpy(prim, dp, n * sizeof(int), cudaMemcpyDeviceToHost));
+    WRB_TRY(cudaMemcpy(t, dt, n * sizeof(double), cudaMemcpyDeviceToHost));
+    if (sub) WRB_TRY(cudaMemcpy(sub, ds, n * sizeof(int), cudaMemcpyDeviceToHost));
+#undef WRB_TRY
+    cleanup();
+    return rc;
+}
+
+extern "C" int mfx_bvh_hit(MfxScene *s, int32_t precision, int32_t any_hit, int64_t n, const double *origins, const double *dirs,
+                           double tmin, double tmax, int32_t *prim, int32_t *sub, double *t)
+{
+    if (!s || !origins || !dirs || !prim || !t) return fail(MFX_ERR_INVALID_ARGUMENT, "mfx_bvh_hit: null argument");
+    if (n <= 0) return MFX_OK;
+    MFX_TRY(ensure_device());
+    LaunchCfg cfg{ s->sm_count, 128, s->stream };
+    if (precision == MFX_EXACT_F64) {
+        MFX_TRY(flatten_exact(s));
+        return with_ray_buffers(s, n, origins, 3, dirs, 3, prim, sub, t, [&](double *o, double *d, int *p, int *sb, double *tt) {
+            mfx_x_bvh_hit(cfg, s->sx, any_hit, n, o, d, tmin, tmax, p, sb, tt);
+        });
+    } else if (precision == MFX_FAST_F32) {
+        MFX_TRY(flatten_fast(s));
+        return with_ray_buffers(s, n, origins, 3, dirs, 3, prim, sub, t, [&](double *o, double *d, int *p, int *sb, double *tt) {
+            mfx_f_bvh_hit(cfg, s->sf, any_hit, n, o, d, tmin, tmax, p, sb, tt);
+        });
+    }
+    return fail(MFX_ERR_INVALID_ARGUMENT, "unknown precision %d", precision);
+}
+
+extern "C" int mfx_trace_primary(MfxScene *s, int32_t precision, int64_t n, const double *uv, int32_t *prim, double *t)
+{
+    if (!s || !prim || !t) return fail(MFX_ERR_INVALID_ARGUMENT, "mfx_trace_primary: null argument");
+    if (!uv && n != (int64_t)s->width * s->height) return fail(MFX_ERR_INVALID_ARGUMENT, "uv == NULL needs n == width*height");
+    if (n <= 0) return MFX_OK;
+    MFX_TRY(ensure_device());
+    LaunchCfg cfg{ s->sm_count, 128, s->stream };
+    if (precision == MFX_EXACT_F64) {
+        MFX_TRY(flatten_exact(s));
+        return with_ray_buffers(s, n, uv, 2, nullptr, 0, prim, nullptr, t, [&](double *u, double *, int *p, int *, double *tt) {
+            mfx_x_primary(cfg, s->sx, n, u, p, tt);
+        });
+    } else if (precision == MFX_FAST_F32) {
+        MFX_TRY(flatten_fast(s));
+        return with_ray_buffers(s, n, uv, 2, nullptr, 0, prim, nullptr, t, [&](double *u, double *, int *p, int *, double *tt) {
+            mfx_f_primary(cfg, s->sf, n, u, p, tt);
+        });
+    }
+    return fail(MFX_ERR_INVALID_ARGUMENT, "unknown precision %d", precision);
+}
+
+// ------------------------------------------------------------------ Film (Film.fs:13-34)
+struct MfxFilm {
+    MfxScene *scene;
+    double *d_sum = nullptr, *d_target = nullptr;   // Color[w,h]
+    uint8_t *d_rgba8 = nullptr;
+    double frame_count = 0.;
+};
+
+extern "C" int mfx_film_create(MfxScene *s, MfxFilm **out)
+{
+    if (!s || !out) return fail(MFX_ERR_INVALID_ARGUMENT, "null argument");
+    MFX_TRY(ensure_device());
+    MfxFilm *f = new MfxFilm();
+    f->scene = s;
+    const size_t npx = (size_t)s->width * s->height;
+    if (cudaMalloc(&f->d_sum, 4 * npx * sizeof(double)) != cudaSuccess || cudaMalloc(&f->d_target, 4 * npx * sizeof(double)) != cudaSuccess ||
+        cudaMalloc(&f->d_rgba8, 4 * npx) != cudaSuccess) {
+        cudaFree(f->d_sum); cudaFree(f->d_target); cudaFree(f->d_rgba8); delete f;
+        return fail(MFX_ERR_OUT_OF_MEMORY, "film allocation failed");
+    }
+    *out = f;
+    return mfx_film_reset(f);
+}
+
+extern "C" int mfx_film_destroy(MfxFilm *f)
+{
+    if (!f) return MFX_OK;
+    cudaSetDevice(f->scene->device);
+    cudaStreamSynchronize(f->scene->stream);
+    cudaFree(f->d_sum); cudaFree(f->d_target); cudaFree(f->d_rgba8);
+    delete f;
+    return MFX_OK;
+}
+
+extern "C" int mfx_film_reset(MfxFilm *f)                      // Film.Reset, Film.fs:26-30
+{
+    if (!f) return fail(MFX_ERR_INVALID_ARGUMENT, "null film");
+    MFX_TRY(ensure_device());
+    const size_t npx = (size_t)f->scene->width * f->scene->height;
+    f->frame_count = 0.;
+    CUDA_TRY(cudaMemsetAsync(f->d_sum, 0, 4 * npx * sizeof(double), f->scene->stream));
+    CUDA_TRY(cudaMemsetAsync(f->d_target, 0, 4 * npx * sizeof(double), f->scene->stream));
+    CUDA_TRY(cudaStreamSynchronize(f->scene->stream));
+    return MFX_OK;
+}
+
+extern "C" int mfx_film_get_frame(MfxFilm *f, const MfxSampleParams *p, double *texture)   // Film.fs:18-23,32-34
+{
+    if (!f || !p) return fail(MFX_ERR_INVALID_ARGUMENT, "null argument");
+    MfxScene *s = f->scene;
+    MFX_TRY(ensure_device()); MFX_TRY(ensure_frame_buffers(s));
+    MFX_TRY(run_sample(s, p, s->d_color_wh, nullptr));
+    f->frame_count += 1.;
+    const size_t npx = (size_t)s->width * s->height;
+    mfx_film_add(s->stream, f->d_sum, s->d_color_wh, f->d_target, (long long)npx, f->frame_count);
+    CUDA_TRY(cudaGetLastError());
+    if (texture) return copy_out(s, texture, f->d_target, npx * 4 * sizeof(double));
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    return MFX_OK;
+}
+
+extern "C" int mfx_film_post_process(MfxFilm *f, uint8_t *rgba8)   // Scene.fs:315-330
+{
+    if (!f || !rgba8) return fail(MFX_ERR_INVALID_ARGUMENT, "null argument");
+    MfxScene *s = f->scene;
+    MFX_TRY(ensure_device());
+    mfx_film_tonemap(s->stream, f->d_target, s->width, s->height, f->d_rgba8);
+    CUDA_TRY(cudaGetLastError());
+    return copy_out(s, rgba8, f->d_rgba8, (size_t)s->width * s->height * 4);
+}
+
+extern "C" int mfx_film_frame_count(const MfxFilm *f, double *out)
+{
+    if (!f || !out) return fail(MFX_ERR_INVALID_ARGUMENT, "null argument");
+    *out = f->frame_count;
+    return MFX_OK;
+}

@@ -1,0 +1,176 @@
+// mfx_internal.h -- structures shared by the host orchestration (mfx_host.cpp) and the two
+// kernel translation units (mfx_exact.cu: f64, --fmad=false; mfx_fast.cu: f32).
+// Nothing here crosses the C ABI.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define MFX_LEAF_NODE_COUNT 3      // Bvh.LeafNodeCount, BvhNode.fs:39
+#define MFX_REJECTION_CAP 128      // cap of the GetRandomInUnitSphere loop (Material.fs:12), see DESIGN.md
+#define MFX_MAX_VERTS 16           // max_depth + 1 shaded vertices per path (max_depth <= 15)
+
+// ------------------------------------------------------------------ exact (f64) device layout
+// One BvhNode, heap-indexed like the reference (children 2i+1 / 2i+2).  64 B.
+struct __align__(16) NodeX {
+    double pmin[3];
+    double pmax[3];
+    int    first;
+    int    count;
+    double pad;
+};
+// One IHitable in LEAF ORDER (the reference's `indices` indirection is applied at flatten time,
+// ref_id[] maps a slot back to the original primitive).  e1=v1-v0, e2=v2-v0, e3=v3-v0 are the
+// same single subtractions Triangle.PreCalcu performs per call (Trangle.fs:124-125), so storing
+// them is bit-neutral.  Sphere: v0 = center, e1[0] = radius.  112 B.
+struct __align__(16) PrimX {
+    double v0[3];
+    double e1[3];
+    double e2[3];
+    double e3[3];
+    int    kind;
+    int    material;
+    double pad;
+};
+struct MatX {
+    int    kind;
+    int    pad;
+    double albedo[3];
+    double fuzz, ei, et;
+};
+struct TriSampleX { double v0[3], e1[3], e2[3]; };
+struct LightX {
+    TriSampleX t1, t2;      // Rect(p0,p1,p2,p3) = Triangle(p0,p1,p2) + Triangle(p0,p2,p3)
+    double area;            // rect.area = t1.area + t2.area
+    double normal[3];
+    double color[3];
+};
+struct CamX { double pos[3], topleft[3], right[3], down[3]; };
+
+struct SceneX {
+    const NodeX *nodes;
+    const PrimX *prims;
+    const int   *ref_id;
+    const MatX  *mats;
+    LightX light;
+    CamX   cam;
+    int    width, height, max_depth, mode;
+    int    n_prims;
+};
+
+// Per-wave path state, exact mode (SoA over P paths).
+struct WaveX {
+    int     P;              // capacity
+    double *ray_o;          // [3][P]
+    double *ray_d;          // [3][P]
+    double *hit_t;          // [P]
+    int    *hit_slot;       // [P]  slot | sub<<30, or -1
+    double *sh_d;           // [3][P] unit direction to the light sample
+    double *sh_dist;        // [P]
+    double *v_l;            // [V][3][P]  l_k   (direct term, zeroed by the shadow kernel when occluded)
+    double *v_col;          // [V][3][P]  col_k
+    double *v_ei;           // [V][P]     Lambertian.Shade cosine (mode B)
+    int    *v_kind;         // [V][P]     material kind at vertex k (mode B)
+    int    *nv;             // [P] number of shaded vertices
+    int    *queue[2];       // ping-pong queues of path ids
+    int    *counts;         // [MFX_MAX_VERTS+2] queue sizes per bounce
+};
+
+// ------------------------------------------------------------------ fast (f32) device layout
+// Children pair of interior heap node i: 64 B = 4 x float4.
+//   q0 = (L.min.x, L.min.y, L.min.z, L.max.x)   q1 = (L.max.y, L.max.z, R.min.x, R.min.y)
+//   q2 = (R.min.z, R.max.x, R.max.y, R.max.z)   q3 = (metaL, metaR, -, -) as int bits
+// meta >= 0: leaf,  first<<3 | count (count <= 6 fast slots);  meta < 0: interior.
+// Boxes are rounded outward from the f64 bounds.
+struct __align__(16) PairF { float4 q0, q1, q2, q3; };
+// One fast primitive slot, 48 B = 3 x float4, leaf order.
+//   triangle: a = (v0.xyz, kind bits), b = (e1.xyz, -), c = (e2.xyz, -)
+//   sphere  : a = (center.xyz, kind bits), b = (radius, r^2, -, -)
+struct __align__(16) SlotF { float4 a, b, c; };
+struct MatF { float albedo[3]; int kind; float fuzz, ei, et, pad; };
+struct LightF {
+    float v0a[3], e1a[3], e2a[3];
+    float v0b[3], e1b[3], e2b[3];
+    float area, inv_pdf;    // inv_pdf = area (pdf_li = 1/area)
+    float normal[3];
+    float color[3];
+};
+struct CamF { float pos[3], topleft[3], right[3], down[3]; };
+
+struct SceneF {
+    const PairF *pairs;     // indexed by interior heap index
+    const SlotF *slots;     // leaf order (rects split in two)
+    const int   *slot_prim; // slot -> leaf-order primitive (exact slot) ; sub in bit 30
+    const int   *ref_id;    // exact slot -> original primitive index
+    const float4 *slot_nrm; // geometric normal per fast slot (xyz), w = material as int bits
+    const MatF  *mats;
+    LightF light;
+    CamF   cam;
+    CamX   camx;            // f64 camera: primary rays are generated in f64 and rounded once
+    float  root_min[3], root_max[3];
+    int    root_meta;       // leaf meta if the whole tree is one leaf, else -1
+    int    width, height, max_depth, mode;
+    int    n_slots;
+};
+
+struct WaveF {
+    int     P;
+    float4 *ray_o;          // [P] o.xyz, w = source fast slot as int bits (-1: camera)
+    float4 *ray_d;          // [P] d.xyz, w unused
+    float2 *hit;            // [P] (t, slot as int bits)
+    float4 *thr;            // [P] throughput rgb
+    float4 *rad;            // [P] accumulated radiance rgb
+    float4 *sh_d;           // [P] shadow dir.xyz, w = dist
+    float4 *sh_c;           // [P] contribution rgb if unoccluded
+    int    *q_ext[2];       // ping-pong extend queues of path ids
+    int    *q_sh;           // shadow queue of the current bounce
+    int    *counts;         // [0 .. MFX_MAX_VERTS+1] extend queue sizes per bounce,
+                            // [MFX_MAX_VERTS+2 + bounce] shadow queue sizes
+};
+#define MFX_COUNTS_LEN (2 * (MFX_MAX_VERTS + 2))
+
+// Traversal counters (instrumented runs only): [class][nodes,tris,spheres]
+struct TravCounters { unsigned long long v[2][3]; };
+
+struct TileMap {
+    const int *pix;         // linear pixel ids (y*width+x) rendered by this rank, or nullptr = identity
+    int  n_pix;
+};
+
+// ------------------------------------------------------------------ launchers (defined in the .cu TUs)
+struct LaunchCfg { int blocks; int threads; cudaStream_t stream; };
+
+// exact
+void mfx_x_raygen(const LaunchCfg &, const SceneX &, const WaveX &, TileMap tm, int pix0, int npix, int s0, int S,
+                  uint64_t seed);
+void mfx_x_extend(const LaunchCfg &, const SceneX &, const WaveX &, int bounce, TravCounters *ctr);
+void mfx_x_shade(const LaunchCfg &, const SceneX &, const WaveX &, TileMap tm, int pix0, int npix, int s0,
+                 int bounce, uint64_t seed);
+void mfx_x_shadow(const LaunchCfg &, const SceneX &, const WaveX &, int bounce, TravCounters *ctr);
+void mfx_x_resolve(const LaunchCfg &, const SceneX &, const WaveX &, TileMap tm, int pix0, int npix, int S,
+                   double *pixsum /* [w*h][4] row-major */);
+void mfx_x_bvh_hit(const LaunchCfg &, const SceneX &, int any_hit, long long n, const double *o, const double *d,
+                   double tmin, double tmax, int *prim, int *sub, double *t);
+void mfx_x_primary(const LaunchCfg &, const SceneX &, long long n, const double *uv, int *prim, double *t);
+void mfx_x_finalize(const LaunchCfg &, const double *pixsum, int width, int height, double inv_unused, int spp,
+                    TileMap tm, double *color_wh /* x-major Color[w,h] or null */, float4 *rgba_f32 /* row-major or null */);
+
+// fast
+void mfx_f_raygen(const LaunchCfg &, const SceneF &, const WaveF &, TileMap tm, int pix0, int npix, int s0, int S,
+                  uint64_t seed);
+void mfx_f_extend(const LaunchCfg &, const SceneF &, const WaveF &, int bounce, TravCounters *ctr);
+void mfx_f_shade(const LaunchCfg &, const SceneF &, const WaveF &, TileMap tm, int pix0, int npix, int s0,
+                 int bounce, uint64_t seed);
+void mfx_f_shadow(const LaunchCfg &, const SceneF &, const WaveF &, int bounce, TravCounters *ctr);
+void mfx_f_resolve(const LaunchCfg &, const SceneF &, const WaveF &, TileMap tm, int pix0, int npix, int S,
+                   double *pixsum);
+void mfx_f_bvh_hit(const LaunchCfg &, const SceneF &, int any_hit, long long n, const double *o, const double *d,
+                   double tmin, double tmax, int *prim, int *sub, double *t);
+void mfx_f_primary(const LaunchCfg &, const SceneF &, long long n, const double *uv, int *prim, double *t);
+
+// misc (mfx_fast.cu)
+// totals[0] += sum counts[ext_lo..+ext_n), totals[1] += sum counts[sh_lo..+sh_n), totals[2] += counts[0]
+void mfx_accum_ray_totals(cudaStream_t, const int *counts, int ext_lo, int ext_n, int sh_lo, int sh_n,
+                          unsigned long long *totals);
+void mfx_film_add(cudaStream_t, double *sum, const double *frame, double *target, long long n_pixels, double frame_count);
+void mfx_film_tonemap(cudaStream_t, const double *target_wh, int width, int height, uint8_t *rgba8);
+void mfx_fill_zero_f64(cudaStream_t, double *p, long long n);
