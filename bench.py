@@ -1,0 +1,321 @@
+#!/usr/bin/env python3
+"""bench.py -- the headline measurement: Mrays/s (primary + secondary) of the path-tracing hot
+path on BASELINE.json configs[1]: spot (cow OBJ) 1920x1080, 64 spp, max depth 5, diffuse + area
+light (SURVEY.md 8(d) "C2"), one step = one IPixelIntegrator.Sample(64) of the whole frame.
+
+  python bench.py --gpus 1 --steps K --warmup W          this repo's CUDA path (libmafrix_cuda)
+  torchrun ... bench.py --gpus N ...                     frame tile-sharded over N GPUs + NCCL reduce
+  python bench.py --impl reference ...                   the reference's CPU algorithm (the oracle
+                                                         restatement; .NET is not in this image)
+
+value   : whole-job Mrays/s, scene + path state resident in HBM, result left in HBM (device timed)
+e2e     : same metric through the reference-facing call with HOST buffers -- scene upload
+          (mfx_scene_create) + Sample -> Color[w,h] on the host, copies inside the timed region
+roofline: closest-hit traversal kernel, algorithmic bytes (32 B/node + 48 B/tri +
+          16 B/sphere + 64 B queue traffic per ray, counted by an instrumented run) / CUDA-event
+          time, against the measured HBM copy bandwidth in MEASURED_PEAKS.json
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "Mrays/s (primary+secondary)"
+WORKLOAD = "c2_spot: spot 5856 tris + floor + back wall, 1920x1080, 64 spp, max depth 5, PathIntegrator, 1 quad light"
+SPP = 64
+REF_SPP = 2            # bounded sample for the CPU arms: same frame, 2 spp per step
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="mafrix", choices=["mafrix", "reference"])
+    ap.add_argument("--spp", type=int, default=SPP)
+    ap.add_argument("--workload", default="c2_spot")
+    ap.add_argument("--precision", default="fast", choices=["fast", "exact"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md, file absent)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def b_ray(nodes, tris, spheres, rays):
+    return (32.0 * nodes + 48.0 * tris + 16.0 * spheres) / max(rays, 1) + 64.0
+
+
+def run_reference(args, rank, world):
+    """The reference's own CPU implementation of the path, restated (oracle/mafrix_oracle.c, f64,
+    exhaustive both-children traversal, recursion to depth -1), OpenMP over pixels on all host
+    cores like Array.Parallel.iter (Integrators.fs:164).  A step = the same frame at REF_SPP spp."""
+    if rank != 0:
+        return
+    from mafrixraytracing_b200 import scenes
+    from oracle import oracle
+    desc = scenes.WORKLOADS[args.workload]()
+    o = oracle.OracleScene(desc)
+    cores = oracle.max_threads()
+    tex = np.zeros((desc.width, desc.height, 4))
+    _, st = o.sample(1, seed=1, region=(0, 0, desc.width, 8), stats=True)      # ray accounting only (untimed)
+    for _ in range(args.warmup):
+        o.sample(REF_SPP, seed=1, out=tex)
+    t0 = time.perf_counter()
+    for k in range(args.steps):
+        o.sample(REF_SPP, seed=1, first_sample=k * REF_SPP, out=tex)
+    dt = time.perf_counter() - t0
+    # rays per step: count them with one instrumented (slower, untimed) step
+    _, st = o.sample(REF_SPP, seed=1, stats=True)
+    rays = st["closest_rays"] + st["wasted_rays"] + st["shadow_rays"]
+    val = rays * args.steps / dt / 1e6
+    sample = f"full 1920x1080 frame at {REF_SPP} spp per step (config is 64 spp; cost is linear in spp), {rays} rays/step incl. the reference's wasted depth -1 query"
+    line = {"metric": METRIC, "value": val, "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "impl": "reference",
+            "config": {"workload": WORKLOAD, "sample": sample},
+            "cpu_baseline": {"value": val, "unit": "Mrays/s", "cores": cores, "kind": "port", "sample": sample,
+                             "spp_per_s": REF_SPP * args.steps / dt},
+            "e2e": {"value": val, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0,
+            "note": "C restatement of the reference CPU path (the F# original needs .NET, absent here); a reported baseline, not the target"}
+    print(json.dumps(line), flush=True)
+
+
+def cpu_baseline(desc):
+    from oracle import oracle
+    o = oracle.OracleScene(desc)
+    cores = oracle.max_threads()
+    _, st = o.sample(1, seed=1, stats=True)                     # instrumented: rays per spp
+    rays_per_spp = st["closest_rays"] + st["wasted_rays"] + st["shadow_rays"]
+    n = 4
+    t0 = time.perf_counter()
+    o.sample(n, seed=1, first_sample=1)
+    dt = time.perf_counter() - t0
+    return {"value": rays_per_spp * n / dt / 1e6, "unit": "Mrays/s", "cores": cores, "kind": "port",
+            "sample": f"full 1920x1080 frame at {n} spp ({rays_per_spp * n} rays incl. the wasted depth -1 queries), {dt:.1f} s on {cores} threads",
+            "spp_per_s": n / dt, "ref_nodes_per_ray": st["ref_nodes"] / rays_per_spp, "ref_prims_per_ray": st["ref_prims"] / rays_per_spp}
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from mafrixraytracing_b200 import scenes, Scene, CudaPixelIntegrator, Bvh, EXACT_F64, FAST_F32, _lib
+    from mafrixraytracing_b200 import dist as mdist
+
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local_rank))
+    prec = FAST_F32 if args.precision == "fast" else EXACT_F64
+    desc = scenes.WORKLOADS[args.workload]()
+    bvh = Bvh.Build(desc.prims)                                 # host, one-off (kept on the host by the north star)
+    scene = Scene(desc, bvh=bvh, device=local_rank)
+    sharded = mdist.ShardedPixelIntegrator(scene, rank, world, precision=prec, seed=1, tile=mdist.TILE)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")           # > 126 MB L2
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def step(k):
+        flush.fill_(k & 0xff)                                   # L2 flush between iterations
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        sharded.Sample(args.spp, first_sample=0, reduce=True)   # render this rank's tiles + NCCL sum-reduce to rank 0
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1), dict(sharded.stats)
+
+    for k in range(max(args.warmup, 3)):
+        step(k)
+    sync_all()
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    wall0 = time.perf_counter()
+    ms_steps, stats = [], []
+    for k in range(args.steps):
+        ms, st = step(k)
+        ms_steps.append(ms)
+        stats.append(st)
+    sync_all()
+    wall = time.perf_counter() - wall0
+    clk = clocks.stop() if rank == 0 else None
+
+    rays_rank = sum(s["closest_rays"] + s["shadow_rays"] for s in stats)
+    t_rank = sum(ms_steps)
+    if world > 1:
+        tt = torch.tensor([t_rank], dtype=torch.float64, device="cuda")
+        rr = torch.tensor([float(rays_rank)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dist.all_reduce(rr, op=dist.ReduceOp.SUM)
+        t_all, rays_all = tt.item(), rr.item()
+    else:
+        t_all, rays_all = t_rank, float(rays_rank)
+    value = rays_all / t_all / 1e3                               # rays / ms / 1e3 = Mrays/s
+
+    # ---- end to end through the reference-facing call, host buffers
+    e2e = None
+    if not args.no_e2e:
+        tex = np.zeros((desc.width, desc.height, 4), dtype=np.float64)
+        host_frame = torch.empty((desc.height, desc.width, 4), dtype=torch.float32).pin_memory()
+        h2d = desc.prims.nbytes + desc.materials.nbytes + bvh.nodes.nbytes + bvh.indices.nbytes + 12 * 8 + 18 * 8
+        rays_e2e, t_e2e = 0.0, 0.0
+        for k in range(args.steps + 1):
+            sync_all()
+            t0 = time.perf_counter()
+            sc = Scene(desc, bvh=bvh, device=local_rank)         # H2D: flattened scene (prims, tree, materials)
+            if world == 1:
+                integ = CudaPixelIntegrator(sc, precision=prec, seed=1)
+                integ.Sample(args.spp, out=tex)                  # D2H: Color[w,h] f64 = the reference's Texture2D
+                d2h = tex.nbytes
+                st = integ.stats
+            else:
+                sh = mdist.ShardedPixelIntegrator(sc, rank, world, precision=prec, seed=1, tile=mdist.TILE)
+                fr = sh.Sample(args.spp)
+                if rank == 0:
+                    host_frame.copy_(fr, non_blocking=False)     # D2H: assembled float4 frame on rank 0
+                d2h = host_frame.numel() * 4
+                st = sh.stats
+            sync_all()
+            dt = time.perf_counter() - t0
+            sc.close()
+            if k == 0:
+                continue                                         # first call allocates the path state
+            rr = torch.tensor([float(st["closest_rays"] + st["shadow_rays"]), dt], dtype=torch.float64, device="cuda")
+            if world > 1:
+                r2 = rr.clone()
+                dist.all_reduce(rr, op=dist.ReduceOp.SUM)
+                dist.all_reduce(r2, op=dist.ReduceOp.MAX)
+                rays_e2e += rr[0].item()
+                t_e2e += r2[1].item()
+            else:
+                rays_e2e += rr[0].item()
+                t_e2e += dt
+        e2e = {"value": rays_e2e / t_e2e / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+               "ms_per_step": t_e2e / args.steps * 1e3,
+               "call": "mfx_scene_create + mfx_pixel_integrator_sample (Color[w,h] f64 to host)" if world == 1 else
+                       "mfx_scene_create + mfx_pixel_integrator_sample_device + NCCL reduce + D2H on rank 0"}
+
+    # ---- roofline of the dominant kernel (closest-hit traversal), rank 0's share
+    roof, cpu = None, None
+    if rank == 0:
+        integ = sharded.integ
+        integ.SampleDevice(2, sharded.frame.data_ptr(), flags=_lib.SAMPLE_COUNT_TRAVERSAL)     # instrumented, untimed
+        cs = integ.stats
+        bc = b_ray(cs["nodes"][0], cs["tris"][0], cs["spheres"][0], cs["closest_rays"])
+        bs = b_ray(cs["nodes"][1], cs["tris"][1], cs["spheres"][1], cs["shadow_rays"])
+        ext_ms = sum(s["ms_extend"] for s in stats)
+        ext_rays = sum(s["closest_rays"] for s in stats)
+        ext_launches = sum(s["launches_extend"] for s in stats)
+        sh_ms = sum(s["ms_shadow"] for s in stats)
+        sh_rays = sum(s["shadow_rays"] for s in stats)
+        peak, how = peaks()
+        achieved = ext_rays * bc / (ext_ms * 1e-3) / 1e9
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+        if os.path.exists(tp):
+            traffic = json.load(open(tp)).get("extend_dram_bytes_per_launch")
+        roof = {"bound": "hbm", "kernel": "k_f_extend (closest-hit BVH traversal)" if prec == FAST_F32 else "k_x_extend",
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": how,
+                "bytes_per_ray_closest": bc, "bytes_per_ray_shadow": bs,
+                "nodes_per_ray": [cs["nodes"][0] / max(cs["closest_rays"], 1), cs["nodes"][1] / max(cs["shadow_rays"], 1)],
+                "tris_per_ray": [cs["tris"][0] / max(cs["closest_rays"], 1), cs["tris"][1] / max(cs["shadow_rays"], 1)],
+                "algorithmic_bytes_per_launch": ext_rays * bc / max(ext_launches, 1),
+                "avg_launch_ms": ext_ms / max(ext_launches, 1), "launches": ext_launches,
+                "share_of_step": ext_ms / max(sum(s["ms_total"] for s in stats), 1e-9),
+                "extend_mrays_s": ext_rays / ext_ms / 1e3, "shadow_mrays_s": sh_rays / max(sh_ms, 1e-9) / 1e3,
+                "shadow_achieved_gbs": sh_rays * bs / max(sh_ms * 1e-3, 1e-12) / 1e9,
+                "whole_step_achieved_gbs": (ext_rays * bc + sh_rays * bs) / (sum(s["ms_total"] for s in stats) * 1e-3) / 1e9,
+                "note": "scene is L2 resident (fast layout %.2f MB): the HBM figure is the north star's stated denominator" %
+                        (scene.device_bytes()["fast"] / 1e6)}
+        if world == 1 and not args.no_cpu_baseline:
+            cpu = cpu_baseline(desc)
+
+    if rank == 0:
+        launches = sum(s["launches"] for s in stats)
+        line = {"metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+                "ms_per_step": t_all / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": "f32" if prec == FAST_F32 else "f64", "data": "synthetic",
+                "config": {"workload": WORKLOAD if args.workload == "c2_spot" else args.workload, "spp": args.spp,
+                           "parallelism": f"tiles{mdist.TILE}x{mdist.TILE} interleaved over {world} GPU(s), scene replicated, 1 NCCL sum-reduce per frame",
+                           "l2": "256 MB buffer written between timed iterations (L2 flush); path state (~400 MB/wave) exceeds L2, scene is L2 resident by nature",
+                           "rays_per_step": rays_all / args.steps, "paths_per_step": desc.width * desc.height * args.spp},
+                "spp_per_s": args.spp * args.steps / (t_all * 1e-3), "wall_s_timed_region": wall,
+                "e2e": e2e, "gpu_launches": int(launches), "clocks": clk, "roofline": roof, "cpu_baseline": cpu}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

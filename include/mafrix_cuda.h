@@ -159,6 +159,12 @@ MFX_API int mfx_camera_pinhole(const double pos[3], const double dir[3], double 
 MFX_API int mfx_bvh_build(const MfxPrim *prims, int32_t n, MfxBvhNode *nodes_out, int32_t n_slots,
                           int32_t *indices_out);
 
+/* Multi-GPU pixel ownership: the frame is cut into tile_size x tile_size tiles numbered row-major;
+ * tile k belongs to rank k % world.  Writes this rank's linear pixel ids (y*width+x, tile after
+ * tile) to pixels_out (capacity width*height, may be NULL to query) and their number to n_out. */
+MFX_API int mfx_tile_map(int32_t width, int32_t height, int32_t tile_size, int32_t rank, int32_t world,
+                         int32_t *pixels_out, int32_t *n_out);
+
 /* ---- scene: replaces `new Scene(state)`'s Bvh + PathIntegrator + PixelIntegrator ------------ */
 MFX_API int mfx_scene_create(const MfxSceneDesc *desc, MfxScene **out);
 MFX_API int mfx_scene_destroy(MfxScene *scene);

@@ -59,6 +59,7 @@ SYMBOLS = {
     "mfx_init": (C.c_int, [C.c_int]),
     "mfx_camera_pinhole": (C.c_int, [_P, _P, C.c_double, C.c_double, C.POINTER(MfxCamera)]),
     "mfx_bvh_build": (C.c_int, [_P, C.c_int32, _P, C.c_int32, _P]),
+    "mfx_tile_map": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, C.POINTER(C.c_int32)]),
     "mfx_scene_create": (C.c_int, [C.POINTER(MfxSceneDesc), C.POINTER(_P)]),
     "mfx_scene_destroy": (C.c_int, [_P]),
     "mfx_scene_get_bvh": (C.c_int, [_P, _P, _P]),

@@ -114,20 +114,36 @@ extern "C" int mfx_camera_pinhole(const double pos[3], const double dir[3], doub
 // ------------------------------------------------------------------ Bvh.Build reproduction
 struct HBound { double lo[3], hi[3]; };
 
+// F# min/max on floats are System.Math.Min/Max: NaN propagates, -0.0 < +0.0.
+static inline double net_min(double a, double b)
+{
+    if (a < b) return a;
+    if (b < a) return b;
+    if (a != a) return a;
+    return std::signbit(a) ? a : b;
+}
+static inline double net_max(double a, double b)
+{
+    if (a > b) return a;
+    if (b > a) return b;
+    if (a != a) return a;
+    return std::signbit(a) ? b : a;
+}
+
 static HBound prim_bound(const MfxPrim &p)
 {
     HBound b;
     if (p.kind == MFX_SPHERE) {                                 // Sphere.fs:17-20: Bound(c - v, c + v)
         for (int a = 0; a < 3; a++) {
             double m0 = p.v[a] - p.v[3], m1 = p.v[a] + p.v[3];
-            b.lo[a] = std::min(m0, m1); b.hi[a] = std::max(m0, m1);
+            b.lo[a] = net_min(m0, m1); b.hi[a] = net_max(m0, m1);
         }
         return b;
     }
     const int nv = (p.kind == MFX_RECT) ? 4 : 3;                // Trangle.fs:113, Rect.fs:23
     for (int a = 0; a < 3; a++) {
         double lo = p.v[a], hi = p.v[a];
-        for (int k = 1; k < nv; k++) { lo = std::min(lo, p.v[3 * k + a]); hi = std::max(hi, p.v[3 * k + a]); }
+        for (int k = 1; k < nv; k++) { lo = net_min(lo, p.v[3 * k + a]); hi = net_max(hi, p.v[3 * k + a]); }
         b.lo[a] = lo; b.hi[a] = hi;
     }
     return b;
@@ -148,7 +164,7 @@ static MfxBvhNode init_node(const BuildCtx &c, int start, int count)    // BvhNo
     for (int a = 0; a < 3; a++) { n.pmin[a] = b0.lo[a]; n.pmax[a] = b0.hi[a]; }
     for (int i = 1; i < count; i++) {
         const HBound &b = (*c.pb)[c.indices[start + i]];
-        for (int a = 0; a < 3; a++) { n.pmin[a] = std::min(n.pmin[a], b.lo[a]); n.pmax[a] = std::max(n.pmax[a], b.hi[a]); }
+        for (int a = 0; a < 3; a++) { n.pmin[a] = net_min(n.pmin[a], b.lo[a]); n.pmax[a] = net_max(n.pmax[a], b.hi[a]); }
     }
     n.first = start; n.count = count;
     return n;
@@ -544,6 +560,28 @@ static int ensure_frame_buffers(MfxScene *s)
 }
 
 // Interleaved square tiles: tile k (row-major over the tile grid) belongs to rank k % world.
+static void tile_pixels(int width, int height, int tile, int rank, int world, std::vector<int> &pix)
+{
+    const int tx = (width + tile - 1) / tile, ty = (height + tile - 1) / tile;
+    for (int t = rank; t < tx * ty; t += world) {
+        const int x0 = (t % tx) * tile, y0 = (t / tx) * tile;
+        for (int y = y0; y < std::min(y0 + tile, height); y++)
+            for (int x = x0; x < std::min(x0 + tile, width); x++) pix.push_back(y * width + x);
+    }
+}
+
+extern "C" int mfx_tile_map(int32_t width, int32_t height, int32_t tile_size, int32_t rank, int32_t world,
+                            int32_t *pixels_out, int32_t *n_out)
+{
+    if (width <= 0 || height <= 0 || tile_size <= 0 || world <= 0 || rank < 0 || rank >= world || !n_out)
+        return fail(MFX_ERR_INVALID_ARGUMENT, "mfx_tile_map: bad arguments (w=%d h=%d tile=%d rank=%d world=%d)", width, height, tile_size, rank, world);
+    std::vector<int> pix;
+    tile_pixels(width, height, tile_size, rank, world, pix);
+    *n_out = (int32_t)pix.size();
+    if (pixels_out) memcpy(pixels_out, pix.data(), pix.size() * sizeof(int));
+    return MFX_OK;
+}
+
 static int get_tilemap(MfxScene *s, int tile, int rank, int world, TileMap *tm)
 {
     if (world <= 1 || tile <= 0) { tm->pix = nullptr; tm->n_pix = s->width * s->height; return MFX_OK; }
@@ -551,12 +589,7 @@ static int get_tilemap(MfxScene *s, int tile, int rank, int world, TileMap *tm)
     auto it = s->tilemaps.find(key);
     if (it == s->tilemaps.end()) {
         std::vector<int> pix;
-        const int tx = (s->width + tile - 1) / tile, ty = (s->height + tile - 1) / tile;
-        for (int t = rank; t < tx * ty; t += world) {
-            const int x0 = (t % tx) * tile, y0 = (t / tx) * tile;
-            for (int y = y0; y < std::min(y0 + tile, s->height); y++)
-                for (int x = x0; x < std::min(x0 + tile, s->width); x++) pix.push_back(y * s->width + x);
-        }
+        tile_pixels(s->width, s->height, tile, rank, world, pix);
         int *d = nullptr;
         MFX_TRY(upload(s, &d, pix));
         it = s->tilemaps.emplace(key, std::make_pair(d, (int)pix.size())).first;

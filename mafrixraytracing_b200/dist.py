@@ -1,0 +1,74 @@
+"""Multi-GPU sharding of one frame: one process per GPU (torchrun), scene replicated, interleaved
+square tiles (tile k -> rank k % world, mfx_tile_map), every rank renders its tiles into a
+zero-initialised full frame on its own GPU, and ONE sum-reduce over NCCL/NVLink assembles the
+frame on rank 0 (zeros elsewhere make the sum exact and order independent).  The counter-based
+RNG is keyed on the absolute pixel/sample, so the frame is bit-identical for any world size.
+
+The reference has no distributed code (its only parallelism is Array.Parallel.iter over pixels,
+Integrators.fs:164); this is the B200 equivalent of that loop across GPUs.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import _lib
+from .scene import CudaPixelIntegrator, FAST_F32
+
+TILE = 64
+
+
+def tile_pixels(width, height, tile, rank, world):
+    """This rank's linear pixel ids (y*width+x), from the library's own ownership rule."""
+    n = C.c_int32()
+    lib = _lib.load()
+    _lib.check(lib.mfx_tile_map(width, height, tile, rank, world, None, C.byref(n)))
+    out = np.zeros(n.value, np.int32)
+    _lib.check(lib.mfx_tile_map(width, height, tile, rank, world, _lib.ptr(out), C.byref(n)))
+    return out
+
+
+def env_rank_world():
+    return (int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")),
+            int(os.environ.get("LOCAL_RANK", "0")))
+
+
+def init_process_group(backend="nccl"):
+    import torch.distributed as dist
+    if not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29511")
+        dist.init_process_group(backend=backend)
+    return dist.get_rank(), dist.get_world_size()
+
+
+def reduce_frame(frame, dst=0):
+    """Sum-reduce of the per-rank frames (torch tensor on this rank's device) onto rank dst."""
+    import torch.distributed as dist
+    if dist.is_initialized() and dist.get_world_size() > 1:
+        dist.reduce(frame, dst=dst, op=dist.ReduceOp.SUM)
+    return frame
+
+
+class ShardedPixelIntegrator:
+    """IPixelIntegrator over `world` GPUs: Sample(n) renders this rank's tiles and reduces.
+    Returns the (height, width, 4) float32 CUDA tensor (complete on rank 0)."""
+
+    def __init__(self, scene, rank, world, precision=FAST_F32, seed=1, tile=TILE, device=None):
+        import torch
+        self.torch = torch
+        self.scene, self.rank, self.world = scene, rank, world
+        self.integ = CudaPixelIntegrator(scene, precision=precision, seed=seed,
+                                         tile_size=tile if world > 1 else 0, rank=rank, world=world)
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else device
+        self.frame = torch.zeros((scene.height, scene.width, 4), dtype=torch.float32, device=self.device)
+
+    def Sample(self, n, first_sample=0, reduce=True):
+        self.integ.SampleDevice(n, self.frame.data_ptr(), first_sample=first_sample)
+        if reduce:
+            reduce_frame(self.frame)
+        return self.frame
+
+    @property
+    def stats(self):
+        return self.integ.stats

@@ -35,9 +35,22 @@ static inline V3 v_normalize(V3 a)                                              
 }
 static inline double v_get(V3 a, int i) { return i == 0 ? a.x : (i == 1 ? a.y : a.z); }
 
-/* F# `min`/`max` on floats (propagate NaN; never reached with NaN on this path) */
-static inline double fs_min(double a, double b) { return a < b ? a : (b < a ? b : (a != a ? a : b)); }
-static inline double fs_max(double a, double b) { return a > b ? a : (b > a ? b : (a != a ? a : b)); }
+/* F# `min`/`max` on floats compile to System.Math.Min/Max (FSharp.Core prim-types, static
+ * optimisation for float): NaN propagates and -0.0 orders below +0.0 (IEEE 754-2019 minimum). */
+static inline double fs_min(double a, double b)
+{
+    if (a < b) return a;
+    if (b < a) return b;
+    if (a != a) return a;
+    return signbit(a) ? a : b;
+}
+static inline double fs_max(double a, double b)
+{
+    if (a > b) return a;
+    if (b > a) return b;
+    if (a != a) return a;
+    return signbit(a) ? b : a;
+}
 
 /* ------------------------------------------------------------------ Core/Color.fs (rgb only) */
 typedef struct { double r, g, b; } Col;

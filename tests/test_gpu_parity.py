@@ -1,0 +1,344 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle and the committed goldens.
+
+Bars (BASELINE.json north_star):
+  * MFX_EXACT_F64: primitive ids, t AND radiance bit-exact (integer/index work: bit-exact;
+    the f64 path reproduces the reference's rounding sequence, so we hold it to bit-exact too);
+  * MFX_FAST_F32 : primary ids agree except on measure-zero edge rays (<= 2e-4 of rays),
+    t within 1e-4 relative, images within a stated relative RMSE of the exact frame at
+    matched spp and seeds.
+"""
+import hashlib
+import os
+
+import numpy as np
+import pytest
+
+from mafrixraytracing_b200 import (scenes, Scene, CudaPixelIntegrator, Film, Bvh, MafrixError, EXACT_F64, FAST_F32,
+                                   PATH_INTEGRATOR, NEW_PATH_TRACER)
+from mafrixraytracing_b200 import _lib
+from mafrixraytracing_b200.scene import (AreaLight, PinholeCamera, SceneDesc, make_materials, make_prims, sphere_prims,
+                                         rect_prim)
+from oracle import oracle
+
+pytestmark = pytest.mark.gpu
+BIG = 99999999.
+
+
+def _sha(a):
+    return np.frombuffer(hashlib.sha256(np.ascontiguousarray(a).tobytes()).digest(), dtype=np.uint8)
+
+
+def _desc(name, **kw):
+    base = name.replace("_small", "")
+    return (scenes.c4_spheres if base == "spheres" else scenes.WORKLOADS[base])(**kw)
+
+
+# ------------------------------------------------------------------ primary-hit buffers
+@pytest.mark.parametrize("name,kw", [("cornell", {}), ("c1_cube", {}), ("c2_spot_small", dict(width=480, height=270)),
+                                     ("c3_renault_small", dict(width=480, height=270))])
+def test_exact_primary_bit_exact_vs_oracle_and_goldens(goldens, name, kw):
+    desc = _desc(name, **kw)
+    s = Scene(desc)
+    prim, t = s.TracePrimary(precision=EXACT_F64)
+    oprim, ot = oracle.OracleScene(desc).trace_primary()
+    assert np.array_equal(prim, oprim) and np.array_equal(t, ot)
+    assert np.array_equal(prim, goldens[f"primary/{name}/prim"])
+    assert np.array_equal(_sha(t), goldens[f"primary/{name}/sha_t"])
+
+
+@pytest.mark.parametrize("name", ["c2_spot", "c3_renault"])
+def test_exact_primary_full_size_matches_golden_checksums(goldens, name):
+    s = Scene(_desc(name))                      # 1920x1080, BASELINE configs[1] / [2]
+    prim, t = s.TracePrimary(precision=EXACT_F64)
+    assert int((prim >= 0).sum()) == int(goldens[f"primary/{name}/hits"])
+    assert np.array_equal(_sha(prim), goldens[f"primary/{name}/sha_prim"])
+    assert np.array_equal(_sha(t), goldens[f"primary/{name}/sha_t"])
+
+
+@pytest.mark.parametrize("name,kw", [("cornell", {}), ("c2_spot", dict(width=640, height=360)), ("c3_renault", dict(width=640, height=360))])
+def test_fast_primary_ids_and_t_tolerance(name, kw):
+    desc = _desc(name, **kw)
+    s = Scene(desc)
+    rng = np.random.default_rng(4)
+    uv = rng.random((300000, 2))                # jittered rays: pixel centres sit on quad diagonals
+    oprim, ot = oracle.OracleScene(desc).trace_primary(uv)
+    prim, t = s.TracePrimary(uv, precision=FAST_F32)
+    mism = (prim != oprim).mean()
+    assert mism <= 2e-4, f"fast primary id mismatch rate {mism:.2e}"
+    both = (prim == oprim) & (oprim >= 0)
+    assert (np.abs(t[both] - ot[both]) <= 1e-4 * np.abs(ot[both])).all()      # north_star: t within 1e-4 relative
+    eprim, et = s.TracePrimary(uv, precision=EXACT_F64)
+    assert np.array_equal(eprim, oprim) and np.array_equal(et, ot)
+
+
+# ------------------------------------------------------------------ Bvh.Hit seam
+@pytest.mark.parametrize("name,kw", [("cornell", {}), ("c1_cube", {}), ("c2_spot", dict(width=8, height=8)),
+                                     ("c3_renault", dict(width=8, height=8)), ("spheres", dict(width=8, height=8, grid=30))])
+def test_bvh_hit_closest_and_shadow(name, kw):
+    desc = _desc(name, **kw)
+    s, o = Scene(desc), oracle.OracleScene(desc)
+    rng = np.random.default_rng(3)
+    n = 100000
+    org = rng.uniform(-3, 3, (n, 3))
+    if name == "spheres":
+        org[:, 1] = rng.uniform(0.05, 3, n)
+    d = rng.normal(size=(n, 3))
+    d /= np.linalg.norm(d, axis=1)[:, None]
+    op, osub, ot = o.hit(org, d, 1e-6, BIG)
+    gp, gsub, gt = s.Hit(org, d, 1e-6, BIG, precision=EXACT_F64)
+    assert np.array_equal(gp, op) and np.array_equal(gsub, osub) and np.array_equal(gt, ot)
+    fp, fsub, ft = s.Hit(org, d, 1e-6, BIG, precision=FAST_F32)
+    assert (fp != op).mean() <= 3e-4
+    same = (fp == op) & (op >= 0)
+    assert (np.abs(ft[same] - ot[same]) <= 1e-4 * np.abs(ot[same]) + 1e-6).all()
+    for tmax in (0.5, 2.0):                      # shadow queries (Integrators.fs:44)
+        op, _, _ = o.hit(org, d, 1e-6, tmax)
+        gp, _, _ = s.Hit(org, d, 1e-6, tmax, precision=EXACT_F64, any_hit=True)
+        assert np.array_equal(gp >= 0, op >= 0)
+        fp, _, _ = s.Hit(org, d, 1e-6, tmax, precision=FAST_F32, any_hit=True)
+        assert ((fp >= 0) != (op >= 0)).mean() <= 3e-4
+
+
+def test_exact_reproduces_the_quirks():
+    # Q1 tie rules, Q2 tMax-blind triangles, Q3 Rect returns tri1 first, Q6 NaN / -0.0 box tests
+    def tri(v0, v1, v2):
+        p = make_prims(1)
+        p["v"][0, :9] = np.concatenate([v0, v1, v2])
+        return p
+
+    def scene_of(prims):
+        mats = make_materials([("lambert", (0.5, 0.5, 0.5))])
+        light = AreaLight(np.array([(-1, 5, 1), (-1, 5, -1), (1, 5, -1), (1, 5, 1)], float), (0, -1, 0), (10, 10, 10))
+        desc = SceneDesc(np.concatenate(prims), mats, light, PinholeCamera((0, 0, 5), (0, 0, -1), 120.0, 1.0), 8, 8, 0)
+        return Scene(desc), oracle.OracleScene(desc)
+
+    unit = tri((0, 0, 0), (1, 0, 0), (0, 1, 0))
+    cases = [
+        ([unit] * 8, (0.25, 0.25, 1), (0, 0, -1), 1e-6, BIG),
+        ([unit] * 3, (0.25, 0.25, 1), (0, 0, -1), 1e-6, BIG),
+        ([tri((0, 0, 0), (1, 0, 1), (0, 1, 0))], (0.1, 0.1, 2), (0, 0, -1), 1e-6, 1.5),
+        ([tri((0, 0, 0), (1, 0, 1), (0, 1, 0)), tri((5, 5, 0), (6, 5, 0), (5, 6, 0))], (0.1, 0.1, 2), (0, 0, -1), 1e-6, 1.5),
+        ([rect_prim((0, 0, 0), (1, 0, 0), (1, 1, 0), (1, 0.2, 0.5))], (0.8, 0.4, 2), (0, 0, -1), 1e-6, BIG),
+        ([unit], (0.0, 0.3, 1), (0, 0, -1), 1e-6, BIG),
+        ([unit], (0.25, 0.25, 2), (-0.0, 0.0, -1.0), 1e-6, BIG),
+        ([unit], (0.5, 0.3, 1), (-0.5, 0, -1), 1e-6, BIG),
+        ([sphere_prims([(0, 0, 0)], 1.0, 0)], (0, 0, 0), (0, 0, -1), 1e-6, BIG),
+        ([sphere_prims([(0, 0, 0)], 1.0, 0)], (1, 0, 3), (0, 0, -1), 1e-6, BIG),
+    ]
+    for prims, org, d, tmin, tmax in cases:
+        s, o = scene_of(prims)
+        for any_hit in (False, True):
+            want = o.hit([org], [d], tmin, tmax)
+            got = s.Hit([org], [d], tmin, tmax, precision=EXACT_F64, any_hit=any_hit)
+            if any_hit:
+                assert (got[0] >= 0) == (want[0] >= 0)
+            else:
+                assert all(np.array_equal(a, b) for a, b in zip(got, want)), (org, d, got, want)
+
+
+# ------------------------------------------------------------------ IPixelIntegrator.Sample
+@pytest.mark.parametrize("name", ["cornell", "c1_cube", "c2_spot", "c3_renault", "spheres"])
+def test_exact_sample_bit_exact_vs_goldens_and_oracle(goldens, name):
+    from tests.golden.make_goldens import IMAGES, builder
+    kw, spp, seed = IMAGES[name]
+    desc = builder(name)(**kw)
+    s = Scene(desc)
+    integ = CudaPixelIntegrator(s, precision=EXACT_F64, seed=seed)
+    tex = integ.Sample(spp)
+    assert tex.shape == (desc.width, desc.height, 4) and (tex[:, :, 3] == 1.0).all()
+    assert np.array_equal(tex[:, :, :3], goldens[f"image/{name}/rgb"])
+    o = oracle.OracleScene(desc)
+    ref, st = o.sample(spp, seed=seed, stats=True)
+    assert np.array_equal(tex[:, :, :3], ref[:, :, :3])
+    assert integ.stats["closest_rays"] == st["closest_rays"] and integ.stats["shadow_rays"] == st["shadow_rays"]
+    assert integ.stats["paths"] == desc.width * desc.height * spp
+
+
+@pytest.mark.parametrize("name,kw,spp,tol", [("cornell", dict(width=150, height=150), 16, 5e-3),
+                                             ("c1_cube", dict(width=160, height=120), 16, 5e-3),
+                                             ("c2_spot", dict(width=240, height=135), 16, 2e-2)])
+def test_fast_sample_tracks_exact_at_matched_seeds(name, kw, spp, tol):
+    """Same Philox stream in both precisions: most paths take identical decisions, so the f32 frame
+    stays within `tol` relative RMSE of the exact frame (stated tolerance, mode A)."""
+    desc = _desc(name, **kw)
+    s = Scene(desc)
+    exact = CudaPixelIntegrator(s, precision=EXACT_F64, seed=5).Sample(spp).copy()
+    fast = CudaPixelIntegrator(s, precision=FAST_F32, seed=5).Sample(spp).copy()
+    rel = np.sqrt(((fast - exact)[:, :, :3] ** 2).mean()) / np.abs(exact[:, :, :3]).mean()
+    assert rel <= tol, f"{name}: relative RMSE {rel:.3e}"
+    assert abs(fast[:, :, :3].mean() / exact[:, :, :3].mean() - 1) < 2e-3
+
+
+@pytest.mark.parametrize("name,kw", [("c3_renault", dict(width=160, height=90)), ("spheres", dict(width=160, height=90, grid=24))])
+def test_fast_sample_mode_b_is_statistically_equal(name, kw):
+    """NewPathTracer scenes have specular chains and 1/|cos| weights: single paths diverge between
+    f32 and f64, so the bar is statistical -- the fast frame must sit inside the exact renderer's
+    own seed-to-seed noise and agree in mean radiance."""
+    desc = _desc(name, **kw)
+    s = Scene(desc)
+    spp = 64
+    ea = CudaPixelIntegrator(s, precision=EXACT_F64, seed=5).Sample(spp).copy()[:, :, :3]
+    eb = CudaPixelIntegrator(s, precision=EXACT_F64, seed=6).Sample(spp).copy()[:, :, :3]
+    fa = CudaPixelIntegrator(s, precision=FAST_F32, seed=5).Sample(spp).copy()[:, :, :3]
+    # robust statistics: heavy-tailed fireflies make plain RMSE meaningless here
+    clip = np.percentile(ea, 99.0)
+    c = lambda x: np.clip(x, -clip, clip)
+    noise = np.sqrt(((c(ea) - c(eb)) ** 2).mean())
+    err = np.sqrt(((c(fa) - c(ea)) ** 2).mean())
+    assert err <= noise, f"{name}: fast-vs-exact {err:.3e} exceeds the seed-to-seed noise {noise:.3e}"
+    assert abs(c(fa).mean() / c(ea).mean() - 1) < 2e-2
+
+
+def test_sample_is_deterministic_and_progressive():
+    desc = _desc("cornell", width=120, height=120)
+    s = Scene(desc)
+    for prec in (EXACT_F64, FAST_F32):
+        a = CudaPixelIntegrator(s, precision=prec, seed=9).Sample(4).copy()
+        b = CudaPixelIntegrator(s, precision=prec, seed=9).Sample(4).copy()
+        assert np.array_equal(a, b)
+        c = CudaPixelIntegrator(s, precision=prec, seed=10).Sample(4).copy()
+        assert not np.array_equal(a, c)
+        lo = CudaPixelIntegrator(s, precision=prec, seed=9).Sample(2, first_sample=0).copy()
+        hi = CudaPixelIntegrator(s, precision=prec, seed=9).Sample(2, first_sample=2).copy()
+        assert np.allclose((lo + hi)[:, :, :3] / 2, a[:, :, :3], rtol=1e-6, atol=1e-9)
+
+
+def test_wave_chunking_does_not_change_the_frame(monkeypatch):
+    desc = _desc("c1_cube", width=96, height=64)
+    ref = {}
+    for prec in (EXACT_F64, FAST_F32):
+        ref[prec] = CudaPixelIntegrator(Scene(desc), precision=prec, seed=3).Sample(5).copy()
+    monkeypatch.setenv("MFX_WAVE_PATHS", "4096")          # < width*height: pixel chunks of one sample each
+    monkeypatch.setenv("MFX_WAVE_PATHS_EXACT", "10000")   # 1 sample per wave, 2 pixel chunks ... and uneven tails
+    for prec in (EXACT_F64, FAST_F32):
+        got = CudaPixelIntegrator(Scene(desc), precision=prec, seed=3).Sample(5).copy()
+        if prec == EXACT_F64:
+            assert np.array_equal(got, ref[prec])
+        else:
+            assert np.allclose(got, ref[prec], rtol=1e-5, atol=1e-7)
+
+
+@pytest.mark.parametrize("world", [2, 3, 8])
+def test_tile_sharding_sums_to_the_whole_frame(world):
+    desc = _desc("c1_cube", width=200, height=136)
+    s = Scene(desc)
+    for prec in (EXACT_F64, FAST_F32):
+        full = CudaPixelIntegrator(s, precision=prec, seed=2).Sample(3).copy()
+        acc = np.zeros_like(full)
+        owned = np.zeros(full.shape[:2], int)
+        for r in range(world):
+            part = CudaPixelIntegrator(s, precision=prec, seed=2, tile_size=32, rank=r, world=world).Sample(3).copy()
+            owned += (part[:, :, 3] == 1.0)
+            acc += part
+        assert (owned == 1).all()
+        assert np.array_equal(acc, full)          # RNG keyed on absolute pixel/sample: bit-identical for any world
+
+
+def test_f32_and_device_outputs_agree_with_color_wh():
+    import torch
+    desc = _desc("cornell", width=90, height=60)
+    s = Scene(desc)
+    integ = CudaPixelIntegrator(s, precision=FAST_F32, seed=4)
+    tex = integ.Sample(3).copy()
+    rows = integ.SampleF32(3)
+    assert rows.shape == (60, 90, 4)
+    assert np.array_equal(rows[:, :, :3], np.transpose(tex[:, :, :3], (1, 0, 2)).astype(np.float32))
+    buf = torch.zeros((60, 90, 4), dtype=torch.float32, device="cuda")
+    integ.SampleDevice(3, buf.data_ptr())
+    torch.cuda.synchronize()
+    assert np.array_equal(buf.cpu().numpy(), rows)
+
+
+# ------------------------------------------------------------------ Film + post-process
+def test_film_accumulation_and_tonemap_match_oracle():
+    desc = _desc("cornell", width=64, height=48)
+    s, o = Scene(desc), oracle.OracleScene(desc)
+    integ = CudaPixelIntegrator(s, precision=EXACT_F64, seed=8)
+    film = Film(s)
+    osum = np.zeros((64, 48, 4))
+    for frame in range(3):                       # Scene.Render: GetFrame(pixelIntegrator, 1) per displayed frame
+        target = film.GetFrame(integ, 1).copy()
+        otarget = oracle.film_add_sample(osum, o.sample(1, seed=8, first_sample=frame), frame + 1.0)
+        assert np.array_equal(target[:, :, :3], otarget[:, :, :3])
+    assert np.array_equal(film.PostProcess(), oracle.tonemap_rgba8(otarget))
+    film.Reset()
+    t0 = film.GetFrame(integ, 1, first_sample=0).copy()
+    assert np.array_equal(t0[:, :, :3], o.sample(1, seed=8)[:, :, :3])
+
+
+# ------------------------------------------------------------------ edge cases
+def test_degenerate_inputs():
+    mats = make_materials([("lambert", (0.7, 0.7, 0.7))])
+    light = AreaLight(np.array([(-1, 3, 1), (-1, 3, -1), (1, 3, -1), (1, 3, 1)], float), (0, -1, 0), (10, 10, 10))
+    cam = PinholeCamera((0, 1, 4), (0, -0.2, -1), 120.0, 1.0)
+    floor = rect_prim((-2, 0, -2), (-2, 0, 2), (2, 0, 2), (2, 0, -2))
+    zero_area = make_prims(1)                    # Renault has 4 of these: NaN normal, can never be hit
+    zero_area["v"][0, :9] = [0, 1, 0, 0, 1, 0, 1, 1, 0]
+    for prims, w, h, depth, spp in [([floor], 1, 1, 0, 1), ([floor], 7, 3, 3, 2), ([floor, zero_area], 16, 16, 2, 2),
+                                    ([sphere_prims([(0, 0.5, 0)], 0.5, 0)], 16, 16, 2, 2),
+                                    ([floor, sphere_prims([(0, 0.5, 0), (1, 0.3, 0.5)], [0.5, 0.3], 0)], 24, 16, 4, 3)]:
+        for mode in (PATH_INTEGRATOR, NEW_PATH_TRACER):
+            desc = SceneDesc(np.concatenate(prims), mats, light, cam, w, h, depth, mode)
+            s, o = Scene(desc), oracle.OracleScene(desc)
+            got = CudaPixelIntegrator(s, precision=EXACT_F64, seed=1).Sample(spp)
+            assert np.array_equal(got[:, :, :3], o.sample(spp, seed=1)[:, :, :3])
+            fast = CudaPixelIntegrator(s, precision=FAST_F32, seed=1).Sample(spp)
+            assert np.isfinite(fast).all()
+
+
+def test_bad_sample_arguments_raise():
+    s = Scene(_desc("cornell", width=16, height=16))
+    with pytest.raises(MafrixError):
+        CudaPixelIntegrator(s).Sample(0)
+    with pytest.raises(MafrixError):
+        CudaPixelIntegrator(s, precision=7).Sample(1)
+    with pytest.raises(MafrixError):
+        CudaPixelIntegrator(s, tile_size=16, rank=2, world=2).Sample(1)
+    with pytest.raises(MafrixError):
+        CudaPixelIntegrator(s, tile_size=0, rank=0, world=2).Sample(1)
+
+
+def test_supplied_tree_is_used_and_equals_host_build():
+    desc = _desc("c2_spot", width=64, height=36)
+    b = Bvh.Build(desc.prims)
+    s1, s2 = Scene(desc), Scene(desc, bvh=b)
+    got = s2.bvh()
+    assert np.array_equal(got.indices, b.indices) and np.array_equal(got.nodes.view(np.uint8), b.nodes.view(np.uint8))
+    a = CudaPixelIntegrator(s1, precision=EXACT_F64, seed=1).Sample(1).copy()
+    c = CudaPixelIntegrator(s2, precision=EXACT_F64, seed=1).Sample(1).copy()
+    assert np.array_equal(a, c)
+
+
+# ------------------------------------------------------------------ full-size properties (BASELINE configs[1])
+def test_c2_full_size_properties():
+    desc = scenes.c2_spot()
+    s = Scene(desc)
+    integ = CudaPixelIntegrator(s, precision=FAST_F32, seed=1)
+    a = integ.SampleF32(2)
+    st = dict(integ.stats)
+    assert st["paths"] == 1920 * 1080 * 2
+    assert st["paths"] <= st["closest_rays"] <= st["paths"] * (desc.max_depth + 1)
+    assert st["shadow_rays"] <= st["closest_rays"]
+    b = integ.SampleF32(2)
+    assert np.array_equal(a, b)                                   # idempotent / deterministic
+    acc = np.zeros_like(a)
+    for r in range(8):                                            # 8-way interleaved 64x64 tiles
+        acc += CudaPixelIntegrator(s, precision=FAST_F32, seed=1, tile_size=64, rank=r, world=8).SampleF32(2)
+    assert np.array_equal(acc, a)
+    # the exact frame of the same samples: f32 frame within the stated tolerance at full size
+    e = np.transpose(CudaPixelIntegrator(s, precision=EXACT_F64, seed=1).Sample(2)[:, :, :3], (1, 0, 2))
+    rel = np.sqrt(((a[:, :, :3] - e) ** 2).mean()) / np.abs(e).mean()
+    assert rel < 5e-2
+
+
+def test_traversal_counters_match_oracle_ordered_counts():
+    desc = _desc("c2_spot", width=192, height=108)
+    s, o = Scene(desc), oracle.OracleScene(desc)
+    integ = CudaPixelIntegrator(s, precision=FAST_F32, seed=2)
+    integ.Sample(2, flags=_lib.SAMPLE_COUNT_TRAVERSAL)
+    st = integ.stats
+    _, ost = o.sample(2, seed=2, stats=True, count_ordered=True)
+    for c, rays in ((0, st["closest_rays"]), (1, st["shadow_rays"])):
+        g_nodes, g_tris = st["nodes"][c] / rays, st["tris"][c] / rays
+        o_nodes, o_tris = ost["ord_nodes"][c] / ost["ord_rays"][c], ost["ord_tris"][c] / ost["ord_rays"][c]
+        assert abs(g_nodes / o_nodes - 1) < 0.10 and abs(g_tris / o_tris - 1) < 0.10, (c, g_nodes, o_nodes, g_tris, o_tris)

@@ -1,0 +1,157 @@
+"""CPU-side checks of the product: the C-ABI library loads and exports every symbol the header
+declares, ctypes layouts equal the C ones, the host reproductions (PinholeCamera, Bvh.Build,
+tile ownership) agree with the oracle, and compute entry points FAIL LOUDLY without a GPU."""
+import ctypes as C
+import os
+import re
+import subprocess
+import tempfile
+
+import numpy as np
+import pytest
+
+from mafrixraytracing_b200 import _lib, scenes, Bvh, PinholeCamera, Scene, MafrixError
+from mafrixraytracing_b200.scene import NODE_DTYPE, make_prims, sphere_prims
+from mafrixraytracing_b200 import dist as mdist
+from oracle import oracle
+from tests.conftest import ROOT, have_gpu
+
+HEADER = os.path.join(ROOT, "include", "mafrix_cuda.h")
+
+
+def test_library_exports_every_declared_symbol():
+    text = open(HEADER).read()
+    declared = set(re.findall(r"MFX_API\s+[\w\s\*]+?\b(mfx_\w+)\s*\(", text))
+    assert len(declared) >= 24
+    assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
+    raw = C.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert getattr(raw, name) is not None
+    assert b"mafrix_cuda" in _lib.load().mfx_version()
+
+
+def test_ctypes_layouts_match_the_header():
+    src = r'''
+#include <stdio.h>
+#include <stddef.h>
+#include "mafrix_cuda.h"
+int main(void) {
+  printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(MfxPrim), sizeof(MfxMaterial), sizeof(MfxBvhNode),
+         sizeof(MfxAreaLight), sizeof(MfxCamera), sizeof(MfxSceneDesc), sizeof(MfxSampleParams), sizeof(MfxStats),
+         offsetof(MfxSceneDesc, light), offsetof(MfxStats, ms_total));
+  return 0; }
+'''
+    with tempfile.TemporaryDirectory() as td:
+        open(os.path.join(td, "s.c"), "w").write(src)
+        subprocess.check_call(["/usr/bin/gcc", "-I", os.path.join(ROOT, "include"), "-o", os.path.join(td, "s"), os.path.join(td, "s.c")])
+        got = [int(x) for x in subprocess.check_output([os.path.join(td, "s")]).split()]
+    from mafrixraytracing_b200.scene import PRIM_DTYPE, MATERIAL_DTYPE
+    want = [PRIM_DTYPE.itemsize, MATERIAL_DTYPE.itemsize, NODE_DTYPE.itemsize, C.sizeof(_lib.MfxAreaLight),
+            C.sizeof(_lib.MfxCamera), C.sizeof(_lib.MfxSceneDesc), C.sizeof(_lib.MfxSampleParams), C.sizeof(_lib.MfxStats),
+            _lib.MfxSceneDesc.light.offset, _lib.MfxStats.ms_total.offset]
+    assert got == want
+
+
+@pytest.mark.parametrize("pos,dir,fov,aspect", [((0, 1, 3), (0, 0, -1), 120.0, 1.0), ((4.5, 1.6, 5.5), (-0.62, -0.18, -0.76), 120.0, 16 / 9),
+                                                ((13, 2, 3), (-13, -2, -3), 90.0, 4 / 3), ((0, 0.1, -2.6), (0, 0, 1), 37.5, 2.0)])
+def test_camera_matches_oracle_bitwise(pos, dir, fov, aspect):
+    cam = PinholeCamera(pos, dir, fov, aspect)
+    assert np.array_equal(cam.derived(), oracle.camera_pinhole(pos, dir, fov, aspect))
+    o, d = cam.GetRay(0.5, 0.5)
+    assert abs(np.linalg.norm(d) - 1) < 1e-15
+
+
+def _same_tree(desc):
+    b = Bvh.Build(desc.prims)
+    nodes, idx = oracle.OracleScene(desc).bvh()
+    assert np.array_equal(idx, b.indices)
+    assert np.array_equal(nodes.view(np.uint8), b.nodes.view(np.uint8))
+    return b
+
+
+@pytest.mark.parametrize("name,kw", [("cornell", {}), ("c1_cube", {}), ("c2_spot", dict(width=8, height=8)),
+                                     ("c3_renault", dict(width=8, height=8)), ("c4_spheres", dict(width=8, height=8, grid=40))])
+def test_bvh_build_matches_oracle(name, kw):
+    b = _same_tree(scenes.WORKLOADS[name](**kw))
+    assert b.nodes[0]["count"] == len(b.indices)
+
+
+def test_bvh_build_ties_and_mixed_primitives():
+    d = scenes.cornell(width=8, height=8)
+    rng = np.random.default_rng(9)
+    tris = make_prims(40)
+    tris["v"][:, :9] = np.repeat(rng.uniform(-1, 1, (8, 9)), 5, axis=0)          # 5 exact duplicates each -> key ties
+    sph = sphere_prims(rng.uniform(-1, 1, (11, 3)), rng.uniform(0.05, 0.3, 11), 0)
+    d.prims = np.concatenate([d.prims, tris, sph])
+    _same_tree(d)
+
+
+def test_bvh_build_rejects_bad_arguments():
+    lib = _lib.load()
+    prims = scenes.cornell(width=8, height=8).prims
+    nodes = np.zeros(2 * len(prims) - 1, NODE_DTYPE)
+    idx = np.zeros(len(prims), np.int32)
+    assert lib.mfx_bvh_build(_lib.ptr(prims), len(prims), _lib.ptr(nodes), len(nodes) - 1, _lib.ptr(idx)) == -1
+    assert b"2n-1" in lib.mfx_last_error()
+    assert lib.mfx_bvh_build(None, 3, _lib.ptr(nodes), 5, _lib.ptr(idx)) == -1
+    bad = prims.copy()
+    bad["kind"][0] = 7
+    assert lib.mfx_bvh_build(_lib.ptr(bad), len(bad), _lib.ptr(nodes), len(nodes), _lib.ptr(idx)) == -1
+
+
+def test_scene_create_validates_before_touching_the_device():
+    d = scenes.cornell(width=8, height=8)
+    d.prims = d.prims.copy()
+    d.prims["material"][3] = 99
+    with pytest.raises(MafrixError) as e:
+        Scene(d)
+    assert e.value.code == -1 and "material" in str(e.value)
+    d2 = scenes.cornell(width=8, height=8)
+    d2.max_depth = 40
+    with pytest.raises(MafrixError) as e:
+        Scene(d2)
+    assert e.value.code == -5
+
+
+@pytest.mark.skipif(have_gpu(), reason="a CUDA device is present")
+def test_no_cpu_fallback_without_a_gpu():
+    lib = _lib.load()
+    assert lib.mfx_device_count() == 0
+    assert lib.mfx_init(0) == -2 and b"no CPU fallback" in lib.mfx_last_error()
+    with pytest.raises(MafrixError) as e:
+        Scene(scenes.cornell(width=8, height=8))
+    assert e.value.code == -2
+
+
+@pytest.mark.parametrize("w,h,tile,world", [(1920, 1080, 64, 8), (300, 300, 64, 2), (17, 5, 4, 3), (64, 64, 64, 4), (100, 37, 16, 1)])
+def test_tile_map_partitions_the_frame(w, h, tile, world):
+    seen = np.zeros(w * h, np.int32)
+    sizes = []
+    for r in range(world):
+        pix = mdist.tile_pixels(w, h, tile, r, world)
+        seen[pix] += 1
+        sizes.append(len(pix))
+        ty, tx = (pix // w) // tile, (pix % w) // tile
+        assert ((ty * ((w + tile - 1) // tile) + tx) % world == r).all()
+    assert (seen == 1).all()
+    if w * h >= world * tile * tile * 8:
+        assert max(sizes) - min(sizes) <= 2 * tile * tile
+    lib = _lib.load()
+    n = C.c_int32()
+    assert lib.mfx_tile_map(w, h, tile, world, world, None, C.byref(n)) == -1
+
+
+def test_workload_builders_match_the_configs():
+    d = scenes.c2_spot()
+    assert (d.width, d.height, d.max_depth, d.integrator, len(d.prims)) == (1920, 1080, 5, 0, 5858)
+    d = scenes.c3_renault()
+    assert (d.width, d.height, d.integrator, len(d.prims)) == (1920, 1080, 1, 36997)
+    assert set(np.unique(d.prims["material"])) == {0, 1, 2}
+    d = scenes.c1_cube()
+    assert (d.width, d.height, d.max_depth, len(d.prims)) == (640, 480, 5, 17)
+    d = scenes.cornell()
+    assert (d.width, d.height, d.max_depth) == (300, 300, 3) and (d.prims["kind"] == 1).all()
+    # every room/box surface faces the way the unflipped-normal integrator needs (quirk Q4)
+    v = d.prims["v"].reshape(-1, 4, 3)
+    n = np.cross(v[:, 1] - v[:, 0], v[:, 2] - v[:, 0])
+    assert n[0][1] > 0 and n[1][1] < 0 and n[2][2] > 0 and n[3][0] < 0 and n[4][0] > 0
