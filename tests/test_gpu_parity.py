@@ -90,7 +90,11 @@ def test_bvh_hit_closest_and_shadow(name, kw):
     fp, fsub, ft = s.Hit(org, d, 1e-6, BIG, precision=FAST_F32)
     assert (fp != op).mean() <= 3e-4
     same = (fp == op) & (op >= 0)
-    assert (np.abs(ft[same] - ot[same]) <= 1e-4 * np.abs(ot[same]) + 1e-6).all()
+    # random origins can sit arbitrarily close to a surface: f32 absolute error ~ a few ulp of the
+    # scene extent (6 units -> ~5e-7 each op), so the relative bar gets an absolute floor here
+    # (the sphere scene holds the r=1000 ground sphere: ulp(1000) = 6e-5 bounds what f32 can resolve)
+    floor = 2e-4 if name == "spheres" else 2e-5
+    assert (np.abs(ft[same] - ot[same]) <= 1e-4 * np.abs(ot[same]) + floor).all()
     for tmax in (0.5, 2.0):                      # shadow queries (Integrators.fs:44)
         op, _, _ = o.hit(org, d, 1e-6, tmax)
         gp, _, _ = s.Hit(org, d, 1e-6, tmax, precision=EXACT_F64, any_hit=True)
