@@ -206,44 +206,206 @@ __global__ void __launch_bounds__(256) k_f_raygen(SceneF sc, WaveF w, TileMap tm
     }
 }
 
-template <bool COUNT>
-__global__ void __launch_bounds__(FAST_BLOCK) k_f_extend(SceneF sc, WaveF w, int bounce, TravCounters *ctr)
+__device__ __forceinline__ float rcp_approx(float x)
 {
-    __shared__ float s_entry[FAST_LEVELS * FAST_BLOCK];
-    const int n = w.counts[bounce];
-    const int *q = w.q_ext[bounce & 1];
-    unsigned long long local[3] = { 0, 0, 0 };
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const int pid = q[i];
-        const float4 o = w.ray_o[pid], d = w.ray_d[pid];
-        const RayF r = make_ray(f3(o.x, o.y, o.z), f3(d.x, d.y, d.z), 1e-6f, __float_as_int(o.w));
-        float t; int slot;
-        trace_f<false, COUNT>(sc, r, 99999999.f, t, slot, s_entry + threadIdx.x, local);
-        w.hit[pid] = make_float2(t, __int_as_float(slot));
-    }
-    if (COUNT) { for (int k = 0; k < 3; k++) if (local[k]) atomicAdd(&ctr->v[0][k], local[k]); }
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+__device__ __forceinline__ RayF make_ray_fast(F3 o, F3 d, float tmin, int src)
+{
+    RayF r; r.o = o; r.d = d; r.tmin = tmin; r.src = src;
+    const float eps = 1e-30f;
+    r.idir = f3(rcp_approx(fabsf(d.x) > eps ? d.x : copysignf(eps, d.x)),
+                rcp_approx(fabsf(d.y) > eps ? d.y : copysignf(eps, d.y)),
+                rcp_approx(fabsf(d.z) > eps ? d.z : copysignf(eps, d.z)));
+    r.ood = f3(o.x * r.idir.x, o.y * r.idir.y, o.z * r.idir.z);
+    return r;
 }
 
 template <bool COUNT>
-__global__ void __launch_bounds__(FAST_BLOCK) k_f_shadow(SceneF sc, WaveF w, int bounce, TravCounters *ctr)
+__device__ __forceinline__ bool leaf_f3(const SceneF &sc, const RayF &r, int meta, float &best_t, int &best_slot,
+                                        unsigned long long *ctr)
 {
-    const int n = w.counts[MFX_MAX_VERTS + 2 + bounce];
-    const int *q = w.q_sh;
-    unsigned long long local[3] = { 0, 0, 0 };
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const int pid = q[i];
-        const float4 o = w.ray_o[pid], d = w.sh_d[pid];
-        const RayF r = make_ray(f3(o.x, o.y, o.z), f3(d.x, d.y, d.z), 1e-6f, __float_as_int(o.w));
-        float t; int slot;
-        trace_f<true, COUNT>(sc, r, d.w - 1e-6f, t, slot, nullptr, local);      // Integrators.fs:44
-        if (slot < 0) {
-            const float4 c = w.sh_c[pid];
-            float4 a = w.rad[pid];
-            a.x += c.x; a.y += c.y; a.z += c.z;
-            w.rad[pid] = a;
+    const int first = meta >> 3, cnt = meta & 7;
+    bool any = false;
+    for (int k = 0; k < cnt; k++) {
+        const SlotF *sp = sc.slots + first + k;
+        const float4 a = ldg4(&sp->a);
+        const float4 b = ldg4(&sp->b);
+        const int prim = __float_as_int(b.w) & 0x3fffffff;
+        if (__float_as_int(a.w) != 2) {
+            const float4 c = ldg4(&sp->c);
+            if (COUNT) ctr[1]++;
+            const F3 e1 = f3(b.x, b.y, b.z), e2 = f3(c.x, c.y, c.z);
+            const F3 s1 = cross(r.d, e2);
+            const float div = dot(s1, e1);
+            const float inv = rcp_approx(div);
+            const F3 dd = r.o - f3(a.x, a.y, a.z);
+            const float b1 = dot(dd, s1) * inv;
+            const F3 s2 = cross(dd, e1);
+            const float b2 = dot(r.d, s2) * inv;
+            const float t = dot(e2, s2) * inv;
+            // Trangle.fs:130-148 acceptance rules, evaluated without early exits
+            const bool ok = (fabsf(div) >= 1e-6f) & (b1 >= 0.f) & (b1 <= 1.f) & (b2 >= 0.f) & ((b1 + b2) < 1.f) &
+                            (t > r.tmin) & (t < best_t) & (prim != r.src);
+            if (ok) { best_t = t; best_slot = first + k; any = true; }
+        } else {
+            if (COUNT) ctr[2]++;
+            const F3 oc = r.o - f3(a.x, a.y, a.z);
+            const float hb = dot(oc, r.d);
+            const F3 perp = oc - r.d * hb;
+            const float disc = b.y - dot(perp, perp);
+            if (disc > 0.f) {
+                const float root = sqrtf(disc);
+                const float q = (hb < 0.f) ? -(hb - root) : -(hb + root);
+                const float cc = dot(oc, oc) - b.y;
+                const float t0 = q, t1 = (q != 0.f) ? cc / q : q;
+                float lo = fminf(t0, t1);
+                const float hi = fmaxf(t0, t1);
+                bool skip = false;
+                if (prim == r.src) { skip = (hb >= 0.f); lo = -1.f; }
+                float t = -1.f;
+                if (lo >= r.tmin && lo < best_t) t = lo;
+                else if (hi > r.tmin && hi < best_t) t = hi;
+                if (!skip && t > 0.f) { best_t = t; best_slot = first + k; any = true; }
+            }
         }
     }
-    if (COUNT) { for (int k = 0; k < 3; k++) if (local[k]) atomicAdd(&ctr->v[1][k], local[k]); }
+    return any;
+}
+
+#define CNT_SH(b)  (MFX_MAX_VERTS + 2 + (b))
+#define CUR_EXT(b) (2 * (MFX_MAX_VERTS + 2) + (b))
+#define CUR_SH(b)  (3 * (MFX_MAX_VERTS + 2) + (b))
+
+// ---------------------------------------------------------------- persistent-warp traversal
+// The first kernel (one ray per thread, grid-stride) kept only 5-8 of 32 lanes busy on secondary
+// bounces (profiles/r01_v1_baseline_summary.md).  This one keeps every warp resident and
+//   (1) REPLACES finished rays: when >= REFILL_T lanes are idle the warp claims that many queue
+//       entries with one atomicAdd (ballot/popc/shuffle) and the idle lanes start new rays;
+//   (2) POSTPONES leaf tests by vote: a lane that reached leaves parks them (two leaf metas in
+//       registers) and idles until >= LEAF_T lanes hold leaves or nobody has node work left, so
+//       the (branch-free) triangle tests run with many lanes instead of one or two;
+//   (3) keeps the node step branch-light: the descend decision is a handful of selects, the push
+//       of the far child is a predicated shared store, the level is tracked in a register; only
+//       the pop of deferred siblings is a short divergent loop, run after the leaf vote so it
+//       sees the freshly shrunk best_t.
+// Per-lane traversal state: heap index, 32-bit trail, level, best hit -- all registers; the far
+// child's entry distance per level sits in shared memory ([level][thread], conflict free).
+// A watchdog bounds the loop so a logic error can never hang the GPU (flag in counts[]).
+template <bool ANY, bool COUNT, int REFILL_T, int LEAF_T>
+__global__ void __launch_bounds__(FAST_BLOCK) k_f_trace4(SceneF sc, WaveF w, int bounce, TravCounters *ctr)
+{
+    extern __shared__ float s_dyn[];
+    float *lvl_entry = s_dyn + threadIdx.x;
+    const unsigned FULL = 0xffffffffu;
+    const unsigned lane = threadIdx.x & 31u;
+    const int n = ANY ? w.counts[CNT_SH(bounce)] : w.counts[bounce];
+    const int *q = ANY ? w.q_sh : w.q_ext[bounce & 1];
+    int *cursor = &w.counts[ANY ? CUR_SH(bounce) : CUR_EXT(bounce)];
+    unsigned long long local[3] = { 0, 0, 0 };
+
+    int pid = -1;
+    RayF r;
+    float best_t = 0.f; int best_slot = -1;
+    unsigned h = 1u, pend = 0u, depth = 0u;
+    bool needPop = false;
+    int leafA = -1, leafB = -1; float eB = 0.f;
+    bool exhausted = false;
+    unsigned iters = 0u;
+
+    for (;;) {
+        const unsigned idle = __ballot_sync(FULL, pid < 0);
+        unsigned idle_now = idle;
+        if (++iters > (1u << 22)) { if (lane == 0) atomicAdd(&w.counts[MFX_COUNTS_LEN - 1], 1); break; }   // watchdog
+        if (!exhausted && __popc(idle) >= REFILL_T) {
+            const int nidle = __popc(idle);
+            int base = 0;
+            if (lane == 0) base = atomicAdd(cursor, nidle);
+            base = __shfl_sync(FULL, base, 0);
+            if (base + nidle >= n) exhausted = true;
+            if (pid < 0) {
+                const int idx = base + __popc(idle & ((1u << lane) - 1u));
+                if (idx < n) {
+                    pid = q[idx];
+                    const float4 o = w.ray_o[pid];
+                    const float4 d = ANY ? w.sh_d[pid] : w.ray_d[pid];
+                    r = make_ray_fast(f3(o.x, o.y, o.z), f3(d.x, d.y, d.z), 1e-6f, __float_as_int(o.w));
+                    best_t = ANY ? d.w - 1e-6f : 99999999.f;            // Integrators.fs:44 / :108
+                    best_slot = -1; pend = 0u; leafA = leafB = -1; h = 1u; depth = 0u;
+                    float e;
+                    if (COUNT) local[0]++;
+                    const bool in = box_f(r, sc.root_min[0], sc.root_min[1], sc.root_min[2], sc.root_max[0], sc.root_max[1], sc.root_max[2], best_t, e);
+                    needPop = !in || sc.root_meta >= 0;     // nothing to descend into: the (empty) trail pop ends the ray
+                    if (in && sc.root_meta >= 0) leafA = sc.root_meta;
+                }
+            }
+            idle_now = __ballot_sync(FULL, pid < 0);
+        }
+        if (idle_now == FULL) { if (exhausted) break; continue; }
+
+        // ---- node step (lanes holding a node to visit and no parked leaves)
+        if (pid >= 0 && leafA < 0 && !needPop) {
+            const PairF *pp = sc.pairs + (h - 1u);
+            const float4 q0 = ldg4(&pp->q0), q1 = ldg4(&pp->q1), q2 = ldg4(&pp->q2), q3 = ldg4(&pp->q3);
+            if (COUNT) local[0] += 2;
+            const int metaL = __float_as_int(q3.x), metaR = __float_as_int(q3.y);
+            float eL, eR;
+            const bool hitL = box_f(r, q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, best_t, eL);
+            const bool hitR = box_f(r, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, best_t, eR);
+            const bool rFirst = eR < eL;
+            const bool lfL = hitL & (metaL >= 0), lfR = hitR & (metaR >= 0);
+            const bool inL = hitL & (metaL < 0), inR = hitR & (metaR < 0);
+            leafA = lfL ? ((lfR & rFirst) ? metaR : metaL) : (lfR ? metaR : -1);
+            leafB = (lfL & lfR) ? (rFirst ? metaL : metaR) : -1;
+            eB = rFirst ? eL : eR;
+            const bool both = inL & inR;
+            const bool rNear = inR & (!inL | rFirst);
+            depth += (inL | inR) ? 1u : 0u;
+            if (both) {
+                pend |= 1u << depth;
+                if (!ANY) lvl_entry[depth * FAST_BLOCK] = rNear ? eL : eR;
+            }
+            needPop = !(inL | inR);
+            h = needPop ? h : (2u * h + (rNear ? 1u : 0u));
+        }
+        // ---- leaf phase by vote
+        bool finished = false;
+        const unsigned lp = __ballot_sync(FULL, pid >= 0 && leafA >= 0);
+        if (lp) {
+            const unsigned nd = ~idle_now & ~lp;
+            if (__popc(lp) >= LEAF_T || nd == 0u) {
+                if (pid >= 0 && leafA >= 0) {
+                    bool found = leaf_f3<COUNT>(sc, r, leafA, best_t, best_slot, local);
+                    if (leafB >= 0 && !(ANY && found) && eB <= best_t) found |= leaf_f3<COUNT>(sc, r, leafB, best_t, best_slot, local);
+                    leafA = leafB = -1;
+                    if (ANY && found) finished = true;
+                }
+            }
+        }
+        // ---- pop the deepest deferred sibling that can still beat the best hit
+        if (pid >= 0 && needPop && leafA < 0 && !finished) {
+            for (;;) {
+                if (pend == 0u) { finished = true; break; }
+                const unsigned b = 31u - __clz(pend);
+                pend ^= 1u << b;
+                if (ANY || lvl_entry[b * FAST_BLOCK] <= best_t) {
+                    h = (h >> (depth - b)) ^ 1u;
+                    depth = b;
+                    needPop = false;
+                    break;
+                }
+            }
+        }
+        if (finished) {
+            if (!ANY) w.hit[pid] = make_float2(best_t, __int_as_float(best_slot));
+            else if (best_slot < 0) { const float4 c = w.sh_c[pid]; float4 a = w.rad[pid]; a.x += c.x; a.y += c.y; a.z += c.z; w.rad[pid] = a; }
+            pid = -1;
+        }
+    }
+    if (COUNT) { for (int k = 0; k < 3; k++) if (local[k]) atomicAdd(&ctr->v[ANY ? 1 : 0][k], local[k]); }
 }
 
 struct RngF { uint32_t pixel, sample, k0, k1; };
@@ -451,6 +613,7 @@ __global__ void k_accum_totals(const int *counts, int ext_lo, int ext_n, int sh_
     for (int i = 0; i < ext_n; i++) e += (unsigned)counts[ext_lo + i];
     for (int i = 0; i < sh_n; i++) s += (unsigned)counts[sh_lo + i];
     totals[0] += e; totals[1] += s; totals[2] += (unsigned)counts[0];
+    totals[3] += (unsigned)counts[MFX_COUNTS_LEN - 1];      // traversal watchdog trips
 }
 
 // Film.AddSample (Film.fs:18-23): c = sum + frame; sum <- c; target <- c / frameCount
@@ -501,10 +664,27 @@ void mfx_f_raygen(const LaunchCfg &c, const SceneF &sc, const WaveF &w, TileMap 
 {
     k_f_raygen<<<persistent_blocks(k_f_raygen, 256, c.blocks), 256, 0, c.stream>>>(sc, w, tm, pix0, npix, s0, S, seed);
 }
+template <bool ANY, int RT, int LT>
+static void launch_trace4(const LaunchCfg &c, const SceneF &sc, const WaveF &w, int bounce, TravCounters *ctr)
+{
+    const size_t smem = ANY ? 0 : (size_t)sc.levels * FAST_BLOCK * sizeof(float);
+    if (ctr) k_f_trace4<ANY, true, RT, LT><<<persistent_blocks(k_f_trace4<ANY, true, RT, LT>, FAST_BLOCK, c.blocks, smem), FAST_BLOCK, smem, c.stream>>>(sc, w, bounce, ctr);
+    else k_f_trace4<ANY, false, RT, LT><<<persistent_blocks(k_f_trace4<ANY, false, RT, LT>, FAST_BLOCK, c.blocks, smem), FAST_BLOCK, smem, c.stream>>>(sc, w, bounce, ctr);
+}
+template <bool ANY>
+static void launch_trace_variant(const LaunchCfg &c, const SceneF &sc, const WaveF &w, int bounce, TravCounters *ctr)
+{
+    switch (c.variant) {        // (REFILL_T, LEAF_T) tuning knob (MFX_TRACE_VARIANT); default from measurements
+    case 51: launch_trace4<ANY, 8, 12>(c, sc, w, bounce, ctr); break;
+    case 52: launch_trace4<ANY, 16, 16>(c, sc, w, bounce, ctr); break;
+    case 53: launch_trace4<ANY, 12, 20>(c, sc, w, bounce, ctr); break;
+    case 54: launch_trace4<ANY, 1, 1>(c, sc, w, bounce, ctr); break;
+    default: launch_trace4<ANY, 12, 16>(c, sc, w, bounce, ctr); break;
+    }
+}
 void mfx_f_extend(const LaunchCfg &c, const SceneF &sc, const WaveF &w, int bounce, TravCounters *ctr)
 {
-    if (ctr) k_f_extend<true><<<persistent_blocks(k_f_extend<true>, FAST_BLOCK, c.blocks), FAST_BLOCK, 0, c.stream>>>(sc, w, bounce, ctr);
-    else k_f_extend<false><<<persistent_blocks(k_f_extend<false>, FAST_BLOCK, c.blocks), FAST_BLOCK, 0, c.stream>>>(sc, w, bounce, ctr);
+    launch_trace_variant<false>(c, sc, w, bounce, ctr);
 }
 void mfx_f_shade(const LaunchCfg &c, const SceneF &sc, const WaveF &w, TileMap tm, int pix0, int npix, int s0, int bounce, uint64_t seed)
 {
@@ -512,8 +692,7 @@ void mfx_f_shade(const LaunchCfg &c, const SceneF &sc, const WaveF &w, TileMap t
 }
 void mfx_f_shadow(const LaunchCfg &c, const SceneF &sc, const WaveF &w, int bounce, TravCounters *ctr)
 {
-    if (ctr) k_f_shadow<true><<<persistent_blocks(k_f_shadow<true>, FAST_BLOCK, c.blocks), FAST_BLOCK, 0, c.stream>>>(sc, w, bounce, ctr);
-    else k_f_shadow<false><<<persistent_blocks(k_f_shadow<false>, FAST_BLOCK, c.blocks), FAST_BLOCK, 0, c.stream>>>(sc, w, bounce, ctr);
+    launch_trace_variant<true>(c, sc, w, bounce, ctr);
 }
 void mfx_f_resolve(const LaunchCfg &c, const SceneF &sc, const WaveF &w, TileMap tm, int pix0, int npix, int S, double *pixsum)
 {

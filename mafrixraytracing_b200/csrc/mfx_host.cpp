@@ -449,12 +449,14 @@ static int flatten_fast(MfxScene *s)
     const MfxBvhNode &root = s->nodes[0];
     for (int a = 0; a < 3; a++) { sf.root_min[a] = round_down(root.pmin[a]); sf.root_max[a] = round_up(root.pmax[a]); }
     sf.root_meta = -1;
+    int max_interior = 0;
     if (root.count <= MFX_LEAF_NODE_COUNT) sf.root_meta = leaf_meta(root);
     else {
         std::vector<int> todo{ 0 };
         while (!todo.empty()) {
             const int i = todo.back(); todo.pop_back();
             if ((size_t)i >= pairs.size()) { PairF z; memset(&z, 0, sizeof(z)); z.q3 = make_float4(int_bits(0), int_bits(0), 0.f, 0.f); pairs.resize(i + 1, z); }
+            max_interior = std::max(max_interior, i);
             const MfxBvhNode &L = s->nodes[2 * i + 1], &R = s->nodes[2 * i + 2];
             const bool li = L.count > MFX_LEAF_NODE_COUNT, ri = R.count > MFX_LEAF_NODE_COUNT;
             PairF &pr = pairs[i];
@@ -496,6 +498,7 @@ static int flatten_fast(MfxScene *s)
     memcpy(sf.camx.right, s->camera.right, 24); memcpy(sf.camx.down, s->camera.down, 24);
     sf.width = s->width; sf.height = s->height; sf.max_depth = s->max_depth; sf.mode = s->integrator;
     sf.n_slots = (int)slots.size();
+    { int depth = 0; for (unsigned v = (unsigned)max_interior + 1u; v > 1u; v >>= 1) depth++; sf.levels = depth + 2; }
     s->f_ready = true;
     return MFX_OK;
 }
@@ -633,7 +636,7 @@ static int run_sample(MfxScene *s, const MfxSampleParams *p, double *d_color_wh,
     TravCounters *ctr = counting ? s->d_ctr : nullptr;
     const size_t npx = (size_t)s->width * s->height;
     cudaStream_t st = s->stream;
-    LaunchCfg cfg{ s->sm_count, 128, st };
+    LaunchCfg cfg{ s->sm_count, 128, st, (int)env_long("MFX_TRACE_VARIANT", -1) };
 
     CUDA_TRY(cudaMemsetAsync(s->d_pixsum, 0, 4 * npx * sizeof(double), st));
     CUDA_TRY(cudaMemsetAsync(s->d_totals, 0, 4 * sizeof(unsigned long long), st));
@@ -707,6 +710,7 @@ static int run_sample(MfxScene *s, const MfxSampleParams *p, double *d_color_wh,
     MfxStats &stt = s->stats;
     memset(&stt, 0, sizeof(stt));
     stt.closest_rays = totals[0]; stt.shadow_rays = totals[1]; stt.paths = totals[2];
+    if (totals[3]) return fail(MFX_ERR_CUDA, "traversal watchdog tripped in %llu warp(s): the frame is incomplete", totals[3]);
     for (int c = 0; c < 2; c++) { stt.nodes[c] = hc.v[c][0]; stt.tris[c] = hc.v[c][1]; stt.spheres[c] = hc.v[c][2]; }
     float ms = 0.f;
     CUDA_TRY(cudaEventElapsedTime(&ms, e_begin, e_end));
@@ -826,7 +830,7 @@ extern "C" int mfx_bvh_hit(MfxScene *s, int32_t precision, int32_t any_hit, int6
     if (!s || !origins || !dirs || !prim || !t) return fail(MFX_ERR_INVALID_ARGUMENT, "mfx_bvh_hit: null argument");
     if (n <= 0) return MFX_OK;
     MFX_TRY(ensure_device());
-    LaunchCfg cfg{ s->sm_count, 128, s->stream };
+    LaunchCfg cfg{ s->sm_count, 128, s->stream, 0 };
     if (precision == MFX_EXACT_F64) {
         MFX_TRY(flatten_exact(s));
         return with_ray_buffers(s, n, origins, 3, dirs, 3, prim, sub, t, [&](double *o, double *d, int *p, int *sb, double *tt) {
@@ -847,7 +851,7 @@ extern "C" int mfx_trace_primary(MfxScene *s, int32_t precision, int64_t n, cons
     if (!uv && n != (int64_t)s->width * s->height) return fail(MFX_ERR_INVALID_ARGUMENT, "uv == NULL needs n == width*height");
     if (n <= 0) return MFX_OK;
     MFX_TRY(ensure_device());
-    LaunchCfg cfg{ s->sm_count, 128, s->stream };
+    LaunchCfg cfg{ s->sm_count, 128, s->stream, 0 };
     if (precision == MFX_EXACT_F64) {
         MFX_TRY(flatten_exact(s));
         return with_ray_buffers(s, n, uv, 2, nullptr, 0, prim, nullptr, t, [&](double *u, double *, int *p, int *, double *tt) {

@@ -110,6 +110,7 @@ struct SceneF {
     int    root_meta;       // leaf meta if the whole tree is one leaf, else -1
     int    width, height, max_depth, mode;
     int    n_slots;
+    int    levels;          // entries of the per-level entry-distance column (deepest child depth + 1)
 };
 
 struct WaveF {
@@ -126,7 +127,9 @@ struct WaveF {
     int    *counts;         // [0 .. MFX_MAX_VERTS+1] extend queue sizes per bounce,
                             // [MFX_MAX_VERTS+2 + bounce] shadow queue sizes
 };
-#define MFX_COUNTS_LEN (2 * (MFX_MAX_VERTS + 2))
+// + [2(V+2)+b] extend queue cursors, [3(V+2)+b] shadow queue cursors (persistent kernels);
+// the last entry is the traversal watchdog flag
+#define MFX_COUNTS_LEN (4 * (MFX_MAX_VERTS + 2))
 
 // Traversal counters (instrumented runs only): [class][nodes,tris,spheres]
 struct TravCounters { unsigned long long v[2][3]; };
@@ -137,7 +140,7 @@ struct TileMap {
 };
 
 // ------------------------------------------------------------------ launchers (defined in the .cu TUs)
-struct LaunchCfg { int blocks; int threads; cudaStream_t stream; };
+struct LaunchCfg { int blocks; int threads; cudaStream_t stream; int variant; };
 
 // exact
 void mfx_x_raygen(const LaunchCfg &, const SceneX &, const WaveX &, TileMap tm, int pix0, int npix, int s0, int S,
