@@ -349,3 +349,24 @@ def test_traversal_counters_match_oracle_ordered_counts():
         g_nodes, g_tris = st["nodes"][c] / rays, st["tris"][c] / rays
         o_nodes, o_tris = ost["ord_nodes"][c] / ost["ord_rays"][c], ost["ord_tris"][c] / ost["ord_rays"][c]
         assert abs(g_nodes / o_nodes - 1) < 0.10 and abs(g_tris / o_tris - 1) < 0.10, (c, g_nodes, o_nodes, g_tris, o_tris)
+
+
+def test_cpp_host_driver_matches_python_host(tmp_path):
+    """host/render_test (the C++ mirror of RenderTest/RayTracing4.fs) against the ctypes host: same
+    Film loop, same frames -> same PFM."""
+    import subprocess
+    from tests.conftest import ROOT
+    exe = os.path.join(ROOT, "host", "render_test")
+    subprocess.check_call(["make", "-C", os.path.join(ROOT, "host"), "-s"])
+    out = str(tmp_path / "cornell")
+    subprocess.check_call([exe, "--frames", "3", "--spp", "2", "--size", "120x90", "--out", out])
+    with open(out + ".pfm", "rb") as fh:
+        assert fh.readline() == b"PF\n" and fh.readline() == b"120 90\n" and fh.readline() == b"-1.0\n"
+        img = np.frombuffer(fh.read(), "<f4").reshape(90, 120, 3)[::-1]
+    s = Scene(scenes.cornell(width=120, height=90))
+    film = Film(s)
+    integ = CudaPixelIntegrator(s, precision=FAST_F32, seed=1)
+    for f in range(3):
+        target = film.GetFrame(integ, 2, first_sample=2 * f)
+    want = np.transpose(target[:, :, :3], (1, 0, 2)).astype(np.float32)
+    assert np.array_equal(img, want)

@@ -155,3 +155,12 @@ def test_workload_builders_match_the_configs():
     v = d.prims["v"].reshape(-1, 4, 3)
     n = np.cross(v[:, 1] - v[:, 0], v[:, 2] - v[:, 0])
     assert n[0][1] > 0 and n[1][1] < 0 and n[2][2] > 0 and n[3][0] < 0 and n[4][0] > 0
+
+
+def test_cpp_host_driver_builds_and_fails_loudly_without_gpu():
+    subprocess.check_call(["make", "-C", os.path.join(ROOT, "host"), "-s"])
+    exe = os.path.join(ROOT, "host", "render_test")
+    assert os.path.exists(exe)
+    if not have_gpu():
+        r = subprocess.run([exe, "--frames", "1"], capture_output=True, text=True)
+        assert r.returncode == 1 and "no CPU fallback" in r.stderr
