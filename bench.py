@@ -112,17 +112,16 @@ def run_reference(args, rank, world):
     from oracle import oracle
     desc = scenes.WORKLOADS[args.workload]()
     o = oracle.OracleScene(desc)
-    cores = oracle.max_threads()
+    cores = host_cores()              # torchrun exports OMP_NUM_THREADS=1: ask for every core explicitly
     tex = np.zeros((desc.width, desc.height, 4))
-    _, st = o.sample(1, seed=1, region=(0, 0, desc.width, 8), stats=True)      # ray accounting only (untimed)
     for _ in range(args.warmup):
-        o.sample(REF_SPP, seed=1, out=tex)
+        o.sample(REF_SPP, seed=1, out=tex, threads=cores)
     t0 = time.perf_counter()
     for k in range(args.steps):
-        o.sample(REF_SPP, seed=1, first_sample=k * REF_SPP, out=tex)
+        o.sample(REF_SPP, seed=1, first_sample=k * REF_SPP, out=tex, threads=cores)
     dt = time.perf_counter() - t0
     # rays per step: count them with one instrumented (slower, untimed) step
-    _, st = o.sample(REF_SPP, seed=1, stats=True)
+    _, st = o.sample(REF_SPP, seed=1, stats=True, threads=cores)
     rays = st["closest_rays"] + st["wasted_rays"] + st["shadow_rays"]
     val = rays * args.steps / dt / 1e6
     sample = f"full 1920x1080 frame at {REF_SPP} spp per step (config is 64 spp; cost is linear in spp), {rays} rays/step incl. the reference's wasted depth -1 query"
@@ -138,15 +137,22 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
 def cpu_baseline(desc):
     from oracle import oracle
     o = oracle.OracleScene(desc)
-    cores = oracle.max_threads()
-    _, st = o.sample(1, seed=1, stats=True)                     # instrumented: rays per spp
+    cores = host_cores()
+    _, st = o.sample(1, seed=1, stats=True, threads=cores)      # instrumented: rays per spp
     rays_per_spp = st["closest_rays"] + st["wasted_rays"] + st["shadow_rays"]
     n = 4
     t0 = time.perf_counter()
-    o.sample(n, seed=1, first_sample=1)
+    o.sample(n, seed=1, first_sample=1, threads=cores)
     dt = time.perf_counter() - t0
     return {"value": rays_per_spp * n / dt / 1e6, "unit": "Mrays/s", "cores": cores, "kind": "port",
             "sample": f"full 1920x1080 frame at {n} spp ({rays_per_spp * n} rays incl. the wasted depth -1 queries), {dt:.1f} s on {cores} threads",

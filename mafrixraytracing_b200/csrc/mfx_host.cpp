@@ -231,7 +231,7 @@ struct MfxScene {
     MfxCamera camera;
     int width = 0, height = 0, max_depth = 0, integrator = 0;
 
-    std::vector<void *> allocs;          // every cudaMalloc of this scene
+    std::vector<std::pair<void *, size_t>> allocs;   // every device buffer of this scene
     bool x_ready = false, f_ready = false, wx_ready = false, wf_ready = false;
     SceneX sx; SceneF sf; WaveX wx; WaveF wf;
     uint64_t x_bytes = 0, f_bytes = 0;
@@ -240,18 +240,49 @@ struct MfxScene {
     float4 *d_rgba = nullptr;            // row-major float4 (internal, when the caller gives none)
     unsigned long long *d_totals = nullptr;   // [3]
     TravCounters *d_ctr = nullptr;
-    void *h_pinned = nullptr; size_t h_pinned_bytes = 0;
     std::map<std::tuple<int, int, int>, std::pair<int *, int>> tilemaps;
     std::vector<cudaEvent_t> events;
     MfxStats stats;
 };
 
+// Process-wide cache of large device buffers (per device, keyed by size): a host that rebuilds its
+// Scene every frame (the e2e path of bench.py) must not pay cudaMalloc/cudaFree for ~0.5 GB of
+// path state each time.  Bounded; everything beyond the bound is really freed.
+#include <mutex>
+static std::mutex g_pool_mu;
+static std::multimap<std::pair<int, size_t>, void *> g_pool;
+static size_t g_pool_bytes = 0;
+static const size_t POOL_MIN = 1u << 20, POOL_MAX = (size_t)8 << 30;
+
 static int dev_alloc(MfxScene *s, void **p, size_t bytes)
 {
-    CUDA_TRY(cudaMalloc(p, bytes ? bytes : 16));
-    s->allocs.push_back(*p);
+    bytes = bytes ? bytes : 16;
+    if (bytes >= POOL_MIN) {
+        std::lock_guard<std::mutex> g(g_pool_mu);
+        auto it = g_pool.find({ s->device, bytes });
+        if (it != g_pool.end()) {
+            *p = it->second; g_pool.erase(it); g_pool_bytes -= bytes;
+            s->allocs.push_back({ *p, bytes });
+            return MFX_OK;
+        }
+    }
+    CUDA_TRY(cudaMalloc(p, bytes));
+    s->allocs.push_back({ *p, bytes });
     return MFX_OK;
 }
+
+static void dev_release(int device, void *p, size_t bytes)
+{
+    if (bytes >= POOL_MIN) {
+        std::lock_guard<std::mutex> g(g_pool_mu);
+        if (g_pool_bytes + bytes <= POOL_MAX) { g_pool.insert({ { device, bytes }, p }); g_pool_bytes += bytes; return; }
+    }
+    cudaFree(p);
+}
+
+// one pinned staging buffer per process for downloads into pageable caller memory
+static void *g_pinned = nullptr;
+static size_t g_pinned_bytes = 0;
 template <typename T> static int dev_alloc_t(MfxScene *s, T **p, size_t count) { return dev_alloc(s, (void **)p, count * sizeof(T)); }
 
 template <typename T> static int upload(MfxScene *s, T **dp, const std::vector<T> &h)
@@ -313,9 +344,8 @@ extern "C" int mfx_scene_destroy(MfxScene *s)
     if (!s) return MFX_OK;
     cudaSetDevice(s->device);
     if (s->stream) cudaStreamSynchronize(s->stream);
-    for (void *p : s->allocs) cudaFree(p);
+    for (auto &a : s->allocs) dev_release(s->device, a.first, a.second);
     for (cudaEvent_t e : s->events) cudaEventDestroy(e);
-    if (s->h_pinned) cudaFreeHost(s->h_pinned);
     if (s->stream) cudaStreamDestroy(s->stream);
     delete s;
     return MFX_OK;
@@ -725,12 +755,12 @@ static int run_sample(MfxScene *s, const MfxSampleParams *p, double *d_color_wh,
     return MFX_OK;
 }
 
-static int ensure_pinned(MfxScene *s, size_t bytes)
+static int ensure_pinned(MfxScene *, size_t bytes)
 {
-    if (s->h_pinned_bytes >= bytes) return MFX_OK;
-    if (s->h_pinned) { cudaFreeHost(s->h_pinned); s->h_pinned = nullptr; s->h_pinned_bytes = 0; }
-    CUDA_TRY(cudaMallocHost(&s->h_pinned, bytes));
-    s->h_pinned_bytes = bytes;
+    if (g_pinned_bytes >= bytes) return MFX_OK;
+    if (g_pinned) { cudaFreeHost(g_pinned); g_pinned = nullptr; g_pinned_bytes = 0; }
+    CUDA_TRY(cudaMallocHost(&g_pinned, bytes));
+    g_pinned_bytes = bytes;
     return MFX_OK;
 }
 
@@ -745,10 +775,11 @@ static int copy_out(MfxScene *s, void *host, const void *dev, size_t bytes)
         CUDA_TRY(cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, s->stream));
         CUDA_TRY(cudaStreamSynchronize(s->stream));
     } else {
+        std::lock_guard<std::mutex> g(g_pool_mu);
         MFX_TRY(ensure_pinned(s, bytes));
-        CUDA_TRY(cudaMemcpyAsync(s->h_pinned, dev, bytes, cudaMemcpyDeviceToHost, s->stream));
+        CUDA_TRY(cudaMemcpyAsync(g_pinned, dev, bytes, cudaMemcpyDeviceToHost, s->stream));
         CUDA_TRY(cudaStreamSynchronize(s->stream));
-        memcpy(host, s->h_pinned, bytes);
+        memcpy(host, g_pinned, bytes);
     }
     return MFX_OK;
 }
