@@ -50,12 +50,30 @@ __device__ __forceinline__ bool box_f(const RayF &r, float lx, float ly, float l
     return tn <= tf;
 }
 
-// Intersects the `cnt` slots of one leaf.  Moller-Trumbore with the reference's rejection rules
-// (Trangle.fs:120-148: |div| < 1e-6, b1 in [0,1], b2 >= 0, b1+b2 < 1, t > tMin) and the stable
-// quadratic of Sphere.fs:21-43.  Closest: keeps t < best_t.  Returns true if anything was hit.
+// Intersects the slots of one leaf: Moller-Trumbore with the reference's acceptance rules
+// (Trangle.fs:130-148) folded into one predicate (no early exits: every lane of a leaf vote runs the
+// same instructions), the stable quadratic of Sphere.fs:21-43 for spheres.
+__device__ __forceinline__ float rcp_approx(float x)
+{
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+__device__ __forceinline__ RayF make_ray_fast(F3 o, F3 d, float tmin, int src)
+{
+    RayF r; r.o = o; r.d = d; r.tmin = tmin; r.src = src;
+    const float eps = 1e-30f;
+    r.idir = f3(rcp_approx(fabsf(d.x) > eps ? d.x : copysignf(eps, d.x)),
+                rcp_approx(fabsf(d.y) > eps ? d.y : copysignf(eps, d.y)),
+                rcp_approx(fabsf(d.z) > eps ? d.z : copysignf(eps, d.z)));
+    r.ood = f3(o.x * r.idir.x, o.y * r.idir.y, o.z * r.idir.z);
+    return r;
+}
+
 template <bool COUNT>
-__device__ __forceinline__ bool leaf_f(const SceneF &sc, const RayF &r, int meta, float &best_t, int &best_slot,
-                                       unsigned long long *ctr)
+__device__ __forceinline__ bool leaf_f3(const SceneF &sc, const RayF &r, int meta, float &best_t, int &best_slot,
+                                        unsigned long long *ctr)
 {
     const int first = meta >> 3, cnt = meta & 7;
     bool any = false;
@@ -64,46 +82,64 @@ __device__ __forceinline__ bool leaf_f(const SceneF &sc, const RayF &r, int meta
         const float4 a = ldg4(&sp->a);
         const float4 b = ldg4(&sp->b);
         const int prim = __float_as_int(b.w) & 0x3fffffff;
-        if (__float_as_int(a.w) != 2) {
+        if (__float_as_int(a.w) < 2) {
             const float4 c = ldg4(&sp->c);
             if (COUNT) ctr[1]++;
-            if (prim == r.src) continue;
             const F3 e1 = f3(b.x, b.y, b.z), e2 = f3(c.x, c.y, c.z);
             const F3 s1 = cross(r.d, e2);
             const float div = dot(s1, e1);
-            if (fabsf(div) < 1e-6f) continue;
-            const float inv = 1.0f / div;
+            const float inv = rcp_approx(div);
             const F3 dd = r.o - f3(a.x, a.y, a.z);
             const float b1 = dot(dd, s1) * inv;
-            if (b1 < 0.f || b1 > 1.f) continue;
             const F3 s2 = cross(dd, e1);
             const float b2 = dot(r.d, s2) * inv;
-            if (b2 < 0.f || (b1 + b2) >= 1.f) continue;
             const float t = dot(e2, s2) * inv;
-            if (t > r.tmin && t < best_t) { best_t = t; best_slot = first + k; any = true; }
+            // Trangle.fs:130-148 acceptance rules, evaluated without early exits
+            const bool ok = (fabsf(div) >= 1e-6f) & (b1 >= 0.f) & (b1 <= 1.f) & (b2 >= 0.f) & ((b1 + b2) < 1.f) &
+                            (t > r.tmin) & (t < best_t) & (prim != r.src);
+            if (ok) { best_t = t; best_slot = first + k; any = true; }
         } else {
             if (COUNT) ctr[2]++;
-            const F3 oc = r.o - f3(a.x, a.y, a.z);
-            const float hb = dot(oc, r.d);                   // b/2
-            // discriminant/4 via the residual of oc against the ray: robust in f32 when
-            // |oc| >> radius (Haines et al., "Precision improvements for ray/sphere intersection")
-            const F3 perp = oc - r.d * hb;
-            const float disc = b.y - dot(perp, perp);        // r^2 - |perp|^2
-            if (disc > 0.f) {
-                const float root = sqrtf(disc);
+            float lo, hi, hb;
+            bool real;
+            if (__float_as_int(a.w) == 3) {
+                // big sphere (r >= 32, e.g. the r = 1000 ground sphere of the RayTracing.fs scenes): |o - c| ~ r makes
+                // the f32 quadratic lose ~1e-4 of t, so this one primitive kind is solved in f64
+                // (Sphere.fs:21-43 verbatim: b = 2 oc.d, c = oc.oc - r^2, q = -0.5 (b -+ sqrt(b^2 - 4c)))
+                const float4 c4 = ldg4(&sp->c);
+                const double cx = __hiloint2double(__float_as_int(b.y), __float_as_int(b.x));
+                const double cy = __hiloint2double(__float_as_int(c4.y), __float_as_int(c4.x));
+                const double cz = __hiloint2double(__float_as_int(c4.w), __float_as_int(c4.z));
+                const double rad = __hiloint2double(__float_as_int(a.y), __float_as_int(a.x));
+                const double ox = (double)r.o.x - cx, oy = (double)r.o.y - cy, oz = (double)r.o.z - cz;
+                const double h2 = ox * (double)r.d.x + oy * (double)r.d.y + oz * (double)r.d.z;
+                const double cc = ox * ox + oy * oy + oz * oz - rad * rad;
+                const double disc = h2 * h2 - cc;
+                real = disc > 0.0;
+                const double root = sqrt(fmax(disc, 0.0));
+                const double q = (h2 < 0.0) ? -(h2 - root) : -(h2 + root);
+                const double t1 = (q != 0.0) ? cc / q : q;
+                lo = (float)fmin(q, t1); hi = (float)fmax(q, t1); hb = (float)h2;
+            } else {
+                const F3 oc = r.o - f3(a.x, a.y, a.z);
+                hb = dot(oc, r.d);
+                const F3 perp = oc - r.d * hb;              // residual form of the discriminant (robust in f32)
+                const float disc = b.y - dot(perp, perp);
+                real = disc > 0.f;
+                const float root = sqrtf(fmaxf(disc, 0.f));
                 const float q = (hb < 0.f) ? -(hb - root) : -(hb + root);
                 const float cc = dot(oc, oc) - b.y;
-                float t0 = q, t1 = (q != 0.f) ? cc / q : q;
-                float lo = fminf(t0, t1), hi = fmaxf(t0, t1);
-                if (prim == r.src) {
-                    // leaving a convex surface outward cannot re-hit it; entering takes the far root
-                    if (hb >= 0.f) continue;
-                    lo = -1.f;
-                }
+                const float t1 = (q != 0.f) ? cc / q : q;
+                lo = fminf(q, t1); hi = fmaxf(q, t1);
+            }
+            if (real) {
+                bool skip = false;
+                // a ray leaving a convex surface outward cannot re-hit it; one entering takes the far root
+                if (prim == r.src) { skip = (hb >= 0.f); lo = -1.f; }
                 float t = -1.f;
                 if (lo >= r.tmin && lo < best_t) t = lo;
                 else if (hi > r.tmin && hi < best_t) t = hi;
-                if (t > 0.f) { best_t = t; best_slot = first + k; any = true; }
+                if (!skip && t > 0.f) { best_t = t; best_slot = first + k; any = true; }
             }
         }
     }
@@ -120,7 +156,7 @@ __device__ __forceinline__ void trace_f(const SceneF &sc, const RayF &r, float t
     float e;
     if (COUNT) ctr[0]++;
     if (!box_f(r, sc.root_min[0], sc.root_min[1], sc.root_min[2], sc.root_max[0], sc.root_max[1], sc.root_max[2], best_t, e)) return;
-    if (sc.root_meta >= 0) { leaf_f<COUNT>(sc, r, sc.root_meta, best_t, best_slot, ctr); return; }
+    if (sc.root_meta >= 0) { leaf_f3<COUNT>(sc, r, sc.root_meta, best_t, best_slot, ctr); return; }
     unsigned h = 1u;        // 1-based heap index of the current interior node
     unsigned pend = 0u;     // bit L set: the sibling of our ancestor at depth L is still to be visited
     for (;;) {
@@ -137,10 +173,10 @@ __device__ __forceinline__ void trace_f(const SceneF &sc, const RayF &r, float t
             bool found = false;
             if (lfL && lfR) {
                 const bool rFirst = eR < eL;
-                found |= leaf_f<COUNT>(sc, r, rFirst ? metaR : metaL, best_t, best_slot, ctr);
+                found |= leaf_f3<COUNT>(sc, r, rFirst ? metaR : metaL, best_t, best_slot, ctr);
                 if (!(ANY && found) && (rFirst ? eL : eR) <= best_t)
-                    found |= leaf_f<COUNT>(sc, r, rFirst ? metaL : metaR, best_t, best_slot, ctr);
-            } else found = leaf_f<COUNT>(sc, r, lfL ? metaL : metaR, best_t, best_slot, ctr);
+                    found |= leaf_f3<COUNT>(sc, r, rFirst ? metaL : metaR, best_t, best_slot, ctr);
+            } else found = leaf_f3<COUNT>(sc, r, lfL ? metaL : metaR, best_t, best_slot, ctr);
             if (ANY && found) return;
         }
         const bool goL = hitL && metaL < 0 && eL <= best_t;
@@ -204,76 +240,6 @@ __global__ void __launch_bounds__(256) k_f_raygen(SceneF sc, WaveF w, TileMap tm
         w.q_ext[0][pid] = (int)pid;
         if (pid == 0) w.counts[0] = (int)total;
     }
-}
-
-__device__ __forceinline__ float rcp_approx(float x)
-{
-    float y;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y;
-}
-
-__device__ __forceinline__ RayF make_ray_fast(F3 o, F3 d, float tmin, int src)
-{
-    RayF r; r.o = o; r.d = d; r.tmin = tmin; r.src = src;
-    const float eps = 1e-30f;
-    r.idir = f3(rcp_approx(fabsf(d.x) > eps ? d.x : copysignf(eps, d.x)),
-                rcp_approx(fabsf(d.y) > eps ? d.y : copysignf(eps, d.y)),
-                rcp_approx(fabsf(d.z) > eps ? d.z : copysignf(eps, d.z)));
-    r.ood = f3(o.x * r.idir.x, o.y * r.idir.y, o.z * r.idir.z);
-    return r;
-}
-
-template <bool COUNT>
-__device__ __forceinline__ bool leaf_f3(const SceneF &sc, const RayF &r, int meta, float &best_t, int &best_slot,
-                                        unsigned long long *ctr)
-{
-    const int first = meta >> 3, cnt = meta & 7;
-    bool any = false;
-    for (int k = 0; k < cnt; k++) {
-        const SlotF *sp = sc.slots + first + k;
-        const float4 a = ldg4(&sp->a);
-        const float4 b = ldg4(&sp->b);
-        const int prim = __float_as_int(b.w) & 0x3fffffff;
-        if (__float_as_int(a.w) != 2) {
-            const float4 c = ldg4(&sp->c);
-            if (COUNT) ctr[1]++;
-            const F3 e1 = f3(b.x, b.y, b.z), e2 = f3(c.x, c.y, c.z);
-            const F3 s1 = cross(r.d, e2);
-            const float div = dot(s1, e1);
-            const float inv = rcp_approx(div);
-            const F3 dd = r.o - f3(a.x, a.y, a.z);
-            const float b1 = dot(dd, s1) * inv;
-            const F3 s2 = cross(dd, e1);
-            const float b2 = dot(r.d, s2) * inv;
-            const float t = dot(e2, s2) * inv;
-            // Trangle.fs:130-148 acceptance rules, evaluated without early exits
-            const bool ok = (fabsf(div) >= 1e-6f) & (b1 >= 0.f) & (b1 <= 1.f) & (b2 >= 0.f) & ((b1 + b2) < 1.f) &
-                            (t > r.tmin) & (t < best_t) & (prim != r.src);
-            if (ok) { best_t = t; best_slot = first + k; any = true; }
-        } else {
-            if (COUNT) ctr[2]++;
-            const F3 oc = r.o - f3(a.x, a.y, a.z);
-            const float hb = dot(oc, r.d);
-            const F3 perp = oc - r.d * hb;
-            const float disc = b.y - dot(perp, perp);
-            if (disc > 0.f) {
-                const float root = sqrtf(disc);
-                const float q = (hb < 0.f) ? -(hb - root) : -(hb + root);
-                const float cc = dot(oc, oc) - b.y;
-                const float t0 = q, t1 = (q != 0.f) ? cc / q : q;
-                float lo = fminf(t0, t1);
-                const float hi = fmaxf(t0, t1);
-                bool skip = false;
-                if (prim == r.src) { skip = (hb >= 0.f); lo = -1.f; }
-                float t = -1.f;
-                if (lo >= r.tmin && lo < best_t) t = lo;
-                else if (hi > r.tmin && hi < best_t) t = hi;
-                if (!skip && t > 0.f) { best_t = t; best_slot = first + k; any = true; }
-            }
-        }
-    }
-    return any;
 }
 
 #define CNT_SH(b)  (MFX_MAX_VERTS + 2 + (b))
@@ -475,6 +441,13 @@ __global__ void __launch_bounds__(FAST_BLOCK) k_f_shade(SceneF sc, WaveF w, Tile
                 const int prim = __float_as_int(sb.w) & 0x3fffffff;
                 F3 normal = f3(nm4.x, nm4.y, nm4.z);
                 if (__float_as_int(sa.w) == 2) normal = normalize_f(point - f3(sa.x, sa.y, sa.z));
+                else if (__float_as_int(sa.w) == 3) {       // big sphere: f64 centre (see leaf_f3)
+                    const float4 sc4 = ldg4(&sc.slots[fs].c);
+                    const double cx = __hiloint2double(__float_as_int(sb.y), __float_as_int(sb.x));
+                    const double cy = __hiloint2double(__float_as_int(sc4.y), __float_as_int(sc4.x));
+                    const double cz = __hiloint2double(__float_as_int(sc4.w), __float_as_int(sc4.z));
+                    normal = normalize_f(f3((float)((double)point.x - cx), (float)((double)point.y - cy), (float)((double)point.z - cz)));
+                }
                 const MatF m = sc.mats[__float_as_int(nm4.w)];
                 const int sl = pid / npix, pl = pid - sl * npix;
                 int pix, px, py;

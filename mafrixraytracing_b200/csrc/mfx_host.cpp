@@ -446,8 +446,17 @@ static int flatten_fast(MfxScene *s)
         ffirst[slot] = (int)slots.size();
         if (p.kind == MFX_SPHERE) {
             SlotF f; memset(&f, 0, sizeof(f));
-            f.a = make_float4((float)p.v[0], (float)p.v[1], (float)p.v[2], int_bits(2));
-            f.b = make_float4((float)p.v[3], (float)(p.v[3] * p.v[3]), 0.f, int_bits(slot));
+            if (std::fabs(p.v[3]) >= 32.0) {
+                // big sphere: centre and radius kept as f64 bit pairs, solved in f64 by the kernel
+                auto lo = [](double x) { uint64_t u; memcpy(&u, &x, 8); return int_bits((int)(uint32_t)u); };
+                auto hi = [](double x) { uint64_t u; memcpy(&u, &x, 8); return int_bits((int)(uint32_t)(u >> 32)); };
+                f.a = make_float4(lo(p.v[3]), hi(p.v[3]), 0.f, int_bits(3));
+                f.b = make_float4(lo(p.v[0]), hi(p.v[0]), 0.f, int_bits(slot));
+                f.c = make_float4(lo(p.v[1]), hi(p.v[1]), lo(p.v[2]), hi(p.v[2]));
+            } else {
+                f.a = make_float4((float)p.v[0], (float)p.v[1], (float)p.v[2], int_bits(2));
+                f.b = make_float4((float)p.v[3], (float)(p.v[3] * p.v[3]), 0.f, int_bits(slot));
+            }
             slots.push_back(f);
             nrm.push_back(make_float4(0.f, 0.f, 0.f, int_bits(p.material)));
         } else {

@@ -84,7 +84,8 @@ struct WaveX {
 struct __align__(16) PairF { float4 q0, q1, q2, q3; };
 // One fast primitive slot, 48 B = 3 x float4, leaf order.
 //   triangle: a = (v0.xyz, kind bits), b = (e1.xyz, -), c = (e2.xyz, -)
-//   sphere  : a = (center.xyz, kind bits), b = (radius, r^2, -, -)
+//   sphere  : a = (center.xyz, kind 2), b = (radius, r^2, -, prim)
+//   big sphere (r >= 32): a = (radius as f64 bit pair, -, kind 3), b = (cx f64 pair, -, prim), c = (cy pair, cz pair)
 struct __align__(16) SlotF { float4 a, b, c; };
 struct MatF { float albedo[3]; int kind; float fuzz, ei, et, pad; };
 struct LightF {

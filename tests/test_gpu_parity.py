@@ -93,12 +93,12 @@ def test_bvh_hit_closest_and_shadow(name, kw):
     # random origins can sit arbitrarily close to a surface: f32 absolute error ~ a few ulp of the
     # scene extent (6 units -> ~5e-7 each op), so the relative bar gets an absolute floor here
     # (the sphere scene holds the r=1000 ground sphere: ulp(1000) = 6e-5 bounds what f32 can resolve)
-    # grazing hits on it cancel ~1e6-sized terms, so the absolute floor is 2e-3 there)
-    floor = 2e-3 if name == "spheres" else 2e-5
+    # the kernel solves that one in f64, small spheres in f32)
+    floor = 5e-5 if name == "spheres" else 2e-5
     bad = np.abs(ft[same] - ot[same]) > 1e-4 * np.abs(ot[same]) + floor
     # an origin within ~1e-6 of a sphere can take the near root in one precision and the far root in
     # the other (same primitive id, t differs by a chord): allowed for at most 1e-4 of the rays
-    assert bad.mean() <= (1e-3 if name == "spheres" else 0.0), (bad.sum(), np.abs(ft[same] - ot[same]).max())
+    assert bad.mean() <= (1e-4 if name == "spheres" else 0.0), (bad.sum(), np.abs(ft[same] - ot[same]).max())
     for tmax in (0.5, 2.0):                      # shadow queries (Integrators.fs:44)
         op, _, _ = o.hit(org, d, 1e-6, tmax)
         gp, _, _ = s.Hit(org, d, 1e-6, tmax, precision=EXACT_F64, any_hit=True)

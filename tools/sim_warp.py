@@ -1,8 +1,9 @@
 #!/usr/bin/env python3
-"""CPU model of the persistent-warp traversal loop (k_f_trace3 in csrc/mfx_fast.cu): 32 lanes in
-lockstep, same state machine (refill / lazy pop / node step / leaf vote), on the same flattened
+"""CPU model of the persistent-warp traversal loop (k_f_trace4 in csrc/mfx_fast.cu): 32 lanes in
+lockstep, same state machine (refill -> node step -> leaf vote -> pop), on the same flattened
 layout (children pairs indexed by heap index, leaf-order slots).  Used to debug the control
-logic without a GPU and to check the stackless bit-trail traversal against the oracle."""
+logic without a GPU and to check the stackless bit-trail traversal against the oracle
+(tests/test_traversal_model.py)."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
@@ -82,12 +83,13 @@ def clz(x):
 
 
 def run_warp(sc, rays, REFILL_T=12, LEAF_T=16, ANY=False, max_iters=200000):
+    """rays: list of (origin f32[3], dir f32[3], tmax).  Returns ({ray: (t, slot)}, iterations, stuck-state or None)."""
     n = len(rays)
     cursor = 0
     L = 32
     pid = [-1] * L; o = [None] * L; d = [None] * L; idir = [None] * L
     best_t = [0.0] * L; best_slot = [-1] * L
-    h = [1] * L; pend = [0] * L; popf = [False] * L
+    h = [1] * L; pend = [0] * L; depth = [0] * L; needPop = [False] * L
     leafA = [-1] * L; leafB = [-1] * L; eB = [0.0] * L
     entry = [dict() for _ in range(L)]
     exhausted = False
@@ -96,8 +98,9 @@ def run_warp(sc, rays, REFILL_T=12, LEAF_T=16, ANY=False, max_iters=200000):
     while True:
         iters += 1
         if iters > max_iters:
-            return out, iters, dict(pid=pid, leafA=leafA, popf=popf, pend=pend, h=h, exhausted=exhausted, cursor=cursor)
+            return out, iters, dict(pid=pid, leafA=leafA, needPop=needPop, pend=pend, h=h, exhausted=exhausted, cursor=cursor)
         idle = sum(1 << l for l in range(L) if pid[l] < 0)
+        idle_now = idle
         if not exhausted and bin(idle).count("1") >= REFILL_T:
             nidle = bin(idle).count("1")
             base = cursor; cursor += nidle
@@ -110,55 +113,56 @@ def run_warp(sc, rays, REFILL_T=12, LEAF_T=16, ANY=False, max_iters=200000):
                         o[l], d[l], tmax = rays[idx]
                         with np.errstate(divide="ignore"):
                             idir[l] = (1.0 / d[l]).astype(np.float32)
-                        best_t[l] = tmax; best_slot[l] = -1; pend[l] = 0; leafA[l] = leafB[l] = -1; h[l] = 1
+                        best_t[l] = tmax; best_slot[l] = -1; pend[l] = 0; leafA[l] = leafB[l] = -1; h[l] = 1; depth[l] = 0
                         inb, _ = box(o[l], idir[l], sc["root"][0], sc["root"][1], 1e-6, best_t[l])
-                        popf[l] = (not inb) or sc["root_meta"] >= 0
+                        needPop[l] = (not inb) or sc["root_meta"] >= 0
                         if inb and sc["root_meta"] >= 0: leafA[l] = sc["root_meta"]
-            idle = sum(1 << l for l in range(L) if pid[l] < 0)
-        if idle == FULL:
+            idle_now = sum(1 << l for l in range(L) if pid[l] < 0)
+        if idle_now == FULL:
             if exhausted: break
             continue
+        for l in range(L):                                   # node step
+            if pid[l] >= 0 and leafA[l] < 0 and not needPop[l]:
+                Lmin, Lmax, Rmin, Rmax, mL, mR = sc["pairs"][h[l]]
+                hitL, eL = box(o[l], idir[l], Lmin, Lmax, 1e-6, best_t[l])
+                hitR, eR = box(o[l], idir[l], Rmin, Rmax, 1e-6, best_t[l])
+                rFirst = eR < eL
+                lfL, lfR = hitL and mL >= 0, hitR and mR >= 0
+                inL, inR = hitL and mL < 0, hitR and mR < 0
+                leafA[l] = ((mR if (lfR and rFirst) else mL) if lfL else (mR if lfR else -1))
+                leafB[l] = (mL if rFirst else mR) if (lfL and lfR) else -1
+                eB[l] = eL if rFirst else eR
+                both = inL and inR
+                rNear = inR and ((not inL) or rFirst)
+                if inL or inR: depth[l] += 1
+                if both:
+                    pend[l] |= 1 << depth[l]
+                    entry[l][depth[l]] = eL if rNear else eR
+                needPop[l] = not (inL or inR)
+                if not needPop[l]: h[l] = 2 * h[l] + (1 if rNear else 0)
         fin = [False] * L
-        for l in range(L):
-            if pid[l] >= 0 and leafA[l] < 0:
-                if popf[l]:
-                    while True:
-                        if pend[l] == 0: fin[l] = True; break
-                        b = 31 - clz(pend[l])
-                        pend[l] ^= 1 << b
-                        dc = 31 - clz(h[l])
-                        assert dc >= b, (dc, b, h[l])
-                        h[l] = (h[l] >> (dc - b)) ^ 1
-                        if ANY or entry[l][b] <= best_t[l]: popf[l] = False; break
-                if not fin[l]:
-                    Lmin, Lmax, Rmin, Rmax, mL, mR = sc["pairs"][h[l]]
-                    hitL, eL = box(o[l], idir[l], Lmin, Lmax, 1e-6, best_t[l])
-                    hitR, eR = box(o[l], idir[l], Rmin, Rmax, 1e-6, best_t[l])
-                    lfL, lfR = hitL and mL >= 0, hitR and mR >= 0
-                    rFirst = eR < eL
-                    if lfL and lfR:
-                        leafA[l] = mR if rFirst else mL; leafB[l] = mL if rFirst else mR; eB[l] = eL if rFirst else eR
-                    elif lfL: leafA[l] = mL
-                    elif lfR: leafA[l] = mR
-                    goL, goR = hitL and mL < 0, hitR and mR < 0
-                    popf[l] = not (goL or goR)
-                    if not popf[l]:
-                        rNear = goR and ((not goL) or rFirst)
-                        if goL and goR:
-                            lvl = 32 - clz(h[l])
-                            pend[l] |= 1 << lvl
-                            entry[l][lvl] = eL if rNear else eR
-                        h[l] = 2 * h[l] + (1 if rNear else 0)
-        lp = sum(1 << l for l in range(L) if leafA[l] >= 0)
-        if lp and (bin(lp).count("1") >= LEAF_T or ((~idle & ~lp) & FULL) == 0):
+        lp = sum(1 << l for l in range(L) if pid[l] >= 0 and leafA[l] >= 0)
+        if lp and (bin(lp).count("1") >= LEAF_T or ((~idle_now & ~lp) & FULL) == 0):     # leaf phase by vote
             for l in range(L):
-                if leafA[l] >= 0:
+                if pid[l] >= 0 and leafA[l] >= 0:
                     found, best_t[l], best_slot[l] = leaf(sc, o[l], d[l], leafA[l], best_t[l], best_slot[l])
                     if leafB[l] >= 0 and not (ANY and found) and eB[l] <= best_t[l]:
                         f2, best_t[l], best_slot[l] = leaf(sc, o[l], d[l], leafB[l], best_t[l], best_slot[l])
                         found = found or f2
                     leafA[l] = leafB[l] = -1
                     if ANY and found: fin[l] = True
+        for l in range(L):                                   # pop
+            if pid[l] >= 0 and needPop[l] and leafA[l] < 0 and not fin[l]:
+                while True:
+                    if pend[l] == 0: fin[l] = True; break
+                    b = 31 - clz(pend[l])
+                    pend[l] ^= 1 << b
+                    if ANY or entry[l][b] <= best_t[l]:
+                        assert depth[l] >= b
+                        h[l] = (h[l] >> (depth[l] - b)) ^ 1
+                        depth[l] = b
+                        needPop[l] = False
+                        break
         for l in range(L):
             if fin[l]:
                 out[pid[l]] = (best_t[l], best_slot[l])
@@ -166,22 +170,24 @@ def run_warp(sc, rays, REFILL_T=12, LEAF_T=16, ANY=False, max_iters=200000):
     return out, iters, None
 
 
-if __name__ == "__main__":
-    desc = scenes.c2_spot(width=24, height=14)
-    sc = flatten(desc)
+def camera_rays(desc, seed=None, uv_out=None):
+    """Pixel-centre rays, or jittered ones (seed given): centres sit exactly on quad diagonals."""
     cam = desc.camera
+    rng = np.random.default_rng(seed) if seed is not None else None
     rays = []
     for j in range(desc.height):
         for i in range(desc.width):
-            oo, dd = cam.GetRay((i + 0.5) / desc.width, (j + 0.5) / desc.height)
+            ju, jv = (rng.random(), rng.random()) if rng is not None else (0.5, 0.5)
+            if uv_out is not None: uv_out.append(((i + ju) / desc.width, (j + jv) / desc.height))
+            oo, dd = cam.GetRay((i + ju) / desc.width, (j + jv) / desc.height)
             rays.append((oo.astype(np.float32), dd.astype(np.float32), 99999999.0))
+    return rays
+
+
+if __name__ == "__main__":
+    desc = scenes.c2_spot(width=24, height=14)
+    sc = flatten(desc)
+    rays = camera_rays(desc)
     for rt, lt in ((1, 1), (12, 16), (1, 32)):
         out, iters, stuck = run_warp(sc, rays, rt, lt)
         print(f"REFILL_T={rt} LEAF_T={lt}: iters={iters} finished={len(out)}/{len(rays)} stuck={stuck is not None}")
-        if stuck:
-            print({k: v for k, v in stuck.items()})
-    from oracle import oracle
-    o = oracle.OracleScene(desc)
-    prim, t = o.trace_primary()
-    got = np.array([sc["ref"][sc["slots"][out[r][1]][-1]] if out[r][1] >= 0 else -1 for r in range(len(rays))])
-    print("id mismatches vs oracle:", int((got != prim).sum()))
