@@ -71,7 +71,29 @@ __device__ __forceinline__ RayF make_ray_fast(F3 o, F3 d, float tmin, int src)
     return r;
 }
 
-template <bool COUNT>
+// Big sphere (r >= 32, e.g. the r = 1000 ground sphere of the RayTracing.fs scenes): |o - c| ~ r makes
+// the f32 quadratic lose ~1e-4 of t, so this one primitive kind is solved in f64 (Sphere.fs:21-43
+// verbatim: b = 2 oc.d, c = oc.oc - r^2, q = -0.5 (b -+ sqrt(b^2 - 4c))).  Kept out of line so its f64
+// registers do not cost the traversal loop its occupancy.
+__device__ __noinline__ bool big_sphere_roots(const SlotF *sp, F3 o, F3 d, float &lo, float &hi, float &hb)
+{
+    const float4 a = ldg4(&sp->a), b = ldg4(&sp->b), c4 = ldg4(&sp->c);
+    const double cx = __hiloint2double(__float_as_int(b.y), __float_as_int(b.x));
+    const double cy = __hiloint2double(__float_as_int(c4.y), __float_as_int(c4.x));
+    const double cz = __hiloint2double(__float_as_int(c4.w), __float_as_int(c4.z));
+    const double rad = __hiloint2double(__float_as_int(a.y), __float_as_int(a.x));
+    const double ox = (double)o.x - cx, oy = (double)o.y - cy, oz = (double)o.z - cz;
+    const double h2 = ox * (double)d.x + oy * (double)d.y + oz * (double)d.z;
+    const double cc = ox * ox + oy * oy + oz * oz - rad * rad;
+    const double disc = h2 * h2 - cc;
+    const double root = sqrt(fmax(disc, 0.0));
+    const double q = (h2 < 0.0) ? -(h2 - root) : -(h2 + root);
+    const double t1 = (q != 0.0) ? cc / q : q;
+    lo = (float)fmin(q, t1); hi = (float)fmax(q, t1); hb = (float)h2;
+    return disc > 0.0;
+}
+
+template <bool COUNT, bool BIG>
 __device__ __forceinline__ bool leaf_f3(const SceneF &sc, const RayF &r, int meta, float &best_t, int &best_slot,
                                         unsigned long long *ctr)
 {
@@ -102,24 +124,8 @@ __device__ __forceinline__ bool leaf_f3(const SceneF &sc, const RayF &r, int met
             if (COUNT) ctr[2]++;
             float lo, hi, hb;
             bool real;
-            if (__float_as_int(a.w) == 3) {
-                // big sphere (r >= 32, e.g. the r = 1000 ground sphere of the RayTracing.fs scenes): |o - c| ~ r makes
-                // the f32 quadratic lose ~1e-4 of t, so this one primitive kind is solved in f64
-                // (Sphere.fs:21-43 verbatim: b = 2 oc.d, c = oc.oc - r^2, q = -0.5 (b -+ sqrt(b^2 - 4c)))
-                const float4 c4 = ldg4(&sp->c);
-                const double cx = __hiloint2double(__float_as_int(b.y), __float_as_int(b.x));
-                const double cy = __hiloint2double(__float_as_int(c4.y), __float_as_int(c4.x));
-                const double cz = __hiloint2double(__float_as_int(c4.w), __float_as_int(c4.z));
-                const double rad = __hiloint2double(__float_as_int(a.y), __float_as_int(a.x));
-                const double ox = (double)r.o.x - cx, oy = (double)r.o.y - cy, oz = (double)r.o.z - cz;
-                const double h2 = ox * (double)r.d.x + oy * (double)r.d.y + oz * (double)r.d.z;
-                const double cc = ox * ox + oy * oy + oz * oz - rad * rad;
-                const double disc = h2 * h2 - cc;
-                real = disc > 0.0;
-                const double root = sqrt(fmax(disc, 0.0));
-                const double q = (h2 < 0.0) ? -(h2 - root) : -(h2 + root);
-                const double t1 = (q != 0.0) ? cc / q : q;
-                lo = (float)fmin(q, t1); hi = (float)fmax(q, t1); hb = (float)h2;
+            if (BIG && __float_as_int(a.w) == 3) {
+                real = big_sphere_roots(sp, r.o, r.d, lo, hi, hb);
             } else {
                 const F3 oc = r.o - f3(a.x, a.y, a.z);
                 hb = dot(oc, r.d);
@@ -156,11 +162,11 @@ __device__ __forceinline__ void trace_f(const SceneF &sc, const RayF &r, float t
     float e;
     if (COUNT) ctr[0]++;
     if (!box_f(r, sc.root_min[0], sc.root_min[1], sc.root_min[2], sc.root_max[0], sc.root_max[1], sc.root_max[2], best_t, e)) return;
-    if (sc.root_meta >= 0) { leaf_f3<COUNT>(sc, r, sc.root_meta, best_t, best_slot, ctr); return; }
+    if (sc.root_meta >= 0) { leaf_f3<COUNT, true>(sc, r, sc.root_meta, best_t, best_slot, ctr); return; }
     unsigned h = 1u;        // 1-based heap index of the current interior node
     unsigned pend = 0u;     // bit L set: the sibling of our ancestor at depth L is still to be visited
     for (;;) {
-        const PairF *pp = sc.pairs + (h - 1u);
+        const PairF *pp = sc.pairs + h;
         const float4 q0 = ldg4(&pp->q0), q1 = ldg4(&pp->q1), q2 = ldg4(&pp->q2), q3 = ldg4(&pp->q3);
         if (COUNT) ctr[0] += 2;
         const int metaL = __float_as_int(q3.x), metaR = __float_as_int(q3.y);
@@ -173,10 +179,10 @@ __device__ __forceinline__ void trace_f(const SceneF &sc, const RayF &r, float t
             bool found = false;
             if (lfL && lfR) {
                 const bool rFirst = eR < eL;
-                found |= leaf_f3<COUNT>(sc, r, rFirst ? metaR : metaL, best_t, best_slot, ctr);
+                found |= leaf_f3<COUNT, true>(sc, r, rFirst ? metaR : metaL, best_t, best_slot, ctr);
                 if (!(ANY && found) && (rFirst ? eL : eR) <= best_t)
-                    found |= leaf_f3<COUNT>(sc, r, rFirst ? metaL : metaR, best_t, best_slot, ctr);
-            } else found = leaf_f3<COUNT>(sc, r, lfL ? metaL : metaR, best_t, best_slot, ctr);
+                    found |= leaf_f3<COUNT, true>(sc, r, rFirst ? metaL : metaR, best_t, best_slot, ctr);
+            } else found = leaf_f3<COUNT, true>(sc, r, lfL ? metaL : metaR, best_t, best_slot, ctr);
             if (ANY && found) return;
         }
         const bool goL = hitL && metaL < 0 && eL <= best_t;
@@ -261,7 +267,7 @@ __global__ void __launch_bounds__(256) k_f_raygen(SceneF sc, WaveF w, TileMap tm
 // Per-lane traversal state: heap index, 32-bit trail, level, best hit -- all registers; the far
 // child's entry distance per level sits in shared memory ([level][thread], conflict free).
 // A watchdog bounds the loop so a logic error can never hang the GPU (flag in counts[]).
-template <bool ANY, bool COUNT, int REFILL_T, int LEAF_T>
+template <bool ANY, bool COUNT, bool BIG, int REFILL_T, int LEAF_T>
 __global__ void __launch_bounds__(FAST_BLOCK) k_f_trace4(SceneF sc, WaveF w, int bounce, TravCounters *ctr)
 {
     extern __shared__ float s_dyn[];
@@ -314,7 +320,7 @@ __global__ void __launch_bounds__(FAST_BLOCK) k_f_trace4(SceneF sc, WaveF w, int
 
         // ---- node step (lanes holding a node to visit and no parked leaves)
         if (pid >= 0 && leafA < 0 && !needPop) {
-            const PairF *pp = sc.pairs + (h - 1u);
+            const PairF *pp = sc.pairs + h;
             const float4 q0 = ldg4(&pp->q0), q1 = ldg4(&pp->q1), q2 = ldg4(&pp->q2), q3 = ldg4(&pp->q3);
             if (COUNT) local[0] += 2;
             const int metaL = __float_as_int(q3.x), metaR = __float_as_int(q3.y);
@@ -344,8 +350,8 @@ __global__ void __launch_bounds__(FAST_BLOCK) k_f_trace4(SceneF sc, WaveF w, int
             const unsigned nd = ~idle_now & ~lp;
             if (__popc(lp) >= LEAF_T || nd == 0u) {
                 if (pid >= 0 && leafA >= 0) {
-                    bool found = leaf_f3<COUNT>(sc, r, leafA, best_t, best_slot, local);
-                    if (leafB >= 0 && !(ANY && found) && eB <= best_t) found |= leaf_f3<COUNT>(sc, r, leafB, best_t, best_slot, local);
+                    bool found = leaf_f3<COUNT, BIG>(sc, r, leafA, best_t, best_slot, local);
+                    if (leafB >= 0 && !(ANY && found) && eB <= best_t) found |= leaf_f3<COUNT, BIG>(sc, r, leafB, best_t, best_slot, local);
                     leafA = leafB = -1;
                     if (ANY && found) finished = true;
                 }
@@ -637,12 +643,19 @@ void mfx_f_raygen(const LaunchCfg &c, const SceneF &sc, const WaveF &w, TileMap 
 {
     k_f_raygen<<<persistent_blocks(k_f_raygen, 256, c.blocks), 256, 0, c.stream>>>(sc, w, tm, pix0, npix, s0, S, seed);
 }
+template <bool ANY, bool BIG, int RT, int LT>
+static void launch_trace4b(const LaunchCfg &c, const SceneF &sc, const WaveF &w, int bounce, TravCounters *ctr)
+{
+    const size_t smem = ANY ? 0 : (size_t)sc.levels * FAST_BLOCK * sizeof(float);
+    if (ctr) k_f_trace4<ANY, true, BIG, RT, LT><<<persistent_blocks(k_f_trace4<ANY, true, BIG, RT, LT>, FAST_BLOCK, c.blocks, smem), FAST_BLOCK, smem, c.stream>>>(sc, w, bounce, ctr);
+    else k_f_trace4<ANY, false, BIG, RT, LT><<<persistent_blocks(k_f_trace4<ANY, false, BIG, RT, LT>, FAST_BLOCK, c.blocks, smem), FAST_BLOCK, smem, c.stream>>>(sc, w, bounce, ctr);
+}
+// scenes without a big (f64) sphere get the kernel compiled without that branch (48 instead of 64+ registers)
 template <bool ANY, int RT, int LT>
 static void launch_trace4(const LaunchCfg &c, const SceneF &sc, const WaveF &w, int bounce, TravCounters *ctr)
 {
-    const size_t smem = ANY ? 0 : (size_t)sc.levels * FAST_BLOCK * sizeof(float);
-    if (ctr) k_f_trace4<ANY, true, RT, LT><<<persistent_blocks(k_f_trace4<ANY, true, RT, LT>, FAST_BLOCK, c.blocks, smem), FAST_BLOCK, smem, c.stream>>>(sc, w, bounce, ctr);
-    else k_f_trace4<ANY, false, RT, LT><<<persistent_blocks(k_f_trace4<ANY, false, RT, LT>, FAST_BLOCK, c.blocks, smem), FAST_BLOCK, smem, c.stream>>>(sc, w, bounce, ctr);
+    if (sc.has_big_sphere) launch_trace4b<ANY, true, RT, LT>(c, sc, w, bounce, ctr);
+    else launch_trace4b<ANY, false, RT, LT>(c, sc, w, bounce, ctr);
 }
 template <bool ANY>
 static void launch_trace_variant(const LaunchCfg &c, const SceneF &sc, const WaveF &w, int bounce, TravCounters *ctr)

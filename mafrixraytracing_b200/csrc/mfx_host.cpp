@@ -439,6 +439,7 @@ static int flatten_fast(MfxScene *s)
     const int n = (int)s->prims.size();
     // fast slots in leaf order; a Rect becomes its two triangles (Rect.fs:17-19)
     std::vector<SlotF> slots; std::vector<float4> nrm; std::vector<int> ffirst(n + 1), ref(n);
+    int has_big = 0;
     slots.reserve(n); nrm.reserve(n);
     for (int slot = 0; slot < n; slot++) {
         const MfxPrim &p = s->prims[s->indices[slot]];
@@ -447,6 +448,7 @@ static int flatten_fast(MfxScene *s)
         if (p.kind == MFX_SPHERE) {
             SlotF f; memset(&f, 0, sizeof(f));
             if (std::fabs(p.v[3]) >= 32.0) {
+                has_big = 1;
                 // big sphere: centre and radius kept as f64 bit pairs, solved in f64 by the kernel
                 auto lo = [](double x) { uint64_t u; memcpy(&u, &x, 8); return int_bits((int)(uint32_t)u); };
                 auto hi = [](double x) { uint64_t u; memcpy(&u, &x, 8); return int_bits((int)(uint32_t)(u >> 32)); };
@@ -494,11 +496,13 @@ static int flatten_fast(MfxScene *s)
         std::vector<int> todo{ 0 };
         while (!todo.empty()) {
             const int i = todo.back(); todo.pop_back();
-            if ((size_t)i >= pairs.size()) { PairF z; memset(&z, 0, sizeof(z)); z.q3 = make_float4(int_bits(0), int_bits(0), 0.f, 0.f); pairs.resize(i + 1, z); }
+            // the record of heap node i (0-based) lives at index i+1 = its 1-based heap index h, so the
+            // records of two siblings (2h, 2h+1) share one 128-byte line
+            if ((size_t)i + 1 >= pairs.size()) { PairF z; memset(&z, 0, sizeof(z)); z.q3 = make_float4(int_bits(0), int_bits(0), 0.f, 0.f); pairs.resize(i + 2, z); }
             max_interior = std::max(max_interior, i);
             const MfxBvhNode &L = s->nodes[2 * i + 1], &R = s->nodes[2 * i + 2];
             const bool li = L.count > MFX_LEAF_NODE_COUNT, ri = R.count > MFX_LEAF_NODE_COUNT;
-            PairF &pr = pairs[i];
+            PairF &pr = pairs[i + 1];
             pr.q0 = make_float4(round_down(L.pmin[0]), round_down(L.pmin[1]), round_down(L.pmin[2]), round_up(L.pmax[0]));
             pr.q1 = make_float4(round_up(L.pmax[1]), round_up(L.pmax[2]), round_down(R.pmin[0]), round_down(R.pmin[1]));
             pr.q2 = make_float4(round_down(R.pmin[2]), round_up(R.pmax[0]), round_up(R.pmax[1]), round_up(R.pmax[2]));
@@ -537,6 +541,7 @@ static int flatten_fast(MfxScene *s)
     memcpy(sf.camx.right, s->camera.right, 24); memcpy(sf.camx.down, s->camera.down, 24);
     sf.width = s->width; sf.height = s->height; sf.max_depth = s->max_depth; sf.mode = s->integrator;
     sf.n_slots = (int)slots.size();
+    sf.has_big_sphere = has_big;
     { int depth = 0; for (unsigned v = (unsigned)max_interior + 1u; v > 1u; v >>= 1) depth++; sf.levels = depth + 2; }
     s->f_ready = true;
     return MFX_OK;

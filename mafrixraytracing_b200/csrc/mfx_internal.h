@@ -112,6 +112,7 @@ struct SceneF {
     int    width, height, max_depth, mode;
     int    n_slots;
     int    levels;          // entries of the per-level entry-distance column (deepest child depth + 1)
+    int    has_big_sphere;  // any kind-3 slot (selects the kernel variant with the f64 sphere branch)
 };
 
 struct WaveF {
