@@ -267,7 +267,7 @@ __global__ void __launch_bounds__(256) k_f_raygen(SceneF sc, WaveF w, TileMap tm
 // Per-lane traversal state: heap index, 32-bit trail, level, best hit -- all registers; the far
 // child's entry distance per level sits in shared memory ([level][thread], conflict free).
 // A watchdog bounds the loop so a logic error can never hang the GPU (flag in counts[]).
-template <bool ANY, bool COUNT, bool BIG, int REFILL_T, int LEAF_T>
+template <bool ANY, bool COUNT, bool BIG, int REFILL_T, int LEAF_T, int NSTEP>
 __global__ void __launch_bounds__(FAST_BLOCK) k_f_trace4(SceneF sc, WaveF w, int bounce, TravCounters *ctr)
 {
     extern __shared__ float s_dyn[];
@@ -318,7 +318,10 @@ __global__ void __launch_bounds__(FAST_BLOCK) k_f_trace4(SceneF sc, WaveF w, int
         }
         if (idle_now == FULL) { if (exhausted) break; continue; }
 
-        // ---- node step (lanes holding a node to visit and no parked leaves)
+        // ---- node step(s) (lanes holding a node to visit and no parked leaves); NSTEP > 1 amortises the
+        //      loop skeleton (ballots, vote, refill test) over several tree levels
+#pragma unroll
+        for (int rep = 0; rep < NSTEP; rep++)
         if (pid >= 0 && leafA < 0 && !needPop) {
             const PairF *pp = sc.pairs + h;
             const float4 q0 = ldg4(&pp->q0), q1 = ldg4(&pp->q1), q2 = ldg4(&pp->q2), q3 = ldg4(&pp->q3);
@@ -643,19 +646,19 @@ void mfx_f_raygen(const LaunchCfg &c, const SceneF &sc, const WaveF &w, TileMap 
 {
     k_f_raygen<<<persistent_blocks(k_f_raygen, 256, c.blocks), 256, 0, c.stream>>>(sc, w, tm, pix0, npix, s0, S, seed);
 }
-template <bool ANY, bool BIG, int RT, int LT>
+template <bool ANY, bool BIG, int RT, int LT, int NS>
 static void launch_trace4b(const LaunchCfg &c, const SceneF &sc, const WaveF &w, int bounce, TravCounters *ctr)
 {
     const size_t smem = ANY ? 0 : (size_t)sc.levels * FAST_BLOCK * sizeof(float);
-    if (ctr) k_f_trace4<ANY, true, BIG, RT, LT><<<persistent_blocks(k_f_trace4<ANY, true, BIG, RT, LT>, FAST_BLOCK, c.blocks, smem), FAST_BLOCK, smem, c.stream>>>(sc, w, bounce, ctr);
-    else k_f_trace4<ANY, false, BIG, RT, LT><<<persistent_blocks(k_f_trace4<ANY, false, BIG, RT, LT>, FAST_BLOCK, c.blocks, smem), FAST_BLOCK, smem, c.stream>>>(sc, w, bounce, ctr);
+    if (ctr) k_f_trace4<ANY, true, BIG, RT, LT, NS><<<persistent_blocks(k_f_trace4<ANY, true, BIG, RT, LT, NS>, FAST_BLOCK, c.blocks, smem), FAST_BLOCK, smem, c.stream>>>(sc, w, bounce, ctr);
+    else k_f_trace4<ANY, false, BIG, RT, LT, NS><<<persistent_blocks(k_f_trace4<ANY, false, BIG, RT, LT, NS>, FAST_BLOCK, c.blocks, smem), FAST_BLOCK, smem, c.stream>>>(sc, w, bounce, ctr);
 }
 // scenes without a big (f64) sphere get the kernel compiled without that branch (48 instead of 64+ registers)
-template <bool ANY, int RT, int LT>
+template <bool ANY, int RT, int LT, int NS = 1>
 static void launch_trace4(const LaunchCfg &c, const SceneF &sc, const WaveF &w, int bounce, TravCounters *ctr)
 {
-    if (sc.has_big_sphere) launch_trace4b<ANY, true, RT, LT>(c, sc, w, bounce, ctr);
-    else launch_trace4b<ANY, false, RT, LT>(c, sc, w, bounce, ctr);
+    if (sc.has_big_sphere) launch_trace4b<ANY, true, RT, LT, NS>(c, sc, w, bounce, ctr);
+    else launch_trace4b<ANY, false, RT, LT, NS>(c, sc, w, bounce, ctr);
 }
 template <bool ANY>
 static void launch_trace_variant(const LaunchCfg &c, const SceneF &sc, const WaveF &w, int bounce, TravCounters *ctr)
@@ -665,7 +668,11 @@ static void launch_trace_variant(const LaunchCfg &c, const SceneF &sc, const Wav
     case 52: launch_trace4<ANY, 16, 16>(c, sc, w, bounce, ctr); break;
     case 53: launch_trace4<ANY, 12, 20>(c, sc, w, bounce, ctr); break;
     case 54: launch_trace4<ANY, 1, 1>(c, sc, w, bounce, ctr); break;
-    default: launch_trace4<ANY, 12, 16>(c, sc, w, bounce, ctr); break;
+    case 60: launch_trace4<ANY, 12, 16, 2>(c, sc, w, bounce, ctr); break;
+    case 61: launch_trace4<ANY, 12, 16, 3>(c, sc, w, bounce, ctr); break;
+    case 62: launch_trace4<ANY, 8, 16, 2>(c, sc, w, bounce, ctr); break;
+    case 63: launch_trace4<ANY, 12, 20, 2>(c, sc, w, bounce, ctr); break;
+    default: launch_trace4<ANY, 12, 16, 2>(c, sc, w, bounce, ctr); break;
     }
 }
 void mfx_f_extend(const LaunchCfg &c, const SceneF &sc, const WaveF &w, int bounce, TravCounters *ctr)
