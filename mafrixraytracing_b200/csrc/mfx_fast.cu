@@ -267,8 +267,8 @@ __global__ void __launch_bounds__(256) k_f_raygen(SceneF sc, WaveF w, TileMap tm
 // Per-lane traversal state: heap index, 32-bit trail, level, best hit -- all registers; the far
 // child's entry distance per level sits in shared memory ([level][thread], conflict free).
 // A watchdog bounds the loop so a logic error can never hang the GPU (flag in counts[]).
-template <bool ANY, bool COUNT, bool BIG, int REFILL_T, int LEAF_T, int NSTEP>
-__global__ void __launch_bounds__(FAST_BLOCK) k_f_trace4(SceneF sc, WaveF w, int bounce, TravCounters *ctr)
+template <bool ANY, bool COUNT, bool BIG, int REFILL_T, int LEAF_T, int NSTEP, int MINB>
+__global__ void __launch_bounds__(FAST_BLOCK, MINB) k_f_trace4(SceneF sc, WaveF w, int bounce, TravCounters *ctr)
 {
     extern __shared__ float s_dyn[];
     float *lvl_entry = s_dyn + threadIdx.x;
@@ -646,12 +646,12 @@ void mfx_f_raygen(const LaunchCfg &c, const SceneF &sc, const WaveF &w, TileMap 
 {
     k_f_raygen<<<persistent_blocks(k_f_raygen, 256, c.blocks), 256, 0, c.stream>>>(sc, w, tm, pix0, npix, s0, S, seed);
 }
-template <bool ANY, bool BIG, int RT, int LT, int NS>
+template <bool ANY, bool BIG, int RT, int LT, int NS, int MB = 1>
 static void launch_trace4b(const LaunchCfg &c, const SceneF &sc, const WaveF &w, int bounce, TravCounters *ctr)
 {
     const size_t smem = ANY ? 0 : (size_t)sc.levels * FAST_BLOCK * sizeof(float);
-    if (ctr) k_f_trace4<ANY, true, BIG, RT, LT, NS><<<persistent_blocks(k_f_trace4<ANY, true, BIG, RT, LT, NS>, FAST_BLOCK, c.blocks, smem), FAST_BLOCK, smem, c.stream>>>(sc, w, bounce, ctr);
-    else k_f_trace4<ANY, false, BIG, RT, LT, NS><<<persistent_blocks(k_f_trace4<ANY, false, BIG, RT, LT, NS>, FAST_BLOCK, c.blocks, smem), FAST_BLOCK, smem, c.stream>>>(sc, w, bounce, ctr);
+    if (ctr) k_f_trace4<ANY, true, BIG, RT, LT, NS, 1><<<persistent_blocks(k_f_trace4<ANY, true, BIG, RT, LT, NS, 1>, FAST_BLOCK, c.blocks, smem), FAST_BLOCK, smem, c.stream>>>(sc, w, bounce, ctr);
+    else k_f_trace4<ANY, false, BIG, RT, LT, NS, MB><<<persistent_blocks(k_f_trace4<ANY, false, BIG, RT, LT, NS, MB>, FAST_BLOCK, c.blocks, smem), FAST_BLOCK, smem, c.stream>>>(sc, w, bounce, ctr);
 }
 // scenes without a big (f64) sphere get the kernel compiled without that branch (48 instead of 64+ registers)
 template <bool ANY, int RT, int LT, int NS = 1>
@@ -669,6 +669,10 @@ static void launch_trace_variant(const LaunchCfg &c, const SceneF &sc, const Wav
     case 53: launch_trace4<ANY, 12, 20>(c, sc, w, bounce, ctr); break;
     case 54: launch_trace4<ANY, 1, 1>(c, sc, w, bounce, ctr); break;
     case 60: launch_trace4<ANY, 12, 16, 2>(c, sc, w, bounce, ctr); break;
+    case 70: launch_trace4b<ANY, false, 12, 16, 2, 12>(c, sc, w, bounce, ctr); break;
+    case 71: launch_trace4b<ANY, false, 12, 16, 1, 12>(c, sc, w, bounce, ctr); break;
+    case 72: launch_trace4b<ANY, false, 12, 16, 2, 11>(c, sc, w, bounce, ctr); break;
+    case 73: launch_trace4b<ANY, false, 12, 16, 2, 14>(c, sc, w, bounce, ctr); break;
     case 61: launch_trace4<ANY, 12, 16, 3>(c, sc, w, bounce, ctr); break;
     case 62: launch_trace4<ANY, 8, 16, 2>(c, sc, w, bounce, ctr); break;
     case 63: launch_trace4<ANY, 12, 20, 2>(c, sc, w, bounce, ctr); break;
