@@ -66,7 +66,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
@@ -232,6 +232,9 @@ def main():
     e2e = None
     if not args.no_e2e:
         tex = np.zeros((desc.width, desc.height, 4), dtype=np.float64)
+        # the host keeps ONE Texture2D<Color> for its lifetime (Integrators.fs:147): pin it once so the
+        # per-frame download is a direct DMA (mfx_host_register)
+        _lib.check(_lib.load().mfx_host_register(_lib.ptr(tex), tex.nbytes))
         host_frame = torch.empty((desc.height, desc.width, 4), dtype=torch.float32).pin_memory()
         h2d = desc.prims.nbytes + desc.materials.nbytes + bvh.nodes.nbytes + bvh.indices.nbytes + 12 * 8 + 18 * 8
         rays_e2e, t_e2e = 0.0, 0.0
@@ -266,6 +269,7 @@ def main():
             else:
                 rays_e2e += rr[0].item()
                 t_e2e += dt
+        _lib.load().mfx_host_unregister(_lib.ptr(tex))
         e2e = {"value": rays_e2e / t_e2e / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                "ms_per_step": t_e2e / args.steps * 1e3,
                "call": "mfx_scene_create + mfx_pixel_integrator_sample (Color[w,h] f64 to host)" if world == 1 else

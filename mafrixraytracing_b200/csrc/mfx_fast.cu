@@ -267,8 +267,8 @@ __global__ void __launch_bounds__(256) k_f_raygen(SceneF sc, WaveF w, TileMap tm
 // Per-lane traversal state: heap index, 32-bit trail, level, best hit -- all registers; the far
 // child's entry distance per level sits in shared memory ([level][thread], conflict free).
 // A watchdog bounds the loop so a logic error can never hang the GPU (flag in counts[]).
-template <bool ANY, bool COUNT, bool BIG, int REFILL_T, int LEAF_T, int NSTEP, int MINB>
-__global__ void __launch_bounds__(FAST_BLOCK, MINB) k_f_trace4(SceneF sc, WaveF w, int bounce, TravCounters *ctr)
+template <bool ANY, bool COUNT, bool BIG, int REFILL_T, int LEAF_T, int NSTEP>
+__global__ void __launch_bounds__(FAST_BLOCK) k_f_trace4(SceneF sc, WaveF w, int bounce, TravCounters *ctr)
 {
     extern __shared__ float s_dyn[];
     float *lvl_entry = s_dyn + threadIdx.x;
@@ -381,6 +381,163 @@ __global__ void __launch_bounds__(FAST_BLOCK, MINB) k_f_trace4(SceneF sc, WaveF 
         }
     }
     if (COUNT) { for (int k = 0; k < 3; k++) if (local[k]) atomicAdd(&ctr->v[ANY ? 1 : 0][k], local[k]); }
+}
+
+
+// ---------------------------------------------------------------- two levels per step (QuadF)
+// Same persistent loop as k_f_trace4 (refill -> node step(s) -> leaf vote -> pop) but every node
+// step fetches ONE 128 B record with the four grandchildren boxes of an even-depth node, so a ray
+// makes half as many dependent steps and the loop skeleton is paid half as often.
+//   * the (<= 4) hits are ordered with a 5-comparator integer min/max network on keys
+//     (entry-distance bits & ~7) | leaf << 2 | slot  (entry >= tMin > 0, so integer order == float order);
+//   * nearest hit interior -> descend; nearest (and second nearest) hit leaves -> parked for the vote;
+//   * the other hits are deferred: their keys go to shared memory [level][3][thread], nearest on
+//     top, and a 2-bit-per-level count lives in a 64-bit trail register; the pop loop takes the
+//     deepest non-empty level, culls by the stored (rounded-down, conservative) entry distance and
+//     rebuilds the heap index from the ancestor: child = 4 * (h >> (depth - 2L)) + slot.
+#define KEY_INF 0x7f800000u
+
+__device__ __forceinline__ unsigned umin_(unsigned a, unsigned b) { return a < b ? a : b; }
+__device__ __forceinline__ unsigned umax_(unsigned a, unsigned b) { return a > b ? a : b; }
+__device__ __forceinline__ int pick4(const float4 &m, unsigned id)
+{
+    const float lo = (id & 1u) ? m.y : m.x, hi = (id & 1u) ? m.w : m.z;
+    return __float_as_int((id & 2u) ? hi : lo);
+}
+__device__ __forceinline__ size_t quad_index(unsigned h, unsigned depth) { return (size_t)(h - ((2u << depth) + 1u) / 3u); }
+
+template <bool ANY, bool BIG, int REFILL_T, int LEAF_T, int NSTEP>
+__global__ void __launch_bounds__(FAST_BLOCK) k_f_trace5(SceneF sc, WaveF w, int bounce)
+{
+    extern __shared__ unsigned s_pend[];            // [qlevels][3][FAST_BLOCK]
+    unsigned *my_pend = s_pend + threadIdx.x;
+    const unsigned FULL = 0xffffffffu;
+    const unsigned lane = threadIdx.x & 31u;
+    const int n = ANY ? w.counts[CNT_SH(bounce)] : w.counts[bounce];
+    const int *q = ANY ? w.q_sh : w.q_ext[bounce & 1];
+    int *cursor = &w.counts[ANY ? CUR_SH(bounce) : CUR_EXT(bounce)];
+
+    int pid = -1;
+    RayF r;
+    float best_t = 0.f; int best_slot = -1;
+    unsigned h = 1u, depth = 0u;                    // current quad node (1-based heap index, even depth)
+    unsigned long long trail = 0ull;                // 2 bits per quad level: deferred hits of that level's node
+    bool needPop = false;
+    int leafA = -1, leafB = -1; float eB = 0.f;
+    bool exhausted = false;
+    unsigned iters = 0u;
+
+    for (;;) {
+        const unsigned idle = __ballot_sync(FULL, pid < 0);
+        unsigned idle_now = idle;
+        if (++iters > (1u << 22)) { if (lane == 0) atomicAdd(&w.counts[MFX_COUNTS_LEN - 1], 1); break; }   // watchdog
+        if (!exhausted && __popc(idle) >= REFILL_T) {
+            const int nidle = __popc(idle);
+            int base = 0;
+            if (lane == 0) base = atomicAdd(cursor, nidle);
+            base = __shfl_sync(FULL, base, 0);
+            if (base + nidle >= n) exhausted = true;
+            if (pid < 0) {
+                const int idx = base + __popc(idle & ((1u << lane) - 1u));
+                if (idx < n) {
+                    pid = q[idx];
+                    const float4 o = w.ray_o[pid];
+                    const float4 d = ANY ? w.sh_d[pid] : w.ray_d[pid];
+                    r = make_ray_fast(f3(o.x, o.y, o.z), f3(d.x, d.y, d.z), 1e-6f, __float_as_int(o.w));
+                    best_t = ANY ? d.w - 1e-6f : 99999999.f;            // Integrators.fs:44 / :108
+                    best_slot = -1; trail = 0ull; leafA = leafB = -1; h = 1u; depth = 0u;
+                    float e;
+                    const bool in = box_f(r, sc.root_min[0], sc.root_min[1], sc.root_min[2], sc.root_max[0], sc.root_max[1], sc.root_max[2], best_t, e);
+                    needPop = !in || sc.root_meta >= 0;
+                    if (in && sc.root_meta >= 0) leafA = sc.root_meta;
+                }
+            }
+            idle_now = __ballot_sync(FULL, pid < 0);
+        }
+        if (idle_now == FULL) { if (exhausted) break; continue; }
+
+#pragma unroll
+        for (int rep = 0; rep < NSTEP; rep++)
+        if (pid >= 0 && leafA < 0 && !needPop) {
+            const QuadF *qp = sc.quads + quad_index(h, depth);
+            const float4 lox = ldg4(&qp->lox), hix = ldg4(&qp->hix), loy = ldg4(&qp->loy), hiy = ldg4(&qp->hiy);
+            const float4 loz = ldg4(&qp->loz), hiz = ldg4(&qp->hiz), m4 = ldg4(&qp->meta);
+            unsigned key[4];
+#define QUAD_SLOT(S, C)                                                                                              \
+            {                                                                                                        \
+                const float x0 = fmaf(lox.C, r.idir.x, -r.ood.x), x1 = fmaf(hix.C, r.idir.x, -r.ood.x);              \
+                const float y0 = fmaf(loy.C, r.idir.y, -r.ood.y), y1 = fmaf(hiy.C, r.idir.y, -r.ood.y);              \
+                const float z0 = fmaf(loz.C, r.idir.z, -r.ood.z), z1 = fmaf(hiz.C, r.idir.z, -r.ood.z);              \
+                const float tn = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fmaxf(fminf(z0, z1), r.tmin));           \
+                const float tf = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fminf(fmaxf(z0, z1), best_t));           \
+                const int mt = __float_as_int(m4.C);                                                                 \
+                key[S] = (tn <= tf && mt != -2) ? ((__float_as_uint(tn) & ~7u) | (mt >= 0 ? 4u : 0u) | (unsigned)S) : KEY_INF; \
+            }
+            QUAD_SLOT(0, x) QUAD_SLOT(1, y) QUAD_SLOT(2, z) QUAD_SLOT(3, w)
+#undef QUAD_SLOT
+            // sorting network (0,1)(2,3)(0,2)(1,3)(1,2)
+            unsigned a0 = umin_(key[0], key[1]), a1 = umax_(key[0], key[1]);
+            unsigned a2 = umin_(key[2], key[3]), a3 = umax_(key[2], key[3]);
+            const unsigned k0 = umin_(a0, a2), t2 = umax_(a0, a2);
+            const unsigned t1 = umin_(a1, a3), k3 = umax_(a1, a3);
+            const unsigned k1 = umin_(t1, t2), k2 = umax_(t1, t2);
+            const bool any0 = k0 != KEY_INF;
+            const bool leaf0 = any0 && (k0 & 4u), leaf1 = leaf0 && (k1 != KEY_INF) && (k1 & 4u);
+            leafA = leaf0 ? pick4(m4, k0 & 3u) : -1;
+            leafB = leaf1 ? pick4(m4, k1 & 3u) : -1;
+            eB = __uint_as_float(k1 & ~7u);
+            // deferred hits: everything behind the one(s) consumed now, nearest on top of the level's column
+            const unsigned p0 = leaf1 ? k2 : k1, p1 = leaf1 ? k3 : k2, p2 = leaf1 ? KEY_INF : k3;
+            const unsigned m = (p0 != KEY_INF ? 1u : 0u) + (p1 != KEY_INF ? 1u : 0u) + (p2 != KEY_INF ? 1u : 0u);
+            const unsigned L = depth >> 1;
+            unsigned *col = my_pend + (size_t)L * 3u * FAST_BLOCK;
+            if (m >= 1u) col[(m - 1u) * FAST_BLOCK] = p0;
+            if (m >= 2u) col[(m - 2u) * FAST_BLOCK] = p1;
+            if (m >= 3u) col[0] = p2;
+            trail |= (unsigned long long)m << (2u * L);
+            const bool descend = any0 && !leaf0;
+            needPop = !descend;
+            h = descend ? (4u * h + (k0 & 3u)) : h;
+            depth += descend ? 2u : 0u;
+        }
+        bool finished = false;
+        const unsigned lp = __ballot_sync(FULL, pid >= 0 && leafA >= 0);
+        if (lp) {
+            const unsigned nd = ~idle_now & ~lp;
+            if (__popc(lp) >= LEAF_T || nd == 0u) {
+                if (pid >= 0 && leafA >= 0) {
+                    bool found = leaf_f3<false, BIG>(sc, r, leafA, best_t, best_slot, nullptr);
+                    if (leafB >= 0 && !(ANY && found) && eB <= best_t) found |= leaf_f3<false, BIG>(sc, r, leafB, best_t, best_slot, nullptr);
+                    leafA = leafB = -1;
+                    if (ANY && found) finished = true;
+                }
+            }
+        }
+        if (pid >= 0 && needPop && leafA < 0 && !finished) {
+            for (;;) {
+                if (trail == 0ull) { finished = true; break; }
+                const unsigned L = (63u - (unsigned)__clzll((long long)trail)) >> 1;
+                const unsigned cnt = (unsigned)(trail >> (2u * L)) & 3u;
+                trail -= 1ull << (2u * L);
+                const unsigned wv = my_pend[((size_t)L * 3u + (cnt - 1u)) * FAST_BLOCK];
+                if (ANY || __uint_as_float(wv & ~7u) <= best_t) {
+                    const unsigned Q = h >> (depth - 2u * L);            // ancestor (or self) at quad level L
+                    if (!(wv & 4u)) { h = 4u * Q + (wv & 3u); depth = 2u * L + 2u; needPop = false; }
+                    else {                                               // a deferred leaf: its meta sits in Q's record
+                        const float4 m4 = ldg4(&sc.quads[quad_index(Q, 2u * L)].meta);
+                        leafA = pick4(m4, wv & 3u); leafB = -1;
+                        h = Q; depth = 2u * L;
+                    }
+                    break;
+                }
+            }
+        }
+        if (finished) {
+            if (!ANY) w.hit[pid] = make_float2(best_t, __int_as_float(best_slot));
+            else if (best_slot < 0) { const float4 c = w.sh_c[pid]; float4 a = w.rad[pid]; a.x += c.x; a.y += c.y; a.z += c.z; w.rad[pid] = a; }
+            pid = -1;
+        }
+    }
 }
 
 struct RngF { uint32_t pixel, sample, k0, k1; };
@@ -646,12 +803,12 @@ void mfx_f_raygen(const LaunchCfg &c, const SceneF &sc, const WaveF &w, TileMap 
 {
     k_f_raygen<<<persistent_blocks(k_f_raygen, 256, c.blocks), 256, 0, c.stream>>>(sc, w, tm, pix0, npix, s0, S, seed);
 }
-template <bool ANY, bool BIG, int RT, int LT, int NS, int MB = 1>
+template <bool ANY, bool BIG, int RT, int LT, int NS>
 static void launch_trace4b(const LaunchCfg &c, const SceneF &sc, const WaveF &w, int bounce, TravCounters *ctr)
 {
     const size_t smem = ANY ? 0 : (size_t)sc.levels * FAST_BLOCK * sizeof(float);
-    if (ctr) k_f_trace4<ANY, true, BIG, RT, LT, NS, 1><<<persistent_blocks(k_f_trace4<ANY, true, BIG, RT, LT, NS, 1>, FAST_BLOCK, c.blocks, smem), FAST_BLOCK, smem, c.stream>>>(sc, w, bounce, ctr);
-    else k_f_trace4<ANY, false, BIG, RT, LT, NS, MB><<<persistent_blocks(k_f_trace4<ANY, false, BIG, RT, LT, NS, MB>, FAST_BLOCK, c.blocks, smem), FAST_BLOCK, smem, c.stream>>>(sc, w, bounce, ctr);
+    if (ctr) k_f_trace4<ANY, true, BIG, RT, LT, NS><<<persistent_blocks(k_f_trace4<ANY, true, BIG, RT, LT, NS>, FAST_BLOCK, c.blocks, smem), FAST_BLOCK, smem, c.stream>>>(sc, w, bounce, ctr);
+    else k_f_trace4<ANY, false, BIG, RT, LT, NS><<<persistent_blocks(k_f_trace4<ANY, false, BIG, RT, LT, NS>, FAST_BLOCK, c.blocks, smem), FAST_BLOCK, smem, c.stream>>>(sc, w, bounce, ctr);
 }
 // scenes without a big (f64) sphere get the kernel compiled without that branch (48 instead of 64+ registers)
 template <bool ANY, int RT, int LT, int NS = 1>
@@ -660,23 +817,29 @@ static void launch_trace4(const LaunchCfg &c, const SceneF &sc, const WaveF &w, 
     if (sc.has_big_sphere) launch_trace4b<ANY, true, RT, LT, NS>(c, sc, w, bounce, ctr);
     else launch_trace4b<ANY, false, RT, LT, NS>(c, sc, w, bounce, ctr);
 }
+template <bool ANY, bool BIG, int RT, int LT, int NS>
+static void launch_trace5b(const LaunchCfg &c, const SceneF &sc, const WaveF &w, int bounce)
+{
+    const size_t smem = (size_t)sc.qlevels * 3 * FAST_BLOCK * sizeof(unsigned);
+    k_f_trace5<ANY, BIG, RT, LT, NS><<<persistent_blocks(k_f_trace5<ANY, BIG, RT, LT, NS>, FAST_BLOCK, c.blocks, smem), FAST_BLOCK, smem, c.stream>>>(sc, w, bounce);
+}
+template <bool ANY, int RT, int LT, int NS>
+static void launch_trace5(const LaunchCfg &c, const SceneF &sc, const WaveF &w, int bounce, TravCounters *ctr)
+{
+    // instrumented (counting) runs and one-leaf trees use the binary kernel: the algorithmic record
+    // counts of the roofline are defined on the reference's binary tree
+    if (ctr || sc.root_meta >= 0) { launch_trace4<ANY, 12, 16, 2>(c, sc, w, bounce, ctr); return; }
+    if (sc.has_big_sphere) launch_trace5b<ANY, true, RT, LT, NS>(c, sc, w, bounce);
+    else launch_trace5b<ANY, false, RT, LT, NS>(c, sc, w, bounce);
+}
 template <bool ANY>
 static void launch_trace_variant(const LaunchCfg &c, const SceneF &sc, const WaveF &w, int bounce, TravCounters *ctr)
 {
-    switch (c.variant) {        // (REFILL_T, LEAF_T) tuning knob (MFX_TRACE_VARIANT); default from measurements
-    case 51: launch_trace4<ANY, 8, 12>(c, sc, w, bounce, ctr); break;
-    case 52: launch_trace4<ANY, 16, 16>(c, sc, w, bounce, ctr); break;
-    case 53: launch_trace4<ANY, 12, 20>(c, sc, w, bounce, ctr); break;
-    case 54: launch_trace4<ANY, 1, 1>(c, sc, w, bounce, ctr); break;
-    case 60: launch_trace4<ANY, 12, 16, 2>(c, sc, w, bounce, ctr); break;
-    case 70: launch_trace4b<ANY, false, 12, 16, 2, 12>(c, sc, w, bounce, ctr); break;
-    case 71: launch_trace4b<ANY, false, 12, 16, 1, 12>(c, sc, w, bounce, ctr); break;
-    case 72: launch_trace4b<ANY, false, 12, 16, 2, 11>(c, sc, w, bounce, ctr); break;
-    case 73: launch_trace4b<ANY, false, 12, 16, 2, 14>(c, sc, w, bounce, ctr); break;
-    case 61: launch_trace4<ANY, 12, 16, 3>(c, sc, w, bounce, ctr); break;
-    case 62: launch_trace4<ANY, 8, 16, 2>(c, sc, w, bounce, ctr); break;
-    case 63: launch_trace4<ANY, 12, 20, 2>(c, sc, w, bounce, ctr); break;
-    default: launch_trace4<ANY, 12, 16, 2>(c, sc, w, bounce, ctr); break;
+    switch (c.variant) {        // tuning knob (MFX_TRACE_VARIANT); the default comes from measurements (profiles/)
+    case 4: launch_trace4<ANY, 12, 16, 2>(c, sc, w, bounce, ctr); break;     // binary steps (one 64 B pair per fetch)
+    case 51: launch_trace5<ANY, 8, 12, 2>(c, sc, w, bounce, ctr); break;
+    case 52: launch_trace5<ANY, 12, 16, 1>(c, sc, w, bounce, ctr); break;
+    default: launch_trace5<ANY, 12, 16, 2>(c, sc, w, bounce, ctr); break;    // two levels per fetch (128 B quad)
     }
 }
 void mfx_f_extend(const LaunchCfg &c, const SceneF &sc, const WaveF &w, int bounce, TravCounters *ctr)

@@ -318,8 +318,17 @@ extern "C" int mfx_scene_create(const MfxSceneDesc *d, MfxScene **out)
     MFX_TRY(ensure_device());
     MfxScene *s = new MfxScene();
     s->device = g_device;
-    cudaDeviceProp prop;
-    if (cudaGetDeviceProperties(&prop, s->device) == cudaSuccess) s->sm_count = prop.multiProcessorCount;
+    {   // cudaGetDeviceProperties costs tens of ms per call: one attribute query, cached per device
+        static std::map<int, int> sm_cache;
+        std::lock_guard<std::mutex> g(g_pool_mu);
+        auto it = sm_cache.find(s->device);
+        if (it == sm_cache.end()) {
+            int sms = 148;
+            if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s->device) != cudaSuccess) { cudaGetLastError(); sms = 148; }
+            it = sm_cache.emplace(s->device, sms).first;
+        }
+        s->sm_count = it->second;
+    }
     s->prims.assign(d->prims, d->prims + d->n_prims);
     s->mats.assign(d->materials, d->materials + d->n_materials);
     s->light = d->light; s->camera = d->camera;
@@ -511,16 +520,61 @@ static int flatten_fast(MfxScene *s)
             if (ri) todo.push_back(2 * i + 2);
         }
     }
+    // quad records: two tree levels per fetch (QuadF in mfx_internal.h)
+    std::vector<QuadF> quads;
+    int qlevels = 0;
+    if (root.count > MFX_LEAF_NODE_COUNT) {
+        auto qindex = [](unsigned h, unsigned depth) { return (size_t)(h - ((2u << depth) + 1u) / 3u); };
+        struct QItem { unsigned h, depth; };
+        std::vector<QItem> todo{ { 1u, 0u } };
+        const float FAR = 1e30f;
+        while (!todo.empty()) {
+            const QItem it = todo.back(); todo.pop_back();
+            const size_t qi = qindex(it.h, it.depth);
+            if (qi >= quads.size()) {
+                QuadF z; memset(&z, 0, sizeof(z));
+                z.lox = z.hix = z.loy = z.hiy = z.loz = z.hiz = make_float4(FAR, FAR, FAR, FAR);
+                z.meta = make_float4(int_bits(-2), int_bits(-2), int_bits(-2), int_bits(-2));
+                quads.resize(qi + 1, z);
+            }
+            qlevels = std::max(qlevels, (int)(it.depth / 2) + 1);
+            float lo[3][4], hi[3][4]; int meta[4];
+            for (int sl = 0; sl < 4; sl++) { for (int a = 0; a < 3; a++) { lo[a][sl] = FAR; hi[a][sl] = FAR; } meta[sl] = -2; }
+            auto put = [&](int sl, const MfxBvhNode &nd, int m) {
+                for (int a = 0; a < 3; a++) { lo[a][sl] = round_down(nd.pmin[a]); hi[a][sl] = round_up(nd.pmax[a]); }
+                meta[sl] = m;
+            };
+            for (unsigned ci = 0; ci < 2; ci++) {
+                const unsigned c = 2u * it.h + ci;                       // 1-based child
+                const MfxBvhNode &C = s->nodes[c - 1];
+                if (C.count <= MFX_LEAF_NODE_COUNT) { put(2 * ci, C, leaf_meta(C)); continue; }
+                for (unsigned gi = 0; gi < 2; gi++) {
+                    const unsigned g = 2u * c + gi;                      // 1-based grandchild = 4h + 2ci + gi
+                    const MfxBvhNode &G = s->nodes[g - 1];
+                    const bool interior = G.count > MFX_LEAF_NODE_COUNT;
+                    put(2 * ci + gi, G, interior ? -1 : leaf_meta(G));
+                    if (interior) todo.push_back({ g, it.depth + 2u });
+                }
+            }
+            QuadF &q = quads[qi];
+            q.lox = make_float4(lo[0][0], lo[0][1], lo[0][2], lo[0][3]); q.hix = make_float4(hi[0][0], hi[0][1], hi[0][2], hi[0][3]);
+            q.loy = make_float4(lo[1][0], lo[1][1], lo[1][2], lo[1][3]); q.hiy = make_float4(hi[1][0], hi[1][1], hi[1][2], hi[1][3]);
+            q.loz = make_float4(lo[2][0], lo[2][1], lo[2][2], lo[2][3]); q.hiz = make_float4(hi[2][0], hi[2][1], hi[2][2], hi[2][3]);
+            q.meta = make_float4(int_bits(meta[0]), int_bits(meta[1]), int_bits(meta[2]), int_bits(meta[3]));
+        }
+    }
     std::vector<MatF> mats(s->mats.size());
     for (size_t i = 0; i < mats.size(); i++) {
         for (int a = 0; a < 3; a++) mats[i].albedo[a] = (float)s->mats[i].albedo[a];
         mats[i].kind = s->mats[i].kind; mats[i].fuzz = (float)s->mats[i].fuzz;
         mats[i].ei = (float)s->mats[i].ei; mats[i].et = (float)s->mats[i].et; mats[i].pad = 0.f;
     }
-    PairF *dpairs; SlotF *dslots; float4 *dnrm; int *dref; MatF *dm;
+    PairF *dpairs; SlotF *dslots; float4 *dnrm; int *dref; MatF *dm; QuadF *dquads;
+    MFX_TRY(upload(s, &dquads, quads));
     MFX_TRY(upload(s, &dpairs, pairs)); MFX_TRY(upload(s, &dslots, slots)); MFX_TRY(upload(s, &dnrm, nrm));
     MFX_TRY(upload(s, &dref, ref)); MFX_TRY(upload(s, &dm, mats));
-    s->f_bytes = pairs.size() * sizeof(PairF) + slots.size() * sizeof(SlotF) + nrm.size() * 16 + ref.size() * 4 + mats.size() * sizeof(MatF);
+    s->f_bytes = quads.size() * sizeof(QuadF) + pairs.size() * sizeof(PairF) + slots.size() * sizeof(SlotF) + nrm.size() * 16 + ref.size() * 4 + mats.size() * sizeof(MatF);
+    sf.quads = dquads; sf.qlevels = qlevels;
     sf.pairs = dpairs; sf.slots = dslots; sf.slot_nrm = dnrm; sf.ref_id = dref; sf.slot_prim = nullptr; sf.mats = dm;
     const double *lp = s->light.p;
     H3 p0 = hld(lp), p1 = hld(lp + 3), p2 = hld(lp + 6), p3 = hld(lp + 9);

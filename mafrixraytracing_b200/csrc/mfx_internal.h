@@ -82,6 +82,13 @@ struct WaveX {
 // meta >= 0: leaf,  first<<3 | count (count <= 6 fast slots);  meta < 0: interior.
 // Boxes are rounded outward from the f64 bounds.
 struct __align__(16) PairF { float4 q0, q1, q2, q3; };
+// Two tree levels per fetch: one 128 B record per interior node at an EVEN depth holding the boxes
+// of its (up to) four grandchildren, SoA so one lane tests four boxes from seven 16 B loads.
+//   slot s <-> grandchild 4h+s (1-based heap index) when child 2h+(s>>1) is interior;
+//   a LEAF child occupies slot 2*(s>>1) itself, the other slot of that half is empty.
+//   meta >= 0: leaf (first<<3 | count), -1: interior (itself a quad node), -2: empty slot.
+// Records are stored compactly: index = h - ((2 << depth) + 1) / 3   (depth even).
+struct __align__(16) QuadF { float4 lox, hix, loy, hiy, loz, hiz, meta, pad; };
 // One fast primitive slot, 48 B = 3 x float4, leaf order.
 //   triangle: a = (v0.xyz, kind bits), b = (e1.xyz, -), c = (e2.xyz, -)
 //   sphere  : a = (center.xyz, kind 2), b = (radius, r^2, -, prim)
@@ -98,7 +105,8 @@ struct LightF {
 struct CamF { float pos[3], topleft[3], right[3], down[3]; };
 
 struct SceneF {
-    const PairF *pairs;     // indexed by interior heap index
+    const PairF *pairs;     // indexed by the interior node's 1-based heap index h (siblings share a 128 B line)
+    const QuadF *quads;     // compact, even-depth interior nodes (see QuadF)
     const SlotF *slots;     // leaf order (rects split in two)
     const int   *slot_prim; // slot -> leaf-order primitive (exact slot) ; sub in bit 30
     const int   *ref_id;    // exact slot -> original primitive index
@@ -113,6 +121,7 @@ struct SceneF {
     int    n_slots;
     int    levels;          // entries of the per-level entry-distance column (deepest child depth + 1)
     int    has_big_sphere;  // any kind-3 slot (selects the kernel variant with the f64 sphere branch)
+    int    qlevels;         // number of quad levels (deepest even interior depth / 2 + 1)
 };
 
 struct WaveF {
