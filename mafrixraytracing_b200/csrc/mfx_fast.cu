@@ -152,63 +152,6 @@ __device__ __forceinline__ bool leaf_f3(const SceneF &sc, const RayF &r, int met
     return any;
 }
 
-// Closest hit (ANY=false) or occlusion (ANY=true) for one ray.
-template <bool ANY, bool COUNT>
-__device__ __forceinline__ void trace_f(const SceneF &sc, const RayF &r, float tmax, float &best_t, int &best_slot,
-                                        float *lvl_entry /* shared: [level*FAST_BLOCK] column of this thread */,
-                                        unsigned long long *ctr)
-{
-    best_t = tmax; best_slot = -1;
-    float e;
-    if (COUNT) ctr[0]++;
-    if (!box_f(r, sc.root_min[0], sc.root_min[1], sc.root_min[2], sc.root_max[0], sc.root_max[1], sc.root_max[2], best_t, e)) return;
-    if (sc.root_meta >= 0) { leaf_f3<COUNT, true>(sc, r, sc.root_meta, best_t, best_slot, ctr); return; }
-    unsigned h = 1u;        // 1-based heap index of the current interior node
-    unsigned pend = 0u;     // bit L set: the sibling of our ancestor at depth L is still to be visited
-    for (;;) {
-        const PairF *pp = sc.pairs + h;
-        const float4 q0 = ldg4(&pp->q0), q1 = ldg4(&pp->q1), q2 = ldg4(&pp->q2), q3 = ldg4(&pp->q3);
-        if (COUNT) ctr[0] += 2;
-        const int metaL = __float_as_int(q3.x), metaR = __float_as_int(q3.y);
-        float eL, eR;
-        bool hitL = box_f(r, q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, best_t, eL);
-        bool hitR = box_f(r, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, best_t, eR);
-        // leaf children are intersected at once, nearer leaf first
-        const bool lfL = hitL && metaL >= 0, lfR = hitR && metaR >= 0;
-        if (lfL || lfR) {
-            bool found = false;
-            if (lfL && lfR) {
-                const bool rFirst = eR < eL;
-                found |= leaf_f3<COUNT, true>(sc, r, rFirst ? metaR : metaL, best_t, best_slot, ctr);
-                if (!(ANY && found) && (rFirst ? eL : eR) <= best_t)
-                    found |= leaf_f3<COUNT, true>(sc, r, rFirst ? metaL : metaR, best_t, best_slot, ctr);
-            } else found = leaf_f3<COUNT, true>(sc, r, lfL ? metaL : metaR, best_t, best_slot, ctr);
-            if (ANY && found) return;
-        }
-        const bool goL = hitL && metaL < 0 && eL <= best_t;
-        const bool goR = hitR && metaR < 0 && eR <= best_t;
-        if (goL || goR) {
-            const bool rNear = goR && (!goL || eR < eL);
-            if (goL && goR) {
-                const unsigned lvl = 32u - __clz(h);       // depth of the children
-                pend |= 1u << lvl;
-                if (!ANY) lvl_entry[lvl * FAST_BLOCK] = rNear ? eL : eR;
-            }
-            h = 2u * h + (rNear ? 1u : 0u);
-            continue;
-        }
-        // pop the deepest deferred sibling that can still beat the best hit
-        for (;;) {
-            if (pend == 0u) return;
-            const unsigned b = 31u - __clz(pend);
-            pend ^= 1u << b;
-            const unsigned dc = 31u - __clz(h);
-            h = (h >> (dc - b)) ^ 1u;
-            if (ANY || lvl_entry[b * FAST_BLOCK] <= best_t) break;
-        }
-    }
-}
-
 // ---------------------------------------------------------------- kernels
 __device__ __forceinline__ F3 normalize_f(F3 a)
 {
@@ -240,7 +183,7 @@ __global__ void __launch_bounds__(256) k_f_raygen(SceneF sc, WaveF w, TileMap tm
         const double v = ((double)py + u32_to_unit_f64(o4[1])) / (double)sc.height;
         const F3 d = camera_dir_f64(sc.camx, u, v);
         w.ray_o[pid] = make_float4(sc.cam.pos[0], sc.cam.pos[1], sc.cam.pos[2], __int_as_float(-1));
-        w.ray_d[pid] = make_float4(d.x, d.y, d.z, 0.f);
+        w.ray_d[pid] = make_float4(d.x, d.y, d.z, 99999999.f);          // w = tMax of the closest query, Integrators.fs:108
         w.thr[pid] = make_float4(1.f, 1.f, 1.f, 0.f);
         w.rad[pid] = make_float4(0.f, 0.f, 0.f, 0.f);
         w.q_ext[0][pid] = (int)pid;
@@ -304,8 +247,8 @@ __global__ void __launch_bounds__(FAST_BLOCK) k_f_trace4(SceneF sc, WaveF w, int
                     pid = q[idx];
                     const float4 o = w.ray_o[pid];
                     const float4 d = ANY ? w.sh_d[pid] : w.ray_d[pid];
-                    r = make_ray_fast(f3(o.x, o.y, o.z), f3(d.x, d.y, d.z), 1e-6f, __float_as_int(o.w));
-                    best_t = ANY ? d.w - 1e-6f : 99999999.f;            // Integrators.fs:44 / :108
+                    r = make_ray_fast(f3(o.x, o.y, o.z), f3(d.x, d.y, d.z), w.tmin, __float_as_int(o.w));
+                    best_t = ANY ? d.w - 1e-6f : d.w;                   // shadow: dist - 1e-6 (Integrators.fs:44); closest: tMax (:108)
                     best_slot = -1; pend = 0u; leafA = leafB = -1; h = 1u; depth = 0u;
                     float e;
                     if (COUNT) local[0]++;
@@ -404,9 +347,24 @@ __device__ __forceinline__ int pick4(const float4 &m, unsigned id)
     const float lo = (id & 1u) ? m.y : m.x, hi = (id & 1u) ? m.w : m.z;
     return __float_as_int((id & 2u) ? hi : lo);
 }
-__device__ __forceinline__ size_t quad_index(unsigned h, unsigned depth) { return (size_t)(h - ((2u << depth) + 1u) / 3u); }
+// Quad levels.  PAR = 0: quad nodes sit at even depths 0,2,4,...  PAR = 1 (trees whose deepest leaves are at an odd
+// depth): the root is a 2-slot pseudo quad (its two children) and the real quads sit at odd depths 1,3,5,... so that
+// the bottom quads still hold four leaf grandchildren.  Level L <-> depth: PAR=0: 2L;  PAR=1: 0, 1, 3, 5, ...
+template <int PAR> __device__ __forceinline__ unsigned qlevel(unsigned depth) { return PAR ? ((depth + 1u) >> 1) : (depth >> 1); }
+template <int PAR> __device__ __forceinline__ unsigned qdepth(unsigned L) { return PAR ? (L ? 2u * L - 1u : 0u) : 2u * L; }
+template <int PAR> __device__ __forceinline__ size_t quad_index(unsigned h, unsigned depth)
+{
+    if (PAR) return depth ? (size_t)(h + 1u - ((4u << (depth - 1u)) + 2u) / 3u) : (size_t)0;
+    return (size_t)(h - ((2u << depth) + 1u) / 3u);
+}
+// heap index / depth of the child in slot `id` of quad node (h, depth)
+template <int PAR> __device__ __forceinline__ void quad_child(unsigned &h, unsigned &depth, unsigned id)
+{
+    if (PAR && depth == 0u) { h = 2u * h + id; depth = 1u; }
+    else { h = 4u * h + id; depth += 2u; }
+}
 
-template <bool ANY, bool BIG, int REFILL_T, int LEAF_T, int NSTEP>
+template <bool ANY, bool BIG, int PAR, int REFILL_T, int LEAF_T, int NSTEP>
 __global__ void __launch_bounds__(FAST_BLOCK) k_f_trace5(SceneF sc, WaveF w, int bounce)
 {
     extern __shared__ unsigned s_pend[];            // [qlevels][3][FAST_BLOCK]
@@ -443,8 +401,8 @@ __global__ void __launch_bounds__(FAST_BLOCK) k_f_trace5(SceneF sc, WaveF w, int
                     pid = q[idx];
                     const float4 o = w.ray_o[pid];
                     const float4 d = ANY ? w.sh_d[pid] : w.ray_d[pid];
-                    r = make_ray_fast(f3(o.x, o.y, o.z), f3(d.x, d.y, d.z), 1e-6f, __float_as_int(o.w));
-                    best_t = ANY ? d.w - 1e-6f : 99999999.f;            // Integrators.fs:44 / :108
+                    r = make_ray_fast(f3(o.x, o.y, o.z), f3(d.x, d.y, d.z), w.tmin, __float_as_int(o.w));
+                    best_t = ANY ? d.w - 1e-6f : d.w;                   // shadow: dist - 1e-6 (Integrators.fs:44); closest: tMax (:108)
                     best_slot = -1; trail = 0ull; leafA = leafB = -1; h = 1u; depth = 0u;
                     float e;
                     const bool in = box_f(r, sc.root_min[0], sc.root_min[1], sc.root_min[2], sc.root_max[0], sc.root_max[1], sc.root_max[2], best_t, e);
@@ -459,7 +417,7 @@ __global__ void __launch_bounds__(FAST_BLOCK) k_f_trace5(SceneF sc, WaveF w, int
 #pragma unroll
         for (int rep = 0; rep < NSTEP; rep++)
         if (pid >= 0 && leafA < 0 && !needPop) {
-            const QuadF *qp = sc.quads + quad_index(h, depth);
+            const QuadF *qp = sc.quads + quad_index<PAR>(h, depth);
             const float4 lox = ldg4(&qp->lox), hix = ldg4(&qp->hix), loy = ldg4(&qp->loy), hiy = ldg4(&qp->hiy);
             const float4 loz = ldg4(&qp->loz), hiz = ldg4(&qp->hiz), m4 = ldg4(&qp->meta);
             unsigned key[4];
@@ -489,7 +447,7 @@ __global__ void __launch_bounds__(FAST_BLOCK) k_f_trace5(SceneF sc, WaveF w, int
             // deferred hits: everything behind the one(s) consumed now, nearest on top of the level's column
             const unsigned p0 = leaf1 ? k2 : k1, p1 = leaf1 ? k3 : k2, p2 = leaf1 ? KEY_INF : k3;
             const unsigned m = (p0 != KEY_INF ? 1u : 0u) + (p1 != KEY_INF ? 1u : 0u) + (p2 != KEY_INF ? 1u : 0u);
-            const unsigned L = depth >> 1;
+            const unsigned L = qlevel<PAR>(depth);
             unsigned *col = my_pend + (size_t)L * 3u * FAST_BLOCK;
             if (m >= 1u) col[(m - 1u) * FAST_BLOCK] = p0;
             if (m >= 2u) col[(m - 2u) * FAST_BLOCK] = p1;
@@ -497,8 +455,7 @@ __global__ void __launch_bounds__(FAST_BLOCK) k_f_trace5(SceneF sc, WaveF w, int
             trail |= (unsigned long long)m << (2u * L);
             const bool descend = any0 && !leaf0;
             needPop = !descend;
-            h = descend ? (4u * h + (k0 & 3u)) : h;
-            depth += descend ? 2u : 0u;
+            if (descend) quad_child<PAR>(h, depth, k0 & 3u);
         }
         bool finished = false;
         const unsigned lp = __ballot_sync(FULL, pid >= 0 && leafA >= 0);
@@ -521,12 +478,13 @@ __global__ void __launch_bounds__(FAST_BLOCK) k_f_trace5(SceneF sc, WaveF w, int
                 trail -= 1ull << (2u * L);
                 const unsigned wv = my_pend[((size_t)L * 3u + (cnt - 1u)) * FAST_BLOCK];
                 if (ANY || __uint_as_float(wv & ~7u) <= best_t) {
-                    const unsigned Q = h >> (depth - 2u * L);            // ancestor (or self) at quad level L
-                    if (!(wv & 4u)) { h = 4u * Q + (wv & 3u); depth = 2u * L + 2u; needPop = false; }
+                    const unsigned dL = qdepth<PAR>(L);
+                    const unsigned Q = h >> (depth - dL);                // ancestor (or self) at quad level L
+                    h = Q; depth = dL;
+                    if (!(wv & 4u)) { quad_child<PAR>(h, depth, wv & 3u); needPop = false; }
                     else {                                               // a deferred leaf: its meta sits in Q's record
-                        const float4 m4 = ldg4(&sc.quads[quad_index(Q, 2u * L)].meta);
+                        const float4 m4 = ldg4(&sc.quads[quad_index<PAR>(Q, dL)].meta);
                         leafA = pick4(m4, wv & 3u); leafB = -1;
-                        h = Q; depth = 2u * L;
                     }
                     break;
                 }
@@ -680,7 +638,7 @@ __global__ void __launch_bounds__(FAST_BLOCK) k_f_shade(SceneF sc, WaveF w, Tile
                     // planar sources are never re-hit; spheres keep themselves as source (far root / none)
                     w.ray_o[pid] = make_float4(point.x, point.y, point.z, __int_as_float(prim));
                 }
-                if (cont) { w.ray_d[pid] = make_float4(wi.x, wi.y, wi.z, 0.f); w.thr[pid] = thr; }
+                if (cont) { w.ray_d[pid] = make_float4(wi.x, wi.y, wi.z, 99999999.f); w.thr[pid] = thr; }
             }
         }
         const int pe = warp_append(cont, &w.counts[bounce + 1]);
@@ -705,43 +663,58 @@ __global__ void __launch_bounds__(256) k_f_resolve(SceneF sc, WaveF w, TileMap t
     }
 }
 
-__global__ void __launch_bounds__(FAST_BLOCK) k_f_bvh_hit(SceneF sc, int any_hit, long long n, const double *o, const double *d,
-                                                          double tmin, double tmax, int *prim, int *sub, double *t)
+// Finer seams (Bvh.Hit, GetRay + Hit) routed through the PRODUCTION traversal kernel: rays are written
+// into the wave's queues, traced by k_f_trace5 / k_f_trace4, and read back.
+__global__ void __launch_bounds__(256) k_f_seam_setup(SceneF sc, WaveF w, int n, const double *o, const double *d, const double *uv,
+                                                      long long first, float tmax, int any_hit)
 {
-    __shared__ float s_entry[FAST_LEVELS * FAST_BLOCK];
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-        const RayF r = make_ray(f3((float)o[3 * i], (float)o[3 * i + 1], (float)o[3 * i + 2]),
-                                f3((float)d[3 * i], (float)d[3 * i + 1], (float)d[3 * i + 2]), (float)tmin, -1);
-        float bt; int slot;
-        if (any_hit) trace_f<true, false>(sc, r, (float)tmax, bt, slot, nullptr, nullptr);
-        else trace_f<false, false>(sc, r, (float)tmax, bt, slot, s_entry + threadIdx.x, nullptr);
-        if (slot < 0) { prim[i] = -1; if (sub) sub[i] = 0; t[i] = 0.; }
-        else {
-            const int ps = __float_as_int(sc.slots[slot].b.w);
-            prim[i] = sc.ref_id[ps & 0x3fffffff];
-            if (sub) sub[i] = (ps >> 30) & 1;
-            t[i] = (double)bt;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const long long r = first + i;
+        F3 oo, dd;
+        if (d) {
+            oo = f3((float)o[3 * r], (float)o[3 * r + 1], (float)o[3 * r + 2]);
+            dd = f3((float)d[3 * r], (float)d[3 * r + 1], (float)d[3 * r + 2]);
+        } else {
+            double u, v;
+            if (uv) { u = uv[2 * r]; v = uv[2 * r + 1]; }
+            else {
+                const int j = (int)(r / sc.width), ii = (int)(r - (long long)j * sc.width);
+                u = ((double)ii + 0.5) / (double)sc.width;
+                v = ((double)j + 0.5) / (double)sc.height;
+            }
+            oo = f3(sc.cam.pos[0], sc.cam.pos[1], sc.cam.pos[2]);
+            dd = camera_dir_f64(sc.camx, u, v);
         }
+        w.ray_o[i] = make_float4(oo.x, oo.y, oo.z, __int_as_float(-1));
+        w.ray_d[i] = make_float4(dd.x, dd.y, dd.z, tmax);
+        w.sh_d[i] = make_float4(dd.x, dd.y, dd.z, tmax + 1e-6f);      // the shadow kernel subtracts 1e-6 (Integrators.fs:44)
+        w.sh_c[i] = make_float4(1.f, 0.f, 0.f, 0.f);                  // unoccluded rays add this to rad
+        w.rad[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        w.hit[i] = make_float2(0.f, __int_as_float(-1));
+        w.q_ext[0][i] = i; w.q_sh[i] = i;
+        if (i == 0) { w.counts[0] = any_hit ? 0 : n; w.counts[CNT_SH(0)] = any_hit ? n : 0; }
     }
 }
 
-__global__ void __launch_bounds__(FAST_BLOCK) k_f_primary(SceneF sc, long long n, const double *uv, int *prim, double *t)
+__global__ void __launch_bounds__(256) k_f_seam_read(SceneF sc, WaveF w, int n, long long first, int any_hit, int *prim, int *sub, double *t)
 {
-    __shared__ float s_entry[FAST_LEVELS * FAST_BLOCK];
-    for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += (long long)gridDim.x * blockDim.x) {
-        double u, v;
-        if (uv) { u = uv[2 * r]; v = uv[2 * r + 1]; }
-        else {
-            const int j = (int)(r / sc.width), i = (int)(r - (long long)j * sc.width);
-            u = ((double)i + 0.5) / (double)sc.width;
-            v = ((double)j + 0.5) / (double)sc.height;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const long long r = first + i;
+        if (any_hit) {                          // only occluded / clear is meaningful
+            prim[r] = (w.rad[i].x == 0.f) ? 0 : -1;
+            if (sub) sub[r] = 0;
+            t[r] = 0.;
+            continue;
         }
-        const F3 d = camera_dir_f64(sc.camx, u, v);
-        const RayF ray = make_ray(f3(sc.cam.pos[0], sc.cam.pos[1], sc.cam.pos[2]), d, 1e-6f, -1);
-        float bt; int slot;
-        trace_f<false, false>(sc, ray, 99999999.f, bt, slot, s_entry + threadIdx.x, nullptr);
-        if (slot < 0) { prim[r] = -1; t[r] = 0.; }
-        else { prim[r] = sc.ref_id[__float_as_int(sc.slots[slot].b.w) & 0x3fffffff]; t[r] = (double)bt; }
+        const float2 h = w.hit[i];
+        const int slot = __float_as_int(h.y);
+        if (slot < 0) { prim[r] = -1; if (sub) sub[r] = 0; t[r] = 0.; }
+        else {
+            const int ps = __float_as_int(sc.slots[slot].b.w);
+            prim[r] = sc.ref_id[ps & 0x3fffffff];
+            if (sub) sub[r] = (ps >> 30) & 1;
+            t[r] = (double)h.x;
+        }
     }
 }
 
@@ -821,7 +794,8 @@ template <bool ANY, bool BIG, int RT, int LT, int NS>
 static void launch_trace5b(const LaunchCfg &c, const SceneF &sc, const WaveF &w, int bounce)
 {
     const size_t smem = (size_t)sc.qlevels * 3 * FAST_BLOCK * sizeof(unsigned);
-    k_f_trace5<ANY, BIG, RT, LT, NS><<<persistent_blocks(k_f_trace5<ANY, BIG, RT, LT, NS>, FAST_BLOCK, c.blocks, smem), FAST_BLOCK, smem, c.stream>>>(sc, w, bounce);
+    if (sc.qpar) k_f_trace5<ANY, BIG, 1, RT, LT, NS><<<persistent_blocks(k_f_trace5<ANY, BIG, 1, RT, LT, NS>, FAST_BLOCK, c.blocks, smem), FAST_BLOCK, smem, c.stream>>>(sc, w, bounce);
+    else k_f_trace5<ANY, BIG, 0, RT, LT, NS><<<persistent_blocks(k_f_trace5<ANY, BIG, 0, RT, LT, NS>, FAST_BLOCK, c.blocks, smem), FAST_BLOCK, smem, c.stream>>>(sc, w, bounce);
 }
 template <bool ANY, int RT, int LT, int NS>
 static void launch_trace5(const LaunchCfg &c, const SceneF &sc, const WaveF &w, int bounce, TravCounters *ctr)
@@ -858,14 +832,14 @@ void mfx_f_resolve(const LaunchCfg &c, const SceneF &sc, const WaveF &w, TileMap
 {
     k_f_resolve<<<persistent_blocks(k_f_resolve, 256, c.blocks), 256, 0, c.stream>>>(sc, w, tm, pix0, npix, S, pixsum);
 }
-void mfx_f_bvh_hit(const LaunchCfg &c, const SceneF &sc, int any_hit, long long n, const double *o, const double *d,
-                   double tmin, double tmax, int *prim, int *sub, double *t)
+void mfx_f_seam_setup(const LaunchCfg &c, const SceneF &sc, const WaveF &w, int n, const double *o, const double *d, const double *uv,
+                      long long first, float tmax, int any_hit)
 {
-    k_f_bvh_hit<<<persistent_blocks(k_f_bvh_hit, FAST_BLOCK, c.blocks), FAST_BLOCK, 0, c.stream>>>(sc, any_hit, n, o, d, tmin, tmax, prim, sub, t);
+    k_f_seam_setup<<<persistent_blocks(k_f_seam_setup, 256, c.blocks), 256, 0, c.stream>>>(sc, w, n, o, d, uv, first, tmax, any_hit);
 }
-void mfx_f_primary(const LaunchCfg &c, const SceneF &sc, long long n, const double *uv, int *prim, double *t)
+void mfx_f_seam_read(const LaunchCfg &c, const SceneF &sc, const WaveF &w, int n, long long first, int any_hit, int *prim, int *sub, double *t)
 {
-    k_f_primary<<<persistent_blocks(k_f_primary, FAST_BLOCK, c.blocks), FAST_BLOCK, 0, c.stream>>>(sc, n, uv, prim, t);
+    k_f_seam_read<<<persistent_blocks(k_f_seam_read, 256, c.blocks), 256, 0, c.stream>>>(sc, w, n, first, any_hit, prim, sub, t);
 }
 void mfx_accum_ray_totals(cudaStream_t s, const int *counts, int ext_lo, int ext_n, int sh_lo, int sh_n, unsigned long long *totals)
 {

@@ -522,9 +522,20 @@ static int flatten_fast(MfxScene *s)
     }
     // quad records: two tree levels per fetch (QuadF in mfx_internal.h)
     std::vector<QuadF> quads;
-    int qlevels = 0;
+    int qlevels = 0, qpar = 0;
     if (root.count > MFX_LEAF_NODE_COUNT) {
-        auto qindex = [](unsigned h, unsigned depth) { return (size_t)(h - ((2u << depth) + 1u) / 3u); };
+        // deepest leaf depth decides the parity so that the bottom quads hold four leaf grandchildren
+        {
+            unsigned maxh = 1;
+            for (size_t i = 0; i < s->nodes.size(); i++) if (s->nodes[i].count > 0) maxh = (unsigned)i + 1u;
+            unsigned D = 0; for (unsigned v = maxh; v > 1u; v >>= 1) D++;
+            qpar = (int)(D & 1u);
+        }
+        auto qindex = [&](unsigned h, unsigned depth) -> size_t {
+            if (qpar) return depth ? (size_t)(h + 1u - ((4u << (depth - 1u)) + 2u) / 3u) : (size_t)0;
+            return (size_t)(h - ((2u << depth) + 1u) / 3u);
+        };
+        auto qlevel = [&](unsigned depth) { return qpar ? (int)((depth + 1u) >> 1) : (int)(depth >> 1); };
         struct QItem { unsigned h, depth; };
         std::vector<QItem> todo{ { 1u, 0u } };
         const float FAR = 1e30f;
@@ -537,23 +548,34 @@ static int flatten_fast(MfxScene *s)
                 z.meta = make_float4(int_bits(-2), int_bits(-2), int_bits(-2), int_bits(-2));
                 quads.resize(qi + 1, z);
             }
-            qlevels = std::max(qlevels, (int)(it.depth / 2) + 1);
+            qlevels = std::max(qlevels, qlevel(it.depth) + 1);
             float lo[3][4], hi[3][4]; int meta[4];
             for (int sl = 0; sl < 4; sl++) { for (int a = 0; a < 3; a++) { lo[a][sl] = FAR; hi[a][sl] = FAR; } meta[sl] = -2; }
             auto put = [&](int sl, const MfxBvhNode &nd, int m) {
                 for (int a = 0; a < 3; a++) { lo[a][sl] = round_down(nd.pmin[a]); hi[a][sl] = round_up(nd.pmax[a]); }
                 meta[sl] = m;
             };
-            for (unsigned ci = 0; ci < 2; ci++) {
-                const unsigned c = 2u * it.h + ci;                       // 1-based child
-                const MfxBvhNode &C = s->nodes[c - 1];
-                if (C.count <= MFX_LEAF_NODE_COUNT) { put(2 * ci, C, leaf_meta(C)); continue; }
-                for (unsigned gi = 0; gi < 2; gi++) {
-                    const unsigned g = 2u * c + gi;                      // 1-based grandchild = 4h + 2ci + gi
-                    const MfxBvhNode &G = s->nodes[g - 1];
-                    const bool interior = G.count > MFX_LEAF_NODE_COUNT;
-                    put(2 * ci + gi, G, interior ? -1 : leaf_meta(G));
-                    if (interior) todo.push_back({ g, it.depth + 2u });
+            if (qpar && it.depth == 0u) {
+                // pseudo root: slots 0/1 are the root's own children (child heap index 2h + slot)
+                for (unsigned ci = 0; ci < 2; ci++) {
+                    const unsigned c = 2u * it.h + ci;
+                    const MfxBvhNode &C = s->nodes[c - 1];
+                    const bool interior = C.count > MFX_LEAF_NODE_COUNT;
+                    put((int)ci, C, interior ? -1 : leaf_meta(C));
+                    if (interior) todo.push_back({ c, 1u });
+                }
+            } else {
+                for (unsigned ci = 0; ci < 2; ci++) {
+                    const unsigned c = 2u * it.h + ci;                       // 1-based child
+                    const MfxBvhNode &C = s->nodes[c - 1];
+                    if (C.count <= MFX_LEAF_NODE_COUNT) { put(2 * ci, C, leaf_meta(C)); continue; }
+                    for (unsigned gi = 0; gi < 2; gi++) {
+                        const unsigned g = 2u * c + gi;                      // 1-based grandchild = 4h + 2ci + gi
+                        const MfxBvhNode &G = s->nodes[g - 1];
+                        const bool interior = G.count > MFX_LEAF_NODE_COUNT;
+                        put(2 * ci + gi, G, interior ? -1 : leaf_meta(G));
+                        if (interior) todo.push_back({ g, it.depth + 2u });
+                    }
                 }
             }
             QuadF &q = quads[qi];
@@ -574,7 +596,7 @@ static int flatten_fast(MfxScene *s)
     MFX_TRY(upload(s, &dpairs, pairs)); MFX_TRY(upload(s, &dslots, slots)); MFX_TRY(upload(s, &dnrm, nrm));
     MFX_TRY(upload(s, &dref, ref)); MFX_TRY(upload(s, &dm, mats));
     s->f_bytes = quads.size() * sizeof(QuadF) + pairs.size() * sizeof(PairF) + slots.size() * sizeof(SlotF) + nrm.size() * 16 + ref.size() * 4 + mats.size() * sizeof(MatF);
-    sf.quads = dquads; sf.qlevels = qlevels;
+    sf.quads = dquads; sf.qlevels = qlevels; sf.qpar = qpar;
     sf.pairs = dpairs; sf.slots = dslots; sf.slot_nrm = dnrm; sf.ref_id = dref; sf.slot_prim = nullptr; sf.mats = dm;
     const double *lp = s->light.p;
     H3 p0 = hld(lp), p1 = hld(lp + 3), p2 = hld(lp + 6), p3 = hld(lp + 9);
@@ -640,6 +662,7 @@ static int ensure_wave_fast(MfxScene *s)
     WaveF &w = s->wf;
     memset(&w, 0, sizeof(w));
     w.P = (int)P;
+    w.tmin = 1e-6f;
     MFX_TRY(dev_alloc_t(s, &w.ray_o, P)); MFX_TRY(dev_alloc_t(s, &w.ray_d, P));
     MFX_TRY(dev_alloc_t(s, &w.hit, P)); MFX_TRY(dev_alloc_t(s, &w.thr, P)); MFX_TRY(dev_alloc_t(s, &w.rad, P));
     MFX_TRY(dev_alloc_t(s, &w.sh_d, P)); MFX_TRY(dev_alloc_t(s, &w.sh_c, P));
@@ -923,13 +946,29 @@ static int with_ray_buffers(MfxScene *s, int64_t n, const double *a, size_t a_pe
     return rc;
 }
 
+// The fast-precision seams run the PRODUCTION wavefront traversal kernel: the rays go through the wave's
+// queues in chunks of its capacity (bounce 0, closest or shadow queue), exactly like rays of a frame.
+static void fast_seam(MfxScene *s, const LaunchCfg &cfg, int any_hit, int64_t n, const double *o, const double *d, const double *uv,
+                      float tmin, float tmax, int *prim, int *sub, double *t)
+{
+    WaveF w = s->wf;
+    w.tmin = tmin;
+    for (int64_t first = 0; first < n; first += w.P) {
+        const int m = (int)std::min<int64_t>(w.P, n - first);
+        cudaMemsetAsync(w.counts, 0, MFX_COUNTS_LEN * sizeof(int), s->stream);
+        mfx_f_seam_setup(cfg, s->sf, w, m, o, d, uv, first, tmax, any_hit);
+        if (any_hit) mfx_f_shadow(cfg, s->sf, w, 0, nullptr); else mfx_f_extend(cfg, s->sf, w, 0, nullptr);
+        mfx_f_seam_read(cfg, s->sf, w, m, first, any_hit, prim, sub, t);
+    }
+}
+
 extern "C" int mfx_bvh_hit(MfxScene *s, int32_t precision, int32_t any_hit, int64_t n, const double *origins, const double *dirs,
                            double tmin, double tmax, int32_t *prim, int32_t *sub, double *t)
 {
     if (!s || !origins || !dirs || !prim || !t) return fail(MFX_ERR_INVALID_ARGUMENT, "mfx_bvh_hit: null argument");
     if (n <= 0) return MFX_OK;
     MFX_TRY(ensure_device());
-    LaunchCfg cfg{ s->sm_count, 128, s->stream, 0 };
+    LaunchCfg cfg{ s->sm_count, 128, s->stream, (int)env_long("MFX_TRACE_VARIANT", -1) };
     if (precision == MFX_EXACT_F64) {
         MFX_TRY(flatten_exact(s));
         return with_ray_buffers(s, n, origins, 3, dirs, 3, prim, sub, t, [&](double *o, double *d, int *p, int *sb, double *tt) {
@@ -937,8 +976,9 @@ extern "C" int mfx_bvh_hit(MfxScene *s, int32_t precision, int32_t any_hit, int6
         });
     } else if (precision == MFX_FAST_F32) {
         MFX_TRY(flatten_fast(s));
+        MFX_TRY(ensure_wave_fast(s));
         return with_ray_buffers(s, n, origins, 3, dirs, 3, prim, sub, t, [&](double *o, double *d, int *p, int *sb, double *tt) {
-            mfx_f_bvh_hit(cfg, s->sf, any_hit, n, o, d, tmin, tmax, p, sb, tt);
+            fast_seam(s, cfg, any_hit, n, o, d, nullptr, (float)tmin, (float)tmax, p, sb, tt);
         });
     }
     return fail(MFX_ERR_INVALID_ARGUMENT, "unknown precision %d", precision);
@@ -950,7 +990,7 @@ extern "C" int mfx_trace_primary(MfxScene *s, int32_t precision, int64_t n, cons
     if (!uv && n != (int64_t)s->width * s->height) return fail(MFX_ERR_INVALID_ARGUMENT, "uv == NULL needs n == width*height");
     if (n <= 0) return MFX_OK;
     MFX_TRY(ensure_device());
-    LaunchCfg cfg{ s->sm_count, 128, s->stream, 0 };
+    LaunchCfg cfg{ s->sm_count, 128, s->stream, (int)env_long("MFX_TRACE_VARIANT", -1) };
     if (precision == MFX_EXACT_F64) {
         MFX_TRY(flatten_exact(s));
         return with_ray_buffers(s, n, uv, 2, nullptr, 0, prim, nullptr, t, [&](double *u, double *, int *p, int *, double *tt) {
@@ -958,8 +998,9 @@ extern "C" int mfx_trace_primary(MfxScene *s, int32_t precision, int64_t n, cons
         });
     } else if (precision == MFX_FAST_F32) {
         MFX_TRY(flatten_fast(s));
+        MFX_TRY(ensure_wave_fast(s));
         return with_ray_buffers(s, n, uv, 2, nullptr, 0, prim, nullptr, t, [&](double *u, double *, int *p, int *, double *tt) {
-            mfx_f_primary(cfg, s->sf, n, u, p, tt);
+            fast_seam(s, cfg, 0, n, nullptr, nullptr, u, 1e-6f, 99999999.f, p, nullptr, tt);
         });
     }
     return fail(MFX_ERR_INVALID_ARGUMENT, "unknown precision %d", precision);

@@ -87,7 +87,8 @@ struct __align__(16) PairF { float4 q0, q1, q2, q3; };
 //   slot s <-> grandchild 4h+s (1-based heap index) when child 2h+(s>>1) is interior;
 //   a LEAF child occupies slot 2*(s>>1) itself, the other slot of that half is empty.
 //   meta >= 0: leaf (first<<3 | count), -1: interior (itself a quad node), -2: empty slot.
-// Records are stored compactly: index = h - ((2 << depth) + 1) / 3   (depth even).
+// Records are stored compactly: index = h - ((2 << depth) + 1) / 3 (quads at even depths); for trees whose deepest
+// leaves sit at an odd depth the root is a 2-slot pseudo quad and the quads sit at odd depths (SceneF.qpar).
 struct __align__(16) QuadF { float4 lox, hix, loy, hiy, loz, hiz, meta, pad; };
 // One fast primitive slot, 48 B = 3 x float4, leaf order.
 //   triangle: a = (v0.xyz, kind bits), b = (e1.xyz, -), c = (e2.xyz, -)
@@ -121,7 +122,8 @@ struct SceneF {
     int    n_slots;
     int    levels;          // entries of the per-level entry-distance column (deepest child depth + 1)
     int    has_big_sphere;  // any kind-3 slot (selects the kernel variant with the f64 sphere branch)
-    int    qlevels;         // number of quad levels (deepest even interior depth / 2 + 1)
+    int    qlevels;         // number of quad levels
+    int    qpar;            // 0: quads at even depths; 1: 2-slot pseudo root + quads at odd depths (odd leaf depth)
 };
 
 struct WaveF {
@@ -135,6 +137,7 @@ struct WaveF {
     float4 *sh_c;           // [P] contribution rgb if unoccluded
     int    *q_ext[2];       // ping-pong extend queues of path ids
     int    *q_sh;           // shadow queue of the current bounce
+    float   tmin;           // tMin of every query (1e-6, Integrators.fs:44,108; the Bvh.Hit seam may pass another)
     int    *counts;         // [0 .. MFX_MAX_VERTS+1] extend queue sizes per bounce,
                             // [MFX_MAX_VERTS+2 + bounce] shadow queue sizes
 };
@@ -177,9 +180,9 @@ void mfx_f_shade(const LaunchCfg &, const SceneF &, const WaveF &, TileMap tm, i
 void mfx_f_shadow(const LaunchCfg &, const SceneF &, const WaveF &, int bounce, TravCounters *ctr);
 void mfx_f_resolve(const LaunchCfg &, const SceneF &, const WaveF &, TileMap tm, int pix0, int npix, int S,
                    double *pixsum);
-void mfx_f_bvh_hit(const LaunchCfg &, const SceneF &, int any_hit, long long n, const double *o, const double *d,
-                   double tmin, double tmax, int *prim, int *sub, double *t);
-void mfx_f_primary(const LaunchCfg &, const SceneF &, long long n, const double *uv, int *prim, double *t);
+void mfx_f_seam_setup(const LaunchCfg &, const SceneF &, const WaveF &, int n, const double *o, const double *d, const double *uv,
+                      long long first, float tmax, int any_hit);
+void mfx_f_seam_read(const LaunchCfg &, const SceneF &, const WaveF &, int n, long long first, int any_hit, int *prim, int *sub, double *t);
 
 // misc (mfx_fast.cu)
 // totals[0] += sum counts[ext_lo..+ext_n), totals[1] += sum counts[sh_lo..+sh_n), totals[2] += counts[0]
