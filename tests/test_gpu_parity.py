@@ -389,5 +389,5 @@ def test_every_traversal_kernel_variant_gives_the_same_hits(monkeypatch, variant
     img1 = CudaPixelIntegrator(s, precision=FAST_F32, seed=3).Sample(4).copy()
     # box tests differ in rounding between the layouts only through the order of visits: ties aside, same hits
     assert (p0 != p1).mean() <= 1e-4 and np.allclose(t0[p0 == p1], t1[p0 == p1], rtol=1e-6, atol=1e-7)
-    rel = np.sqrt(((img0 - img1)[:, :, :3] ** 2).mean()) / np.abs(img0[:, :, :3]).mean()
-    assert rel < 5e-2
+    # paths are deterministic given their hits: only pixels behind one of the rare tie-broken hits may change
+    assert (img0 != img1).any(axis=2).mean() <= 5e-3
