@@ -212,6 +212,11 @@ MFX_API int mfx_film_get_frame(MfxFilm *film, const MfxSampleParams *params, dou
  * applied on the device to the film's current target. */
 MFX_API int mfx_film_post_process(MfxFilm *film, uint8_t *rgba8);
 MFX_API int mfx_film_frame_count(const MfxFilm *film, double *out);
+/* Checkpoint / resume of the only state the reference's renderer carries between frames: Film.texture (the
+ * running sum, Color[w,h]) and frameCount (Film.fs:14-17).  With the counter-based RNG a resumed film continues
+ * bit-exactly (pass first_sample = frames already rendered x spp). */
+MFX_API int mfx_film_export(MfxFilm *film, double *sum_color_wh, double *frame_count);
+MFX_API int mfx_film_import(MfxFilm *film, const double *sum_color_wh, double frame_count);
 
 #ifdef __cplusplus
 }

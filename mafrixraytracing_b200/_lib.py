@@ -78,6 +78,8 @@ SYMBOLS = {
     "mfx_film_get_frame": (C.c_int, [_P, C.POINTER(MfxSampleParams), _P]),
     "mfx_film_post_process": (C.c_int, [_P, _P]),
     "mfx_film_frame_count": (C.c_int, [_P, C.POINTER(C.c_double)]),
+    "mfx_film_export": (C.c_int, [_P, _P, C.POINTER(C.c_double)]),
+    "mfx_film_import": (C.c_int, [_P, _P, C.c_double]),
 }
 
 _lib = None

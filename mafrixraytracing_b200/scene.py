@@ -326,6 +326,17 @@ class Film:
         integrator._after()
         return self.target
 
+    def Export(self):
+        """Checkpoint: (running sum Color[w,h], frameCount) -- all the state Film carries (Film.fs:14-17)."""
+        s = np.zeros((self.scene.width, self.scene.height, 4), dtype=np.float64)
+        fc = C.c_double()
+        _lib.check(_lib.load().mfx_film_export(self._h, _lib.ptr(s), C.byref(fc)))
+        return s, fc.value
+
+    def Import(self, sum_wh, frame_count):
+        sum_wh = np.ascontiguousarray(sum_wh, dtype=np.float64)
+        _lib.check(_lib.load().mfx_film_import(self._h, _lib.ptr(sum_wh), float(frame_count)))
+
     def PostProcess(self):
         """Scene.PostProcessAndToScreenBuffer (Scene.fs:315-330) -> (height, width, 4) uint8."""
         out = np.zeros((self.scene.height, self.scene.width, 4), dtype=np.uint8)

@@ -391,3 +391,24 @@ def test_every_traversal_kernel_variant_gives_the_same_hits(monkeypatch, variant
     assert (p0 != p1).mean() <= 1e-4 and np.allclose(t0[p0 == p1], t1[p0 == p1], rtol=1e-6, atol=1e-7)
     # paths are deterministic given their hits: only pixels behind one of the rare tie-broken hits may change
     assert (img0 != img1).any(axis=2).mean() <= 5e-3
+
+
+def test_film_checkpoint_resume_is_exact():
+    desc = _desc("cornell", width=48, height=40)
+    s = Scene(desc)
+    integ = CudaPixelIntegrator(s, precision=EXACT_F64, seed=5)
+    a = Film(s)
+    for _ in range(4):
+        full = a.GetFrame(integ, 2).copy()
+    b = Film(s)
+    for _ in range(2):
+        b.GetFrame(integ, 2)
+    saved, count = b.Export()
+    assert count == 2.0
+    c = Film(Scene(desc))                      # a fresh process would do exactly this
+    c.Import(saved, count)
+    integ2 = CudaPixelIntegrator(c.scene, precision=EXACT_F64, seed=5)
+    for _ in range(2):
+        resumed = c.GetFrame(integ2, 2).copy()   # first_sample continues at frameCount * spp
+    assert np.array_equal(resumed, full)
+    assert np.array_equal(c.PostProcess(), a.PostProcess())
