@@ -403,11 +403,9 @@ __global__ void __launch_bounds__(FAST_BLOCK) k_f_trace5(SceneF sc, WaveF w, int
                     const float4 d = ANY ? w.sh_d[pid] : w.ray_d[pid];
                     r = make_ray_fast(f3(o.x, o.y, o.z), f3(d.x, d.y, d.z), w.tmin, __float_as_int(o.w));
                     best_t = ANY ? d.w - 1e-6f : d.w;                   // shadow: dist - 1e-6 (Integrators.fs:44); closest: tMax (:108)
-                    best_slot = -1; trail = 0ull; leafA = leafB = -1; h = 1u; depth = 0u;
-                    float e;
-                    const bool in = box_f(r, sc.root_min[0], sc.root_min[1], sc.root_min[2], sc.root_max[0], sc.root_max[1], sc.root_max[2], best_t, e);
-                    needPop = !in || sc.root_meta >= 0;
-                    if (in && sc.root_meta >= 0) leafA = sc.root_meta;
+                    // no root-box test: the root quad's four boxes lie inside it, a ray that misses the scene simply
+                    // finds no hit slot in its first node step and pops an empty trail (one-leaf trees never get here)
+                    best_slot = -1; trail = 0ull; leafA = leafB = -1; h = 1u; depth = 0u; needPop = false;
                 }
             }
             idle_now = __ballot_sync(FULL, pid < 0);
