@@ -78,8 +78,8 @@ __device__ __forceinline__ void pixel_of(const TileMap &tm, int width, int pl, i
 template <typename K>
 static inline int persistent_blocks(K kernel, int threads, int sms, size_t dyn_smem = 0)
 {
-    static std::map<const void *, int> cache;
-    const void *key = (const void *)kernel;
+    static std::map<std::pair<const void *, size_t>, int> cache;
+    const std::pair<const void *, size_t> key((const void *)kernel, dyn_smem);
     auto it = cache.find(key);
     if (it == cache.end()) {
         int occ = 0;

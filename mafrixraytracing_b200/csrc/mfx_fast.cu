@@ -496,6 +496,141 @@ __global__ void __launch_bounds__(FAST_BLOCK) k_f_trace5(SceneF sc, WaveF w, int
     }
 }
 
+// ---------------------------------------------------------------- own tree: SAH, four children per record, child links
+// Same warp organisation as k_f_trace5 (ray replacement, two node steps per iteration, vote-postponed
+// leaves, sorted 4-wide node step) over the library's own binned-SAH tree (SceneF.own_tree, built by
+// flatten_fast_own in mfx_host.cpp).  The tree is not heap-shaped, so the deferred hits go to a real stack:
+// 8-byte entries (sort key, record that holds the child) in shared memory [entry][thread]; trees deeper than the
+// shared-memory budget overflow into a per-thread global column.  A pop re-reads the child link (one 4-byte load
+// from a record the lane fetched a few steps earlier) instead of carrying it through the sorting network.
+template <bool ANY, bool BIG, int REFILL_T, int LEAF_T, int NSTEP>
+__global__ void __launch_bounds__(FAST_BLOCK) k_f_trace6(SceneF sc, WaveF w, int bounce)
+{
+    extern __shared__ uint2 s_stack[];              // [stack_smem][FAST_BLOCK]
+    uint2 *my_stack = s_stack + threadIdx.x;
+    const int S = sc.stack_smem;
+    uint2 *my_spill = sc.stack_spill + ((size_t)blockIdx.x * FAST_BLOCK + threadIdx.x);
+    const size_t spill_stride = (size_t)sc.spill_threads;
+    const unsigned FULL = 0xffffffffu;
+    const unsigned lane = threadIdx.x & 31u;
+    const int n = ANY ? w.counts[CNT_SH(bounce)] : w.counts[bounce];
+    const int *q = ANY ? w.q_sh : w.q_ext[bounce & 1];
+    int *cursor = &w.counts[ANY ? CUR_SH(bounce) : CUR_EXT(bounce)];
+
+    int pid = -1;
+    RayF r;
+    float best_t = 0.f; int best_slot = -1;
+    int node = 0, sp = 0;                           // current record, stack height
+    bool needPop = false;
+    int leafA = -1, leafB = -1; float eB = 0.f;
+    bool exhausted = false;
+    unsigned iters = 0u;
+
+    for (;;) {
+        const unsigned idle = __ballot_sync(FULL, pid < 0);
+        unsigned idle_now = idle;
+        if (++iters > (1u << 22)) { if (lane == 0) atomicAdd(&w.counts[MFX_COUNTS_LEN - 1], 1); break; }   // watchdog
+        if (!exhausted && __popc(idle) >= REFILL_T) {
+            const int nidle = __popc(idle);
+            int base = 0;
+            if (lane == 0) base = atomicAdd(cursor, nidle);
+            base = __shfl_sync(FULL, base, 0);
+            if (base + nidle >= n) exhausted = true;
+            if (pid < 0) {
+                const int idx = base + __popc(idle & ((1u << lane) - 1u));
+                if (idx < n) {
+                    pid = q[idx];
+                    const float4 o = w.ray_o[pid];
+                    const float4 d = ANY ? w.sh_d[pid] : w.ray_d[pid];
+                    r = make_ray_fast(f3(o.x, o.y, o.z), f3(d.x, d.y, d.z), w.tmin, __float_as_int(o.w));
+                    best_t = ANY ? d.w - 1e-6f : d.w;                   // shadow: dist - 1e-6 (Integrators.fs:44); closest: tMax (:108)
+                    best_slot = -1; sp = 0; leafA = leafB = -1; node = 0; needPop = false;
+                }
+            }
+            idle_now = __ballot_sync(FULL, pid < 0);
+        }
+        if (idle_now == FULL) { if (exhausted) break; continue; }
+
+#pragma unroll
+        for (int rep = 0; rep < NSTEP; rep++)
+        if (pid >= 0 && leafA < 0 && !needPop) {
+            const QuadF *qp = sc.quads + node;
+            const float4 lox = ldg4(&qp->lox), hix = ldg4(&qp->hix), loy = ldg4(&qp->loy), hiy = ldg4(&qp->hiy);
+            const float4 loz = ldg4(&qp->loz), hiz = ldg4(&qp->hiz), m4 = ldg4(&qp->meta);
+            unsigned key[4];
+#define QUAD_SLOT(S_, C)                                                                                             \
+            {                                                                                                        \
+                const float x0 = fmaf(lox.C, r.idir.x, -r.ood.x), x1 = fmaf(hix.C, r.idir.x, -r.ood.x);              \
+                const float y0 = fmaf(loy.C, r.idir.y, -r.ood.y), y1 = fmaf(hiy.C, r.idir.y, -r.ood.y);              \
+                const float z0 = fmaf(loz.C, r.idir.z, -r.ood.z), z1 = fmaf(hiz.C, r.idir.z, -r.ood.z);              \
+                const float tn = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fmaxf(fminf(z0, z1), r.tmin));           \
+                const float tf = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fminf(fmaxf(z0, z1), best_t));           \
+                const int mt = __float_as_int(m4.C);                                                                 \
+                key[S_] = (tn <= tf && mt != MFX_QUAD_EMPTY) ? ((__float_as_uint(tn) & ~7u) | (mt >= 0 ? 4u : 0u) | (unsigned)S_) : KEY_INF; \
+            }
+            QUAD_SLOT(0, x) QUAD_SLOT(1, y) QUAD_SLOT(2, z) QUAD_SLOT(3, w)
+#undef QUAD_SLOT
+            // sorting network (0,1)(2,3)(0,2)(1,3)(1,2)
+            unsigned a0 = umin_(key[0], key[1]), a1 = umax_(key[0], key[1]);
+            unsigned a2 = umin_(key[2], key[3]), a3 = umax_(key[2], key[3]);
+            const unsigned k0 = umin_(a0, a2), t2 = umax_(a0, a2);
+            const unsigned t1 = umin_(a1, a3), k3 = umax_(a1, a3);
+            const unsigned k1 = umin_(t1, t2), k2 = umax_(t1, t2);
+            const bool any0 = k0 != KEY_INF;
+            const bool leaf0 = any0 && (k0 & 4u), leaf1 = leaf0 && (k1 != KEY_INF) && (k1 & 4u);
+            const int c0 = pick4(m4, k0 & 3u);
+            leafA = leaf0 ? c0 : -1;
+            leafB = leaf1 ? pick4(m4, k1 & 3u) : -1;
+            eB = __uint_as_float(k1 & ~7u);
+            // deferred hits: everything behind the one(s) consumed now, nearest on top of the stack
+            const unsigned p0 = leaf1 ? k2 : k1, p1 = leaf1 ? k3 : k2, p2 = leaf1 ? KEY_INF : k3;
+            const int m = (p0 != KEY_INF ? 1 : 0) + (p1 != KEY_INF ? 1 : 0) + (p2 != KEY_INF ? 1 : 0);
+#define STACK_PUT(I, K)                                                                                              \
+            { const int i_ = (I); const uint2 v_ = make_uint2((K), (unsigned)node);                                  \
+              if (i_ < S) my_stack[(size_t)i_ * FAST_BLOCK] = v_; else my_spill[(size_t)(i_ - S) * spill_stride] = v_; }
+            if (m >= 1) STACK_PUT(sp + m - 1, p0)
+            if (m >= 2) STACK_PUT(sp + m - 2, p1)
+            if (m >= 3) STACK_PUT(sp, p2)
+#undef STACK_PUT
+            sp += m;
+            const bool descend = any0 && !leaf0;
+            needPop = !descend;
+            if (descend) node = ~c0;
+        }
+        bool finished = false;
+        const unsigned lp = __ballot_sync(FULL, pid >= 0 && leafA >= 0);
+        if (lp) {
+            const unsigned nd = ~idle_now & ~lp;
+            if (__popc(lp) >= LEAF_T || nd == 0u) {
+                if (pid >= 0 && leafA >= 0) {
+                    bool found = leaf_f3<false, BIG>(sc, r, leafA, best_t, best_slot, nullptr);
+                    if (leafB >= 0 && !(ANY && found) && eB <= best_t) found |= leaf_f3<false, BIG>(sc, r, leafB, best_t, best_slot, nullptr);
+                    leafA = leafB = -1;
+                    if (ANY && found) finished = true;
+                }
+            }
+        }
+        if (pid >= 0 && needPop && leafA < 0 && !finished) {
+            for (;;) {
+                if (sp == 0) { finished = true; break; }
+                --sp;
+                const uint2 e = (sp < S) ? my_stack[(size_t)sp * FAST_BLOCK] : my_spill[(size_t)(sp - S) * spill_stride];
+                if (ANY || __uint_as_float(e.x & ~7u) <= best_t) {
+                    const int link = __ldg(reinterpret_cast<const int *>(&sc.quads[e.y].meta) + (e.x & 3u));
+                    if (e.x & 4u) { leafA = link; leafB = -1; }
+                    else { node = ~link; needPop = false; }
+                    break;
+                }
+            }
+        }
+        if (finished) {
+            if (!ANY) w.hit[pid] = make_float2(best_t, __int_as_float(best_slot));
+            else if (best_slot < 0) { const float4 c = w.sh_c[pid]; float4 a = w.rad[pid]; a.x += c.x; a.y += c.y; a.z += c.z; w.rad[pid] = a; }
+            pid = -1;
+        }
+    }
+}
+
 struct RngF { uint32_t pixel, sample, k0, k1; };
 
 // GetRandomInUnitSphere (Material.fs:9-14) on the f32 view of the same Philox stream.
@@ -709,7 +844,7 @@ __global__ void __launch_bounds__(256) k_f_seam_read(SceneF sc, WaveF w, int n, 
         if (slot < 0) { prim[r] = -1; if (sub) sub[r] = 0; t[r] = 0.; }
         else {
             const int ps = __float_as_int(sc.slots[slot].b.w);
-            prim[r] = sc.ref_id[ps & 0x3fffffff];
+            prim[r] = sc.ref_id ? sc.ref_id[ps & 0x3fffffff] : (ps & 0x3fffffff);
             if (sub) sub[r] = (ps >> 30) & 1;
             t[r] = (double)h.x;
         }
@@ -804,9 +939,33 @@ static void launch_trace5(const LaunchCfg &c, const SceneF &sc, const WaveF &w, 
     if (sc.has_big_sphere) launch_trace5b<ANY, true, RT, LT, NS>(c, sc, w, bounce);
     else launch_trace5b<ANY, false, RT, LT, NS>(c, sc, w, bounce);
 }
+template <bool ANY, bool BIG, int RT, int LT, int NS>
+static void launch_trace6b(const LaunchCfg &c, const SceneF &sc, const WaveF &w, int bounce)
+{
+    const size_t smem = (size_t)sc.stack_smem * FAST_BLOCK * sizeof(uint2);
+    // the spill columns were sized for spill_threads: never launch more threads than that
+    int blocks = persistent_blocks(k_f_trace6<ANY, BIG, RT, LT, NS>, FAST_BLOCK, c.blocks, smem);
+    if (sc.stack_spill && blocks * FAST_BLOCK > sc.spill_threads) blocks = sc.spill_threads / FAST_BLOCK;
+    k_f_trace6<ANY, BIG, RT, LT, NS><<<blocks, FAST_BLOCK, smem, c.stream>>>(sc, w, bounce);
+}
+template <bool ANY, int RT, int LT, int NS>
+static void launch_trace6(const LaunchCfg &c, const SceneF &sc, const WaveF &w, int bounce)
+{
+    if (sc.has_big_sphere) launch_trace6b<ANY, true, RT, LT, NS>(c, sc, w, bounce);
+    else launch_trace6b<ANY, false, RT, LT, NS>(c, sc, w, bounce);
+}
 template <bool ANY>
 static void launch_trace_variant(const LaunchCfg &c, const SceneF &sc, const WaveF &w, int bounce, TravCounters *ctr)
 {
+    if (sc.own_tree) {          // the library's SAH tree (default); the host passes the reference-tree layout for the others
+        switch (c.variant) {
+        case 61: launch_trace6<ANY, 8, 12, 2>(c, sc, w, bounce); break;
+        case 62: launch_trace6<ANY, 12, 16, 1>(c, sc, w, bounce); break;
+        case 63: launch_trace6<ANY, 16, 20, 2>(c, sc, w, bounce); break;
+        default: launch_trace6<ANY, 12, 16, 2>(c, sc, w, bounce); break;
+        }
+        return;
+    }
     switch (c.variant) {        // tuning knob (MFX_TRACE_VARIANT); the default comes from measurements (profiles/)
     case 4: launch_trace4<ANY, 12, 16, 2>(c, sc, w, bounce, ctr); break;     // binary steps (one 64 B pair per fetch)
     case 51: launch_trace5<ANY, 8, 12, 2>(c, sc, w, bounce, ctr); break;

@@ -8,6 +8,7 @@
 #include "mfx_internal.h"
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -247,9 +248,10 @@ struct MfxScene {
     int width = 0, height = 0, max_depth = 0, integrator = 0;
 
     std::vector<std::pair<void *, size_t>> allocs;   // every device buffer of this scene
-    bool x_ready = false, f_ready = false, wx_ready = false, wf_ready = false;
-    SceneX sx; SceneF sf; WaveX wx; WaveF wf;
-    uint64_t x_bytes = 0, f_bytes = 0;
+    bool x_ready = false, f_ready = false, fr_ready = false, wx_ready = false, wf_ready = false;
+    SceneX sx; SceneF sf; SceneF sf_ref; WaveX wx; WaveF wf;     // sf: own SAH tree; sf_ref: reference-tree layout
+    uint64_t x_bytes = 0, f_bytes = 0, fr_bytes = 0;
+    MatF *d_matf = nullptr;
     double *d_pixsum = nullptr;          // [w*h][4] row-major sums
     double *d_color_wh = nullptr;        // Color[w,h]
     float4 *d_rgba = nullptr;            // row-major float4 (internal, when the caller gives none)
@@ -457,50 +459,92 @@ static float round_up(double x)
 }
 static float int_bits(int v) { float f; memcpy(&f, &v, 4); return f; }
 
-static int flatten_fast(MfxScene *s)
+// Materials, light, camera and frame constants shared by both fast layouts.
+static int fill_fast_common(MfxScene *s, SceneF &sf)
 {
-    if (s->f_ready) return MFX_OK;
+    if (!s->d_matf) {
+        std::vector<MatF> mats(s->mats.size());
+        for (size_t i = 0; i < mats.size(); i++) {
+            for (int a = 0; a < 3; a++) mats[i].albedo[a] = (float)s->mats[i].albedo[a];
+            mats[i].kind = s->mats[i].kind; mats[i].fuzz = (float)s->mats[i].fuzz;
+            mats[i].ei = (float)s->mats[i].ei; mats[i].et = (float)s->mats[i].et; mats[i].pad = 0.f;
+        }
+        MFX_TRY(upload(s, &s->d_matf, mats));
+    }
+    sf.mats = s->d_matf;
+    const double *lp = s->light.p;
+    H3 p0 = hld(lp), p1 = hld(lp + 3), p2 = hld(lp + 6), p3 = hld(lp + 9);
+    H3 e;
+    for (int a = 0; a < 3; a++) { sf.light.v0a[a] = (float)lp[a]; sf.light.v0b[a] = (float)lp[a]; }
+    e = hsub(p1, p0); sf.light.e1a[0] = (float)e.x; sf.light.e1a[1] = (float)e.y; sf.light.e1a[2] = (float)e.z;
+    e = hsub(p2, p0); sf.light.e2a[0] = (float)e.x; sf.light.e2a[1] = (float)e.y; sf.light.e2a[2] = (float)e.z;
+    sf.light.e1b[0] = (float)e.x; sf.light.e1b[1] = (float)e.y; sf.light.e1b[2] = (float)e.z;
+    e = hsub(p3, p0); sf.light.e2b[0] = (float)e.x; sf.light.e2b[1] = (float)e.y; sf.light.e2b[2] = (float)e.z;
+    const double area = tri_area(p0, p1, p2) + tri_area(p0, p2, p3);
+    sf.light.area = (float)area; sf.light.inv_pdf = (float)area;
+    for (int a = 0; a < 3; a++) { sf.light.normal[a] = (float)s->light.normal[a]; sf.light.color[a] = (float)s->light.color[a]; }
+    for (int a = 0; a < 3; a++) {
+        sf.cam.pos[a] = (float)s->camera.pos[a]; sf.cam.topleft[a] = (float)s->camera.topleft[a];
+        sf.cam.right[a] = (float)s->camera.right[a]; sf.cam.down[a] = (float)s->camera.down[a];
+    }
+    memcpy(sf.camx.pos, s->camera.pos, 24); memcpy(sf.camx.topleft, s->camera.topleft, 24);
+    memcpy(sf.camx.right, s->camera.right, 24); memcpy(sf.camx.down, s->camera.down, 24);
+    sf.width = s->width; sf.height = s->height; sf.max_depth = s->max_depth; sf.mode = s->integrator;
+    return MFX_OK;
+}
+
+// Fast slots of one primitive: a Rect becomes its two triangles (Rect.fs:17-19).  `id` (< 2^30) is what a ray that
+// starts on the primitive carries to avoid re-hitting it; bit 30 of b.w tells the two halves of a Rect apart.
+static void make_fast_slots(const MfxPrim &p, int id, std::vector<SlotF> &slots, std::vector<float4> &nrm, int &has_big)
+{
+    if (p.kind == MFX_SPHERE) {
+        SlotF f; memset(&f, 0, sizeof(f));
+        if (std::fabs(p.v[3]) >= 32.0) {
+            has_big = 1;
+            // big sphere: centre and radius kept as f64 bit pairs, solved in f64 by the kernel
+            auto lo = [](double x) { uint64_t u; memcpy(&u, &x, 8); return int_bits((int)(uint32_t)u); };
+            auto hi = [](double x) { uint64_t u; memcpy(&u, &x, 8); return int_bits((int)(uint32_t)(u >> 32)); };
+            f.a = make_float4(lo(p.v[3]), hi(p.v[3]), 0.f, int_bits(3));
+            f.b = make_float4(lo(p.v[0]), hi(p.v[0]), 0.f, int_bits(id));
+            f.c = make_float4(lo(p.v[1]), hi(p.v[1]), lo(p.v[2]), hi(p.v[2]));
+        } else {
+            f.a = make_float4((float)p.v[0], (float)p.v[1], (float)p.v[2], int_bits(2));
+            f.b = make_float4((float)p.v[3], (float)(p.v[3] * p.v[3]), 0.f, int_bits(id));
+        }
+        slots.push_back(f);
+        nrm.push_back(make_float4(0.f, 0.f, 0.f, int_bits(p.material)));
+        return;
+    }
+    const int ntri = (p.kind == MFX_RECT) ? 2 : 1;
+    for (int k = 0; k < ntri; k++) {
+        H3 v0 = hld(p.v), v1 = hld(p.v + 3 * (1 + k)), v2 = hld(p.v + 3 * (2 + k));
+        H3 e1 = hsub(v1, v0), e2 = hsub(v2, v0);
+        H3 a = hcross(e1, e2);
+        double al = hlen(a);
+        H3 nm = h3(a.x / al, a.y / al, a.z / al);       // Trangle.fs:110-112
+        SlotF f; memset(&f, 0, sizeof(f));
+        f.a = make_float4((float)v0.x, (float)v0.y, (float)v0.z, int_bits(0));
+        f.b = make_float4((float)e1.x, (float)e1.y, (float)e1.z, int_bits(id | (k << 30)));
+        f.c = make_float4((float)e2.x, (float)e2.y, (float)e2.z, 0.f);
+        slots.push_back(f);
+        nrm.push_back(make_float4((float)nm.x, (float)nm.y, (float)nm.z, int_bits(p.material)));
+    }
+}
+
+// Reference-tree layout (children pairs + heap-indexed quads): used by the instrumented counting runs (the roofline's
+// record counts are defined on the reference tree) and by the k_f_trace4 / k_f_trace5 variants.
+static int flatten_fast_ref(MfxScene *s)
+{
+    if (s->fr_ready) return MFX_OK;
     const int n = (int)s->prims.size();
-    // fast slots in leaf order; a Rect becomes its two triangles (Rect.fs:17-19)
+    // fast slots in leaf order
     std::vector<SlotF> slots; std::vector<float4> nrm; std::vector<int> ffirst(n + 1), ref(n);
     int has_big = 0;
     slots.reserve(n); nrm.reserve(n);
     for (int slot = 0; slot < n; slot++) {
-        const MfxPrim &p = s->prims[s->indices[slot]];
         ref[slot] = s->indices[slot];
         ffirst[slot] = (int)slots.size();
-        if (p.kind == MFX_SPHERE) {
-            SlotF f; memset(&f, 0, sizeof(f));
-            if (std::fabs(p.v[3]) >= 32.0) {
-                has_big = 1;
-                // big sphere: centre and radius kept as f64 bit pairs, solved in f64 by the kernel
-                auto lo = [](double x) { uint64_t u; memcpy(&u, &x, 8); return int_bits((int)(uint32_t)u); };
-                auto hi = [](double x) { uint64_t u; memcpy(&u, &x, 8); return int_bits((int)(uint32_t)(u >> 32)); };
-                f.a = make_float4(lo(p.v[3]), hi(p.v[3]), 0.f, int_bits(3));
-                f.b = make_float4(lo(p.v[0]), hi(p.v[0]), 0.f, int_bits(slot));
-                f.c = make_float4(lo(p.v[1]), hi(p.v[1]), lo(p.v[2]), hi(p.v[2]));
-            } else {
-                f.a = make_float4((float)p.v[0], (float)p.v[1], (float)p.v[2], int_bits(2));
-                f.b = make_float4((float)p.v[3], (float)(p.v[3] * p.v[3]), 0.f, int_bits(slot));
-            }
-            slots.push_back(f);
-            nrm.push_back(make_float4(0.f, 0.f, 0.f, int_bits(p.material)));
-        } else {
-            const int ntri = (p.kind == MFX_RECT) ? 2 : 1;
-            for (int k = 0; k < ntri; k++) {
-                H3 v0 = hld(p.v), v1 = hld(p.v + 3 * (1 + k)), v2 = hld(p.v + 3 * (2 + k));
-                H3 e1 = hsub(v1, v0), e2 = hsub(v2, v0);
-                H3 a = hcross(e1, e2);
-                double al = hlen(a);
-                H3 nm = h3(a.x / al, a.y / al, a.z / al);       // Trangle.fs:110-112
-                SlotF f; memset(&f, 0, sizeof(f));
-                f.a = make_float4((float)v0.x, (float)v0.y, (float)v0.z, int_bits(0));
-                f.b = make_float4((float)e1.x, (float)e1.y, (float)e1.z, int_bits(slot | (k << 30)));
-                f.c = make_float4((float)e2.x, (float)e2.y, (float)e2.z, 0.f);
-                slots.push_back(f);
-                nrm.push_back(make_float4((float)nm.x, (float)nm.y, (float)nm.z, int_bits(p.material)));
-            }
-        }
+        make_fast_slots(s->prims[s->indices[slot]], slot, slots, nrm, has_big);
     }
     ffirst[n] = (int)slots.size();
     auto leaf_meta = [&](const MfxBvhNode &nd) {
@@ -509,7 +553,7 @@ static int flatten_fast(MfxScene *s)
     };
     // children pairs, indexed by the interior node's heap index
     std::vector<PairF> pairs;
-    SceneF &sf = s->sf;
+    SceneF &sf = s->sf_ref;
     memset(&sf, 0, sizeof(sf));
     const MfxBvhNode &root = s->nodes[0];
     for (int a = 0; a < 3; a++) { sf.root_min[a] = round_down(root.pmin[a]); sf.root_max[a] = round_up(root.pmax[a]); }
@@ -600,41 +644,271 @@ static int flatten_fast(MfxScene *s)
             q.meta = make_float4(int_bits(meta[0]), int_bits(meta[1]), int_bits(meta[2]), int_bits(meta[3]));
         }
     }
-    std::vector<MatF> mats(s->mats.size());
-    for (size_t i = 0; i < mats.size(); i++) {
-        for (int a = 0; a < 3; a++) mats[i].albedo[a] = (float)s->mats[i].albedo[a];
-        mats[i].kind = s->mats[i].kind; mats[i].fuzz = (float)s->mats[i].fuzz;
-        mats[i].ei = (float)s->mats[i].ei; mats[i].et = (float)s->mats[i].et; mats[i].pad = 0.f;
-    }
-    PairF *dpairs; SlotF *dslots; float4 *dnrm; int *dref; MatF *dm; QuadF *dquads;
+    PairF *dpairs; SlotF *dslots; float4 *dnrm; int *dref; QuadF *dquads;
     MFX_TRY(upload(s, &dquads, quads));
     MFX_TRY(upload(s, &dpairs, pairs)); MFX_TRY(upload(s, &dslots, slots)); MFX_TRY(upload(s, &dnrm, nrm));
-    MFX_TRY(upload(s, &dref, ref)); MFX_TRY(upload(s, &dm, mats));
-    s->f_bytes = quads.size() * sizeof(QuadF) + pairs.size() * sizeof(PairF) + slots.size() * sizeof(SlotF) + nrm.size() * 16 + ref.size() * 4 + mats.size() * sizeof(MatF);
+    MFX_TRY(upload(s, &dref, ref));
+    s->fr_bytes = quads.size() * sizeof(QuadF) + pairs.size() * sizeof(PairF) + slots.size() * sizeof(SlotF) + nrm.size() * 16 + ref.size() * 4;
     sf.quads = dquads; sf.qlevels = qlevels; sf.qpar = qpar;
-    sf.pairs = dpairs; sf.slots = dslots; sf.slot_nrm = dnrm; sf.ref_id = dref; sf.slot_prim = nullptr; sf.mats = dm;
-    const double *lp = s->light.p;
-    H3 p0 = hld(lp), p1 = hld(lp + 3), p2 = hld(lp + 6), p3 = hld(lp + 9);
-    H3 e;
-    for (int a = 0; a < 3; a++) { sf.light.v0a[a] = (float)lp[a]; sf.light.v0b[a] = (float)lp[a]; }
-    e = hsub(p1, p0); sf.light.e1a[0] = (float)e.x; sf.light.e1a[1] = (float)e.y; sf.light.e1a[2] = (float)e.z;
-    e = hsub(p2, p0); sf.light.e2a[0] = (float)e.x; sf.light.e2a[1] = (float)e.y; sf.light.e2a[2] = (float)e.z;
-    sf.light.e1b[0] = (float)e.x; sf.light.e1b[1] = (float)e.y; sf.light.e1b[2] = (float)e.z;
-    e = hsub(p3, p0); sf.light.e2b[0] = (float)e.x; sf.light.e2b[1] = (float)e.y; sf.light.e2b[2] = (float)e.z;
-    const double area = tri_area(p0, p1, p2) + tri_area(p0, p2, p3);
-    sf.light.area = (float)area; sf.light.inv_pdf = (float)area;
-    for (int a = 0; a < 3; a++) { sf.light.normal[a] = (float)s->light.normal[a]; sf.light.color[a] = (float)s->light.color[a]; }
-    for (int a = 0; a < 3; a++) {
-        sf.cam.pos[a] = (float)s->camera.pos[a]; sf.cam.topleft[a] = (float)s->camera.topleft[a];
-        sf.cam.right[a] = (float)s->camera.right[a]; sf.cam.down[a] = (float)s->camera.down[a];
-    }
-    memcpy(sf.camx.pos, s->camera.pos, 24); memcpy(sf.camx.topleft, s->camera.topleft, 24);
-    memcpy(sf.camx.right, s->camera.right, 24); memcpy(sf.camx.down, s->camera.down, 24);
-    sf.width = s->width; sf.height = s->height; sf.max_depth = s->max_depth; sf.mode = s->integrator;
+    sf.pairs = dpairs; sf.slots = dslots; sf.slot_nrm = dnrm; sf.ref_id = dref; sf.slot_prim = nullptr;
+    MFX_TRY(fill_fast_common(s, sf));
     sf.n_slots = (int)slots.size();
     sf.has_big_sphere = has_big;
     { int depth = 0; for (unsigned v = (unsigned)max_interior + 1u; v > 1u; v >>= 1) depth++; sf.levels = depth + 2; }
+    s->fr_ready = true;
+    return MFX_OK;
+}
+
+// ---- flatten: fast layout over the library's own tree (binned SAH, collapsed to four children per record)
+struct SahNode { float lo[3], hi[3]; int left, right, first, count; };   // count > 0: leaf over order[first .. first+count)
+struct SahCtx {
+    const float (*lo)[3]; const float (*hi)[3];
+    int *idx;
+    SahNode *nodes;
+    std::atomic<int> next{ 0 };
+    int max_leaf;
+    float c_trav;       // cost of one node step relative to one primitive test
+};
+static inline float half_area(const float *lo, const float *hi)
+{
+    const float x = hi[0] - lo[0], y = hi[1] - lo[1], z = hi[2] - lo[2];
+    return x * y + y * z + z * x;
+}
+static inline void grow(float *lo, float *hi, const float *blo, const float *bhi)
+{
+    for (int a = 0; a < 3; a++) { lo[a] = std::min(lo[a], blo[a]); hi[a] = std::max(hi[a], bhi[a]); }
+}
+static const float SAH_INF = 3.0e38f;
+
+// Splits idx[first .. first+count) by the surface-area heuristic; returns the size of the left part (0 = keep as leaf).
+static int sah_split(SahCtx &c, const SahNode &nd)
+{
+    const int first = nd.first, count = nd.count;
+    const float area = half_area(nd.lo, nd.hi);
+    const float leaf_cost = (float)count;                    // in units of (node area x primitive test)
+    float best = SAH_INF; int best_axis = -1, best_pos = -1;
+    float clo[3] = { SAH_INF, SAH_INF, SAH_INF }, chi[3] = { -SAH_INF, -SAH_INF, -SAH_INF };
+    for (int k = 0; k < count; k++) {
+        const int id = c.idx[first + k];
+        for (int a = 0; a < 3; a++) { const float ce = 0.5f * (c.lo[id][a] + c.hi[id][a]); clo[a] = std::min(clo[a], ce); chi[a] = std::max(chi[a], ce); }
+    }
+    const float inv_area = area > 0.f ? 1.0f / area : 0.f;
+    if (count <= 24) {
+        // exact sweep: sort by centroid on each axis, try every split position
+        std::vector<std::pair<float, int>> key(count);
+        std::vector<float> right(count);
+        std::vector<int> best_order;
+        for (int ax = 0; ax < 3; ax++) {
+            for (int k = 0; k < count; k++) { const int id = c.idx[first + k]; key[k] = { c.lo[id][ax] + c.hi[id][ax], id }; }
+            std::stable_sort(key.begin(), key.end(), [](const std::pair<float, int> &x, const std::pair<float, int> &y) { return x.first < y.first; });
+            float lo[3] = { SAH_INF, SAH_INF, SAH_INF }, hi[3] = { -SAH_INF, -SAH_INF, -SAH_INF };
+            for (int k = count - 1; k > 0; k--) { grow(lo, hi, c.lo[key[k].second], c.hi[key[k].second]); right[k] = half_area(lo, hi); }
+            for (int a = 0; a < 3; a++) { lo[a] = SAH_INF; hi[a] = -SAH_INF; }
+            bool improved = false;
+            for (int k = 1; k < count; k++) {
+                grow(lo, hi, c.lo[key[k - 1].second], c.hi[key[k - 1].second]);
+                const float cost = c.c_trav + (half_area(lo, hi) * k + right[k] * (count - k)) * inv_area;
+                if (cost < best) { best = cost; best_axis = ax; best_pos = k; improved = true; }
+            }
+            if (improved) { best_order.resize(count); for (int k = 0; k < count; k++) best_order[k] = key[k].second; }
+        }
+        if (best_axis < 0 || (count <= c.max_leaf && leaf_cost <= best)) return count <= c.max_leaf ? 0 : count / 2;
+        for (int k = 0; k < count; k++) c.idx[first + k] = best_order[k];
+        return best_pos;
+    }
+    // binned: 32 centroid bins per axis
+    const int NB = 32;
+    int best_bin = -1;
+    for (int ax = 0; ax < 3; ax++) {
+        const float ext = chi[ax] - clo[ax];
+        if (!(ext > 0.f)) continue;
+        const float scale = (float)NB * (1.0f - 1e-6f) / ext;
+        float blo[NB][3], bhi[NB][3]; int bn[NB];
+        for (int b = 0; b < NB; b++) { bn[b] = 0; for (int a = 0; a < 3; a++) { blo[b][a] = SAH_INF; bhi[b][a] = -SAH_INF; } }
+        for (int k = 0; k < count; k++) {
+            const int id = c.idx[first + k];
+            int b = (int)((0.5f * (c.lo[id][ax] + c.hi[id][ax]) - clo[ax]) * scale);
+            b = b < 0 ? 0 : (b >= NB ? NB - 1 : b);
+            bn[b]++; grow(blo[b], bhi[b], c.lo[id], c.hi[id]);
+        }
+        float right[NB]; int rn[NB];
+        float lo[3] = { SAH_INF, SAH_INF, SAH_INF }, hi[3] = { -SAH_INF, -SAH_INF, -SAH_INF };
+        int cnt = 0;
+        for (int b = NB - 1; b > 0; b--) { if (bn[b]) grow(lo, hi, blo[b], bhi[b]); cnt += bn[b]; right[b] = cnt ? half_area(lo, hi) : 0.f; rn[b] = cnt; }
+        for (int a = 0; a < 3; a++) { lo[a] = SAH_INF; hi[a] = -SAH_INF; }
+        cnt = 0;
+        for (int b = 1; b < NB; b++) {
+            if (bn[b - 1]) grow(lo, hi, blo[b - 1], bhi[b - 1]);
+            cnt += bn[b - 1];
+            if (cnt == 0 || rn[b] == 0) continue;
+            const float cost = c.c_trav + (half_area(lo, hi) * cnt + right[b] * rn[b]) * inv_area;
+            if (cost < best) { best = cost; best_axis = ax; best_bin = b; }
+        }
+    }
+    if (best_axis < 0) {
+        // all centroids coincide: nothing to choose between, cut the list in half
+        return count / 2;
+    }
+    const float scale = (float)NB * (1.0f - 1e-6f) / (chi[best_axis] - clo[best_axis]);
+    int *mid = std::partition(c.idx + first, c.idx + first + count, [&](int id) {
+        int b = (int)((0.5f * (c.lo[id][best_axis] + c.hi[id][best_axis]) - clo[best_axis]) * scale);
+        b = b < 0 ? 0 : (b >= NB ? NB - 1 : b);
+        return b < best_bin;
+    });
+    const int left = (int)(mid - (c.idx + first));
+    return (left == 0 || left == count) ? count / 2 : left;
+}
+
+static void sah_bound(const SahCtx &c, SahNode &nd)
+{
+    for (int a = 0; a < 3; a++) { nd.lo[a] = SAH_INF; nd.hi[a] = -SAH_INF; }
+    for (int k = 0; k < nd.count; k++) grow(nd.lo, nd.hi, c.lo[c.idx[nd.first + k]], c.hi[c.idx[nd.first + k]]);
+}
+
+// Builds the subtree of node `root` (its first/count/bounds are set).  Disjoint ranges => the top levels fork.
+static void sah_build(SahCtx &c, int root, int par_depth)
+{
+    std::vector<int> todo{ root };
+    std::vector<std::future<void>> spawned;
+    while (!todo.empty()) {
+        const int i = todo.back(); todo.pop_back();
+        SahNode nd = c.nodes[i];
+        if (nd.count <= 1) continue;
+        const int left = sah_split(c, nd);
+        if (left == 0) continue;                                 // stays a leaf
+        const int li = c.next.fetch_add(2), ri = li + 1;
+        SahNode &L = c.nodes[li], &R = c.nodes[ri];
+        L.first = nd.first; L.count = left; L.left = L.right = -1;
+        R.first = nd.first + left; R.count = nd.count - left; R.left = R.right = -1;
+        sah_bound(c, L); sah_bound(c, R);
+        c.nodes[i].left = li; c.nodes[i].right = ri; c.nodes[i].count = 0;
+        if (par_depth > 0 && i == root && nd.count > (1 << 15)) {
+            spawned.push_back(std::async(std::launch::async, [&c, li, par_depth]() { sah_build(c, li, par_depth - 1); }));
+            root = ri; par_depth--;
+            todo.push_back(ri);
+        } else {
+            todo.push_back(ri); todo.push_back(li);
+        }
+    }
+    for (auto &f : spawned) f.get();
+}
+
+static int flatten_fast(MfxScene *s)
+{
+    if (s->f_ready) return MFX_OK;
+    const int n = (int)s->prims.size();
+    std::vector<SlotF> raw; std::vector<float4> raw_nrm;
+    int has_big = 0;
+    raw.reserve(n); raw_nrm.reserve(n);
+    std::vector<int> owner;                                     // raw slot -> primitive
+    owner.reserve(n);
+    for (int i = 0; i < n; i++) {
+        const size_t before = raw.size();
+        make_fast_slots(s->prims[i], i, raw, raw_nrm, has_big);
+        for (size_t k = before; k < raw.size(); k++) owner.push_back(i);
+    }
+    const int ns = (int)raw.size();
+    // slot bounds, rounded outward from the f64 vertices
+    std::vector<float> blo((size_t)ns * 3), bhi((size_t)ns * 3);
+    for (int k = 0; k < ns; k++) {
+        const MfxPrim &p = s->prims[owner[k]];
+        double lo[3], hi[3];
+        if (p.kind == MFX_SPHERE) {
+            for (int a = 0; a < 3; a++) { lo[a] = p.v[a] - std::fabs(p.v[3]); hi[a] = p.v[a] + std::fabs(p.v[3]); }
+        } else {
+            const int sub = (p.kind == MFX_RECT && k > 0 && owner[k - 1] == owner[k]) ? 1 : 0;
+            const double *v[3] = { p.v, p.v + 3 * (1 + sub), p.v + 3 * (2 + sub) };
+            for (int a = 0; a < 3; a++) { lo[a] = std::min(v[0][a], std::min(v[1][a], v[2][a])); hi[a] = std::max(v[0][a], std::max(v[1][a], v[2][a])); }
+        }
+        for (int a = 0; a < 3; a++) { blo[(size_t)k * 3 + a] = round_down(lo[a]); bhi[(size_t)k * 3 + a] = round_up(hi[a]); }
+    }
+    std::vector<int> idx(ns);
+    for (int k = 0; k < ns; k++) idx[k] = k;
+    std::vector<SahNode> nodes((size_t)2 * ns + 2);
+    SahCtx c;
+    c.lo = reinterpret_cast<const float (*)[3]>(blo.data()); c.hi = reinterpret_cast<const float (*)[3]>(bhi.data());
+    c.idx = idx.data(); c.nodes = nodes.data(); c.next = 1;
+    c.max_leaf = (int)std::min(7L, std::max(1L, env_long("MFX_SAH_MAX_LEAF", 4)));
+    c.c_trav = (float)env_long("MFX_SAH_TRAV_COST_PCT", 100) * 0.01f;
+    nodes[0].first = 0; nodes[0].count = ns; nodes[0].left = nodes[0].right = -1;
+    sah_bound(c, nodes[0]);
+    sah_build(c, 0, (int)env_long("MFX_BVH_BUILD_PAR_DEPTH", 5));
+
+    // collapse to four children per record, depth-first; leaves of a record get consecutive slots
+    std::vector<QuadF> quads;
+    std::vector<int> order; order.reserve(ns);
+    int own_depth = 0;
+    struct Item { int bnode; int level; int parent; int pslot; };
+    std::vector<Item> todo{ { 0, 0, -1, 0 } };
+    quads.reserve((size_t)ns / 2 + 4);
+    const float FAR = 1e30f;
+    while (!todo.empty()) {
+        const Item it = todo.back(); todo.pop_back();
+        const int qi = (int)quads.size();
+        if (it.parent >= 0) reinterpret_cast<int *>(&quads[it.parent].meta)[it.pslot] = ~qi;
+        own_depth = std::max(own_depth, it.level + 1);
+        int kids[4], nk = 0;
+        if (nodes[it.bnode].count > 0) kids[nk++] = it.bnode;           // a one-leaf tree: the root record holds it
+        else { kids[nk++] = nodes[it.bnode].left; kids[nk++] = nodes[it.bnode].right; }
+        while (nk < 4) {
+            int pick = -1; float pa = -1.f;
+            for (int k = 0; k < nk; k++) if (nodes[kids[k]].count == 0) { const float ar = half_area(nodes[kids[k]].lo, nodes[kids[k]].hi); if (ar > pa) { pa = ar; pick = k; } }
+            if (pick < 0) break;
+            const int b = kids[pick];
+            kids[pick] = nodes[b].left; kids[nk++] = nodes[b].right;
+        }
+        QuadF q; memset(&q, 0, sizeof(q));
+        float lo[3][4], hi[3][4]; int meta[4];
+        for (int sl = 0; sl < 4; sl++) { for (int a = 0; a < 3; a++) { lo[a][sl] = FAR; hi[a][sl] = FAR; } meta[sl] = MFX_QUAD_EMPTY; }
+        for (int k = 0; k < nk; k++) {
+            const SahNode &nd = nodes[kids[k]];
+            for (int a = 0; a < 3; a++) { lo[a][k] = nd.lo[a]; hi[a][k] = nd.hi[a]; }
+            if (nd.count > 0) {
+                meta[k] = ((int)order.size() << 3) | nd.count;
+                for (int j = 0; j < nd.count; j++) order.push_back(idx[nd.first + j]);
+            }
+        }
+        q.lox = make_float4(lo[0][0], lo[0][1], lo[0][2], lo[0][3]); q.hix = make_float4(hi[0][0], hi[0][1], hi[0][2], hi[0][3]);
+        q.loy = make_float4(lo[1][0], lo[1][1], lo[1][2], lo[1][3]); q.hiy = make_float4(hi[1][0], hi[1][1], hi[1][2], hi[1][3]);
+        q.loz = make_float4(lo[2][0], lo[2][1], lo[2][2], lo[2][3]); q.hiz = make_float4(hi[2][0], hi[2][1], hi[2][2], hi[2][3]);
+        q.meta = make_float4(int_bits(meta[0]), int_bits(meta[1]), int_bits(meta[2]), int_bits(meta[3]));
+        quads.push_back(q);
+        for (int k = nk - 1; k >= 0; k--) if (nodes[kids[k]].count == 0) todo.push_back({ kids[k], it.level + 1, qi, k });
+    }
+    if ((size_t)ns > ((size_t)1 << 28)) return fail(MFX_ERR_INVALID_ARGUMENT, "too many fast slots (%d)", ns);
+    std::vector<SlotF> slots(ns); std::vector<float4> nrm(ns);
+    for (int k = 0; k < ns; k++) { slots[k] = raw[order[k]]; nrm[k] = raw_nrm[order[k]]; }
+
+    SceneF &sf = s->sf;
+    memset(&sf, 0, sizeof(sf));
+    SlotF *dslots; float4 *dnrm; QuadF *dquads;
+    MFX_TRY(upload(s, &dquads, quads)); MFX_TRY(upload(s, &dslots, slots)); MFX_TRY(upload(s, &dnrm, nrm));
+    s->f_bytes = quads.size() * sizeof(QuadF) + slots.size() * sizeof(SlotF) + nrm.size() * 16 + s->mats.size() * sizeof(MatF);
+    sf.quads = dquads; sf.slots = dslots; sf.slot_nrm = dnrm;
+    sf.ref_id = nullptr;                                        // b.w already holds the caller's primitive index
+    sf.root_meta = -1;
+    sf.own_tree = 1; sf.own_depth = own_depth;
+    const int need = 3 * own_depth;
+    sf.stack_smem = (int)std::min((long)need, std::max(1L, env_long("MFX_STACK_SMEM", 24)));
+    sf.spill_threads = s->sm_count * 16 * 128;                  // most threads a persistent 128-thread grid can hold
+    if (need > sf.stack_smem) {
+        MFX_TRY(dev_alloc_t(s, &sf.stack_spill, (size_t)(need - sf.stack_smem) * sf.spill_threads));
+        s->f_bytes += (uint64_t)(need - sf.stack_smem) * sf.spill_threads * sizeof(uint2);
+    }
+    MFX_TRY(fill_fast_common(s, sf));
+    sf.n_slots = ns;
+    sf.has_big_sphere = has_big;
     s->f_ready = true;
+    return MFX_OK;
+}
+
+// Which fast layout a call runs on: the own tree, unless the caller asked for traversal counters (defined on the
+// reference tree) or pinned one of the reference-tree kernels with MFX_TRACE_VARIANT (4, 5, 51, 52).
+static int fast_layout(MfxScene *s, bool counting, int variant, const SceneF **out)
+{
+    const bool ref = counting || variant == 4 || variant == 5 || variant == 51 || variant == 52;
+    if (ref) { MFX_TRY(flatten_fast_ref(s)); *out = &s->sf_ref; }
+    else { MFX_TRY(flatten_fast(s)); *out = &s->sf; }
     return MFX_OK;
 }
 
@@ -764,15 +1038,17 @@ static int run_sample(MfxScene *s, const MfxSampleParams *p, double *d_color_wh,
     MFX_TRY(ensure_device());
     const bool exact = (p->precision == MFX_EXACT_F64);
     if (exact) { MFX_TRY(flatten_exact(s)); MFX_TRY(ensure_wave_exact(s)); }
-    else { MFX_TRY(flatten_fast(s)); MFX_TRY(ensure_wave_fast(s)); }
+    const bool counting = (p->flags & MFX_SAMPLE_COUNT_TRAVERSAL) != 0;
+    const int variant = (int)env_long("MFX_TRACE_VARIANT", -1);
+    const SceneF *sfp = nullptr;
+    if (!exact) { MFX_TRY(fast_layout(s, counting, variant, &sfp)); MFX_TRY(ensure_wave_fast(s)); }
     MFX_TRY(ensure_frame_buffers(s));
     TileMap tm;
     MFX_TRY(get_tilemap(s, p->tile_size, p->rank, p->world, &tm));
-    const bool counting = (p->flags & MFX_SAMPLE_COUNT_TRAVERSAL) != 0;
     TravCounters *ctr = counting ? s->d_ctr : nullptr;
     const size_t npx = (size_t)s->width * s->height;
     cudaStream_t st = s->stream;
-    LaunchCfg cfg{ s->sm_count, 128, st, (int)env_long("MFX_TRACE_VARIANT", -1) };
+    LaunchCfg cfg{ s->sm_count, 128, st, variant };
 
     CUDA_TRY(cudaMemsetAsync(s->d_pixsum, 0, 4 * npx * sizeof(double), st));
     CUDA_TRY(cudaMemsetAsync(s->d_totals, 0, 4 * sizeof(unsigned long long), st));
@@ -811,21 +1087,21 @@ static int run_sample(MfxScene *s, const MfxSampleParams *p, double *d_color_wh,
             const int sabs = p->first_sample + s0;
             CUDA_TRY(cudaMemsetAsync(counts, 0, MFX_COUNTS_LEN * sizeof(int), st));
             if (exact) mfx_x_raygen(cfg, s->sx, s->wx, tm, pix0, np, sabs, S, p->seed);
-            else mfx_f_raygen(cfg, s->sf, s->wf, tm, pix0, np, sabs, S, p->seed);
+            else mfx_f_raygen(cfg, *sfp, s->wf, tm, pix0, np, sabs, S, p->seed);
             launches++;
             for (int b = 0; b <= D; b++) {
                 MFX_TRY(timed(0));
-                if (exact) mfx_x_extend(cfg, s->sx, s->wx, b, ctr); else mfx_f_extend(cfg, s->sf, s->wf, b, ctr);
+                if (exact) mfx_x_extend(cfg, s->sx, s->wx, b, ctr); else mfx_f_extend(cfg, *sfp, s->wf, b, ctr);
                 MFX_TRY(timed_end());
                 if (exact) mfx_x_shade(cfg, s->sx, s->wx, tm, pix0, np, sabs, b, p->seed);
-                else mfx_f_shade(cfg, s->sf, s->wf, tm, pix0, np, sabs, b, p->seed);
+                else mfx_f_shade(cfg, *sfp, s->wf, tm, pix0, np, sabs, b, p->seed);
                 MFX_TRY(timed(1));
-                if (exact) mfx_x_shadow(cfg, s->sx, s->wx, b, ctr); else mfx_f_shadow(cfg, s->sf, s->wf, b, ctr);
+                if (exact) mfx_x_shadow(cfg, s->sx, s->wx, b, ctr); else mfx_f_shadow(cfg, *sfp, s->wf, b, ctr);
                 MFX_TRY(timed_end());
                 launches += 3; l_ext++; l_sh++;
             }
             if (exact) mfx_x_resolve(cfg, s->sx, s->wx, tm, pix0, np, S, s->d_pixsum);
-            else mfx_f_resolve(cfg, s->sf, s->wf, tm, pix0, np, S, s->d_pixsum);
+            else mfx_f_resolve(cfg, *sfp, s->wf, tm, pix0, np, S, s->d_pixsum);
             // rays traced: exact: closest = counts[0..D], shadow = counts[1..D+1];
             //              fast : closest = counts[0..D], shadow = counts[V+2 .. V+2+D]
             if (exact) mfx_accum_ray_totals(st, counts, 0, D + 1, 1, D + 1, s->d_totals);
@@ -963,7 +1239,7 @@ static int with_ray_buffers(MfxScene *s, int64_t n, const double *a, size_t a_pe
 
 // The fast-precision seams run the PRODUCTION wavefront traversal kernel: the rays go through the wave's
 // queues in chunks of its capacity (bounce 0, closest or shadow queue), exactly like rays of a frame.
-static void fast_seam(MfxScene *s, const LaunchCfg &cfg, int any_hit, int64_t n, const double *o, const double *d, const double *uv,
+static void fast_seam(MfxScene *s, const SceneF *sfp, const LaunchCfg &cfg, int any_hit, int64_t n, const double *o, const double *d, const double *uv,
                       float tmin, float tmax, int *prim, int *sub, double *t)
 {
     WaveF w = s->wf;
@@ -971,9 +1247,9 @@ static void fast_seam(MfxScene *s, const LaunchCfg &cfg, int any_hit, int64_t n,
     for (int64_t first = 0; first < n; first += w.P) {
         const int m = (int)std::min<int64_t>(w.P, n - first);
         cudaMemsetAsync(w.counts, 0, MFX_COUNTS_LEN * sizeof(int), s->stream);
-        mfx_f_seam_setup(cfg, s->sf, w, m, o, d, uv, first, tmax, any_hit);
-        if (any_hit) mfx_f_shadow(cfg, s->sf, w, 0, nullptr); else mfx_f_extend(cfg, s->sf, w, 0, nullptr);
-        mfx_f_seam_read(cfg, s->sf, w, m, first, any_hit, prim, sub, t);
+        mfx_f_seam_setup(cfg, *sfp, w, m, o, d, uv, first, tmax, any_hit);
+        if (any_hit) mfx_f_shadow(cfg, *sfp, w, 0, nullptr); else mfx_f_extend(cfg, *sfp, w, 0, nullptr);
+        mfx_f_seam_read(cfg, *sfp, w, m, first, any_hit, prim, sub, t);
     }
 }
 
@@ -990,10 +1266,11 @@ extern "C" int mfx_bvh_hit(MfxScene *s, int32_t precision, int32_t any_hit, int6
             mfx_x_bvh_hit(cfg, s->sx, any_hit, n, o, d, tmin, tmax, p, sb, tt);
         });
     } else if (precision == MFX_FAST_F32) {
-        MFX_TRY(flatten_fast(s));
+        const SceneF *sfp = nullptr;
+        MFX_TRY(fast_layout(s, false, cfg.variant, &sfp));
         MFX_TRY(ensure_wave_fast(s));
         return with_ray_buffers(s, n, origins, 3, dirs, 3, prim, sub, t, [&](double *o, double *d, int *p, int *sb, double *tt) {
-            fast_seam(s, cfg, any_hit, n, o, d, nullptr, (float)tmin, (float)tmax, p, sb, tt);
+            fast_seam(s, sfp, cfg, any_hit, n, o, d, nullptr, (float)tmin, (float)tmax, p, sb, tt);
         });
     }
     return fail(MFX_ERR_INVALID_ARGUMENT, "unknown precision %d", precision);
@@ -1012,10 +1289,11 @@ extern "C" int mfx_trace_primary(MfxScene *s, int32_t precision, int64_t n, cons
             mfx_x_primary(cfg, s->sx, n, u, p, tt);
         });
     } else if (precision == MFX_FAST_F32) {
-        MFX_TRY(flatten_fast(s));
+        const SceneF *sfp = nullptr;
+        MFX_TRY(fast_layout(s, false, cfg.variant, &sfp));
         MFX_TRY(ensure_wave_fast(s));
         return with_ray_buffers(s, n, uv, 2, nullptr, 0, prim, nullptr, t, [&](double *u, double *, int *p, int *, double *tt) {
-            fast_seam(s, cfg, 0, n, nullptr, nullptr, u, 1e-6f, 99999999.f, p, nullptr, tt);
+            fast_seam(s, sfp, cfg, 0, n, nullptr, nullptr, u, 1e-6f, 99999999.f, p, nullptr, tt);
         });
     }
     return fail(MFX_ERR_INVALID_ARGUMENT, "unknown precision %d", precision);

@@ -90,6 +90,12 @@ struct __align__(16) PairF { float4 q0, q1, q2, q3; };
 // Records are stored compactly: index = h - ((2 << depth) + 1) / 3 (quads at even depths); for trees whose deepest
 // leaves sit at an odd depth the root is a 2-slot pseudo quad and the quads sit at odd depths (SceneF.qpar).
 struct __align__(16) QuadF { float4 lox, hix, loy, hiy, loz, hiz, meta, pad; };
+// The same 128 B record also carries the library's OWN tree (SceneF.own_tree = 1): a binned-SAH BVH over the fast
+// slots collapsed to four children per node.  The tree only decides the visiting order -- a nearest-hit query has one
+// answer whichever BVH finds it -- so MFX_FAST_F32 is free to use a better one than the reference's median split
+// (BvhNode.fs:42-61), which MFX_EXACT_F64 keeps because its tie rules are tree-shaped (quirk Q1).  Own-tree meta:
+//   meta >= 0: leaf (first<<3 | count), MFX_QUAD_EMPTY: empty slot, other negatives: interior, child record = ~meta.
+#define MFX_QUAD_EMPTY ((int)0x80000000)
 // One fast primitive slot, 48 B = 3 x float4, leaf order.
 //   triangle: a = (v0.xyz, kind bits), b = (e1.xyz, -), c = (e2.xyz, -)
 //   sphere  : a = (center.xyz, kind 2), b = (radius, r^2, -, prim)
@@ -124,6 +130,11 @@ struct SceneF {
     int    has_big_sphere;  // any kind-3 slot (selects the kernel variant with the f64 sphere branch)
     int    qlevels;         // number of quad levels
     int    qpar;            // 0: quads at even depths; 1: 2-slot pseudo root + quads at odd depths (odd leaf depth)
+    int    own_tree;        // 0: pairs/quads follow the reference tree (heap-indexed); 1: quads are the SAH 4-wide tree
+    int    own_depth;       // own tree: number of quad levels (deferred-hit stack holds <= 3 per level)
+    int    stack_smem;      // own tree: stack entries kept in shared memory per thread
+    uint2 *stack_spill;     // own tree: [3*own_depth - stack_smem][spill_threads] overflow entries (null if none)
+    int    spill_threads;
 };
 
 struct WaveF {
