@@ -122,6 +122,11 @@ typedef struct {
 } MfxSampleParams;
 
 #define MFX_SAMPLE_COUNT_TRAVERSAL 1   /* instrumented kernels: fill node/prim counters in MfxStats */
+/* MFX_FAST_F32 only.  By default the fast path draws the hemisphere direction of GetRandomInUnitSphere
+ * (Material.fs:9-14) and the light point (Rect.fs:33-38) directly -- same distributions, one RNG call per vertex,
+ * no rejection loop.  With this bit it runs the reference's rejection loop on the f32 view of the very random
+ * stream MFX_EXACT_F64 uses, so a fast frame can be compared with the exact one sample for sample. */
+#define MFX_SAMPLE_REFERENCE_STREAM 2
 
 typedef struct {
     uint64_t closest_rays;       /* closest-hit queries traced by the last Sample call             */

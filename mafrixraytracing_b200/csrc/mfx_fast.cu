@@ -645,6 +645,21 @@ __device__ __forceinline__ F3 random_in_unit_sphere_f(F3 nm, const RngF &g, uint
     return nm;
 }
 
+// The same distribution without the loop (MFX_FAST_F32 default): GetRandomInUnitSphere(nm) is a uniform point of
+// the half unit ball about nm, so its direction is uniform on the hemisphere and its radius is u^(1/3).  One Philox
+// call feeds a whole vertex: o0,o1 -> direction, o2,o3 -> light point, spare low bits -> coin flip and radius.
+// MFX_SAMPLE_REFERENCE_STREAM switches back to the reference's rejection loop on the exact mode's stream.
+#define MFX_ITER_DIRECT 0xffffffffu
+__device__ __forceinline__ F3 uniform_hemisphere_f(F3 nm, uint32_t a, uint32_t b)
+{
+    const float z = 1.f - 2.f * u32_to_unit_f32(a);
+    const float r = sqrtf(fmaxf(0.f, 1.f - z * z));
+    float sn, cs;
+    __sincosf(6.283185307179586477f * u32_to_unit_f32(b), &sn, &cs);
+    const F3 wdir = f3(r * cs, r * sn, z);
+    return dot(nm, wdir) < 0.f ? -wdir : wdir;
+}
+
 __device__ __forceinline__ F3 tri_sample_f(const float *v0, const float *e1, const float *e2, float tu, float tv)
 {
     float u = tu, v = tv;
@@ -671,6 +686,7 @@ __device__ __forceinline__ float fresnel_f(float eta_i, float eta_t, float cosi)
 // warp-aggregated appends.  Radiance bookkeeping (both integrators unrolled):
 //   mode 0 (Integrators.fs:136):  L += T * (l/pdf_li) * col ;  T *= col/pdf
 //   mode 1 (PathTracer.fs:40-41): L += T * l * col          ;  T *= col * shadeFactor
+template <bool DIRECT>
 __global__ void __launch_bounds__(FAST_BLOCK) k_f_shade(SceneF sc, WaveF w, TileMap tm, int pix0, int npix, int s0, int bounce, uint64_t seed)
 {
     const int n = w.counts[bounce];
@@ -711,21 +727,32 @@ __global__ void __launch_bounds__(FAST_BLOCK) k_f_shade(SceneF sc, WaveF w, Tile
                 pixel_of(tm, sc.width, pix0 + pl, pix, px, py);
                 RngF g; g.pixel = (uint32_t)pix; g.sample = (uint32_t)(s0 + sl); g.k0 = (uint32_t)seed; g.k1 = (uint32_t)(seed >> 32);
 
+                uint32_t dz[4] = { 0u, 0u, 0u, 0u };
+                F3 hemi = normal;                          // DIRECT: unit vector, uniform on the hemisphere about `normal`
+                if (DIRECT) {
+                    philox4x32_10(g.pixel, g.sample, MFX_DIM_BSDF(k), MFX_ITER_DIRECT, g.k0, g.k1, dz);
+                    hemi = uniform_hemisphere_f(normal, dz[0], dz[1]);
+                }
                 F3 wi; float cr, cg, cb; float sf = 1.f;   // col and the Shade factor applied to the continuation
                 if (sc.mode == 0) {
                     const float z = (m.kind == 2) ? 0.f : 1.f;
-                    wi = normalize_f(random_in_unit_sphere_f(normal, g, MFX_DIM_BSDF(k)));
+                    wi = DIRECT ? hemi : normalize_f(random_in_unit_sphere_f(normal, g, MFX_DIM_BSDF(k)));
                     const float ei2 = 2.f * dot(normal, wi);                 // INVPI * a * ei * TwoPi
                     cr = z * m.albedo[0] * ei2; cg = z * m.albedo[1] * ei2; cb = z * m.albedo[2] * ei2;
                 } else if (m.kind == 0) {
-                    wi = normalize_f(random_in_unit_sphere_f(normal, g, MFX_DIM_BSDF(k)));
+                    wi = DIRECT ? hemi : normalize_f(random_in_unit_sphere_f(normal, g, MFX_DIM_BSDF(k)));
                     const float ip = 0.318309886183790672f;
                     cr = m.albedo[0] * ip; cg = m.albedo[1] * ip; cb = m.albedo[2] * ip;
                     sf = 6.283185307179586477f * dot(normal, wi);            // Lambertian.Shade
                 } else if (m.kind == 1) {
                     const float fuzz = fminf(m.fuzz, 1.f);
                     const F3 refl = d - normal * (2.f * dot(d, normal));
-                    wi = normalize_f(refl + random_in_unit_sphere_f(normal, g, MFX_DIM_BSDF(k)) * fuzz);
+                    F3 ball;
+                    if (DIRECT) {       // radius of a uniform ball point from the 24 spare low bits of o1..o3
+                        const uint32_t rb = ((dz[1] & 0xffu) << 24) | ((dz[2] & 0xffu) << 16) | ((dz[3] & 0xffu) << 8);
+                        ball = hemi * cbrtf(u32_to_unit_f32(rb));
+                    } else ball = random_in_unit_sphere_f(normal, g, MFX_DIM_BSDF(k));
+                    wi = normalize_f(refl + ball * fuzz);
                     cr = m.albedo[0]; cg = m.albedo[1]; cb = m.albedo[2];
                 } else {
                     const F3 dir = -d;
@@ -746,12 +773,12 @@ __global__ void __launch_bounds__(FAST_BLOCK) k_f_shade(SceneF sc, WaveF w, Tile
                 }
                 // light sample (Rect.fs:33-38, Trangle.fs:157-169, Light.fs:42-59)
                 uint32_t lo4[4];
-                philox4x32_10(g.pixel, g.sample, MFX_DIM_LIGHT(k), 0, g.k0, g.k1, lo4);
-                const float us = u32_to_unit_f32(lo4[0]), tu = u32_to_unit_f32(lo4[1]), tv = u32_to_unit_f32(lo4[2]);
+                if (DIRECT) { lo4[0] = dz[0] << 31; lo4[1] = dz[2]; lo4[2] = dz[3]; }     // coin = spare low bit of o0
+                else philox4x32_10(g.pixel, g.sample, MFX_DIM_LIGHT(k), 0, g.k0, g.k1, lo4);
+                const float tu = u32_to_unit_f32(lo4[1]), tv = u32_to_unit_f32(lo4[2]);
                 // the coin uses the full 32-bit value so it matches the f64 stream's `s < 0.5`
                 const F3 lp = (lo4[0] < 0x80000000u) ? tri_sample_f(sc.light.v0a, sc.light.e1a, sc.light.e2a, tu, tv)
                                                      : tri_sample_f(sc.light.v0b, sc.light.e1b, sc.light.e2b, tu, tv);
-                (void)us;
                 const F3 toLight = lp - point;
                 const float d2 = len2(toLight);
                 const float dist = sqrtf(d2);
@@ -979,7 +1006,8 @@ void mfx_f_extend(const LaunchCfg &c, const SceneF &sc, const WaveF &w, int boun
 }
 void mfx_f_shade(const LaunchCfg &c, const SceneF &sc, const WaveF &w, TileMap tm, int pix0, int npix, int s0, int bounce, uint64_t seed)
 {
-    k_f_shade<<<persistent_blocks(k_f_shade, FAST_BLOCK, c.blocks), FAST_BLOCK, 0, c.stream>>>(sc, w, tm, pix0, npix, s0, bounce, seed);
+    if (c.reference_stream) k_f_shade<false><<<persistent_blocks(k_f_shade<false>, FAST_BLOCK, c.blocks), FAST_BLOCK, 0, c.stream>>>(sc, w, tm, pix0, npix, s0, bounce, seed);
+    else k_f_shade<true><<<persistent_blocks(k_f_shade<true>, FAST_BLOCK, c.blocks), FAST_BLOCK, 0, c.stream>>>(sc, w, tm, pix0, npix, s0, bounce, seed);
 }
 void mfx_f_shadow(const LaunchCfg &c, const SceneF &sc, const WaveF &w, int bounce, TravCounters *ctr)
 {

@@ -889,7 +889,7 @@ static int flatten_fast(MfxScene *s)
     sf.root_meta = -1;
     sf.own_tree = 1; sf.own_depth = own_depth;
     const int need = 3 * own_depth;
-    sf.stack_smem = (int)std::min((long)need, std::max(1L, env_long("MFX_STACK_SMEM", 24)));
+    sf.stack_smem = (int)std::min((long)need, std::max(1L, env_long("MFX_STACK_SMEM", 12)));
     sf.spill_threads = s->sm_count * 16 * 128;                  // most threads a persistent 128-thread grid can hold
     if (need > sf.stack_smem) {
         MFX_TRY(dev_alloc_t(s, &sf.stack_spill, (size_t)(need - sf.stack_smem) * sf.spill_threads));
@@ -1048,7 +1048,7 @@ static int run_sample(MfxScene *s, const MfxSampleParams *p, double *d_color_wh,
     TravCounters *ctr = counting ? s->d_ctr : nullptr;
     const size_t npx = (size_t)s->width * s->height;
     cudaStream_t st = s->stream;
-    LaunchCfg cfg{ s->sm_count, 128, st, variant };
+    LaunchCfg cfg{ s->sm_count, 128, st, variant, (p->flags & MFX_SAMPLE_REFERENCE_STREAM) ? 1 : 0 };
 
     CUDA_TRY(cudaMemsetAsync(s->d_pixsum, 0, 4 * npx * sizeof(double), st));
     CUDA_TRY(cudaMemsetAsync(s->d_totals, 0, 4 * sizeof(unsigned long long), st));
@@ -1259,7 +1259,7 @@ extern "C" int mfx_bvh_hit(MfxScene *s, int32_t precision, int32_t any_hit, int6
     if (!s || !origins || !dirs || !prim || !t) return fail(MFX_ERR_INVALID_ARGUMENT, "mfx_bvh_hit: null argument");
     if (n <= 0) return MFX_OK;
     MFX_TRY(ensure_device());
-    LaunchCfg cfg{ s->sm_count, 128, s->stream, (int)env_long("MFX_TRACE_VARIANT", -1) };
+    LaunchCfg cfg{ s->sm_count, 128, s->stream, (int)env_long("MFX_TRACE_VARIANT", -1), 0 };
     if (precision == MFX_EXACT_F64) {
         MFX_TRY(flatten_exact(s));
         return with_ray_buffers(s, n, origins, 3, dirs, 3, prim, sub, t, [&](double *o, double *d, int *p, int *sb, double *tt) {
@@ -1282,7 +1282,7 @@ extern "C" int mfx_trace_primary(MfxScene *s, int32_t precision, int64_t n, cons
     if (!uv && n != (int64_t)s->width * s->height) return fail(MFX_ERR_INVALID_ARGUMENT, "uv == NULL needs n == width*height");
     if (n <= 0) return MFX_OK;
     MFX_TRY(ensure_device());
-    LaunchCfg cfg{ s->sm_count, 128, s->stream, (int)env_long("MFX_TRACE_VARIANT", -1) };
+    LaunchCfg cfg{ s->sm_count, 128, s->stream, (int)env_long("MFX_TRACE_VARIANT", -1), 0 };
     if (precision == MFX_EXACT_F64) {
         MFX_TRY(flatten_exact(s));
         return with_ray_buffers(s, n, uv, 2, nullptr, 0, prim, nullptr, t, [&](double *u, double *, int *p, int *, double *tt) {

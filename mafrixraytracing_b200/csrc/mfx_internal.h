@@ -165,7 +165,7 @@ struct TileMap {
 };
 
 // ------------------------------------------------------------------ launchers (defined in the .cu TUs)
-struct LaunchCfg { int blocks; int threads; cudaStream_t stream; int variant; };
+struct LaunchCfg { int blocks; int threads; cudaStream_t stream; int variant; int reference_stream; };
 
 // exact
 void mfx_x_raygen(const LaunchCfg &, const SceneX &, const WaveX &, TileMap tm, int pix0, int npix, int s0, int S,

@@ -166,15 +166,39 @@ def test_exact_sample_bit_exact_vs_goldens_and_oracle(goldens, name):
                                              ("c1_cube", dict(width=160, height=120), 16, 5e-3),
                                              ("c2_spot", dict(width=240, height=135), 16, 2e-2)])
 def test_fast_sample_tracks_exact_at_matched_seeds(name, kw, spp, tol):
-    """Same Philox stream in both precisions: most paths take identical decisions, so the f32 frame
+    """Same Philox stream in both precisions (MFX_SAMPLE_REFERENCE_STREAM: the fast path runs the reference's
+    rejection loop on the f32 view of the exact stream): most paths take identical decisions, so the f32 frame
     stays within `tol` relative RMSE of the exact frame (stated tolerance, mode A)."""
     desc = _desc(name, **kw)
     s = Scene(desc)
     exact = CudaPixelIntegrator(s, precision=EXACT_F64, seed=5).Sample(spp).copy()
-    fast = CudaPixelIntegrator(s, precision=FAST_F32, seed=5).Sample(spp).copy()
+    fast = CudaPixelIntegrator(s, precision=FAST_F32, seed=5).Sample(spp, flags=_lib.SAMPLE_REFERENCE_STREAM).copy()
     rel = np.sqrt(((fast - exact)[:, :, :3] ** 2).mean()) / np.abs(exact[:, :, :3]).mean()
     assert rel <= tol, f"{name}: relative RMSE {rel:.3e}"
     assert abs(fast[:, :, :3].mean() / exact[:, :, :3].mean() - 1) < 2e-3
+
+
+@pytest.mark.parametrize("name,kw,mode", [("cornell", dict(width=96, height=96), None), ("c2_spot", dict(width=128, height=72), None),
+                                          ("c3_renault", dict(width=128, height=72), None),
+                                          ("spheres", dict(width=128, height=72, grid=16), None)])
+def test_direct_sampler_converges_to_the_rejection_sampler(name, kw, mode):
+    """The default fast sampler draws the hemisphere direction / half-ball point / light point directly (one RNG call
+    per vertex) instead of the reference's rejection loop (Material.fs:9-14).  Same distributions => same expected
+    frame: the difference between the two samplers must be no larger than the difference between two seeds of the
+    rejection sampler, and the mean radiance must agree."""
+    desc = _desc(name, **kw)
+    s = Scene(desc)
+    spp = 512
+    ra = CudaPixelIntegrator(s, precision=FAST_F32, seed=11).Sample(spp, flags=_lib.SAMPLE_REFERENCE_STREAM).copy()[:, :, :3]
+    rb = CudaPixelIntegrator(s, precision=FAST_F32, seed=12).Sample(spp, flags=_lib.SAMPLE_REFERENCE_STREAM).copy()[:, :, :3]
+    da = CudaPixelIntegrator(s, precision=FAST_F32, seed=11).Sample(spp).copy()[:, :, :3]
+    assert not np.array_equal(da, ra)
+    clip = np.percentile(np.abs(ra), 99.5)
+    c = lambda x: np.clip(x, -clip, clip)
+    noise = np.sqrt(((c(ra) - c(rb)) ** 2).mean())
+    err = np.sqrt(((c(da) - c(ra)) ** 2).mean())
+    assert err <= 1.1 * noise, f"{name}: direct-vs-rejection {err:.3e} exceeds the seed-to-seed noise {noise:.3e}"
+    assert abs(c(da).mean() / c(ra).mean() - 1) < 5e-3, f"{name}: mean radiance {c(da).mean():.5e} vs {c(ra).mean():.5e}"
 
 
 @pytest.mark.parametrize("name,kw", [("c3_renault", dict(width=160, height=90)), ("spheres", dict(width=160, height=90, grid=24))])
@@ -333,10 +357,13 @@ def test_c2_full_size_properties():
     for r in range(8):                                            # 8-way interleaved 64x64 tiles
         acc += CudaPixelIntegrator(s, precision=FAST_F32, seed=1, tile_size=64, rank=r, world=8).SampleF32(2)
     assert np.array_equal(acc, a)
-    # the exact frame of the same samples: f32 frame within the stated tolerance at full size
+    # the exact frame of the same samples (matched random stream): f32 frame within the stated tolerance at full size
+    m = integ.SampleF32(2, flags=_lib.SAMPLE_REFERENCE_STREAM)
     e = np.transpose(CudaPixelIntegrator(s, precision=EXACT_F64, seed=1).Sample(2)[:, :, :3], (1, 0, 2))
-    rel = np.sqrt(((a[:, :, :3] - e) ** 2).mean()) / np.abs(e).mean()
+    rel = np.sqrt(((m[:, :, :3] - e) ** 2).mean()) / np.abs(e).mean()
     assert rel < 5e-2
+    # the production sampler estimates the same frame: means agree (2 spp of 2 M pixels)
+    assert abs(a[:, :, :3].mean() / e.mean() - 1) < 5e-3
 
 
 def test_traversal_counters_match_oracle_ordered_counts():
