@@ -503,8 +503,8 @@ __global__ void __launch_bounds__(FAST_BLOCK) k_f_trace5(SceneF sc, WaveF w, int
 // 8-byte entries (sort key, record that holds the child) in shared memory [entry][thread]; trees deeper than the
 // shared-memory budget overflow into a per-thread global column.  A pop re-reads the child link (one 4-byte load
 // from a record the lane fetched a few steps earlier) instead of carrying it through the sorting network.
-template <bool ANY, bool BIG, int REFILL_T, int LEAF_T, int NSTEP>
-__global__ void __launch_bounds__(FAST_BLOCK) k_f_trace6(SceneF sc, WaveF w, int bounce)
+template <bool ANY, bool BIG, int REFILL_T, int LEAF_T, int NSTEP, int NLEAF, int MINB>
+__global__ void __launch_bounds__(FAST_BLOCK, MINB) k_f_trace6(SceneF sc, WaveF w, int bounce)
 {
     extern __shared__ uint2 s_stack[];              // [stack_smem][FAST_BLOCK]
     uint2 *my_stack = s_stack + threadIdx.x;
@@ -577,11 +577,10 @@ __global__ void __launch_bounds__(FAST_BLOCK) k_f_trace6(SceneF sc, WaveF w, int
             const unsigned t1 = umin_(a1, a3), k3 = umax_(a1, a3);
             const unsigned k1 = umin_(t1, t2), k2 = umax_(t1, t2);
             const bool any0 = k0 != KEY_INF;
-            const bool leaf0 = any0 && (k0 & 4u), leaf1 = leaf0 && (k1 != KEY_INF) && (k1 & 4u);
+            const bool leaf0 = any0 && (k0 & 4u), leaf1 = (NLEAF > 1) && leaf0 && (k1 != KEY_INF) && (k1 & 4u);
             const int c0 = pick4(m4, k0 & 3u);
             leafA = leaf0 ? c0 : -1;
-            leafB = leaf1 ? pick4(m4, k1 & 3u) : -1;
-            eB = __uint_as_float(k1 & ~7u);
+            if (NLEAF > 1) { leafB = leaf1 ? pick4(m4, k1 & 3u) : -1; eB = __uint_as_float(k1 & ~7u); }
             // deferred hits: everything behind the one(s) consumed now, nearest on top of the stack
             const unsigned p0 = leaf1 ? k2 : k1, p1 = leaf1 ? k3 : k2, p2 = leaf1 ? KEY_INF : k3;
             const int m = (p0 != KEY_INF ? 1 : 0) + (p1 != KEY_INF ? 1 : 0) + (p2 != KEY_INF ? 1 : 0);
@@ -604,7 +603,7 @@ __global__ void __launch_bounds__(FAST_BLOCK) k_f_trace6(SceneF sc, WaveF w, int
             if (__popc(lp) >= LEAF_T || nd == 0u) {
                 if (pid >= 0 && leafA >= 0) {
                     bool found = leaf_f3<false, BIG>(sc, r, leafA, best_t, best_slot, nullptr);
-                    if (leafB >= 0 && !(ANY && found) && eB <= best_t) found |= leaf_f3<false, BIG>(sc, r, leafB, best_t, best_slot, nullptr);
+                    if (NLEAF > 1 && leafB >= 0 && !(ANY && found) && eB <= best_t) found |= leaf_f3<false, BIG>(sc, r, leafB, best_t, best_slot, nullptr);
                     leafA = leafB = -1;
                     if (ANY && found) finished = true;
                 }
@@ -695,17 +694,28 @@ __global__ void __launch_bounds__(FAST_BLOCK) k_f_shade(SceneF sc, WaveF w, Tile
     const int k = bounce;
     const bool last = (bounce >= sc.max_depth);
     const int nwarp_iters = (n + 31) / 32;
-    for (int it = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); it < nwarp_iters; it += gridDim.x * (blockDim.x >> 5)) {
-        const int i = it * 32 + (threadIdx.x & 31);
+    // The kernel is bound by the latency of a chain of dependent loads (queue -> hit -> path state -> slot), so the
+    // first two links are software-pipelined: the path id is fetched two iterations ahead, its hit one ahead.
+    const int stride = gridDim.x * (blockDim.x >> 5);
+    const int lane = threadIdx.x & 31;
+    int it = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    auto queue_at = [&](int iter) { const int i = iter * 32 + lane; return (iter < nwarp_iters && i < n) ? qin[i] : -1; };
+    int pid_n = queue_at(it), pid_nn = queue_at(it + stride);
+    float2 hit_n = make_float2(0.f, __int_as_float(-1));
+    if (pid_n >= 0) hit_n = w.hit[pid_n];
+    for (; it < nwarp_iters; it += stride) {
         bool cont = false, shadow = false;
-        int pid = -1;
-        if (i < n) {
-            pid = qin[i];
-            const float2 hr = w.hit[pid];
+        const int pid = pid_n;
+        const float2 hr = hit_n;
+        pid_n = pid_nn;
+        pid_nn = queue_at(it + 2 * stride);
+        if (pid_n >= 0) hit_n = w.hit[pid_n];
+        if (pid >= 0) {
             const int fs = __float_as_int(hr.y);
             if (fs >= 0) {
                 const float t = hr.x;
                 const float4 o4 = w.ray_o[pid], d4 = w.ray_d[pid];
+                float4 thr = w.thr[pid];
                 const F3 o = f3(o4.x, o4.y, o4.z), d = f3(d4.x, d4.y, d4.z);
                 const F3 point = o + d * t;
                 const float4 sa = ldg4(&sc.slots[fs].a);
@@ -784,7 +794,6 @@ __global__ void __launch_bounds__(FAST_BLOCK) k_f_shade(SceneF sc, WaveF w, Tile
                 const float dist = sqrtf(d2);
                 const F3 unit = toLight * (1.f / dist);
                 const float cos_o = dot(toLight, f3(sc.light.normal[0], sc.light.normal[1], sc.light.normal[2]));
-                float4 thr = w.thr[pid];
                 float lscale = 0.f;
                 if (cos_o < 0.f) lscale = dot(unit, normal) * (fabsf(cos_o) * sc.light.area / d2);
                 if (sc.mode == 0) lscale *= sc.light.inv_pdf;                // l / pdf_li
@@ -966,20 +975,20 @@ static void launch_trace5(const LaunchCfg &c, const SceneF &sc, const WaveF &w, 
     if (sc.has_big_sphere) launch_trace5b<ANY, true, RT, LT, NS>(c, sc, w, bounce);
     else launch_trace5b<ANY, false, RT, LT, NS>(c, sc, w, bounce);
 }
-template <bool ANY, bool BIG, int RT, int LT, int NS>
+template <bool ANY, bool BIG, int RT, int LT, int NS, int NL, int MB>
 static void launch_trace6b(const LaunchCfg &c, const SceneF &sc, const WaveF &w, int bounce)
 {
     const size_t smem = (size_t)sc.stack_smem * FAST_BLOCK * sizeof(uint2);
     // the spill columns were sized for spill_threads: never launch more threads than that
-    int blocks = persistent_blocks(k_f_trace6<ANY, BIG, RT, LT, NS>, FAST_BLOCK, c.blocks, smem);
+    int blocks = persistent_blocks(k_f_trace6<ANY, BIG, RT, LT, NS, NL, MB>, FAST_BLOCK, c.blocks, smem);
     if (sc.stack_spill && blocks * FAST_BLOCK > sc.spill_threads) blocks = sc.spill_threads / FAST_BLOCK;
-    k_f_trace6<ANY, BIG, RT, LT, NS><<<blocks, FAST_BLOCK, smem, c.stream>>>(sc, w, bounce);
+    k_f_trace6<ANY, BIG, RT, LT, NS, NL, MB><<<blocks, FAST_BLOCK, smem, c.stream>>>(sc, w, bounce);
 }
-template <bool ANY, int RT, int LT, int NS>
+template <bool ANY, int RT, int LT, int NS, int NL = 2, int MB = 1>
 static void launch_trace6(const LaunchCfg &c, const SceneF &sc, const WaveF &w, int bounce)
 {
-    if (sc.has_big_sphere) launch_trace6b<ANY, true, RT, LT, NS>(c, sc, w, bounce);
-    else launch_trace6b<ANY, false, RT, LT, NS>(c, sc, w, bounce);
+    if (sc.has_big_sphere) launch_trace6b<ANY, true, RT, LT, NS, NL, 1>(c, sc, w, bounce);
+    else launch_trace6b<ANY, false, RT, LT, NS, NL, MB>(c, sc, w, bounce);
 }
 template <bool ANY>
 static void launch_trace_variant(const LaunchCfg &c, const SceneF &sc, const WaveF &w, int bounce, TravCounters *ctr)
@@ -988,8 +997,14 @@ static void launch_trace_variant(const LaunchCfg &c, const SceneF &sc, const Wav
         switch (c.variant) {
         case 61: launch_trace6<ANY, 8, 12, 2>(c, sc, w, bounce); break;
         case 62: launch_trace6<ANY, 12, 16, 1>(c, sc, w, bounce); break;
-        case 63: launch_trace6<ANY, 16, 20, 2>(c, sc, w, bounce); break;
-        default: launch_trace6<ANY, 12, 16, 2>(c, sc, w, bounce); break;
+        case 63: launch_trace6<ANY, 6, 10, 2>(c, sc, w, bounce); break;
+        case 64: launch_trace6<ANY, 12, 16, 2, 1>(c, sc, w, bounce); break;
+        case 65: launch_trace6<ANY, 8, 12, 2, 1>(c, sc, w, bounce); break;
+        case 66: launch_trace6<ANY, 8, 8, 2>(c, sc, w, bounce); break;
+        case 67: launch_trace6<ANY, 8, 12, 3>(c, sc, w, bounce); break;
+        case 68: launch_trace6<ANY, 8, 12, 2, 2, 10>(c, sc, w, bounce); break;
+        case 69: launch_trace6<ANY, 8, 12, 2, 1, 10>(c, sc, w, bounce); break;
+        default: launch_trace6<ANY, 8, 12, 2, 1>(c, sc, w, bounce); break;   // measured best (profiles/)
         }
         return;
     }
