@@ -685,25 +685,31 @@ __device__ __forceinline__ float fresnel_f(float eta_i, float eta_t, float cosi)
 // warp-aggregated appends.  Radiance bookkeeping (both integrators unrolled):
 //   mode 0 (Integrators.fs:136):  L += T * (l/pdf_li) * col ;  T *= col/pdf
 //   mode 1 (PathTracer.fs:40-41): L += T * l * col          ;  T *= col * shadeFactor
+#define SHADE_BLOCK 256
 template <bool DIRECT>
-__global__ void __launch_bounds__(FAST_BLOCK) k_f_shade(SceneF sc, WaveF w, TileMap tm, int pix0, int npix, int s0, int bounce, uint64_t seed)
+__global__ void __launch_bounds__(SHADE_BLOCK) k_f_shade(SceneF sc, WaveF w, TileMap tm, int pix0, int npix, int s0, int bounce, uint64_t seed)
 {
+    // Queue appends are aggregated per block: 5 000 resident warps hammering two counters with one atomic each per
+    // iteration made the kernel wait on same-address atomics (72 % of its stall samples, profiles/); one atomic per
+    // 256 paths and queue keeps the order inside a block.  Double-buffered by iteration parity: two barriers per pass.
+    __shared__ int s_cnt[2][2][SHADE_BLOCK / 32];
+    __shared__ int s_base[2][2];
     const int n = w.counts[bounce];
     const int *qin = w.q_ext[bounce & 1];
     int *qout = w.q_ext[(bounce + 1) & 1];
     const int k = bounce;
     const bool last = (bounce >= sc.max_depth);
-    const int nwarp_iters = (n + 31) / 32;
+    const int nblock_iters = (n + SHADE_BLOCK - 1) / SHADE_BLOCK;
     // The kernel is bound by the latency of a chain of dependent loads (queue -> hit -> path state -> slot), so the
     // first two links are software-pipelined: the path id is fetched two iterations ahead, its hit one ahead.
-    const int stride = gridDim.x * (blockDim.x >> 5);
-    const int lane = threadIdx.x & 31;
-    int it = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    auto queue_at = [&](int iter) { const int i = iter * 32 + lane; return (iter < nwarp_iters && i < n) ? qin[i] : -1; };
+    const int stride = gridDim.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int it = blockIdx.x, par = 0;
+    auto queue_at = [&](int iter) { const int i = iter * SHADE_BLOCK + threadIdx.x; return (iter < nblock_iters && i < n) ? qin[i] : -1; };
     int pid_n = queue_at(it), pid_nn = queue_at(it + stride);
     float2 hit_n = make_float2(0.f, __int_as_float(-1));
     if (pid_n >= 0) hit_n = w.hit[pid_n];
-    for (; it < nwarp_iters; it += stride) {
+    for (; it < nblock_iters; it += stride, par ^= 1) {
         bool cont = false, shadow = false;
         const int pid = pid_n;
         const float2 hr = hit_n;
@@ -810,10 +816,19 @@ __global__ void __launch_bounds__(FAST_BLOCK) k_f_shade(SceneF sc, WaveF w, Tile
                 if (cont) { w.ray_d[pid] = make_float4(wi.x, wi.y, wi.z, 99999999.f); w.thr[pid] = thr; }
             }
         }
-        const int pe = warp_append(cont, &w.counts[bounce + 1]);
-        if (cont) qout[pe] = pid;
-        const int ps = warp_append(shadow, &w.counts[MFX_MAX_VERTS + 2 + bounce]);
-        if (shadow) w.q_sh[ps] = pid;
+        const unsigned mc = __ballot_sync(0xffffffffu, cont), ms = __ballot_sync(0xffffffffu, shadow);
+        if (lane == 0) { s_cnt[par][0][warp] = __popc(mc); s_cnt[par][1][warp] = __popc(ms); }
+        __syncthreads();
+        if (threadIdx.x < 2) {
+            int tot = 0;
+            for (int j = 0; j < SHADE_BLOCK / 32; j++) { const int c = s_cnt[par][threadIdx.x][j]; s_cnt[par][threadIdx.x][j] = tot; tot += c; }
+            int *counter = &w.counts[threadIdx.x == 0 ? bounce + 1 : MFX_MAX_VERTS + 2 + bounce];
+            s_base[par][threadIdx.x] = tot ? atomicAdd(counter, tot) : 0;
+        }
+        __syncthreads();
+        const unsigned below = (1u << lane) - 1u;
+        if (cont) qout[s_base[par][0] + s_cnt[par][0][warp] + __popc(mc & below)] = pid;
+        if (shadow) w.q_sh[s_base[par][1] + s_cnt[par][1][warp] + __popc(ms & below)] = pid;
     }
 }
 
@@ -1021,8 +1036,8 @@ void mfx_f_extend(const LaunchCfg &c, const SceneF &sc, const WaveF &w, int boun
 }
 void mfx_f_shade(const LaunchCfg &c, const SceneF &sc, const WaveF &w, TileMap tm, int pix0, int npix, int s0, int bounce, uint64_t seed)
 {
-    if (c.reference_stream) k_f_shade<false><<<persistent_blocks(k_f_shade<false>, FAST_BLOCK, c.blocks), FAST_BLOCK, 0, c.stream>>>(sc, w, tm, pix0, npix, s0, bounce, seed);
-    else k_f_shade<true><<<persistent_blocks(k_f_shade<true>, FAST_BLOCK, c.blocks), FAST_BLOCK, 0, c.stream>>>(sc, w, tm, pix0, npix, s0, bounce, seed);
+    if (c.reference_stream) k_f_shade<false><<<persistent_blocks(k_f_shade<false>, SHADE_BLOCK, c.blocks), SHADE_BLOCK, 0, c.stream>>>(sc, w, tm, pix0, npix, s0, bounce, seed);
+    else k_f_shade<true><<<persistent_blocks(k_f_shade<true>, SHADE_BLOCK, c.blocks), SHADE_BLOCK, 0, c.stream>>>(sc, w, tm, pix0, npix, s0, bounce, seed);
 }
 void mfx_f_shadow(const LaunchCfg &c, const SceneF &sc, const WaveF &w, int bounce, TravCounters *ctr)
 {
