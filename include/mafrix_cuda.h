@@ -127,6 +127,9 @@ typedef struct {
  * no rejection loop.  With this bit it runs the reference's rejection loop on the f32 view of the very random
  * stream MFX_EXACT_F64 uses, so a fast frame can be compared with the exact one sample for sample. */
 #define MFX_SAMPLE_REFERENCE_STREAM 2
+/* MFX_FAST_F32 only: instrumented run on the library's own tree (what the shipped kernel really fetches):
+ * MfxStats.nodes counts 128-byte four-child records, tris / spheres count primitive tests. */
+#define MFX_SAMPLE_COUNT_OWN_TREE 4
 
 typedef struct {
     uint64_t closest_rays;       /* closest-hit queries traced by the last Sample call             */

@@ -50,6 +50,7 @@ class MfxStats(C.Structure):
 
 SAMPLE_COUNT_TRAVERSAL = 1
 SAMPLE_REFERENCE_STREAM = 2
+SAMPLE_COUNT_OWN_TREE = 4
 
 # every symbol include/mafrix_cuda.h declares: name -> (restype, argtypes)
 _P = C.c_void_p

@@ -503,8 +503,8 @@ __global__ void __launch_bounds__(FAST_BLOCK) k_f_trace5(SceneF sc, WaveF w, int
 // 8-byte entries (sort key, record that holds the child) in shared memory [entry][thread]; trees deeper than the
 // shared-memory budget overflow into a per-thread global column.  A pop re-reads the child link (one 4-byte load
 // from a record the lane fetched a few steps earlier) instead of carrying it through the sorting network.
-template <bool ANY, bool BIG, int REFILL_T, int LEAF_T, int NSTEP, int NLEAF, int MINB>
-__global__ void __launch_bounds__(FAST_BLOCK, MINB) k_f_trace6(SceneF sc, WaveF w, int bounce)
+template <bool ANY, bool BIG, int REFILL_T, int LEAF_T, int NSTEP, int NLEAF, int MINB, bool COUNT>
+__global__ void __launch_bounds__(FAST_BLOCK, MINB) k_f_trace6(SceneF sc, WaveF w, int bounce, TravCounters *ctr)
 {
     extern __shared__ uint2 s_stack[];              // [stack_smem][FAST_BLOCK]
     uint2 *my_stack = s_stack + threadIdx.x;
@@ -525,6 +525,7 @@ __global__ void __launch_bounds__(FAST_BLOCK, MINB) k_f_trace6(SceneF sc, WaveF 
     int leafA = -1, leafB = -1; float eB = 0.f;
     bool exhausted = false;
     unsigned iters = 0u;
+    unsigned long long local[3] = { 0ull, 0ull, 0ull };   // COUNT: 128 B records fetched, triangle tests, sphere tests
 
     for (;;) {
         const unsigned idle = __ballot_sync(FULL, pid < 0);
@@ -555,6 +556,7 @@ __global__ void __launch_bounds__(FAST_BLOCK, MINB) k_f_trace6(SceneF sc, WaveF 
         for (int rep = 0; rep < NSTEP; rep++)
         if (pid >= 0 && leafA < 0 && !needPop) {
             const QuadF *qp = sc.quads + node;
+            if (COUNT) local[0]++;
             const float4 lox = ldg4(&qp->lox), hix = ldg4(&qp->hix), loy = ldg4(&qp->loy), hiy = ldg4(&qp->hiy);
             const float4 loz = ldg4(&qp->loz), hiz = ldg4(&qp->hiz), m4 = ldg4(&qp->meta);
             unsigned key[4];
@@ -602,8 +604,8 @@ __global__ void __launch_bounds__(FAST_BLOCK, MINB) k_f_trace6(SceneF sc, WaveF 
             const unsigned nd = ~idle_now & ~lp;
             if (__popc(lp) >= LEAF_T || nd == 0u) {
                 if (pid >= 0 && leafA >= 0) {
-                    bool found = leaf_f3<false, BIG>(sc, r, leafA, best_t, best_slot, nullptr);
-                    if (NLEAF > 1 && leafB >= 0 && !(ANY && found) && eB <= best_t) found |= leaf_f3<false, BIG>(sc, r, leafB, best_t, best_slot, nullptr);
+                    bool found = leaf_f3<COUNT, BIG>(sc, r, leafA, best_t, best_slot, local);
+                    if (NLEAF > 1 && leafB >= 0 && !(ANY && found) && eB <= best_t) found |= leaf_f3<COUNT, BIG>(sc, r, leafB, best_t, best_slot, local);
                     leafA = leafB = -1;
                     if (ANY && found) finished = true;
                 }
@@ -628,6 +630,7 @@ __global__ void __launch_bounds__(FAST_BLOCK, MINB) k_f_trace6(SceneF sc, WaveF 
             pid = -1;
         }
     }
+    if (COUNT) { for (int j = 0; j < 3; j++) if (local[j]) atomicAdd(&ctr->v[ANY ? 1 : 0][j], local[j]); }
 }
 
 struct RngF { uint32_t pixel, sample, k0, k1; };
@@ -990,14 +993,14 @@ static void launch_trace5(const LaunchCfg &c, const SceneF &sc, const WaveF &w, 
     if (sc.has_big_sphere) launch_trace5b<ANY, true, RT, LT, NS>(c, sc, w, bounce);
     else launch_trace5b<ANY, false, RT, LT, NS>(c, sc, w, bounce);
 }
-template <bool ANY, bool BIG, int RT, int LT, int NS, int NL, int MB>
-static void launch_trace6b(const LaunchCfg &c, const SceneF &sc, const WaveF &w, int bounce)
+template <bool ANY, bool BIG, int RT, int LT, int NS, int NL, int MB, bool CNT = false>
+static void launch_trace6b(const LaunchCfg &c, const SceneF &sc, const WaveF &w, int bounce, TravCounters *ctr = nullptr)
 {
     const size_t smem = (size_t)sc.stack_smem * FAST_BLOCK * sizeof(uint2);
     // the spill columns were sized for spill_threads: never launch more threads than that
-    int blocks = persistent_blocks(k_f_trace6<ANY, BIG, RT, LT, NS, NL, MB>, FAST_BLOCK, c.blocks, smem);
+    int blocks = persistent_blocks(k_f_trace6<ANY, BIG, RT, LT, NS, NL, MB, CNT>, FAST_BLOCK, c.blocks, smem);
     if (sc.stack_spill && blocks * FAST_BLOCK > sc.spill_threads) blocks = sc.spill_threads / FAST_BLOCK;
-    k_f_trace6<ANY, BIG, RT, LT, NS, NL, MB><<<blocks, FAST_BLOCK, smem, c.stream>>>(sc, w, bounce);
+    k_f_trace6<ANY, BIG, RT, LT, NS, NL, MB, CNT><<<blocks, FAST_BLOCK, smem, c.stream>>>(sc, w, bounce, ctr);
 }
 template <bool ANY, int RT, int LT, int NS, int NL = 2, int MB = 1>
 static void launch_trace6(const LaunchCfg &c, const SceneF &sc, const WaveF &w, int bounce)
@@ -1009,6 +1012,11 @@ template <bool ANY>
 static void launch_trace_variant(const LaunchCfg &c, const SceneF &sc, const WaveF &w, int bounce, TravCounters *ctr)
 {
     if (sc.own_tree) {          // the library's SAH tree (default); the host passes the reference-tree layout for the others
+        if (ctr) {              // MFX_SAMPLE_COUNT_OWN_TREE: the shipped configuration, instrumented
+            if (sc.has_big_sphere) launch_trace6b<ANY, true, 8, 12, 2, 1, 1, true>(c, sc, w, bounce, ctr);
+            else launch_trace6b<ANY, false, 8, 12, 2, 1, 1, true>(c, sc, w, bounce, ctr);
+            return;
+        }
         switch (c.variant) {
         case 61: launch_trace6<ANY, 8, 12, 2>(c, sc, w, bounce); break;
         case 62: launch_trace6<ANY, 12, 16, 1>(c, sc, w, bounce); break;

@@ -1038,10 +1038,11 @@ static int run_sample(MfxScene *s, const MfxSampleParams *p, double *d_color_wh,
     MFX_TRY(ensure_device());
     const bool exact = (p->precision == MFX_EXACT_F64);
     if (exact) { MFX_TRY(flatten_exact(s)); MFX_TRY(ensure_wave_exact(s)); }
-    const bool counting = (p->flags & MFX_SAMPLE_COUNT_TRAVERSAL) != 0;
+    const bool count_ref = (p->flags & MFX_SAMPLE_COUNT_TRAVERSAL) != 0;
+    const bool counting = count_ref || (p->flags & MFX_SAMPLE_COUNT_OWN_TREE) != 0;
     const int variant = (int)env_long("MFX_TRACE_VARIANT", -1);
     const SceneF *sfp = nullptr;
-    if (!exact) { MFX_TRY(fast_layout(s, counting, variant, &sfp)); MFX_TRY(ensure_wave_fast(s)); }
+    if (!exact) { MFX_TRY(fast_layout(s, count_ref, variant, &sfp)); MFX_TRY(ensure_wave_fast(s)); }
     MFX_TRY(ensure_frame_buffers(s));
     TileMap tm;
     MFX_TRY(get_tilemap(s, p->tile_size, p->rank, p->world, &tm));

@@ -21,6 +21,7 @@ for name, spp_fast, spp_exact in RUNS:
         if name == "c5_soup" and prec == EXACT_F64:
             continue
         integ = CudaPixelIntegrator(s, precision=prec, seed=1)
+        t0 = time.time(); integ.SampleF32(1); t_first = time.time() - t0      # includes the layout build (fast: own SAH tree)
         best = None
         for _ in range(2):
             integ.SampleF32(spp)
@@ -31,7 +32,7 @@ for name, spp_fast, spp_exact in RUNS:
         row[label] = {"spp": spp, "rays": rays, "ms": round(best["ms_total"], 3), "mrays_s": round(rays / best["ms_total"] / 1e3, 1),
                       "extend_mrays_s": round(best["closest_rays"] / max(best["ms_extend"], 1e-9) / 1e3, 1),
                       "shadow_mrays_s": round(best["shadow_rays"] / max(best["ms_shadow"], 1e-9) / 1e3, 1),
-                      "spp_per_s": round(spp / (best["ms_total"] * 1e-3), 2)}
+                      "spp_per_s": round(spp / (best["ms_total"] * 1e-3), 2), "first_call_s": round(t_first, 2)}
     row["device_bytes"] = s.device_bytes() if name != "c5_soup" else None
     print(json.dumps(row), flush=True)
     out.append(row)
