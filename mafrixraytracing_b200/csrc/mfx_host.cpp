@@ -269,7 +269,7 @@ struct MfxScene {
 static std::mutex g_pool_mu;
 static std::multimap<std::pair<int, size_t>, void *> g_pool;
 static size_t g_pool_bytes = 0;
-static const size_t POOL_MIN = 1u << 20, POOL_MAX = (size_t)8 << 30;
+static const size_t POOL_MIN = 1u << 20, POOL_MAX = (size_t)24 << 30;
 
 static int dev_alloc(MfxScene *s, void **p, size_t bytes)
 {
@@ -295,6 +295,18 @@ static void dev_release(int device, void *p, size_t bytes)
         if (g_pool_bytes + bytes <= POOL_MAX) { g_pool.insert({ { device, bytes }, p }); g_pool_bytes += bytes; return; }
     }
     cudaFree(p);
+}
+
+// gives one buffer of the scene back (to the pool) before the scene dies: the wave state grows on demand
+static void dev_free_one(MfxScene *s, void *p)
+{
+    if (!p) return;
+    for (size_t i = 0; i < s->allocs.size(); i++)
+        if (s->allocs[i].first == p) {
+            dev_release(s->device, p, s->allocs[i].second);
+            s->allocs.erase(s->allocs.begin() + (long)i);
+            return;
+        }
 }
 
 // one pinned staging buffer per process for downloads into pageable caller memory
@@ -944,11 +956,22 @@ static int ensure_wave_exact(MfxScene *s)
     return MFX_OK;
 }
 
-static int ensure_wave_fast(MfxScene *s)
+// Path state of one wave, fast precision.  Bigger waves mean fewer, longer launches: on C2 a 4 Mi-path wave (2 spp of
+// 1080p) costs 25 % against 32-64 Mi because every persistent launch pays its ramp-up and its tail (profiles/), so
+// the wave is sized for the call at hand -- pixels x spp -- up to MFX_WAVE_PATHS (default 64 Mi paths = 7.8 GB of
+// the 180 GB) and only ever grows.
+static int ensure_wave_fast(MfxScene *s, size_t want)
 {
-    if (s->wf_ready) return MFX_OK;
-    const size_t P = (size_t)env_long("MFX_WAVE_PATHS", 1 << 22);
+    const size_t cap = (size_t)std::max(1024L, env_long("MFX_WAVE_PATHS", 1L << 26));
+    size_t P = std::min(cap, std::max(want, (size_t)1 << 16));
+    if (s->wf_ready && (size_t)s->wf.P >= P) return MFX_OK;
     WaveF &w = s->wf;
+    if (s->wf_ready) {
+        CUDA_TRY(cudaStreamSynchronize(s->stream));
+        void *old[] = { w.ray_o, w.ray_d, w.hit, w.thr, w.rad, w.sh_d, w.sh_c, w.q_ext[0], w.q_ext[1], w.q_sh, w.counts };
+        for (void *q : old) dev_free_one(s, q);
+        s->wf_ready = false;
+    }
     memset(&w, 0, sizeof(w));
     w.P = (int)P;
     w.tmin = 1e-6f;
@@ -1042,10 +1065,11 @@ static int run_sample(MfxScene *s, const MfxSampleParams *p, double *d_color_wh,
     const bool counting = count_ref || (p->flags & MFX_SAMPLE_COUNT_OWN_TREE) != 0;
     const int variant = (int)env_long("MFX_TRACE_VARIANT", -1);
     const SceneF *sfp = nullptr;
-    if (!exact) { MFX_TRY(fast_layout(s, count_ref, variant, &sfp)); MFX_TRY(ensure_wave_fast(s)); }
+    if (!exact) MFX_TRY(fast_layout(s, count_ref, variant, &sfp));
     MFX_TRY(ensure_frame_buffers(s));
     TileMap tm;
     MFX_TRY(get_tilemap(s, p->tile_size, p->rank, p->world, &tm));
+    if (!exact) MFX_TRY(ensure_wave_fast(s, (size_t)tm.n_pix * (size_t)p->spp));
     TravCounters *ctr = counting ? s->d_ctr : nullptr;
     const size_t npx = (size_t)s->width * s->height;
     cudaStream_t st = s->stream;
@@ -1269,7 +1293,7 @@ extern "C" int mfx_bvh_hit(MfxScene *s, int32_t precision, int32_t any_hit, int6
     } else if (precision == MFX_FAST_F32) {
         const SceneF *sfp = nullptr;
         MFX_TRY(fast_layout(s, false, cfg.variant, &sfp));
-        MFX_TRY(ensure_wave_fast(s));
+        MFX_TRY(ensure_wave_fast(s, (size_t)n));
         return with_ray_buffers(s, n, origins, 3, dirs, 3, prim, sub, t, [&](double *o, double *d, int *p, int *sb, double *tt) {
             fast_seam(s, sfp, cfg, any_hit, n, o, d, nullptr, (float)tmin, (float)tmax, p, sb, tt);
         });
@@ -1292,7 +1316,7 @@ extern "C" int mfx_trace_primary(MfxScene *s, int32_t precision, int64_t n, cons
     } else if (precision == MFX_FAST_F32) {
         const SceneF *sfp = nullptr;
         MFX_TRY(fast_layout(s, false, cfg.variant, &sfp));
-        MFX_TRY(ensure_wave_fast(s));
+        MFX_TRY(ensure_wave_fast(s, (size_t)n));
         return with_ray_buffers(s, n, uv, 2, nullptr, 0, prim, nullptr, t, [&](double *u, double *, int *p, int *, double *tt) {
             fast_seam(s, sfp, cfg, 0, n, nullptr, nullptr, u, 1e-6f, 99999999.f, p, nullptr, tt);
         });
