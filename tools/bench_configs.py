@@ -6,7 +6,7 @@ import json, os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from mafrixraytracing_b200 import scenes, Scene, CudaPixelIntegrator, Bvh, EXACT_F64, FAST_F32
 
-RUNS = [("cornell", 64, 16), ("c1_cube", 16, 16), ("c2_spot", 16, 2), ("c3_renault", 16, 2), ("c4_spheres", 4, 1), ("c5_soup", 2, 1)]
+RUNS = [("cornell", 256, 16), ("c1_cube", 64, 16), ("c2_spot", 64, 2), ("c3_renault", 64, 2), ("c4_spheres", 8, 1), ("c5_soup", 8, 1)]
 out = []
 only = sys.argv[2].split(",") if len(sys.argv) > 2 else None
 for name, spp_fast, spp_exact in RUNS:
