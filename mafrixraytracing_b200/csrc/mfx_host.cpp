@@ -9,6 +9,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -706,13 +707,16 @@ static int sah_split(SahCtx &c, const SahNode &nd)
     }
     const float inv_area = area > 0.f ? 1.0f / area : 0.f;
     if (count <= 24) {
-        // exact sweep: sort by centroid on each axis, try every split position
-        std::vector<std::pair<float, int>> key(count);
-        std::vector<float> right(count);
-        std::vector<int> best_order;
+        // exact sweep: sort by centroid on each axis (insertion sort, stable), try every split position
+        std::pair<float, int> key[24]; float right[24]; int best_order[24];
         for (int ax = 0; ax < 3; ax++) {
-            for (int k = 0; k < count; k++) { const int id = c.idx[first + k]; key[k] = { c.lo[id][ax] + c.hi[id][ax], id }; }
-            std::stable_sort(key.begin(), key.end(), [](const std::pair<float, int> &x, const std::pair<float, int> &y) { return x.first < y.first; });
+            for (int k = 0; k < count; k++) {
+                const int id = c.idx[first + k];
+                const std::pair<float, int> e{ c.lo[id][ax] + c.hi[id][ax], id };
+                int j = k;
+                while (j > 0 && key[j - 1].first > e.first) { key[j] = key[j - 1]; j--; }
+                key[j] = e;
+            }
             float lo[3] = { SAH_INF, SAH_INF, SAH_INF }, hi[3] = { -SAH_INF, -SAH_INF, -SAH_INF };
             for (int k = count - 1; k > 0; k--) { grow(lo, hi, c.lo[key[k].second], c.hi[key[k].second]); right[k] = half_area(lo, hi); }
             for (int a = 0; a < 3; a++) { lo[a] = SAH_INF; hi[a] = -SAH_INF; }
@@ -722,7 +726,7 @@ static int sah_split(SahCtx &c, const SahNode &nd)
                 const float cost = c.c_trav + (half_area(lo, hi) * k + right[k] * (count - k)) * inv_area;
                 if (cost < best) { best = cost; best_axis = ax; best_pos = k; improved = true; }
             }
-            if (improved) { best_order.resize(count); for (int k = 0; k < count; k++) best_order[k] = key[k].second; }
+            if (improved) for (int k = 0; k < count; k++) best_order[k] = key[k].second;
         }
         if (best_axis < 0 || (count <= c.max_leaf && leaf_cost <= best)) return count <= c.max_leaf ? 0 : count / 2;
         for (int k = 0; k < count; k++) c.idx[first + k] = best_order[k];
@@ -794,7 +798,7 @@ static void sah_build(SahCtx &c, int root, int par_depth)
         R.first = nd.first + left; R.count = nd.count - left; R.left = R.right = -1;
         sah_bound(c, L); sah_bound(c, R);
         c.nodes[i].left = li; c.nodes[i].right = ri; c.nodes[i].count = 0;
-        if (par_depth > 0 && i == root && nd.count > (1 << 15)) {
+        if (par_depth > 0 && i == root && nd.count > 1024) {
             spawned.push_back(std::async(std::launch::async, [&c, li, par_depth]() { sah_build(c, li, par_depth - 1); }));
             root = ri; par_depth--;
             todo.push_back(ri);
@@ -808,6 +812,11 @@ static void sah_build(SahCtx &c, int root, int par_depth)
 static int flatten_fast(MfxScene *s)
 {
     if (s->f_ready) return MFX_OK;
+    const auto t_begin = std::chrono::steady_clock::now();
+    auto lap = [&](const char *what) {
+        if (env_long("MFX_DEBUG", 0))
+            fprintf(stderr, "[mfx] flatten_fast %-10s %8.2f ms\n", what, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count());
+    };
     const int n = (int)s->prims.size();
     std::vector<SlotF> raw; std::vector<float4> raw_nrm;
     int has_big = 0;
@@ -844,7 +853,9 @@ static int flatten_fast(MfxScene *s)
     c.c_trav = (float)env_long("MFX_SAH_TRAV_COST_PCT", 100) * 0.01f;
     nodes[0].first = 0; nodes[0].count = ns; nodes[0].left = nodes[0].right = -1;
     sah_bound(c, nodes[0]);
+    lap("slots");
     sah_build(c, 0, (int)env_long("MFX_BVH_BUILD_PAR_DEPTH", 5));
+    lap("sah");
 
     // collapse to four children per record, depth-first; leaves of a record get consecutive slots
     std::vector<QuadF> quads;
@@ -891,10 +902,12 @@ static int flatten_fast(MfxScene *s)
     std::vector<SlotF> slots(ns); std::vector<float4> nrm(ns);
     for (int k = 0; k < ns; k++) { slots[k] = raw[order[k]]; nrm[k] = raw_nrm[order[k]]; }
 
+    lap("collapse");
     SceneF &sf = s->sf;
     memset(&sf, 0, sizeof(sf));
     SlotF *dslots; float4 *dnrm; QuadF *dquads;
     MFX_TRY(upload(s, &dquads, quads)); MFX_TRY(upload(s, &dslots, slots)); MFX_TRY(upload(s, &dnrm, nrm));
+    lap("upload");
     s->f_bytes = quads.size() * sizeof(QuadF) + slots.size() * sizeof(SlotF) + nrm.size() * 16 + s->mats.size() * sizeof(MatF);
     sf.quads = dquads; sf.slots = dslots; sf.slot_nrm = dnrm;
     sf.ref_id = nullptr;                                        // b.w already holds the caller's primitive index
