@@ -379,6 +379,61 @@ def test_traversal_counters_match_oracle_ordered_counts():
         assert abs(g_nodes / o_nodes - 1) < 0.10 and abs(g_tris / o_tris - 1) < 0.10, (c, g_nodes, o_nodes, g_tris, o_tris)
 
 
+def test_own_tree_counters_and_image_match_the_reference_tree_run():
+    """MFX_SAMPLE_COUNT_OWN_TREE instruments the shipped kernel on the library's SAH tree: it must fetch far fewer
+    records than the reference tree has node tests, and render the same frame as the uninstrumented run."""
+    desc = _desc("c2_spot", width=240, height=135)
+    s = Scene(desc)
+    integ = CudaPixelIntegrator(s, precision=FAST_F32, seed=2)
+    plain = integ.Sample(2).copy()
+    own = integ.Sample(2, flags=_lib.SAMPLE_COUNT_OWN_TREE).copy()
+    so = dict(integ.stats)
+    assert np.array_equal(plain, own)
+    integ.Sample(2, flags=_lib.SAMPLE_COUNT_TRAVERSAL)
+    sr = dict(integ.stats)
+    assert so["closest_rays"] == sr["closest_rays"] or abs(so["closest_rays"] / sr["closest_rays"] - 1) < 1e-3
+    for c, rays in ((0, "closest_rays"), (1, "shadow_rays")):
+        rec, ref_nodes = so["nodes"][c] / so[rays], sr["nodes"][c] / sr[rays]
+        assert 1.0 <= rec < 0.25 * ref_nodes, (c, rec, ref_nodes)          # 128 B records vs 32 B reference nodes
+        assert so["tris"][c] / so[rays] < sr["tris"][c] / sr[rays]
+
+
+def test_wave_grows_with_the_call_and_frames_do_not_depend_on_it():
+    """The path-state wave is sized for pixels x spp of the call and only grows: a scene that first renders 1 spp and
+    then 40 spp must give the same 40-spp frame as a fresh scene (and as a run chunked into small waves)."""
+    desc = _desc("c1_cube", width=320, height=200)
+    a = Scene(desc)
+    ia = CudaPixelIntegrator(a, precision=FAST_F32, seed=6)
+    ia.Sample(1)
+    grown = ia.Sample(40).copy()
+    fresh = CudaPixelIntegrator(Scene(desc), precision=FAST_F32, seed=6).Sample(40).copy()
+    assert np.array_equal(grown, fresh)
+    p, t = a.TracePrimary(np.random.default_rng(0).random((300000, 2)), precision=FAST_F32)     # seam after growth
+    assert (p >= 0).all() and np.isfinite(t).all()
+
+
+@pytest.mark.parametrize("n_tris", [1, 2, 3, 5, 9])
+def test_tiny_own_trees(n_tris):
+    """One-record trees with 1..4 leaves and the first two-level trees: fast ids must equal the oracle's."""
+    rng = np.random.default_rng(n_tris)
+    prims = make_prims(n_tris)
+    for i in range(n_tris):
+        c = np.array([(i % 3) - 1.0, (i // 3) - 1.0, -0.3 * i])
+        prims["v"][i, :9] = (c + rng.uniform(-0.45, 0.45, (3, 3))).ravel()
+    mats = make_materials([("lambert", (0.7, 0.7, 0.7))])
+    light = AreaLight(np.array([(-1, 3, 1), (-1, 3, -1), (1, 3, -1), (1, 3, 1)], float), (0, -1, 0), (10, 10, 10))
+    cam = PinholeCamera((0, 0, 4), (0, 0, -1), 120.0, 1.0)
+    desc = SceneDesc(prims, mats, light, cam, 64, 64, 2, PATH_INTEGRATOR)
+    s, o = Scene(desc), oracle.OracleScene(desc)
+    uv = rng.random((20000, 2))
+    op, ot = o.trace_primary(uv)
+    fp, ft = s.TracePrimary(uv, precision=FAST_F32)
+    assert (fp != op).mean() <= 2e-3
+    both = (fp == op) & (op >= 0)
+    assert both.sum() > 100 and np.allclose(ft[both], ot[both], rtol=1e-4, atol=2e-5)
+    assert np.isfinite(CudaPixelIntegrator(s, precision=FAST_F32, seed=1).Sample(2)).all()
+
+
 def test_cpp_host_driver_matches_python_host(tmp_path):
     """host/render_test (the C++ mirror of RenderTest/RayTracing4.fs) against the ctypes host: same
     Film loop, same frames -> same PFM."""

@@ -52,6 +52,46 @@ int main(void) {
     assert got == want
 
 
+def test_fsharp_shim_offsets_match_the_header():
+    """host/fsharp/MafrixCuda.fs writes the C structs into unmanaged memory by hand (no .NET here to compile it):
+    every offset it uses must be the header's."""
+    fields = [("MfxPrim", "kind"), ("MfxPrim", "material"), ("MfxPrim", "v"), ("MfxMaterial", "albedo"), ("MfxMaterial", "fuzz"),
+              ("MfxMaterial", "ei"), ("MfxMaterial", "et"), ("MfxBvhNode", "pmax"), ("MfxBvhNode", "first"), ("MfxBvhNode", "count"),
+              ("MfxSceneDesc", "n_prims"), ("MfxSceneDesc", "materials"), ("MfxSceneDesc", "n_materials"), ("MfxSceneDesc", "nodes"),
+              ("MfxSceneDesc", "n_node_slots"), ("MfxSceneDesc", "indices"), ("MfxSceneDesc", "light"), ("MfxSceneDesc", "camera"),
+              ("MfxSceneDesc", "width"), ("MfxSceneDesc", "height"), ("MfxSceneDesc", "max_depth"), ("MfxSceneDesc", "integrator"),
+              ("MfxAreaLight", "normal"), ("MfxAreaLight", "color"), ("MfxCamera", "topleft"), ("MfxCamera", "right"), ("MfxCamera", "down"),
+              ("MfxSampleParams", "seed"), ("MfxSampleParams", "first_sample"), ("MfxSampleParams", "flags")]
+    body = "".join(f'  printf("%zu\\n", offsetof({t}, {f}));\n' for t, f in fields)
+    src = '#include <stdio.h>\n#include <stddef.h>\n#include "mafrix_cuda.h"\nint main(void) {\n' + body + \
+          '  printf("%zu %zu %zu %zu %zu\\n", sizeof(MfxPrim), sizeof(MfxMaterial), sizeof(MfxBvhNode), sizeof(MfxSceneDesc), sizeof(MfxSampleParams));\n  return 0; }\n'
+    with tempfile.TemporaryDirectory() as td:
+        open(os.path.join(td, "s.c"), "w").write(src)
+        subprocess.check_call(["/usr/bin/gcc", "-I", os.path.join(ROOT, "include"), "-o", os.path.join(td, "s"), os.path.join(td, "s.c")])
+        out = subprocess.check_output([os.path.join(td, "s")]).split()
+    off = {tf: int(v) for tf, v in zip(fields, out)}
+    sizes = [int(v) for v in out[len(fields):]]
+    assert sizes == [104, 56, 56, 312, 40]
+    want = {("MfxPrim", "kind"): 0, ("MfxPrim", "material"): 4, ("MfxPrim", "v"): 8, ("MfxMaterial", "albedo"): 8, ("MfxMaterial", "fuzz"): 32,
+            ("MfxMaterial", "ei"): 40, ("MfxMaterial", "et"): 48, ("MfxBvhNode", "pmax"): 24, ("MfxBvhNode", "first"): 48, ("MfxBvhNode", "count"): 52,
+            ("MfxSceneDesc", "n_prims"): 8, ("MfxSceneDesc", "materials"): 16, ("MfxSceneDesc", "n_materials"): 24, ("MfxSceneDesc", "nodes"): 32,
+            ("MfxSceneDesc", "n_node_slots"): 40, ("MfxSceneDesc", "indices"): 48, ("MfxSceneDesc", "light"): 56, ("MfxSceneDesc", "camera"): 200,
+            ("MfxSceneDesc", "width"): 296, ("MfxSceneDesc", "height"): 300, ("MfxSceneDesc", "max_depth"): 304, ("MfxSceneDesc", "integrator"): 308,
+            ("MfxAreaLight", "normal"): 96, ("MfxAreaLight", "color"): 120, ("MfxCamera", "topleft"): 24, ("MfxCamera", "right"): 48, ("MfxCamera", "down"): 72,
+            ("MfxSampleParams", "seed"): 8, ("MfxSampleParams", "first_sample"): 16, ("MfxSampleParams", "flags"): 32}
+    assert off == want
+    # ... and the shim really uses those numbers (the table above is what its comments and writes state)
+    fs = open(os.path.join(ROOT, "host", "fsharp", "MafrixCuda.fs")).read()
+    for needle in ("AllocHGlobal(104 * hs.Length)", "AllocHGlobal 312", "WriteInt32(d, 296, width)", "WriteInt32(d, 300, height)",
+                   "WriteInt32(d, 304, maxDepth)", "WriteInt32(d, 308,", "Interop.wpt d 200 cam.position", "Interop.wpt d 224 cam.topleft",
+                   "Interop.wd d 248 cam.coord.right.x", "Interop.wd d 272 cam.coord.down.x", "Interop.wd d 152 light.normal.x",
+                   "Interop.wd d 176 light.color.r", "WriteIntPtr(d, 48, pIdx)", "WriteInt32(mem, b + 48, n.first)", "wd mem (b + 32) fuzz"):
+        assert needle in fs, needle
+    import re
+    for sym in re.findall(r"extern \w+ (mfx_\w+)\(", fs):
+        assert sym in _lib.SYMBOLS, sym
+
+
 @pytest.mark.parametrize("pos,dir,fov,aspect", [((0, 1, 3), (0, 0, -1), 120.0, 1.0), ((4.5, 1.6, 5.5), (-0.62, -0.18, -0.76), 120.0, 16 / 9),
                                                 ((13, 2, 3), (-13, -2, -3), 90.0, 4 / 3), ((0, 0.1, -2.6), (0, 0, 1), 37.5, 2.0)])
 def test_camera_matches_oracle_bitwise(pos, dir, fov, aspect):
