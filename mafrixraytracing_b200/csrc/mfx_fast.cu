@@ -1027,6 +1027,7 @@ static void launch_trace_variant(const LaunchCfg &c, const SceneF &sc, const Wav
         case 67: launch_trace6<ANY, 8, 12, 3>(c, sc, w, bounce); break;
         case 68: launch_trace6<ANY, 8, 12, 2, 2, 10>(c, sc, w, bounce); break;
         case 69: launch_trace6<ANY, 8, 12, 2, 1, 10>(c, sc, w, bounce); break;
+        case 74: launch_trace6<ANY, 8, 12, 2, 1, 9>(c, sc, w, bounce); break;
         default: launch_trace6<ANY, 8, 12, 2, 1>(c, sc, w, bounce); break;   // measured best (profiles/)
         }
         return;
