@@ -298,13 +298,23 @@ static void dev_release(int device, void *p, size_t bytes)
     cudaFree(p);
 }
 
+// frees every cached buffer of one device (called when an allocation fails before giving up on its size)
+static void pool_trim(int device)
+{
+    std::lock_guard<std::mutex> g(g_pool_mu);
+    for (auto it = g_pool.begin(); it != g_pool.end();) {
+        if (it->first.first == device) { cudaFree(it->second); g_pool_bytes -= it->first.second; it = g_pool.erase(it); }
+        else ++it;
+    }
+}
+
 // gives one buffer of the scene back (to the pool) before the scene dies: the wave state grows on demand
-static void dev_free_one(MfxScene *s, void *p)
+static void dev_free_one(MfxScene *s, void *p, bool to_pool = true)
 {
     if (!p) return;
     for (size_t i = 0; i < s->allocs.size(); i++)
         if (s->allocs[i].first == p) {
-            dev_release(s->device, p, s->allocs[i].second);
+            if (to_pool) dev_release(s->device, p, s->allocs[i].second); else cudaFree(p);
             s->allocs.erase(s->allocs.begin() + (long)i);
             return;
         }
@@ -985,14 +995,28 @@ static int ensure_wave_fast(MfxScene *s, size_t want)
         for (void *q : old) dev_free_one(s, q);
         s->wf_ready = false;
     }
-    memset(&w, 0, sizeof(w));
-    w.P = (int)P;
-    w.tmin = 1e-6f;
-    MFX_TRY(dev_alloc_t(s, &w.ray_o, P)); MFX_TRY(dev_alloc_t(s, &w.ray_d, P));
-    MFX_TRY(dev_alloc_t(s, &w.hit, P)); MFX_TRY(dev_alloc_t(s, &w.thr, P)); MFX_TRY(dev_alloc_t(s, &w.rad, P));
-    MFX_TRY(dev_alloc_t(s, &w.sh_d, P)); MFX_TRY(dev_alloc_t(s, &w.sh_c, P));
-    MFX_TRY(dev_alloc_t(s, &w.q_ext[0], P)); MFX_TRY(dev_alloc_t(s, &w.q_ext[1], P)); MFX_TRY(dev_alloc_t(s, &w.q_sh, P));
-    MFX_TRY(dev_alloc_t(s, &w.counts, MFX_COUNTS_LEN));
+    // a wave that does not fit (another tenant on the GPU) is halved until it does: same frame, more launches
+    bool trimmed = false;
+    for (;;) {
+        memset(&w, 0, sizeof(w));
+        w.P = (int)P;
+        w.tmin = 1e-6f;
+        auto all = [&]() -> int {
+            MFX_TRY(dev_alloc_t(s, &w.ray_o, P)); MFX_TRY(dev_alloc_t(s, &w.ray_d, P));
+            MFX_TRY(dev_alloc_t(s, &w.hit, P)); MFX_TRY(dev_alloc_t(s, &w.thr, P)); MFX_TRY(dev_alloc_t(s, &w.rad, P));
+            MFX_TRY(dev_alloc_t(s, &w.sh_d, P)); MFX_TRY(dev_alloc_t(s, &w.sh_c, P));
+            MFX_TRY(dev_alloc_t(s, &w.q_ext[0], P)); MFX_TRY(dev_alloc_t(s, &w.q_ext[1], P)); MFX_TRY(dev_alloc_t(s, &w.q_sh, P));
+            MFX_TRY(dev_alloc_t(s, &w.counts, MFX_COUNTS_LEN));
+            return MFX_OK;
+        };
+        const int rc = all();
+        if (rc == MFX_OK) break;
+        void *part[] = { w.ray_o, w.ray_d, w.hit, w.thr, w.rad, w.sh_d, w.sh_c, w.q_ext[0], w.q_ext[1], w.q_sh, w.counts };
+        for (void *q : part) dev_free_one(s, q, false);
+        if (rc != MFX_ERR_OUT_OF_MEMORY || P <= ((size_t)1 << 20)) return rc;
+        cudaGetLastError();                                       // clear the allocation error
+        if (!trimmed) { pool_trim(s->device); trimmed = true; } else P /= 2;
+    }
     s->wf_ready = true;
     return MFX_OK;
 }

@@ -412,6 +412,24 @@ def test_wave_grows_with_the_call_and_frames_do_not_depend_on_it():
     assert (p >= 0).all() and np.isfinite(t).all()
 
 
+def test_wave_shrinks_when_the_gpu_is_nearly_full():
+    """Another tenant holds almost all HBM: the path-state wave (3.9 GB wanted here) must fall back to a smaller one
+    -- more launches, same frame -- instead of failing."""
+    import torch
+    desc = _desc("c2_spot", width=1920, height=1080)
+    spp = 17                                        # 35 M paths = 4.1 GB of path state, a size no other test leaves pooled
+    torch.cuda.synchronize()
+    free, _total = torch.cuda.mem_get_info()
+    hog = torch.empty(max(free - (3 << 30), 1 << 20), dtype=torch.uint8, device="cuda")
+    try:
+        got = CudaPixelIntegrator(Scene(desc), precision=FAST_F32, seed=3).SampleF32(spp)
+    finally:
+        del hog
+        torch.cuda.empty_cache()
+    want = CudaPixelIntegrator(Scene(desc), precision=FAST_F32, seed=3).SampleF32(spp)
+    assert np.allclose(got, want, rtol=1e-5, atol=1e-7)
+
+
 @pytest.mark.parametrize("n_tris", [1, 2, 3, 5, 9])
 def test_tiny_own_trees(n_tris):
     """One-record trees with 1..4 leaves and the first two-level trees: fast ids must equal the oracle's."""
