@@ -17,6 +17,16 @@ def write_pfm(path, rows_rgb):
 
 
 def write_png(path, rgba8_rows):
-    """rgba8_rows: (height, width, 4) uint8 as produced by Film.PostProcess()."""
-    from PIL import Image
-    Image.fromarray(np.asarray(rgba8_rows, np.uint8), "RGBA").save(path)
+    """rgba8_rows: (height, width, 4) uint8 as produced by Film.PostProcess().  Plain zlib PNG, no imaging library."""
+    import struct
+    import zlib
+    img = np.ascontiguousarray(np.asarray(rgba8_rows, np.uint8))
+    h, w, c = img.shape
+    assert c == 4
+    raw = b"".join(b"\x00" + img[y].tobytes() for y in range(h))
+
+    def chunk(tag, data):
+        return struct.pack(">I", len(data)) + tag + data + struct.pack(">I", zlib.crc32(tag + data) & 0xffffffff)
+    with open(path, "wb") as fh:
+        fh.write(b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", struct.pack(">IIBBBBB", w, h, 8, 6, 0, 0, 0)) +
+                 chunk(b"IDAT", zlib.compress(raw, 6)) + chunk(b"IEND", b""))

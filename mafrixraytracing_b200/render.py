@@ -1,0 +1,45 @@
+"""Headless driver: `python -m mafrixraytracing_b200.render scene.xml --frames 16 --spp 1 --out cornell`.
+
+The window loop of RenderTest/Sample/RayTracing4.fs:73-80 without the window: InitSceneState (here: ingest.py),
+`new Scene(state)`, then per displayed frame `film.GetFrame(pixelIntegrator, spp)` (Scene.fs:331-333) and, at the
+end, the tone-mapped RGBA8 buffer (Scene.fs:315-330) as PNG plus the accumulated radiance as PFM."""
+import argparse
+import os
+import sys
+
+import numpy as np
+
+from . import Scene, CudaPixelIntegrator, Film, EXACT_F64, FAST_F32
+from .imageio import texture_to_rows, write_pfm, write_png
+from .ingest import init_scene_state
+
+
+def main(argv=None):
+    ap = argparse.ArgumentParser(description=__doc__.splitlines()[0])
+    ap.add_argument("scene", help="XML scene description (the reference's Scene.xml format)")
+    ap.add_argument("--frames", type=int, default=16)
+    ap.add_argument("--spp", type=int, default=1, help="samples per pixel and frame (Scene.Render uses 1)")
+    ap.add_argument("--exact", action="store_true", help="MFX_EXACT_F64 instead of MFX_FAST_F32")
+    ap.add_argument("--seed", type=int, default=1)
+    ap.add_argument("--out", default="frame")
+    a = ap.parse_args(argv)
+    with open(a.scene, "r", encoding="utf-8-sig") as fh:
+        desc = init_scene_state(fh.read(), base_dir=os.path.dirname(os.path.abspath(a.scene)))
+    scene = Scene(desc)
+    integ = CudaPixelIntegrator(scene, precision=EXACT_F64 if a.exact else FAST_F32, seed=a.seed)
+    film = Film(scene)
+    rays = ms = 0.0
+    for f in range(a.frames):
+        target = film.GetFrame(integ, a.spp, first_sample=f * a.spp)
+        rays += integ.stats["closest_rays"] + integ.stats["shadow_rays"]
+        ms += integ.stats["ms_total"]
+    write_pfm(a.out + ".pfm", texture_to_rows(target)[:, :, :3].astype(np.float32))
+    write_png(a.out + ".png", film.PostProcess())
+    print(f"{desc.width}x{desc.height}, {len(desc.prims)} shapes, {a.frames} frames x {a.spp} spp: "
+          f"{rays / 1e6:.1f} Mrays in {ms:.1f} ms ({rays / max(ms, 1e-9) / 1e3:.0f} Mrays/s) -> {a.out}.pfm, {a.out}.png")
+    scene.close()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

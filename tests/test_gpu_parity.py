@@ -452,6 +452,50 @@ def test_tiny_own_trees(n_tris):
     assert np.isfinite(CudaPixelIntegrator(s, precision=FAST_F32, seed=1).Sample(2)).all()
 
 
+def test_ingested_xml_scene_renders_like_the_procedural_one(tmp_path):
+    """Scene.xml-style description + OBJ (mafrixraytracing_b200/ingest.py) -> same frame, bit for bit, as the
+    procedural Cornell scene; the oracle agrees."""
+    from tests.test_ingest import _write_cornell
+    from mafrixraytracing_b200.ingest import init_scene_state
+    xml, want = _write_cornell(str(tmp_path))
+    desc = init_scene_state(xml, base_dir=str(tmp_path))
+    desc.width = want.width = 120
+    desc.height = want.height = 120
+    a = CudaPixelIntegrator(Scene(desc), precision=EXACT_F64, seed=4).Sample(2).copy()
+    b = CudaPixelIntegrator(Scene(want), precision=EXACT_F64, seed=4).Sample(2).copy()
+    assert np.array_equal(a, b)
+    assert np.array_equal(a[:, :, :3], oracle.OracleScene(desc).sample(2, seed=4)[:, :, :3])
+    f = CudaPixelIntegrator(Scene(desc), precision=FAST_F32, seed=4).Sample(2).copy()
+    g = CudaPixelIntegrator(Scene(want), precision=FAST_F32, seed=4).Sample(2).copy()
+    assert np.array_equal(f, g)
+
+
+def test_headless_render_cli_from_a_scene_file(tmp_path):
+    """python -m mafrixraytracing_b200.render scene.xml: the RenderTest loop without the window."""
+    from tests.test_ingest import _write_cornell
+    from mafrixraytracing_b200 import render
+    xml, want = _write_cornell(str(tmp_path))
+    (tmp_path / "scene.xml").write_text(xml.replace('value="300"', 'value="96"'))
+    out = str(tmp_path / "img")
+    assert render.main([str(tmp_path / "scene.xml"), "--frames", "3", "--spp", "2", "--out", out]) == 0
+    with open(out + ".pfm", "rb") as fh:
+        assert fh.readline() == b"PF\n" and fh.readline() == b"96 96\n" and fh.readline() == b"-1.0\n"
+        img = np.frombuffer(fh.read(), "<f4").reshape(96, 96, 3)[::-1]
+    want.width = want.height = 96
+    s = Scene(want)
+    film = Film(s)
+    integ = CudaPixelIntegrator(s, precision=FAST_F32, seed=1)
+    for f in range(3):
+        target = film.GetFrame(integ, 2, first_sample=2 * f)
+    assert np.array_equal(img, np.transpose(target[:, :, :3], (1, 0, 2)).astype(np.float32))
+    png = open(out + ".png", "rb").read()
+    assert png[:8] == b"\x89PNG\r\n\x1a\n" and png[12:16] == b"IHDR" and png[16:24] == (96).to_bytes(4, "big") * 2
+    import zlib
+    idat = png[png.index(b"IDAT") + 4: png.index(b"IEND") - 8]
+    rows = np.frombuffer(zlib.decompress(idat), np.uint8).reshape(96, 1 + 96 * 4)[:, 1:].reshape(96, 96, 4)
+    assert np.array_equal(rows, film.PostProcess())
+
+
 def test_cpp_host_driver_matches_python_host(tmp_path):
     """host/render_test (the C++ mirror of RenderTest/RayTracing4.fs) against the ctypes host: same
     Film loop, same frames -> same PFM."""
