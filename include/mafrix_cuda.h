@@ -210,6 +210,7 @@ MFX_API int mfx_host_register(void *ptr, uint64_t bytes);
 MFX_API int mfx_host_unregister(void *ptr);
 
 /* ---- Film (Film.fs:13-34): progressive accumulation, state kept in HBM ----------------------- */
+/* Lifetime: a film borrows its scene's stream -- destroy every film BEFORE mfx_scene_destroy of its scene. */
 MFX_API int mfx_film_create(MfxScene *scene, MfxFilm **out);
 MFX_API int mfx_film_destroy(MfxFilm *film);
 MFX_API int mfx_film_reset(MfxFilm *film);                                   /* Film.Reset, :26-30 */

@@ -35,6 +35,7 @@ def main(argv=None):
         ms += integ.stats["ms_total"]
     write_pfm(a.out + ".pfm", texture_to_rows(target)[:, :, :3].astype(np.float32))
     write_png(a.out + ".png", film.PostProcess())
+    film.close()
     print(f"{desc.width}x{desc.height}, {len(desc.prims)} shapes, {a.frames} frames x {a.spp} spp: "
           f"{rays / 1e6:.1f} Mrays in {ms:.1f} ms ({rays / max(ms, 1e-9) / 1e3:.0f} Mrays/s) -> {a.out}.pfm, {a.out}.png")
     scene.close()

@@ -13,6 +13,7 @@ Names and argument meaning follow the F# types they stand in for (paths under
 All compute goes through libmafrix_cuda; nothing here renders on the CPU.
 """
 import ctypes as C
+import weakref
 from dataclasses import dataclass, field
 
 import numpy as np
@@ -197,9 +198,12 @@ class Scene:
         h = C.c_void_p()
         _lib.check(lib.mfx_scene_create(C.byref(d), C.byref(h)))
         self._h = h
+        self._films = weakref.WeakSet()
 
     def close(self):
         if getattr(self, "_h", None):
+            for f in list(getattr(self, "_films", ())):      # a Film borrows the scene's stream and buffers: it goes first
+                f.close()
             _lib.load().mfx_scene_destroy(self._h)
             self._h = None
 
@@ -300,6 +304,7 @@ class Film:
         h = C.c_void_p()
         _lib.check(_lib.load().mfx_film_create(scene._h, C.byref(h)))
         self._h = h
+        scene._films.add(self)
         self.target = np.zeros((scene.width, scene.height, 4), dtype=np.float64)
 
     def close(self):
