@@ -1012,7 +1012,7 @@ static void launch_trace6b(const LaunchCfg &c, const SceneF &sc, const WaveF &w,
 template <bool ANY, int RT, int LT, int NS, int NL = 2, int MB = 1>
 static void launch_trace6(const LaunchCfg &c, const SceneF &sc, const WaveF &w, int bounce)
 {
-    if (sc.has_big_sphere) launch_trace6b<ANY, true, RT, LT, NS, NL, 1>(c, sc, w, bounce);
+    if (sc.has_big_sphere) launch_trace6b<ANY, true, RT, LT, NS, NL, MB>(c, sc, w, bounce);
     else launch_trace6b<ANY, false, RT, LT, NS, NL, MB>(c, sc, w, bounce);
 }
 template <bool ANY>
@@ -1020,22 +1020,17 @@ static void launch_trace_variant(const LaunchCfg &c, const SceneF &sc, const Wav
 {
     if (sc.own_tree) {          // the library's SAH tree (default); the host passes the reference-tree layout for the others
         if (ctr) {              // MFX_SAMPLE_COUNT_OWN_TREE: the shipped configuration, instrumented
-            if (sc.has_big_sphere) launch_trace6b<ANY, true, 8, 12, 2, 1, 1, true>(c, sc, w, bounce, ctr);
-            else launch_trace6b<ANY, false, 8, 12, 2, 1, 1, true>(c, sc, w, bounce, ctr);
+            if (sc.has_big_sphere) launch_trace6b<ANY, true, 16, 10, 2, 1, 1, true>(c, sc, w, bounce, ctr);
+            else launch_trace6b<ANY, false, 16, 10, 2, 1, 1, true>(c, sc, w, bounce, ctr);
             return;
         }
-        switch (c.variant) {
-        case 61: launch_trace6<ANY, 8, 12, 2>(c, sc, w, bounce); break;
-        case 62: launch_trace6<ANY, 12, 16, 1>(c, sc, w, bounce); break;
-        case 63: launch_trace6<ANY, 6, 10, 2>(c, sc, w, bounce); break;
-        case 64: launch_trace6<ANY, 12, 16, 2, 1>(c, sc, w, bounce); break;
+        switch (c.variant) {    // tuning knobs kept for A/B runs (tools/kb2.py); the default is the measured best (profiles/)
+        case 61: launch_trace6<ANY, 8, 12, 2, 2>(c, sc, w, bounce); break;      // two parked leaves
+        case 62: launch_trace6<ANY, 12, 16, 1, 2>(c, sc, w, bounce); break;     // one node step per iteration
         case 65: launch_trace6<ANY, 8, 12, 2, 1>(c, sc, w, bounce); break;
-        case 66: launch_trace6<ANY, 8, 8, 2>(c, sc, w, bounce); break;
-        case 67: launch_trace6<ANY, 8, 12, 3>(c, sc, w, bounce); break;
-        case 68: launch_trace6<ANY, 8, 12, 2, 2, 10>(c, sc, w, bounce); break;
-        case 69: launch_trace6<ANY, 8, 12, 2, 1, 10>(c, sc, w, bounce); break;
-        case 74: launch_trace6<ANY, 8, 12, 2, 1, 9>(c, sc, w, bounce); break;
-        default: launch_trace6<ANY, 8, 12, 2, 1>(c, sc, w, bounce); break;   // measured best (profiles/)
+        case 84: launch_trace6<ANY, 12, 12, 2, 1>(c, sc, w, bounce); break;
+        case 85: launch_trace6<ANY, 16, 8, 2, 1>(c, sc, w, bounce); break;
+        default: launch_trace6<ANY, 16, 10, 2, 1>(c, sc, w, bounce); break;
         }
         return;
     }
