@@ -6,6 +6,7 @@
 // basis) must round exactly like the reference's f64 expressions.
 #include "../../include/mafrix_cuda.h"
 #include "mfx_internal.h"
+#include "mfx_build.h"
 
 #include <algorithm>
 #include <atomic>
@@ -23,8 +24,10 @@
 
 // ------------------------------------------------------------------ errors
 static thread_local std::string g_err;
+#define fail mfx_fail
+#define env_long mfx_env_long
 
-static int fail(int code, const char *fmt, ...)
+int mfx_fail(int code, const char *fmt, ...)
 {
     char buf[1024];
     va_list ap;
@@ -114,126 +117,6 @@ extern "C" int mfx_camera_pinhole(const double pos[3], const double dir[3], doub
     return MFX_OK;
 }
 
-static long env_long(const char *name, long dflt);
-
-// ------------------------------------------------------------------ Bvh.Build reproduction
-struct HBound { double lo[3], hi[3]; };
-
-// F# min/max on floats are System.Math.Min/Max: NaN propagates, -0.0 < +0.0.
-static inline double net_min(double a, double b)
-{
-    if (a < b) return a;
-    if (b < a) return b;
-    if (a != a) return a;
-    return std::signbit(a) ? a : b;
-}
-static inline double net_max(double a, double b)
-{
-    if (a > b) return a;
-    if (b > a) return b;
-    if (a != a) return a;
-    return std::signbit(a) ? b : a;
-}
-
-static HBound prim_bound(const MfxPrim &p)
-{
-    HBound b;
-    if (p.kind == MFX_SPHERE) {                                 // Sphere.fs:17-20: Bound(c - v, c + v)
-        for (int a = 0; a < 3; a++) {
-            double m0 = p.v[a] - p.v[3], m1 = p.v[a] + p.v[3];
-            b.lo[a] = net_min(m0, m1); b.hi[a] = net_max(m0, m1);
-        }
-        return b;
-    }
-    const int nv = (p.kind == MFX_RECT) ? 4 : 3;                // Trangle.fs:113, Rect.fs:23
-    for (int a = 0; a < 3; a++) {
-        double lo = p.v[a], hi = p.v[a];
-        for (int k = 1; k < nv; k++) { lo = net_min(lo, p.v[3 * k + a]); hi = net_max(hi, p.v[3 * k + a]); }
-        b.lo[a] = lo; b.hi[a] = hi;
-    }
-    return b;
-}
-
-struct BuildCtx {
-    const std::vector<HBound> *pb;
-    MfxBvhNode *nodes;
-    int32_t *indices;
-    int32_t n_slots;
-};
-
-static MfxBvhNode init_node(const BuildCtx &c, int start, int count)    // BvhNode.fs:32-37
-{
-    MfxBvhNode n;
-    const HBound &b0 = (*c.pb)[c.indices[start]];
-    for (int a = 0; a < 3; a++) { n.pmin[a] = b0.lo[a]; n.pmax[a] = b0.hi[a]; }
-    for (int i = 1; i < count; i++) {
-        const HBound &b = (*c.pb)[c.indices[start + i]];
-        for (int a = 0; a < 3; a++) { n.pmin[a] = net_min(n.pmin[a], b.lo[a]); n.pmax[a] = net_max(n.pmax[a], b.hi[a]); }
-    }
-    n.first = start; n.count = count;
-    return n;
-}
-
-// Bvh.Subdivide (BvhNode.fs:42-61) for the subtree rooted at heap slot `root`.  Subtrees are independent (disjoint
-// index ranges and heap slots), so the top `par_depth` levels hand their left child to another thread: the result
-// is identical to the serial recursion, a 10 M-primitive build just finishes ~4x sooner.
-static int subdivide(const BuildCtx &c, int root, int par_depth)
-{
-    std::vector<std::pair<double, int32_t>> scratch;
-    std::vector<int> todo{ root };
-    std::vector<std::future<int>> spawned;
-    int rc = MFX_OK;
-    while (!todo.empty()) {
-        const int i = todo.back(); todo.pop_back();
-        const MfxBvhNode node = c.nodes[i];
-        if (node.count <= MFX_LEAF_NODE_COUNT) continue;
-        // Bound.MaximumExtent, Aggregate.fs:29-36
-        const double dx = node.pmax[0] - node.pmin[0], dy = node.pmax[1] - node.pmin[1], dz = node.pmax[2] - node.pmin[2];
-        const int axis = (dx > dy && dx > dz) ? 0 : (dy > dz ? 1 : 2);
-        scratch.resize(node.count);
-        for (int k = 0; k < node.count; k++) {
-            const int32_t id = c.indices[node.first + k];
-            const HBound &b = (*c.pb)[id];
-            const double dig = (b.hi[axis] - b.lo[axis]) * 0.5;           // b.Diagnal() * 0.5
-            scratch[k] = { b.lo[axis] + dig, id };                        // b.pMin + dig
-        }
-        // Array.sortInPlaceBy is an unstable introsort in .NET (quirk Q9); ties are fixed to "stable"
-        std::stable_sort(scratch.begin(), scratch.end(),
-                         [](const std::pair<double, int32_t> &a, const std::pair<double, int32_t> &b) { return a.first < b.first; });
-        for (int k = 0; k < node.count; k++) c.indices[node.first + k] = scratch[k].second;
-        const int leftcount = node.count / 2;
-        const int li = i * 2 + 1, ri = i * 2 + 2;
-        if (ri >= c.n_slots) { rc = fail(MFX_ERR_INVALID_ARGUMENT, "mfx_bvh_build: heap index %d exceeds %d slots", ri, c.n_slots); break; }
-        c.nodes[li] = init_node(c, node.first, leftcount);
-        c.nodes[ri] = init_node(c, node.first + leftcount, node.count - leftcount);
-        if (par_depth > 0 && i == root && node.count > (1 << 16)) {
-            spawned.push_back(std::async(std::launch::async, [&c, li, par_depth]() { return subdivide(c, li, par_depth - 1); }));
-            root = ri; par_depth--;                                       // keep splitting the right child on this thread
-            todo.push_back(ri);
-        } else {
-            todo.push_back(ri);
-            todo.push_back(li);
-        }
-    }
-    for (auto &f : spawned) { const int r = f.get(); if (r != MFX_OK) rc = r; }
-    return rc;
-}
-
-extern "C" int mfx_bvh_build(const MfxPrim *prims, int32_t n, MfxBvhNode *nodes_out, int32_t n_slots, int32_t *indices_out)
-{
-    if (!prims || !nodes_out || !indices_out || n <= 0) return fail(MFX_ERR_INVALID_ARGUMENT, "mfx_bvh_build: null/empty input");
-    if (n_slots != 2 * n - 1) return fail(MFX_ERR_INVALID_ARGUMENT, "mfx_bvh_build: n_slots must be 2n-1 = %d, got %d", 2 * n - 1, n_slots);
-    std::vector<HBound> pb(n);
-    for (int i = 0; i < n; i++) {
-        if (prims[i].kind < 0 || prims[i].kind > 2) return fail(MFX_ERR_INVALID_ARGUMENT, "primitive %d: unknown kind %d", i, prims[i].kind);
-        pb[i] = prim_bound(prims[i]);
-    }
-    for (int i = 0; i < n; i++) indices_out[i] = i;
-    memset(nodes_out, 0, sizeof(MfxBvhNode) * (size_t)n_slots);
-    BuildCtx c{ &pb, nodes_out, indices_out, n_slots };
-    nodes_out[0] = init_node(c, 0, n);
-    return subdivide(c, 0, (int)env_long("MFX_BVH_BUILD_PAR_DEPTH", 5));
-}
 
 // ------------------------------------------------------------------ scene
 struct MfxScene {
@@ -333,7 +216,7 @@ template <typename T> static int upload(MfxScene *s, T **dp, const std::vector<T
     return MFX_OK;
 }
 
-static long env_long(const char *name, long dflt)
+long mfx_env_long(const char *name, long dflt)
 {
     const char *v = getenv(name);
     if (!v || !*v) return dflt;
@@ -682,143 +565,7 @@ static int flatten_fast_ref(MfxScene *s)
     return MFX_OK;
 }
 
-// ---- flatten: fast layout over the library's own tree (binned SAH, collapsed to four children per record)
-struct SahNode { float lo[3], hi[3]; int left, right, first, count; };   // count > 0: leaf over order[first .. first+count)
-struct SahCtx {
-    const float (*lo)[3]; const float (*hi)[3];
-    int *idx;
-    SahNode *nodes;
-    std::atomic<int> next{ 0 };
-    int max_leaf;
-    float c_trav;       // cost of one node step relative to one primitive test
-};
-static inline float half_area(const float *lo, const float *hi)
-{
-    const float x = hi[0] - lo[0], y = hi[1] - lo[1], z = hi[2] - lo[2];
-    return x * y + y * z + z * x;
-}
-static inline void grow(float *lo, float *hi, const float *blo, const float *bhi)
-{
-    for (int a = 0; a < 3; a++) { lo[a] = std::min(lo[a], blo[a]); hi[a] = std::max(hi[a], bhi[a]); }
-}
-static const float SAH_INF = 3.0e38f;
-
-// Splits idx[first .. first+count) by the surface-area heuristic; returns the size of the left part (0 = keep as leaf).
-static int sah_split(SahCtx &c, const SahNode &nd)
-{
-    const int first = nd.first, count = nd.count;
-    const float area = half_area(nd.lo, nd.hi);
-    const float leaf_cost = (float)count;                    // in units of (node area x primitive test)
-    float best = SAH_INF; int best_axis = -1, best_pos = -1;
-    float clo[3] = { SAH_INF, SAH_INF, SAH_INF }, chi[3] = { -SAH_INF, -SAH_INF, -SAH_INF };
-    for (int k = 0; k < count; k++) {
-        const int id = c.idx[first + k];
-        for (int a = 0; a < 3; a++) { const float ce = 0.5f * (c.lo[id][a] + c.hi[id][a]); clo[a] = std::min(clo[a], ce); chi[a] = std::max(chi[a], ce); }
-    }
-    const float inv_area = area > 0.f ? 1.0f / area : 0.f;
-    if (count <= 24) {
-        // exact sweep: sort by centroid on each axis (insertion sort, stable), try every split position
-        std::pair<float, int> key[24]; float right[24]; int best_order[24];
-        for (int ax = 0; ax < 3; ax++) {
-            for (int k = 0; k < count; k++) {
-                const int id = c.idx[first + k];
-                const std::pair<float, int> e{ c.lo[id][ax] + c.hi[id][ax], id };
-                int j = k;
-                while (j > 0 && key[j - 1].first > e.first) { key[j] = key[j - 1]; j--; }
-                key[j] = e;
-            }
-            float lo[3] = { SAH_INF, SAH_INF, SAH_INF }, hi[3] = { -SAH_INF, -SAH_INF, -SAH_INF };
-            for (int k = count - 1; k > 0; k--) { grow(lo, hi, c.lo[key[k].second], c.hi[key[k].second]); right[k] = half_area(lo, hi); }
-            for (int a = 0; a < 3; a++) { lo[a] = SAH_INF; hi[a] = -SAH_INF; }
-            bool improved = false;
-            for (int k = 1; k < count; k++) {
-                grow(lo, hi, c.lo[key[k - 1].second], c.hi[key[k - 1].second]);
-                const float cost = c.c_trav + (half_area(lo, hi) * k + right[k] * (count - k)) * inv_area;
-                if (cost < best) { best = cost; best_axis = ax; best_pos = k; improved = true; }
-            }
-            if (improved) for (int k = 0; k < count; k++) best_order[k] = key[k].second;
-        }
-        if (best_axis < 0 || (count <= c.max_leaf && leaf_cost <= best)) return count <= c.max_leaf ? 0 : count / 2;
-        for (int k = 0; k < count; k++) c.idx[first + k] = best_order[k];
-        return best_pos;
-    }
-    // binned: 32 centroid bins per axis
-    const int NB = 32;
-    int best_bin = -1;
-    for (int ax = 0; ax < 3; ax++) {
-        const float ext = chi[ax] - clo[ax];
-        if (!(ext > 0.f)) continue;
-        const float scale = (float)NB * (1.0f - 1e-6f) / ext;
-        float blo[NB][3], bhi[NB][3]; int bn[NB];
-        for (int b = 0; b < NB; b++) { bn[b] = 0; for (int a = 0; a < 3; a++) { blo[b][a] = SAH_INF; bhi[b][a] = -SAH_INF; } }
-        for (int k = 0; k < count; k++) {
-            const int id = c.idx[first + k];
-            int b = (int)((0.5f * (c.lo[id][ax] + c.hi[id][ax]) - clo[ax]) * scale);
-            b = b < 0 ? 0 : (b >= NB ? NB - 1 : b);
-            bn[b]++; grow(blo[b], bhi[b], c.lo[id], c.hi[id]);
-        }
-        float right[NB]; int rn[NB];
-        float lo[3] = { SAH_INF, SAH_INF, SAH_INF }, hi[3] = { -SAH_INF, -SAH_INF, -SAH_INF };
-        int cnt = 0;
-        for (int b = NB - 1; b > 0; b--) { if (bn[b]) grow(lo, hi, blo[b], bhi[b]); cnt += bn[b]; right[b] = cnt ? half_area(lo, hi) : 0.f; rn[b] = cnt; }
-        for (int a = 0; a < 3; a++) { lo[a] = SAH_INF; hi[a] = -SAH_INF; }
-        cnt = 0;
-        for (int b = 1; b < NB; b++) {
-            if (bn[b - 1]) grow(lo, hi, blo[b - 1], bhi[b - 1]);
-            cnt += bn[b - 1];
-            if (cnt == 0 || rn[b] == 0) continue;
-            const float cost = c.c_trav + (half_area(lo, hi) * cnt + right[b] * rn[b]) * inv_area;
-            if (cost < best) { best = cost; best_axis = ax; best_bin = b; }
-        }
-    }
-    if (best_axis < 0) {
-        // all centroids coincide: nothing to choose between, cut the list in half
-        return count / 2;
-    }
-    const float scale = (float)NB * (1.0f - 1e-6f) / (chi[best_axis] - clo[best_axis]);
-    int *mid = std::partition(c.idx + first, c.idx + first + count, [&](int id) {
-        int b = (int)((0.5f * (c.lo[id][best_axis] + c.hi[id][best_axis]) - clo[best_axis]) * scale);
-        b = b < 0 ? 0 : (b >= NB ? NB - 1 : b);
-        return b < best_bin;
-    });
-    const int left = (int)(mid - (c.idx + first));
-    return (left == 0 || left == count) ? count / 2 : left;
-}
-
-static void sah_bound(const SahCtx &c, SahNode &nd)
-{
-    for (int a = 0; a < 3; a++) { nd.lo[a] = SAH_INF; nd.hi[a] = -SAH_INF; }
-    for (int k = 0; k < nd.count; k++) grow(nd.lo, nd.hi, c.lo[c.idx[nd.first + k]], c.hi[c.idx[nd.first + k]]);
-}
-
-// Builds the subtree of node `root` (its first/count/bounds are set).  Disjoint ranges => the top levels fork.
-static void sah_build(SahCtx &c, int root, int par_depth)
-{
-    std::vector<int> todo{ root };
-    std::vector<std::future<void>> spawned;
-    while (!todo.empty()) {
-        const int i = todo.back(); todo.pop_back();
-        SahNode nd = c.nodes[i];
-        if (nd.count <= 1) continue;
-        const int left = sah_split(c, nd);
-        if (left == 0) continue;                                 // stays a leaf
-        const int li = c.next.fetch_add(2), ri = li + 1;
-        SahNode &L = c.nodes[li], &R = c.nodes[ri];
-        L.first = nd.first; L.count = left; L.left = L.right = -1;
-        R.first = nd.first + left; R.count = nd.count - left; R.left = R.right = -1;
-        sah_bound(c, L); sah_bound(c, R);
-        c.nodes[i].left = li; c.nodes[i].right = ri; c.nodes[i].count = 0;
-        if (par_depth > 0 && i == root && nd.count > 1024) {
-            spawned.push_back(std::async(std::launch::async, [&c, li, par_depth]() { sah_build(c, li, par_depth - 1); }));
-            root = ri; par_depth--;
-            todo.push_back(ri);
-        } else {
-            todo.push_back(ri); todo.push_back(li);
-        }
-    }
-    for (auto &f : spawned) f.get();
-}
-
+// ---- flatten: fast layout over the library's own tree (mfx_build.cpp: binned SAH, collapsed to four children per record)
 static int flatten_fast(MfxScene *s)
 {
     if (s->f_ready) return MFX_OK;
@@ -853,66 +600,18 @@ static int flatten_fast(MfxScene *s)
         }
         for (int a = 0; a < 3; a++) { blo[(size_t)k * 3 + a] = round_down(lo[a]); bhi[(size_t)k * 3 + a] = round_up(hi[a]); }
     }
-    std::vector<int> idx(ns);
-    for (int k = 0; k < ns; k++) idx[k] = k;
-    std::vector<SahNode> nodes((size_t)2 * ns + 2);
-    SahCtx c;
-    c.lo = reinterpret_cast<const float (*)[3]>(blo.data()); c.hi = reinterpret_cast<const float (*)[3]>(bhi.data());
-    c.idx = idx.data(); c.nodes = nodes.data(); c.next = 1;
-    c.max_leaf = (int)std::min(7L, std::max(1L, env_long("MFX_SAH_MAX_LEAF", 4)));
-    c.c_trav = (float)env_long("MFX_SAH_TRAV_COST_PCT", 100) * 0.01f;
-    nodes[0].first = 0; nodes[0].count = ns; nodes[0].left = nodes[0].right = -1;
-    sah_bound(c, nodes[0]);
     lap("slots");
-    sah_build(c, 0, (int)env_long("MFX_BVH_BUILD_PAR_DEPTH", 5));
-    lap("sah");
-
-    // collapse to four children per record, depth-first; leaves of a record get consecutive slots
-    std::vector<QuadF> quads;
-    std::vector<int> order; order.reserve(ns);
-    int own_depth = 0;
-    struct Item { int bnode; int level; int parent; int pslot; };
-    std::vector<Item> todo{ { 0, 0, -1, 0 } };
-    quads.reserve((size_t)ns / 2 + 4);
-    const float FAR = 1e30f;
-    while (!todo.empty()) {
-        const Item it = todo.back(); todo.pop_back();
-        const int qi = (int)quads.size();
-        if (it.parent >= 0) reinterpret_cast<int *>(&quads[it.parent].meta)[it.pslot] = ~qi;
-        own_depth = std::max(own_depth, it.level + 1);
-        int kids[4], nk = 0;
-        if (nodes[it.bnode].count > 0) kids[nk++] = it.bnode;           // a one-leaf tree: the root record holds it
-        else { kids[nk++] = nodes[it.bnode].left; kids[nk++] = nodes[it.bnode].right; }
-        while (nk < 4) {
-            int pick = -1; float pa = -1.f;
-            for (int k = 0; k < nk; k++) if (nodes[kids[k]].count == 0) { const float ar = half_area(nodes[kids[k]].lo, nodes[kids[k]].hi); if (ar > pa) { pa = ar; pick = k; } }
-            if (pick < 0) break;
-            const int b = kids[pick];
-            kids[pick] = nodes[b].left; kids[nk++] = nodes[b].right;
-        }
-        QuadF q; memset(&q, 0, sizeof(q));
-        float lo[3][4], hi[3][4]; int meta[4];
-        for (int sl = 0; sl < 4; sl++) { for (int a = 0; a < 3; a++) { lo[a][sl] = FAR; hi[a][sl] = FAR; } meta[sl] = MFX_QUAD_EMPTY; }
-        for (int k = 0; k < nk; k++) {
-            const SahNode &nd = nodes[kids[k]];
-            for (int a = 0; a < 3; a++) { lo[a][k] = nd.lo[a]; hi[a][k] = nd.hi[a]; }
-            if (nd.count > 0) {
-                meta[k] = ((int)order.size() << 3) | nd.count;
-                for (int j = 0; j < nd.count; j++) order.push_back(idx[nd.first + j]);
-            }
-        }
-        q.lox = make_float4(lo[0][0], lo[0][1], lo[0][2], lo[0][3]); q.hix = make_float4(hi[0][0], hi[0][1], hi[0][2], hi[0][3]);
-        q.loy = make_float4(lo[1][0], lo[1][1], lo[1][2], lo[1][3]); q.hiy = make_float4(hi[1][0], hi[1][1], hi[1][2], hi[1][3]);
-        q.loz = make_float4(lo[2][0], lo[2][1], lo[2][2], lo[2][3]); q.hiz = make_float4(hi[2][0], hi[2][1], hi[2][2], hi[2][3]);
-        q.meta = make_float4(int_bits(meta[0]), int_bits(meta[1]), int_bits(meta[2]), int_bits(meta[3]));
-        quads.push_back(q);
-        for (int k = nk - 1; k >= 0; k--) if (nodes[kids[k]].count == 0) todo.push_back({ kids[k], it.level + 1, qi, k });
-    }
     if ((size_t)ns > ((size_t)1 << 28)) return fail(MFX_ERR_INVALID_ARGUMENT, "too many fast slots (%d)", ns);
+    MfxOwnTree tree;
+    mfx_build_own_tree(blo.data(), bhi.data(), ns, (int)std::min(7L, std::max(1L, env_long("MFX_SAH_MAX_LEAF", 4))),
+                       (float)env_long("MFX_SAH_TRAV_COST_PCT", 100) * 0.01f, (int)env_long("MFX_BVH_BUILD_PAR_DEPTH", 5), tree);
+    lap("own tree");
+    const std::vector<QuadF> &quads = tree.quads;
+    const std::vector<int> &order = tree.order;
+    const int own_depth = tree.depth;
     std::vector<SlotF> slots(ns); std::vector<float4> nrm(ns);
     for (int k = 0; k < ns; k++) { slots[k] = raw[order[k]]; nrm[k] = raw_nrm[order[k]]; }
 
-    lap("collapse");
     SceneF &sf = s->sf;
     memset(&sf, 0, sizeof(sf));
     SlotF *dslots; float4 *dnrm; QuadF *dquads;

@@ -52,6 +52,19 @@ int main(void) {
     assert got == want
 
 
+def test_own_tree_builder_is_a_valid_bvh(tmp_path):
+    """The fast path's own SAH tree (csrc/mfx_build.cpp) compiled for the host alone and checked structurally: every
+    slot exactly once, every stored box contains its subtree, leaves <= 4, links and depth consistent -- for random
+    boxes, coincident boxes (no centroid spread to split on) and a few huge boxes among many small ones."""
+    exe = str(tmp_path / "check_own_tree")
+    csrc = os.path.join(ROOT, "mafrixraytracing_b200", "csrc")
+    subprocess.check_call(["/usr/bin/g++", "-std=c++17", "-O2", "-pthread", "-I", "/usr/local/cuda/include", "-I", csrc, "-o", exe,
+                           os.path.join(ROOT, "tests", "native", "check_own_tree.cpp"), os.path.join(csrc, "mfx_build.cpp")])
+    for n, mode in [(1, 0), (2, 0), (3, 0), (5, 0), (17, 0), (1000, 0), (150000, 0), (3000, 1), (5000, 2)]:
+        out = subprocess.check_output([exe, str(n), str(mode)], text=True)
+        assert out.startswith(f"ok n={n} mode={mode}"), out
+
+
 def test_fsharp_shim_offsets_match_the_header():
     """host/fsharp/MafrixCuda.fs writes the C structs into unmanaged memory by hand (no .NET here to compile it):
     every offset it uses must be the header's."""
