@@ -145,6 +145,7 @@ struct SahCtx {
     std::atomic<int> next{ 0 };
     int max_leaf;
     float c_trav;       // cost of one node step relative to one primitive test
+    int sweep_below;    // nodes with at most this many primitives get the exact sweep, larger ones 32 bins
 };
 static inline float half_area(const float *lo, const float *hi)
 {
@@ -163,23 +164,31 @@ static int sah_split(SahCtx &c, const SahNode &nd)
     const int first = nd.first, count = nd.count;
     const float area = half_area(nd.lo, nd.hi);
     const float leaf_cost = (float)count;                    // in units of (node area x primitive test)
-    float best = SAH_INF; int best_axis = -1, best_pos = -1;
+    float best = SAH_INF; int best_axis = -1, best_pos = -1, best_bal = 0x7fffffff;
     float clo[3] = { SAH_INF, SAH_INF, SAH_INF }, chi[3] = { -SAH_INF, -SAH_INF, -SAH_INF };
     for (int k = 0; k < count; k++) {
         const int id = c.idx[first + k];
         for (int a = 0; a < 3; a++) { const float ce = 0.5f * (c.lo[id][a] + c.hi[id][a]); clo[a] = std::min(clo[a], ce); chi[a] = std::max(chi[a], ce); }
     }
     const float inv_area = area > 0.f ? 1.0f / area : 0.f;
-    if (count <= 24) {
-        // exact sweep: sort by centroid on each axis (insertion sort, stable), try every split position
-        std::pair<float, int> key[24]; float right[24]; int best_order[24];
+    if (count <= c.sweep_below) {
+        // exact sweep: sort by centroid on each axis (stable), try every split position
+        static thread_local std::vector<std::pair<float, int>> key;
+        static thread_local std::vector<float> right;
+        static thread_local std::vector<int> best_order;
+        key.resize(count); right.resize(count); best_order.resize(count);
         for (int ax = 0; ax < 3; ax++) {
-            for (int k = 0; k < count; k++) {
-                const int id = c.idx[first + k];
-                const std::pair<float, int> e{ c.lo[id][ax] + c.hi[id][ax], id };
-                int j = k;
-                while (j > 0 && key[j - 1].first > e.first) { key[j] = key[j - 1]; j--; }
-                key[j] = e;
+            if (count <= 24) {
+                for (int k = 0; k < count; k++) {
+                    const int id = c.idx[first + k];
+                    const std::pair<float, int> e{ c.lo[id][ax] + c.hi[id][ax], id };
+                    int j = k;
+                    while (j > 0 && key[j - 1].first > e.first) { key[j] = key[j - 1]; j--; }
+                    key[j] = e;
+                }
+            } else {
+                for (int k = 0; k < count; k++) { const int id = c.idx[first + k]; key[k] = { c.lo[id][ax] + c.hi[id][ax], id }; }
+                std::stable_sort(key.begin(), key.end(), [](const std::pair<float, int> &x, const std::pair<float, int> &y) { return x.first < y.first; });
             }
             float lo[3] = { SAH_INF, SAH_INF, SAH_INF }, hi[3] = { -SAH_INF, -SAH_INF, -SAH_INF };
             for (int k = count - 1; k > 0; k--) { grow(lo, hi, c.lo[key[k].second], c.hi[key[k].second]); right[k] = half_area(lo, hi); }
@@ -188,7 +197,9 @@ static int sah_split(SahCtx &c, const SahNode &nd)
             for (int k = 1; k < count; k++) {
                 grow(lo, hi, c.lo[key[k - 1].second], c.hi[key[k - 1].second]);
                 const float cost = c.c_trav + (half_area(lo, hi) * k + right[k] * (count - k)) * inv_area;
-                if (cost < best) { best = cost; best_axis = ax; best_pos = k; improved = true; }
+                // equal costs (coincident boxes): take the most balanced split, or the tree degenerates into a chain
+                const int bal = std::abs(2 * k - count);
+                if (cost < best || (cost == best && bal < best_bal)) { best = cost; best_bal = bal; best_axis = ax; best_pos = k; improved = true; }
             }
             if (improved) for (int k = 0; k < count; k++) best_order[k] = key[k].second;
         }
@@ -196,29 +207,36 @@ static int sah_split(SahCtx &c, const SahNode &nd)
         for (int k = 0; k < count; k++) c.idx[first + k] = best_order[k];
         return best_pos;
     }
-    // binned: 32 centroid bins per axis
-    const int NB = 32;
+    // binned: up to 1024 centroid bins per axis.  Few bins are not enough here: one outlier (the floor quad under a
+    // 6 k-triangle model) stretches the centroid range until the model falls into three or four of 32 bins, and the
+    // tree built that way needs a third more node steps per ray than the exact sweep's (C2: 4.4 vs 3.3 records/ray).
+    const int NBMAX = 1024;
+    const int NB = std::min(NBMAX, std::max(32, count / 2));
     int best_bin = -1;
+    static thread_local std::vector<float> bin_box;     // [NB][6] lo.xyz hi.xyz
+    static thread_local std::vector<int> bin_n;
+    static thread_local std::vector<float> right_area;
+    static thread_local std::vector<int> right_n;
+    bin_box.resize((size_t)NB * 6); bin_n.resize(NB); right_area.resize(NB); right_n.resize(NB);
     for (int ax = 0; ax < 3; ax++) {
         const float ext = chi[ax] - clo[ax];
         if (!(ext > 0.f)) continue;
         const float scale = (float)NB * (1.0f - 1e-6f) / ext;
-        float blo[NB][3], bhi[NB][3]; int bn[NB];
-        for (int b = 0; b < NB; b++) { bn[b] = 0; for (int a = 0; a < 3; a++) { blo[b][a] = SAH_INF; bhi[b][a] = -SAH_INF; } }
+        float *bb = bin_box.data(); int *bn = bin_n.data(); float *right = right_area.data(); int *rn = right_n.data();
+        for (int b = 0; b < NB; b++) { bn[b] = 0; for (int a = 0; a < 3; a++) { bb[6 * b + a] = SAH_INF; bb[6 * b + 3 + a] = -SAH_INF; } }
         for (int k = 0; k < count; k++) {
             const int id = c.idx[first + k];
             int b = (int)((0.5f * (c.lo[id][ax] + c.hi[id][ax]) - clo[ax]) * scale);
             b = b < 0 ? 0 : (b >= NB ? NB - 1 : b);
-            bn[b]++; grow(blo[b], bhi[b], c.lo[id], c.hi[id]);
+            bn[b]++; grow(bb + 6 * b, bb + 6 * b + 3, c.lo[id], c.hi[id]);
         }
-        float right[NB]; int rn[NB];
         float lo[3] = { SAH_INF, SAH_INF, SAH_INF }, hi[3] = { -SAH_INF, -SAH_INF, -SAH_INF };
         int cnt = 0;
-        for (int b = NB - 1; b > 0; b--) { if (bn[b]) grow(lo, hi, blo[b], bhi[b]); cnt += bn[b]; right[b] = cnt ? half_area(lo, hi) : 0.f; rn[b] = cnt; }
+        for (int b = NB - 1; b > 0; b--) { if (bn[b]) grow(lo, hi, bb + 6 * b, bb + 6 * b + 3); cnt += bn[b]; right[b] = cnt ? half_area(lo, hi) : 0.f; rn[b] = cnt; }
         for (int a = 0; a < 3; a++) { lo[a] = SAH_INF; hi[a] = -SAH_INF; }
         cnt = 0;
         for (int b = 1; b < NB; b++) {
-            if (bn[b - 1]) grow(lo, hi, blo[b - 1], bhi[b - 1]);
+            if (bn[b - 1]) grow(lo, hi, bb + 6 * (b - 1), bb + 6 * (b - 1) + 3);
             cnt += bn[b - 1];
             if (cnt == 0 || rn[b] == 0) continue;
             const float cost = c.c_trav + (half_area(lo, hi) * cnt + right[b] * rn[b]) * inv_area;
@@ -283,6 +301,7 @@ void mfx_build_own_tree(const float *lo, const float *hi, int ns, int max_leaf, 
     c.idx = idx.data(); c.nodes = nodes.data(); c.next = 1;
     c.max_leaf = max_leaf;
     c.c_trav = trav_cost;
+    c.sweep_below = (int)std::max(24L, env_long("MFX_SAH_SWEEP_BELOW", 64));
     nodes[0].first = 0; nodes[0].count = ns; nodes[0].left = nodes[0].right = -1;
     sah_bound(c, nodes[0]);
     sah_build(c, 0, par_depth);
