@@ -1,12 +1,16 @@
 // mfx_fast.cu -- MFX_FAST_F32 wavefront kernels (the throughput path) + small utility kernels.
 //
-// Layout (mfx_internal.h): children-pair records of 64 B (4 x float4, one per interior heap
-// node, boxes rounded outward), 48 B primitive slots in leaf order (3 x float4), geometric
-// normals + material in a 16 B side array touched only by the shading kernel.
-// Traversal: one ray per thread, ordered descent (near child first), t-shrink, STACKLESS --
-// the reference tree is heap-indexed (BvhNode.fs:40-41), so the deferred far children are a
-// 32-bit trail register (one bit per level) and the only per-level state kept is the far
-// child's entry distance, in shared memory (conflict-free: column = thread).
+// Layouts (mfx_internal.h, built by mfx_host.cpp / mfx_build.cpp):
+//   * own tree (default): 128 B records of four child boxes + links over a binned-SAH BVH of the fast slots,
+//     48 B primitive slots in that tree's leaf order, 16 B normal+material side array for the shade kernel;
+//   * reference tree (instrumented counting runs, cross-check variants): 64 B children pairs and 128 B
+//     grandchildren quads indexed by the reference's heap index (BvhNode.fs:40-41), slots in its leaf order.
+// Traversal kernels: one ray per lane in persistent warps, ordered descent, t-shrink, ray replacement from the
+// bounce's queue, vote-postponed leaf tests.
+//   k_f_trace6  own tree, sorted 4-wide node step, stack of (key, record) entries in shared memory   <- shipped
+//   k_f_trace5  reference tree, two levels per fetch, stackless (2 bits per level trail + heap index)
+//   k_f_trace4  reference tree, binary, stackless (1 bit per level); also the COUNT-instrumented kernel
+// Shading: k_f_shade (BSDF + light sample, block-aggregated queue appends); k_f_raygen / k_f_resolve bracket a wave.
 #include "mfx_device.cuh"
 
 typedef V3<float> F3;
