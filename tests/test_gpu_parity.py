@@ -452,6 +452,31 @@ def test_tiny_own_trees(n_tris):
     assert np.isfinite(CudaPixelIntegrator(s, precision=FAST_F32, seed=1).Sample(2)).all()
 
 
+def test_coincident_primitives_and_deepest_paths():
+    """200 copies of one triangle (no centroid spread: the own-tree builder must still terminate and balance) in front
+    of a floor, traced with the deepest path length the library allows (max_depth 15 = 16 vertices)."""
+    tri = make_prims(200)
+    tri["v"][:, :9] = [-0.5, 0.2, 0.0, 0.5, 0.2, 0.0, 0.0, 1.2, 0.0]
+    floor = rect_prim((-3, 0, -3), (-3, 0, 3), (3, 0, 3), (3, 0, -3))
+    mats = make_materials([("lambert", (0.8, 0.8, 0.8))])
+    light = AreaLight(np.array([(-1, 3, 1), (-1, 3, -1), (1, 3, -1), (1, 3, 1)], float), (0, -1, 0), (10, 10, 10))
+    cam = PinholeCamera((0, 1, 4), (0, -0.1, -1), 120.0, 1.0)
+    desc = SceneDesc(np.concatenate([tri, floor]), mats, light, cam, 64, 64, 15, PATH_INTEGRATOR)
+    s, o = Scene(desc), oracle.OracleScene(desc)
+    uv = np.random.default_rng(3).random((20000, 2))
+    op, ot = o.trace_primary(uv)
+    fp, ft = s.TracePrimary(uv, precision=FAST_F32)
+    hit_tri = (op >= 0) & (op < 200)
+    assert hit_tri.sum() > 100
+    assert ((fp >= 0) & (fp < 200))[hit_tri].mean() > 0.999          # some copy of the triangle (ties are free)
+    assert np.allclose(ft[hit_tri & (fp < 200)], ot[hit_tri & (fp < 200)], rtol=1e-4, atol=2e-5)
+    assert ((fp == 200) == (op == 200)).mean() > 0.999
+    exact = CudaPixelIntegrator(s, precision=EXACT_F64, seed=2).Sample(2)
+    assert np.array_equal(exact[:, :, :3], o.sample(2, seed=2)[:, :, :3])
+    fast = CudaPixelIntegrator(s, precision=FAST_F32, seed=2).Sample(8)
+    assert np.isfinite(fast).all() and fast[:, :, :3].mean() > 0
+
+
 def test_ingested_xml_scene_renders_like_the_procedural_one(tmp_path):
     """Scene.xml-style description + OBJ (mafrixraytracing_b200/ingest.py) -> same frame, bit for bit, as the
     procedural Cornell scene; the oracle agrees."""
