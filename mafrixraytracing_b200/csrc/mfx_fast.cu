@@ -193,9 +193,9 @@ __global__ void __launch_bounds__(256) k_f_raygen(SceneF sc, WaveF w, TileMap tm
         const double u = ((double)px + u32_to_unit_f64(o4[0])) / (double)sc.width;
         const double v = ((double)py + u32_to_unit_f64(o4[1])) / (double)sc.height;
         const F3 d = camera_dir_f64(sc.camx, u, v);
-        w.ray_o[pid] = make_float4(sc.cam.pos[0], sc.cam.pos[1], sc.cam.pos[2], __int_as_float(-1));
+        if (!w.cam_origin) w.ray_o[pid] = make_float4(sc.cam.pos[0], sc.cam.pos[1], sc.cam.pos[2], __int_as_float(-1));
         w.ray_d[pid] = make_float4(d.x, d.y, d.z, 99999999.f);          // w = tMax of the closest query, Integrators.fs:108
-        w.thr[pid] = make_float4(1.f, 1.f, 1.f, 0.f);
+        // throughput starts at 1: vertex 0 of k_f_shade knows that and the 16 B per path are neither written nor read
         w.rad[pid] = make_float4(0.f, 0.f, 0.f, 0.f);
         w.q_ext[0][pid] = (int)pid;
         if (pid == 0) w.counts[0] = (int)total;
@@ -527,6 +527,7 @@ __global__ void __launch_bounds__(FAST_BLOCK, MINB) k_f_trace6(SceneF sc, WaveF 
     const int n = ANY ? w.counts[CNT_SH(bounce)] : w.counts[bounce];
     const int *q = ANY ? w.q_sh : w.q_ext[bounce & 1];
     int *cursor = &w.counts[ANY ? CUR_SH(bounce) : CUR_EXT(bounce)];
+    const bool cam0 = !ANY && bounce == 0 && w.cam_origin;      // primary rays of a pinhole frame: the origin is a constant
 
     int pid = -1;
     RayF r;
@@ -552,7 +553,8 @@ __global__ void __launch_bounds__(FAST_BLOCK, MINB) k_f_trace6(SceneF sc, WaveF 
                 const int idx = base + __popc(idle & ((1u << lane) - 1u));
                 if (idx < n) {
                     pid = q[idx];
-                    const float4 o = w.ray_o[pid];
+                    float4 o = make_float4(sc.cam.pos[0], sc.cam.pos[1], sc.cam.pos[2], __int_as_float(-1));
+                    if (!cam0) o = w.ray_o[pid];
                     const float4 d = ANY ? w.sh_d[pid] : w.ray_d[pid];
                     r = make_ray_fast(f3(o.x, o.y, o.z), f3(d.x, d.y, d.z), w.tmin, __float_as_int(o.w));
                     best_t = ANY ? d.w - 1e-6f : d.w;                   // shadow: dist - 1e-6 (Integrators.fs:44); closest: tMax (:108)
@@ -734,8 +736,11 @@ __global__ void __launch_bounds__(SHADE_BLOCK) k_f_shade(SceneF sc, WaveF w, Til
             const int fs = __float_as_int(hr.y);
             if (fs >= 0) {
                 const float t = hr.x;
-                const float4 o4 = w.ray_o[pid], d4 = w.ray_d[pid];
-                float4 thr = w.thr[pid];
+                float4 o4 = make_float4(sc.cam.pos[0], sc.cam.pos[1], sc.cam.pos[2], __int_as_float(-1));
+                if (!(bounce == 0 && w.cam_origin)) o4 = w.ray_o[pid];
+                const float4 d4 = w.ray_d[pid];
+                float4 thr = make_float4(1.f, 1.f, 1.f, 0.f);
+                if (bounce > 0) thr = w.thr[pid];
                 const F3 o = f3(o4.x, o4.y, o4.z), d = f3(d4.x, d4.y, d4.z);
                 const F3 point = o + d * t;
                 const float4 sa = ldg4(&sc.slots[fs].a);

@@ -807,6 +807,7 @@ static int run_sample(MfxScene *s, const MfxSampleParams *p, double *d_color_wh,
     MFX_TRY(get_tilemap(s, p->tile_size, p->rank, p->world, &tm));
     if (!exact) MFX_TRY(ensure_wave_fast(s, (size_t)tm.n_pix * (size_t)p->spp));
     TravCounters *ctr = counting ? s->d_ctr : nullptr;
+    if (!exact) s->wf.cam_origin = (sfp->own_tree && !counting) ? 1 : 0;
     const size_t npx = (size_t)s->width * s->height;
     cudaStream_t st = s->stream;
     LaunchCfg cfg{ s->sm_count, 128, st, variant, (p->flags & MFX_SAMPLE_REFERENCE_STREAM) ? 1 : 0 };
@@ -1005,6 +1006,7 @@ static void fast_seam(MfxScene *s, const SceneF *sfp, const LaunchCfg &cfg, int 
 {
     WaveF w = s->wf;
     w.tmin = tmin;
+    w.cam_origin = 0;
     for (int64_t first = 0; first < n; first += w.P) {
         const int m = (int)std::min<int64_t>(w.P, n - first);
         cudaMemsetAsync(w.counts, 0, MFX_COUNTS_LEN * sizeof(int), s->stream);

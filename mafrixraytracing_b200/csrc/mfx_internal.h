@@ -149,6 +149,8 @@ struct WaveF {
     int    *q_ext[2];       // ping-pong extend queues of path ids
     int    *q_sh;           // shadow queue of the current bounce
     float   tmin;           // tMin of every query (1e-6, Integrators.fs:44,108; the Bvh.Hit seam may pass another)
+    int     cam_origin;     // 1: every bounce-0 ray starts at the camera position (pinhole): ray_o is neither written by
+                            //    raygen nor read by the bounce-0 extend / shade (own-tree frames only; 0 for the seams)
     int    *counts;         // [0 .. MFX_MAX_VERTS+1] extend queue sizes per bounce,
                             // [MFX_MAX_VERTS+2 + bounce] shadow queue sizes
 };
