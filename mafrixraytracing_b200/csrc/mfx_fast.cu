@@ -703,7 +703,7 @@ __device__ __forceinline__ float fresnel_f(float eta_i, float eta_t, float cosi)
 //   mode 1 (PathTracer.fs:40-41): L += T * l * col          ;  T *= col * shadeFactor
 #define SHADE_BLOCK 256
 template <bool DIRECT>
-__global__ void __launch_bounds__(SHADE_BLOCK) k_f_shade(SceneF sc, WaveF w, TileMap tm, int pix0, int npix, int s0, int bounce, uint64_t seed)
+__global__ void __launch_bounds__(SHADE_BLOCK, 5) k_f_shade(SceneF sc, WaveF w, TileMap tm, int pix0, int npix, int s0, int bounce, uint64_t seed)
 {
     // Queue appends are aggregated per block: 5 000 resident warps hammering two counters with one atomic each per
     // iteration made the kernel wait on same-address atomics (72 % of its stall samples, profiles/); one atomic per
