@@ -1,5 +1,6 @@
 // CPU-only check of the fast path's own tree builder (csrc/mfx_build.cpp); built and run by tests/test_host_abi.py.
 // usage: check_own_tree <n> <mode>   mode 0: random small boxes, 1: all boxes identical, 2: a few huge + many small
+//        check_own_tree <n> 3 <tris.bin>   boxes of n triangles (9 doubles each) read from a file; prints histograms
 #include "mfx_build.h"
 
 #include <cstdarg>
@@ -27,6 +28,17 @@ int main(int argc, char **argv)
             if (mode == 2 && i < 4) { c = 0.f; e = 12.f; }
             lo[3 * (size_t)i + a] = c - e; hi[3 * (size_t)i + a] = c + e;
         }
+    if (mode == 3 && argc > 3) {
+        FILE *f = fopen(argv[3], "rb");
+        if (!f) { fprintf(stderr, "cannot open %s\n", argv[3]); return 2; }
+        std::vector<double> tri(9 * (size_t)n);
+        if (fread(tri.data(), 72, n, f) != (size_t)n) { fprintf(stderr, "short read\n"); return 2; }
+        fclose(f);
+        for (int i = 0; i < n; i++) for (int a = 0; a < 3; a++) {
+            const double v0 = tri[9 * (size_t)i + a], v1 = tri[9 * (size_t)i + 3 + a], v2 = tri[9 * (size_t)i + 6 + a];
+            lo[3 * (size_t)i + a] = (float)std::min(v0, std::min(v1, v2)) - 1e-6f; hi[3 * (size_t)i + a] = (float)std::max(v0, std::max(v1, v2)) + 1e-6f;
+        }
+    }
     MfxOwnTree t;
     mfx_build_own_tree(lo.data(), hi.data(), n, max_leaf, 1.0f, 3, t);
     REQUIRE((int)t.order.size() == n);
@@ -68,5 +80,20 @@ int main(int argc, char **argv)
     REQUIRE(leaf_slots == n);
     REQUIRE(depth == t.depth);
     printf("ok n=%d mode=%d records=%zu depth=%d\n", n, mode, t.quads.size(), t.depth);
+    if (mode == 3) {
+        long kids[5] = { 0, 0, 0, 0, 0 }, leafsz[8] = { 0, 0, 0, 0, 0, 0, 0, 0 }, leaves = 0, inner = 0;
+        for (const QuadF &q : t.quads) {
+            int k = 0;
+            for (int s = 0; s < 4; s++) {
+                const int link = as_int((&q.meta.x)[s]);
+                if (link == MFX_QUAD_EMPTY) continue;
+                k++;
+                if (link >= 0) { leaves++; leafsz[link & 7]++; } else inner++;
+            }
+            kids[k]++;
+        }
+        printf("children per record: 1:%ld 2:%ld 3:%ld 4:%ld   leaf children %ld, interior children %ld\n", kids[1], kids[2], kids[3], kids[4], leaves, inner);
+        printf("slots per leaf: 1:%ld 2:%ld 3:%ld 4:%ld 5+:%ld\n", leafsz[1], leafsz[2], leafsz[3], leafsz[4], leafsz[5] + leafsz[6] + leafsz[7]);
+    }
     return 0;
 }
