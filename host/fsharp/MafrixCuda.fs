@@ -53,8 +53,9 @@ let private check rc =
 
 /// Unmanaged images of the C structs.  Offsets: MfxPrim 104 B {kind@0, material@4, v[12]@8}; MfxMaterial 56 B
 /// {kind@0, albedo@8, fuzz@32, ei@40, et@48}; MfxBvhNode 56 B {pmin@0, pmax@24, first@48, count@52};
-/// MfxSceneDesc 312 B {prims@0, n@8, materials@16, n@24, nodes@32, n@40, indices@48, light@56, camera@200,
-/// width@296, height@300, max_depth@304, integrator@308}.
+/// MfxSceneDesc 320 B {prims@0, n@8, materials@16, n@24, nodes@32, n@40, indices@48, light@56, camera@200,
+/// width@296, height@300, max_depth@304, integrator@308, sky@312 (NULL here: the sphere sample of
+/// RenderTest/Sample/RayTracing.fs has no F# host types to marshal from -- its scene is built by the caller)}.
 module private Interop =
     let inline wd (p:nativeint) (off:int) (v:float) = Marshal.WriteInt64(p, off, BitConverter.DoubleToInt64Bits v)
     let inline wpt (p:nativeint) (off:int) (q:Point) = wd p off q.x; wd p (off + 8) q.y; wd p (off + 16) q.z
@@ -116,7 +117,7 @@ type CudaPixelIntegrator(width:int, height:int, cam:PinholeCamera, bvh:Bvh, ligh
         let mats = MaterialManager.GetManager().materials
         let pPrims, pMats = Interop.prims bvh.primitives, Interop.materials mats materialProps
         let pNodes, pIdx = Interop.nodes bvh.nodes, Interop.ints bvh.indices
-        let d = Marshal.AllocHGlobal 312
+        let d = Marshal.AllocHGlobal 320
         try
             Marshal.WriteIntPtr(d, 0, pPrims);  Marshal.WriteInt32(d, 8, bvh.primitives.Length)
             Marshal.WriteIntPtr(d, 16, pMats);  Marshal.WriteInt32(d, 24, mats.Length)
@@ -133,6 +134,7 @@ type CudaPixelIntegrator(width:int, height:int, cam:PinholeCamera, bvh:Bvh, ligh
             Marshal.WriteInt32(d, 296, width); Marshal.WriteInt32(d, 300, height)
             Marshal.WriteInt32(d, 304, maxDepth)
             Marshal.WriteInt32(d, 308, (if defaultArg newPathTracer false then 1 else 0))
+            Marshal.WriteIntPtr(d, 312, 0n)                      // MfxSceneDesc.sky: only MFX_SKY_TRACER reads it
             check (Native.mfx_init 0)
             let mutable h = 0n
             check (Native.mfx_scene_create(d, &h))               // copies everything: the buffers die right here

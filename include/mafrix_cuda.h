@@ -40,10 +40,15 @@ typedef enum {
 /* IHitable implementations on the path: Shape/Trangle.fs:98, Shape/Rect.fs:11, Shape/Sphere.fs:9 */
 typedef enum { MFX_TRIANGLE = 0, MFX_RECT = 1, MFX_SPHERE = 2 } MfxPrimKind;
 /* IMaterial implementations: Materials/Material.fs:39 (Lambertian), :56 (Metal), :98 (SpecularTransmission) */
-typedef enum { MFX_LAMBERT = 0, MFX_METAL = 1, MFX_SPECTRANS = 2 } MfxMaterialKind;
+/* MFX_SKY_TRACER only (RenderTest/Sample/RayTracing.fs): :300-325 Dielectric(ri), :282-290 Lambertian over a
+ * CheckerTexture (:54-61) of two constant colours, Lambertian over the NoiseTexture (:96-99). */
+typedef enum { MFX_LAMBERT = 0, MFX_METAL = 1, MFX_SPECTRANS = 2,
+               MFX_DIELECTRIC = 3, MFX_LAMBERT_CHECKER = 4, MFX_LAMBERT_NOISE = 5 } MfxMaterialKind;
 /* IPathTracer implementations: Integrator/Integrators.fs:96 (PathIntegrator, the live one),
- * Tracer/PathTracer.fs:13 (NewPathTracer, where Metal/SpecularTransmission act) */
-typedef enum { MFX_PATH_INTEGRATOR = 0, MFX_NEW_PATH_TRACER = 1 } MfxIntegrator;
+ * Tracer/PathTracer.fs:13 (NewPathTracer, where Metal/SpecularTransmission act);
+ * MFX_SKY_TRACER = GetColor of the sphere sample (RenderTest/Sample/RayTracing.fs:367-382): no light, sky
+ * gradient on a miss, black at the depth limit, closest hit = ListHit over the whole list (:256-258). */
+typedef enum { MFX_PATH_INTEGRATOR = 0, MFX_NEW_PATH_TRACER = 1, MFX_SKY_TRACER = 2 } MfxIntegrator;
 /* Arithmetic of the device path.
  *   MFX_EXACT_F64: f64, reference operation order, no FMA contraction -- primitive ids, t and
  *                  radiance are bit-identical to the reference algorithm.
@@ -59,7 +64,9 @@ typedef struct {
     double  v[12];
 } MfxPrim;
 
-/* One IMaterial: Lambertian(albedo) | Metal(albedo, fuzz) | SpecularTransmission(T=albedo, ei, et). */
+/* One IMaterial: Lambertian(albedo) | Metal(albedo, fuzz) | SpecularTransmission(T=albedo, ei, et).
+ * MFX_SKY_TRACER: Lambertian(ConstantTexture albedo) | Metal(albedo, fuzz) | Dielectric(ri = ei) |
+ * Lambertian(CheckerTexture(even = albedo, odd = (fuzz, ei, et))) | Lambertian(NoiseTexture) (tables in MfxSkyTracer). */
 typedef struct {
     int32_t kind;
     int32_t pad;
@@ -93,6 +100,27 @@ typedef struct {
     double down[3];
 } MfxCamera;
 
+/* RayTraceCamera, already derived (RayTracing.fs:335-358): origin, lowerLeftCorner, horizontal, vertical, the lens
+ * basis u, v and lensRadius = aperture/2.  mfx_camera_lens reproduces the constructor. */
+typedef struct {
+    double origin[3];
+    double lower_left[3];
+    double horizontal[3];
+    double vertical[3];
+    double u[3];
+    double v[3];
+    double lens_radius;
+} MfxLensCamera;
+
+/* What the sphere sample needs beyond prims/materials (RayTracing.fs:384-415).  perlin_* may be NULL when no
+ * material is MFX_LAMBERT_NOISE: Perlin's static tables (:81-95) -- ranfloat[256], perm_x|perm_y|perm_z[3*256] --
+ * which the reference fills from Random.Shared, so the host supplies them. */
+typedef struct {
+    MfxLensCamera  camera;
+    const double  *perlin_ranfloat;
+    const int32_t *perlin_perm;
+} MfxSkyTracer;
+
 /* What `new Scene(state)` holds for the path (Scene/Scene.fs:298-313). */
 typedef struct {
     const MfxPrim     *prims;          /* state.shapes                                          */
@@ -107,6 +135,9 @@ typedef struct {
     int32_t            width, height;  /* state.film.Size                                        */
     int32_t            max_depth;      /* PathIntegrator(bvh, maxDepth, light), Scene.fs:304     */
     int32_t            integrator;     /* MfxIntegrator                                          */
+    const MfxSkyTracer *sky;           /* MFX_SKY_TRACER: lens camera + noise tables (light and camera above are
+                                          ignored, prims must be spheres, max_depth = the `depth < 50` of
+                                          RayTracing.fs:373); NULL otherwise                      */
 } MfxSceneDesc;
 
 /* Arguments of one IPixelIntegrator.Sample call. */
@@ -162,6 +193,10 @@ MFX_API int mfx_init(int device);
 /* PinholeCamera(pos, dir, fov, aspect) constructor, Camera.fs:96-133 (effective FOV = fov/2). */
 MFX_API int mfx_camera_pinhole(const double pos[3], const double dir[3], double fov, double aspect,
                                MfxCamera *out);
+/* RayTraceCamera(lookfrom, lookat, vup, vfov, aspect, aperture, focus_dist, _, _) constructor,
+ * RenderTest/Sample/RayTracing.fs:335-358. */
+MFX_API int mfx_camera_lens(const double lookfrom[3], const double lookat[3], const double vup[3], double vfov,
+                            double aspect, double aperture, double focus_dist, MfxLensCamera *out);
 /* Bvh.Build, BvhNode.fs:24-61: median split on the node bound's longest axis, leaf <= 3,
  * heap-indexed nodes (n_slots must be 2n-1), stable sort (the reference's sort is unstable). */
 MFX_API int mfx_bvh_build(const MfxPrim *prims, int32_t n, MfxBvhNode *nodes_out, int32_t n_slots,

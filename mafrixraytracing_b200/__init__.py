@@ -5,17 +5,19 @@ Only what the hot path needs lives here:
   csrc/        CUDA kernels + the C ABI (built in-tree into libmafrix_cuda.so)
   _lib.py      ctypes binding of every symbol in include/mafrix_cuda.h (fails loudly if absent)
   scene.py     PinholeCamera / Bvh / Scene / CudaPixelIntegrator / Film -- the reference's names
-  scenes.py    the BASELINE workload builders (C1..C5)
+  scenes.py    the BASELINE workload builders (C1..C5) and the sphere sample's RandomScene
   imageio.py   headless PFM / PNG writers (replace the reference's ImGui window)
   dist.py      tile sharding over ranks + the NCCL reduce of the accumulation buffers
 There is no CPU fallback: without the CUDA library or a GPU every compute call raises.
 """
 from .scene import (PRIM_DTYPE, MATERIAL_DTYPE, NODE_DTYPE, TRIANGLE, RECT, SPHERE, LAMBERT, METAL,
-                    SPECTRANS, PATH_INTEGRATOR, NEW_PATH_TRACER, EXACT_F64, FAST_F32,
-                    PinholeCamera, AreaLight, SceneDesc, Bvh, Scene, CudaPixelIntegrator, Film,
-                    MafrixError)
+                    SPECTRANS, DIELECTRIC, LAMBERT_CHECKER, LAMBERT_NOISE, PATH_INTEGRATOR, NEW_PATH_TRACER,
+                    SKY_TRACER, EXACT_F64, FAST_F32,
+                    PinholeCamera, RayTraceCamera, SkyTracer, AreaLight, SceneDesc, Bvh, Scene, CudaPixelIntegrator,
+                    Film, MafrixError)
 
 __all__ = ["PRIM_DTYPE", "MATERIAL_DTYPE", "NODE_DTYPE", "TRIANGLE", "RECT", "SPHERE", "LAMBERT",
-           "METAL", "SPECTRANS", "PATH_INTEGRATOR", "NEW_PATH_TRACER", "EXACT_F64", "FAST_F32",
-           "PinholeCamera", "AreaLight", "SceneDesc", "Bvh", "Scene", "CudaPixelIntegrator", "Film",
+           "METAL", "SPECTRANS", "DIELECTRIC", "LAMBERT_CHECKER", "LAMBERT_NOISE", "PATH_INTEGRATOR",
+           "NEW_PATH_TRACER", "SKY_TRACER", "EXACT_F64", "FAST_F32",
+           "PinholeCamera", "RayTraceCamera", "SkyTracer", "AreaLight", "SceneDesc", "Bvh", "Scene", "CudaPixelIntegrator", "Film",
            "MafrixError"]

@@ -23,6 +23,16 @@ class MfxCamera(C.Structure):
                 ("down", C.c_double * 3)]
 
 
+class MfxLensCamera(C.Structure):
+    _fields_ = [("origin", C.c_double * 3), ("lower_left", C.c_double * 3), ("horizontal", C.c_double * 3),
+                ("vertical", C.c_double * 3), ("u", C.c_double * 3), ("v", C.c_double * 3),
+                ("lens_radius", C.c_double)]
+
+
+class MfxSkyTracer(C.Structure):
+    _fields_ = [("camera", MfxLensCamera), ("perlin_ranfloat", C.c_void_p), ("perlin_perm", C.c_void_p)]
+
+
 class MfxSceneDesc(C.Structure):
     _fields_ = [("prims", C.c_void_p), ("n_prims", C.c_int32),
                 ("materials", C.c_void_p), ("n_materials", C.c_int32),
@@ -30,7 +40,8 @@ class MfxSceneDesc(C.Structure):
                 ("indices", C.c_void_p),
                 ("light", MfxAreaLight), ("camera", MfxCamera),
                 ("width", C.c_int32), ("height", C.c_int32),
-                ("max_depth", C.c_int32), ("integrator", C.c_int32)]
+                ("max_depth", C.c_int32), ("integrator", C.c_int32),
+                ("sky", C.POINTER(MfxSkyTracer))]
 
 
 class MfxSampleParams(C.Structure):
@@ -60,6 +71,7 @@ SYMBOLS = {
     "mfx_device_count": (C.c_int, []),
     "mfx_init": (C.c_int, [C.c_int]),
     "mfx_camera_pinhole": (C.c_int, [_P, _P, C.c_double, C.c_double, C.POINTER(MfxCamera)]),
+    "mfx_camera_lens": (C.c_int, [_P, _P, _P, C.c_double, C.c_double, C.c_double, C.c_double, C.POINTER(MfxLensCamera)]),
     "mfx_bvh_build": (C.c_int, [_P, C.c_int32, _P, C.c_int32, _P]),
     "mfx_tile_map": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, C.POINTER(C.c_int32)]),
     "mfx_scene_create": (C.c_int, [C.POINTER(MfxSceneDesc), C.POINTER(_P)]),

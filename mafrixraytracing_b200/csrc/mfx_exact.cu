@@ -152,6 +152,82 @@ __device__ HitX bvh_hit_x(const SceneX &sc, D3 o, D3 dir, double tMin, double tM
     return best;
 }
 
+// ---------------------------------------------------------------- MFX_SKY_TRACER closest hit
+// Sphere.Hit of the sphere sample (RenderTest/Sample/RayTracing.fs:188-207): a = d.d, near root first, strict bounds.
+__device__ __forceinline__ bool sphere_hit_sky_x(D3 center, double radius, D3 o, D3 dir, double tMin, double tMax, double &t_out)
+{
+    const D3 oc = o - center;
+    const double a = dot(dir, dir);
+    const double b = 2.0 * dot(oc, dir);
+    const double c = dot(oc, oc) - radius * radius;
+    const double disc = b * b - 4.0 * a * c;
+    if (disc > 0) {
+        double tmp = (-b - sqrt(disc)) / (2.0 * a);
+        if (tmp < tMax && tmp > tMin) { t_out = tmp; return true; }
+        tmp = (-b + sqrt(disc)) / (2.0 * a);
+        if (tmp < tMax && tmp > tMin) { t_out = tmp; return true; }
+    }
+    return false;
+}
+
+// ListHit (RayTracing.fs:256-258) tests EVERY sphere and keeps the first minimal t in list order.  The answer --
+// smallest t, ties to the smaller list index -- does not depend on the order the spheres are visited in, so the
+// kernel walks the scene's tree near-first with the conservative t-shrink of bvh_hit_x and applies the tie rule
+// explicitly.  The tree's boxes were padded at flatten time (flatten_exact): the reference tests no boxes here, so
+// a box must never reject a ray the sphere formula accepts.
+template <bool COUNT>
+__device__ HitX sky_hit_x(const SceneX &sc, D3 o, D3 dir, double tMin, double tMax, unsigned long long *ctr)
+{
+    HitX best; best.slot = -1; best.sub = 0; best.t = 0.;
+    int bestRef = 0x7fffffff;
+    int stack[40];
+    int sp = 0;
+    double e;
+    NodeX node = sc.nodes[0];
+    if (COUNT) ctr[0]++;
+    if (!aabb_hit_x(node, o, dir, tMin, tMax, e)) return best;
+    int cur = 0;
+    for (;;) {
+        if (node.count > MFX_LEAF_NODE_COUNT) {
+            const int li = 2 * cur + 1, ri = 2 * cur + 2;
+            const NodeX L = sc.nodes[li];
+            const NodeX R = sc.nodes[ri];
+            if (COUNT) ctr[0] += 2;
+            double el, er;
+            bool hl = aabb_hit_x(L, o, dir, tMin, tMax, el);
+            bool hr = aabb_hit_x(R, o, dir, tMin, tMax, er);
+            if (best.slot >= 0) {
+                const double lim = best.t + best.t * 1e-9;
+                if (el > lim) hl = false;
+                if (er > lim) hr = false;
+            }
+            if (hl && hr) {
+                const bool rightNear = er < el;
+                stack[sp++] = rightNear ? li : ri;
+                cur = rightNear ? ri : li;
+                node = rightNear ? R : L;
+                continue;
+            } else if (hl) { cur = li; node = L; continue; }
+            else if (hr) { cur = ri; node = R; continue; }
+        } else {
+            for (int k = 0; k < node.count; k++) {
+                const PrimX p = sc.prims[node.first + k];
+                if (COUNT) ctr[2]++;
+                double t;
+                if (sphere_hit_sky_x(ld3(p.v0), p.e1[0], o, dir, tMin, tMax, t)) {
+                    const int ref = sc.ref_id[node.first + k];
+                    if (best.slot < 0 || t < best.t || (t == best.t && ref < bestRef)) { best.slot = node.first + k; best.t = t; bestRef = ref; }
+                }
+            }
+        }
+        if (sp == 0) break;
+        cur = stack[--sp];
+        node = sc.nodes[cur];
+        if (COUNT) ctr[0]++;
+    }
+    return best;
+}
+
 // ---------------------------------------------------------------- RNG-driven samplers
 struct RngX { uint32_t pixel, sample, k0, k1; };
 
@@ -221,6 +297,49 @@ __device__ __forceinline__ D3 tri_normal_x(D3 e1, D3 e2)
     return a / al;
 }
 
+// GetRandomInUnitSphere of the sphere sample (RayTracing.fs:261-266): the whole ball, no hemisphere test
+__device__ D3 random_in_unit_ball_x(const RngX &g, uint32_t dim)
+{
+    D3 p = mk3<double>(20., 20., 20.);
+    uint32_t it = 0;
+    while (dot(p, p) >= 1.0) {
+        if (it >= MFX_REJECTION_CAP) return mk3<double>(0., 0., 0.);
+        double u[4];
+        rng_draw_x(g, dim, it++, u);
+        p = mk3<double>(u[0], u[1], u[2]) * 2.0 - mk3<double>(1., 1., 1.);
+    }
+    return p;
+}
+
+// RandomInUnitDisk (RayTracing.fs:327-333): the loop runs at least once; draws (dim 0, iter 1, 2, ..)
+__device__ D3 random_in_unit_disk_x(const RngX &g)
+{
+    D3 p = mk3<double>(0., 0., 0.);
+    double dt = 1.0;
+    uint32_t it = 0;
+    while (dt >= 1.0) {
+        if (it >= MFX_REJECTION_CAP) return mk3<double>(0., 0., 0.);
+        double u[4];
+        rng_draw_x(g, MFX_DIM_CAMERA, 1u + it++, u);
+        p = mk3<double>(u[0], u[1], 0.) * 2.0 - mk3<double>(1., 1., 0.);
+        dt = dot(p, p);
+    }
+    return p;
+}
+
+// RayTraceCamera.GetRay(s, t) (RayTracing.fs:360-364); the Ray constructor normalises (:14-16)
+__device__ __forceinline__ void lens_ray_x(const CamX &c, const LensX &lens, double s, double t, const RngX *g, D3 &origin, D3 &dir)
+{
+    D3 offset = mk3<double>(0., 0., 0.);
+    if (g) {
+        const D3 rd = random_in_unit_disk_x(*g) * lens.radius;
+        offset = ld3(lens.u) * rd.x + ld3(lens.v) * rd.y;
+    }
+    const D3 target = (((ld3(c.topleft) + ld3(c.right) * s) + ld3(c.down) * t) - ld3(c.pos)) - offset;
+    origin = ld3(c.pos) + offset;
+    dir = normalize_x(target);
+}
+
 __device__ __forceinline__ D3 camera_ray_dir_x(const CamX &c, double u, double v)   // Camera.fs:134-139
 {
     const D3 target = (ld3(c.topleft) + ld3(c.right) * u) + ld3(c.down) * v;
@@ -243,9 +362,11 @@ __global__ void __launch_bounds__(128) k_x_raygen(SceneX sc, WaveX w, TileMap tm
         rng_draw_x(g, MFX_DIM_CAMERA, 0, u4);
         const double u = ((double)px + u4[0]) / (double)sc.width;      // Integrators.fs:167
         const double v = ((double)py + u4[1]) / (double)sc.height;     // Integrators.fs:168
-        const D3 d = camera_ray_dir_x(sc.cam, u, v);
+        D3 d, org = ld3(sc.cam.pos);
+        if (sc.mode == MFX_MODE_SKY) lens_ray_x(sc.cam, sc.lens, u, v, &g, org, d);     // RayTracing.fs:450-452
+        else d = camera_ray_dir_x(sc.cam, u, v);
         const size_t P = (size_t)w.P;
-        w.ray_o[pid] = sc.cam.pos[0]; w.ray_o[P + pid] = sc.cam.pos[1]; w.ray_o[2 * P + pid] = sc.cam.pos[2];
+        w.ray_o[pid] = org.x; w.ray_o[P + pid] = org.y; w.ray_o[2 * P + pid] = org.z;
         w.ray_d[pid] = d.x; w.ray_d[P + pid] = d.y; w.ray_d[2 * P + pid] = d.z;
         w.nv[pid] = 0;
         w.queue[0][pid] = (int)pid;
@@ -264,7 +385,8 @@ __global__ void __launch_bounds__(128) k_x_extend(SceneX sc, WaveX w, int bounce
         const int pid = q[i];
         const D3 o = mk3<double>(w.ray_o[pid], w.ray_o[P + pid], w.ray_o[2 * P + pid]);
         const D3 d = mk3<double>(w.ray_d[pid], w.ray_d[P + pid], w.ray_d[2 * P + pid]);
-        const HitX h = bvh_hit_x<false, COUNT>(sc, o, d, 1e-6, 99999999., local);   // Integrators.fs:108
+        const HitX h = (sc.mode == MFX_MODE_SKY) ? sky_hit_x<COUNT>(sc, o, d, MFX_SKY_TMIN, MFX_SKY_TMAX, local)     // RayTracing.fs:368
+                                                 : bvh_hit_x<false, COUNT>(sc, o, d, 1e-6, 99999999., local);   // Integrators.fs:108
         w.hit_t[pid] = h.t;
         w.hit_slot[pid] = (h.slot < 0) ? -1 : (h.slot | (h.sub << 30));
     }
@@ -382,6 +504,110 @@ __global__ void __launch_bounds__(128) k_x_shade(SceneX sc, WaveX w, TileMap tm,
     }
 }
 
+// Texture.Value(0, 0, p): ConstantTexture (RayTracing.fs:50-52), CheckerTexture (:54-61), NoiseTexture over
+// Perlin.Noise (:86-99).  Checker: even = albedo, odd = (fuzz, ei, et) -- see MfxMaterial.
+__device__ __forceinline__ D3 texture_value_x(const SceneX &sc, const MatX &m, D3 p)
+{
+    if (m.kind == 4) {
+        const double sines = sin(10. * p.x) * sin(10. * p.y) * sin(10. * p.z);
+        if (sines < 0.) return mk3<double>(m.fuzz, m.ei, m.et);
+        return ld3(m.albedo);
+    }
+    if (m.kind == 5) {
+        const int i = (int)(4. * p.x) & 255, j = (int)(4. * p.y) & 255, k = (int)(4. * p.z) & 255;
+        const double nz = sc.perlin_rf[sc.perlin_perm[i] ^ sc.perlin_perm[256 + j] ^ sc.perlin_perm[512 + k]];
+        return mk3<double>(1., 1., 1.) * nz;
+    }
+    return ld3(m.albedo);
+}
+
+// One level of GetColor (RayTracing.fs:367-382) minus its ListHit: miss -> sky gradient, hit -> Material.Scatter
+// (Lambertian :282-290, Metal :291-299, Dielectric :300-325) and either the next ray or black.  The attenuation of
+// vertex k is stored; k_x_resolve multiplies them inside-out like the recursion returns.
+__global__ void __launch_bounds__(128) k_x_shade_sky(SceneX sc, WaveX w, TileMap tm, int pix0, int npix, int s0, int bounce, uint64_t seed)
+{
+    const int n = w.counts[bounce];
+    const int *qin = w.queue[bounce & 1];
+    int *qout = w.queue[(bounce + 1) & 1];
+    const size_t P = (size_t)w.P;
+    const int nwarp_iters = (n + 31) / 32;
+    const int k = bounce;
+    for (int it = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); it < nwarp_iters; it += gridDim.x * (blockDim.x >> 5)) {
+        const int i = it * 32 + (threadIdx.x & 31);
+        bool alive = false;
+        int pid = -1;
+        if (i < n) {
+            pid = qin[i];
+            const int hs = w.hit_slot[pid];
+            const D3 o = mk3<double>(w.ray_o[pid], w.ray_o[P + pid], w.ray_o[2 * P + pid]);
+            const D3 d = mk3<double>(w.ray_d[pid], w.ray_d[P + pid], w.ray_d[2 * P + pid]);
+            D3 term = mk3<double>(0., 0., 0.);
+            if (hs < 0) {
+                const D3 unit = normalize_x(d);                               // :378-381
+                const double t = 0.5 * (unit.y + 1.0);
+                term = mk3<double>(1., 1., 1.) * (1.0 - t) + mk3<double>(0.5, 0.7, 1.0) * t;
+            } else {
+                const double t = w.hit_t[pid];
+                const PrimX p = sc.prims[hs];
+                const D3 point = o + d * t;                                   // PointAtParameter, :21
+                const D3 normal = (point - ld3(p.v0)) / p.e1[0];              // :198
+                const MatX m = sc.mats[p.material];
+                const int sl = pid / npix, pl = pid - sl * npix;
+                int pix, px, py;
+                pixel_of(tm, sc.width, pix0 + pl, pix, px, py);
+                RngX g; g.pixel = (uint32_t)pix; g.sample = (uint32_t)(s0 + sl); g.k0 = (uint32_t)seed; g.k1 = (uint32_t)(seed >> 32);
+                D3 att, wi; bool ok = true;
+                if (m.kind == 1) {                                            // Metal.Scatter
+                    const double fuzz = (m.fuzz < 1.0) ? m.fuzz : 1.0;
+                    const D3 reflected = reflect_x(normalize_x(d), normal);
+                    wi = normalize_x(reflected + random_in_unit_ball_x(g, MFX_DIM_BSDF(k)) * fuzz);
+                    att = ld3(m.albedo);
+                    ok = dot(wi, normal) > 0;
+                } else if (m.kind == 3) {                                     // Dielectric.Scatter
+                    const double ref_idx = m.ei;
+                    const D3 reflected = reflect_x(d, normal);
+                    D3 outward; double ni_over_nt, cosine;
+                    const double dn = dot(d, normal);
+                    if (dn > 0) { outward = -normal; ni_over_nt = ref_idx; cosine = ref_idx * dn; }
+                    else { outward = normal; ni_over_nt = 1.0 / ref_idx; cosine = -dn; }
+                    // Refract (:269-276)
+                    const D3 uv = normalize_x(d);
+                    const double dt = dot(uv, outward);
+                    const double disc = 1.0 - ni_over_nt * ni_over_nt * (1.0 - dt * dt);
+                    double reflect_prob = 1.0;
+                    D3 ref_dir = mk3<double>(0., 0., 0.);
+                    if (disc > 0) {
+                        ref_dir = (d - outward * dt) * ni_over_nt - outward * sqrt(disc);
+                        // Schlick (:277-280); (1-cosine)^5 by products, see the oracle's header
+                        const double r0 = (1. - ref_idx) / (1. + ref_idx);
+                        const double r1 = r0 * r0;
+                        const double x = 1. - cosine, x2 = x * x, x4 = x2 * x2;
+                        reflect_prob = r1 + (1. - r1) * (x4 * x);
+                    }
+                    double u[4];
+                    rng_draw_x(g, MFX_DIM_LIGHT(k), 0, u);
+                    wi = normalize_x((u[0] < reflect_prob) ? reflected : ref_dir);
+                    att = mk3<double>(1., 1., 1.);
+                } else {                                                      // Lambertian.Scatter over a texture
+                    wi = normalize_x(normalize_x(normal) + random_in_unit_ball_x(g, MFX_DIM_BSDF(k)));
+                    att = texture_value_x(sc, m, point);
+                }
+                if (k < sc.max_depth && ok) {                                 // `if depth < 50 && ishit`, :373
+                    alive = true;
+                    const size_t vb = (size_t)k * 3 * P;
+                    w.v_col[vb + pid] = att.x; w.v_col[vb + P + pid] = att.y; w.v_col[vb + 2 * P + pid] = att.z;
+                    w.nv[pid] = k + 1;
+                    w.ray_o[pid] = point.x; w.ray_o[P + pid] = point.y; w.ray_o[2 * P + pid] = point.z;
+                    w.ray_d[pid] = wi.x; w.ray_d[P + pid] = wi.y; w.ray_d[2 * P + pid] = wi.z;
+                }
+            }
+            if (!alive) { w.v_l[pid] = term.x; w.v_l[P + pid] = term.y; w.v_l[2 * P + pid] = term.z; }
+        }
+        const int pos = warp_append(alive, &w.counts[bounce + 1]);
+        if (alive) qout[pos] = pid;
+    }
+}
+
 // Shadow query of SingleDirectLightIntegrator (Integrators.fs:44): occluded -> Color().
 template <bool COUNT>
 __global__ void __launch_bounds__(128) k_x_shadow(SceneX sc, WaveX w, int bounce, TravCounters *ctr)
@@ -408,6 +634,7 @@ __global__ void __launch_bounds__(128) k_x_shadow(SceneX sc, WaveX w, int bounce
 // Unwinds the recursion inside-out so the rounding sequence equals the reference's:
 //   mode 0: L_k = ((l_k / pdf_li + L_{k+1}) * col_k) / pdf          (Integrators.fs:136)
 //   mode 1: L_k = l_k * col_k + col_k * Shade(L_{k+1})              (PathTracer.fs:40-41)
+//   sky   : L_k = L_{k+1} * attenuation_k, L_nv = sky or black        (RayTracing.fs:374-381)
 // then color <- color + L_0 per sample in sample order                (Integrators.fs:170).
 __global__ void __launch_bounds__(128) k_x_resolve(SceneX sc, WaveX w, TileMap tm, int pix0, int npix, int S, double *pixsum)
 {
@@ -422,6 +649,13 @@ __global__ void __launch_bounds__(128) k_x_resolve(SceneX sc, WaveX w, TileMap t
             const size_t pid = (size_t)sl * npix + pl;
             const int nv = w.nv[pid];
             double Lr = 0., Lg = 0., Lb = 0.;
+            if (sc.mode == MFX_MODE_SKY) {      // Color(c.r*attenuation.x, ..) on the way out of the recursion, RayTracing.fs:375
+                Lr = w.v_l[pid]; Lg = w.v_l[P + pid]; Lb = w.v_l[2 * P + pid];
+                for (int k = nv - 1; k >= 0; k--) {
+                    const size_t vb = (size_t)k * 3 * P;
+                    Lr = Lr * w.v_col[vb + pid]; Lg = Lg * w.v_col[vb + P + pid]; Lb = Lb * w.v_col[vb + 2 * P + pid];
+                }
+            } else
             for (int k = nv - 1; k >= 0; k--) {
                 const size_t vb = (size_t)k * 3 * P;
                 const double lr = w.v_l[vb + pid], lg = w.v_l[vb + P + pid], lb = w.v_l[vb + 2 * P + pid];
@@ -454,7 +688,9 @@ __global__ void __launch_bounds__(128) k_x_bvh_hit(SceneX sc, int any_hit, long 
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         const D3 oo = mk3<double>(o[3 * i], o[3 * i + 1], o[3 * i + 2]);
         const D3 dd = mk3<double>(d[3 * i], d[3 * i + 1], d[3 * i + 2]);
-        const HitX h = any_hit ? bvh_hit_x<true, false>(sc, oo, dd, tmin, tmax, nullptr)
+        // MFX_SKY_TRACER: ListHit(items, Ray(origin, dir), tmin, tmax) -- the Ray constructor normalises
+        const HitX h = (sc.mode == MFX_MODE_SKY) ? sky_hit_x<false>(sc, oo, normalize_x(dd), tmin, tmax, nullptr)
+                     : any_hit ? bvh_hit_x<true, false>(sc, oo, dd, tmin, tmax, nullptr)
                                : bvh_hit_x<false, false>(sc, oo, dd, tmin, tmax, nullptr);
         prim[i] = (h.slot < 0) ? -1 : sc.ref_id[h.slot];
         if (sub) sub[i] = (h.slot < 0) ? 0 : h.sub;
@@ -472,8 +708,15 @@ __global__ void __launch_bounds__(128) k_x_primary(SceneX sc, long long n, const
             u = ((double)i + 0.5) / (double)sc.width;
             v = ((double)j + 0.5) / (double)sc.height;
         }
-        const D3 d = camera_ray_dir_x(sc.cam, u, v);
-        const HitX h = bvh_hit_x<false, false>(sc, ld3(sc.cam.pos), d, 1e-6, 99999999., nullptr);
+        HitX h;
+        if (sc.mode == MFX_MODE_SKY) {      // GetRay without a lens sample + ListHit(ray, 0.00001, 10000000)
+            D3 org, d;
+            lens_ray_x(sc.cam, sc.lens, u, v, nullptr, org, d);
+            h = sky_hit_x<false>(sc, org, d, MFX_SKY_TMIN, MFX_SKY_TMAX, nullptr);
+        } else {
+            const D3 d = camera_ray_dir_x(sc.cam, u, v);
+            h = bvh_hit_x<false, false>(sc, ld3(sc.cam.pos), d, 1e-6, 99999999., nullptr);
+        }
         prim[r] = (h.slot < 0) ? -1 : sc.ref_id[h.slot];
         t[r] = (h.slot < 0) ? 0. : h.t;
     }
@@ -510,6 +753,10 @@ void mfx_x_extend(const LaunchCfg &c, const SceneX &sc, const WaveX &w, int boun
 void mfx_x_shade(const LaunchCfg &c, const SceneX &sc, const WaveX &w, TileMap tm, int pix0, int npix, int s0, int bounce, uint64_t seed)
 {
     k_x_shade<<<persistent_blocks(k_x_shade, c.threads, c.blocks), c.threads, 0, c.stream>>>(sc, w, tm, pix0, npix, s0, bounce, seed);
+}
+void mfx_x_shade_sky(const LaunchCfg &c, const SceneX &sc, const WaveX &w, TileMap tm, int pix0, int npix, int s0, int bounce, uint64_t seed)
+{
+    k_x_shade_sky<<<persistent_blocks(k_x_shade_sky, c.threads, c.blocks), c.threads, 0, c.stream>>>(sc, w, tm, pix0, npix, s0, bounce, seed);
 }
 void mfx_x_shadow(const LaunchCfg &c, const SceneX &sc, const WaveX &w, int bounce, TravCounters *ctr)
 {

@@ -192,9 +192,32 @@ __global__ void __launch_bounds__(256) k_f_raygen(SceneF sc, WaveF w, TileMap tm
         philox4x32_10((uint32_t)pix, (uint32_t)(s0 + sl), MFX_DIM_CAMERA, 0, (uint32_t)seed, (uint32_t)(seed >> 32), o4);
         const double u = ((double)px + u32_to_unit_f64(o4[0])) / (double)sc.width;
         const double v = ((double)py + u32_to_unit_f64(o4[1])) / (double)sc.height;
-        const F3 d = camera_dir_f64(sc.camx, u, v);
-        if (!w.cam_origin) w.ray_o[pid] = make_float4(sc.cam.pos[0], sc.cam.pos[1], sc.cam.pos[2], __int_as_float(-1));
-        w.ray_d[pid] = make_float4(d.x, d.y, d.z, 99999999.f);          // w = tMax of the closest query, Integrators.fs:108
+        F3 d;
+        if (sc.mode == MFX_MODE_SKY && sc.lens.radius != 0.0) {
+            // RayTraceCamera.GetRay with a lens sample (RayTracing.fs:360-364), f64, rounded once.  RandomInUnitDisk
+            // (:327-333) on the exact mode's stream: (dim 0, iter 1, 2, ..)
+            double dx = 0., dy = 0.;
+            for (uint32_t it = 0; it < MFX_REJECTION_CAP; it++) {
+                uint32_t l4[4];
+                philox4x32_10((uint32_t)pix, (uint32_t)(s0 + sl), MFX_DIM_CAMERA, 1u + it, (uint32_t)seed, (uint32_t)(seed >> 32), l4);
+                const double a = 2.0 * u32_to_unit_f64(l4[0]) - 1.0, b = 2.0 * u32_to_unit_f64(l4[1]) - 1.0;
+                if (a * a + b * b < 1.0) { dx = a; dy = b; break; }
+            }
+            dx *= sc.lens.radius; dy *= sc.lens.radius;
+            const double ox = sc.lens.u[0] * dx + sc.lens.v[0] * dy, oy = sc.lens.u[1] * dx + sc.lens.v[1] * dy, oz = sc.lens.u[2] * dx + sc.lens.v[2] * dy;
+            const CamX &c = sc.camx;
+            const double tx = (c.topleft[0] + c.right[0] * u) + c.down[0] * v - c.pos[0] - ox;
+            const double ty = (c.topleft[1] + c.right[1] * u) + c.down[1] * v - c.pos[1] - oy;
+            const double tz = (c.topleft[2] + c.right[2] * u) + c.down[2] * v - c.pos[2] - oz;
+            const double l = sqrt(tx * tx + ty * ty + tz * tz);
+            d = f3((float)(tx / l), (float)(ty / l), (float)(tz / l));
+            w.ray_o[pid] = make_float4((float)(c.pos[0] + ox), (float)(c.pos[1] + oy), (float)(c.pos[2] + oz), __int_as_float(-1));
+        } else {
+            d = camera_dir_f64(sc.camx, u, v);
+            if (!w.cam_origin) w.ray_o[pid] = make_float4(sc.cam.pos[0], sc.cam.pos[1], sc.cam.pos[2], __int_as_float(-1));
+        }
+        // w = tMax of the closest query: Integrators.fs:108 / RayTracing.fs:368
+        w.ray_d[pid] = make_float4(d.x, d.y, d.z, sc.mode == MFX_MODE_SKY ? (float)MFX_SKY_TMAX : 99999999.f);
         // throughput starts at 1: vertex 0 of k_f_shade knows that and the 16 B per path are neither written nor read
         w.rad[pid] = make_float4(0.f, 0.f, 0.f, 0.f);
         w.q_ext[0][pid] = (int)pid;
@@ -851,6 +874,146 @@ __global__ void __launch_bounds__(SHADE_BLOCK, 5) k_f_shade(SceneF sc, WaveF w, 
     }
 }
 
+// ---------------------------------------------------------------- MFX_SKY_TRACER shading
+// One level of GetColor (RenderTest/Sample/RayTracing.fs:367-382) for every path in the extend queue, unrolled like
+// the other integrators: T = product of the attenuations so far; a miss ends the path with rad = T * sky, a hit at
+// the depth limit or a failed scatter ends it black, anything else scatters (Lambertian :282-290, Metal :291-299,
+// Dielectric :300-325) and joins the next extend queue.  No light, no shadow queue.
+// DIRECT (default): GetRandomInUnitSphere (:261-266, the whole ball) drawn without the loop -- uniform direction,
+// radius u^(1/3) -- one Philox call per vertex feeds the ball and the dielectric coin.  MFX_SAMPLE_REFERENCE_STREAM
+// runs the rejection loop on the exact mode's stream instead.
+__device__ __forceinline__ F3 random_in_unit_ball_f(const RngF &g, uint32_t dim)
+{
+    for (uint32_t it = 0; it < MFX_REJECTION_CAP; it++) {
+        uint32_t o[4];
+        philox4x32_10(g.pixel, g.sample, dim, it, g.k0, g.k1, o);
+        const F3 p = f3(2.f * u32_to_unit_f32(o[0]) - 1.f, 2.f * u32_to_unit_f32(o[1]) - 1.f, 2.f * u32_to_unit_f32(o[2]) - 1.f);
+        if (dot(p, p) < 1.0f) return p;
+    }
+    return f3(0.f, 0.f, 0.f);
+}
+
+template <bool DIRECT>
+__global__ void __launch_bounds__(SHADE_BLOCK, 4) k_f_shade_sky(SceneF sc, WaveF w, TileMap tm, int pix0, int npix, int s0, int bounce, uint64_t seed)
+{
+    __shared__ int s_cnt[2][SHADE_BLOCK / 32];
+    __shared__ int s_base[2];
+    const int n = w.counts[bounce];
+    const int *qin = w.q_ext[bounce & 1];
+    int *qout = w.q_ext[(bounce + 1) & 1];
+    const int k = bounce;
+    const bool last = (bounce >= sc.max_depth);          // `depth < 50`, :373
+    const int nblock_iters = (n + SHADE_BLOCK - 1) / SHADE_BLOCK;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int par = 0;
+    for (int it = blockIdx.x; it < nblock_iters; it += gridDim.x, par ^= 1) {
+        const int i = it * SHADE_BLOCK + threadIdx.x;
+        bool cont = false;
+        int pid = -1;
+        if (i < n) {
+            pid = qin[i];
+            const float2 hr = w.hit[pid];
+            const int fs = __float_as_int(hr.y);
+            const float4 d4 = w.ray_d[pid];
+            float4 thr = make_float4(1.f, 1.f, 1.f, 0.f);
+            if (bounce > 0) thr = w.thr[pid];
+            const F3 d = f3(d4.x, d4.y, d4.z);
+            if (fs < 0) {
+                const float t = 0.5f * (d.y + 1.0f);                               // :378-381 (d is unit)
+                w.rad[pid] = make_float4(thr.x * ((1.f - t) + t * 0.5f), thr.y * ((1.f - t) + t * 0.7f), thr.z * ((1.f - t) + t), 0.f);
+            } else if (!last) {
+                float4 o4 = make_float4(sc.cam.pos[0], sc.cam.pos[1], sc.cam.pos[2], __int_as_float(-1));
+                if (!(bounce == 0 && w.cam_origin)) o4 = w.ray_o[pid];
+                const F3 point = f3(o4.x, o4.y, o4.z) + d * hr.x;
+                const float4 sa = ldg4(&sc.slots[fs].a);
+                const float4 sb = ldg4(&sc.slots[fs].b);
+                const int prim = __float_as_int(sb.w) & 0x3fffffff;
+                F3 normal;                                                         // (p - center) / radius, :198
+                if (__float_as_int(sa.w) == 3) {                                   // big sphere: f64 centre (see leaf_f3)
+                    const float4 sc4 = ldg4(&sc.slots[fs].c);
+                    const double cx = __hiloint2double(__float_as_int(sb.y), __float_as_int(sb.x));
+                    const double cy = __hiloint2double(__float_as_int(sc4.y), __float_as_int(sc4.x));
+                    const double cz = __hiloint2double(__float_as_int(sc4.w), __float_as_int(sc4.z));
+                    normal = normalize_f(f3((float)((double)point.x - cx), (float)((double)point.y - cy), (float)((double)point.z - cz)));
+                } else normal = normalize_f(point - f3(sa.x, sa.y, sa.z));
+                const MatF m = sc.mats[__float_as_int(ldg4(&sc.slot_nrm[fs]).w)];
+                const int sl = pid / npix, pl = pid - sl * npix;
+                int pix, px, py;
+                pixel_of(tm, sc.width, pix0 + pl, pix, px, py);
+                RngF g; g.pixel = (uint32_t)pix; g.sample = (uint32_t)(s0 + sl); g.k0 = (uint32_t)seed; g.k1 = (uint32_t)(seed >> 32);
+                uint32_t dz[4] = { 0u, 0u, 0u, 0u };
+                if (DIRECT) philox4x32_10(g.pixel, g.sample, MFX_DIM_BSDF(k), MFX_ITER_DIRECT, g.k0, g.k1, dz);
+                F3 wi, att;
+                bool ok = true;
+                if (m.kind == 3) {                                                 // Dielectric
+                    const float dn = dot(d, normal);
+                    const F3 reflected = d - normal * (2.f * dn);
+                    const F3 outward = dn > 0.f ? -normal : normal;
+                    const float nint = dn > 0.f ? m.ei : 1.f / m.ei;
+                    const float cosine = dn > 0.f ? m.ei * dn : -dn;
+                    const float dt = dot(d, outward);
+                    const float disc = 1.f - nint * nint * (1.f - dt * dt);
+                    float reflect_prob = 1.f;
+                    F3 ref_dir = reflected;
+                    if (disc > 0.f) {
+                        ref_dir = (d - outward * dt) * nint - outward * sqrtf(disc);
+                        const float r0 = (1.f - m.ei) / (1.f + m.ei), r1 = r0 * r0;
+                        const float x = 1.f - cosine, x2 = x * x;
+                        reflect_prob = r1 + (1.f - r1) * (x2 * x2 * x);
+                    }
+                    uint32_t coin = dz[3];
+                    if (!DIRECT) { uint32_t c4[4]; philox4x32_10(g.pixel, g.sample, MFX_DIM_LIGHT(k), 0, g.k0, g.k1, c4); coin = c4[0]; }
+                    // the coin uses the full 32-bit value like the f64 stream's `NextDouble() < reflect_prob`
+                    wi = normalize_f(((double)coin * (1.0 / 4294967296.0) < (double)reflect_prob) ? reflected : ref_dir);
+                    att = f3(1.f, 1.f, 1.f);
+                } else {
+                    F3 ball;
+                    if (DIRECT) {
+                        const float z = 1.f - 2.f * u32_to_unit_f32(dz[0]);
+                        const float r = sqrtf(fmaxf(0.f, 1.f - z * z));
+                        float sn, cs;
+                        __sincosf(6.283185307179586477f * u32_to_unit_f32(dz[1]), &sn, &cs);
+                        ball = f3(r * cs, r * sn, z) * cbrtf(u32_to_unit_f32(dz[2]));
+                    } else ball = random_in_unit_ball_f(g, MFX_DIM_BSDF(k));
+                    if (m.kind == 1) {                                             // Metal
+                        const float fuzz = fminf(m.fuzz, 1.f);
+                        wi = normalize_f(d - normal * (2.f * dot(d, normal)) + ball * fuzz);
+                        att = f3(m.albedo[0], m.albedo[1], m.albedo[2]);
+                        ok = dot(wi, normal) > 0.f;
+                    } else {                                                       // Lambertian over a texture (:50-61, :86-99)
+                        wi = normalize_f(normal + ball);
+                        att = f3(m.albedo[0], m.albedo[1], m.albedo[2]);
+                        if (m.kind == 4) {
+                            if (sinf(10.f * point.x) * sinf(10.f * point.y) * sinf(10.f * point.z) < 0.f) att = f3(m.fuzz, m.ei, m.et);
+                        } else if (m.kind == 5) {
+                            const int a = (int)(4.f * point.x) & 255, b = (int)(4.f * point.y) & 255, c = (int)(4.f * point.z) & 255;
+                            const float nz = __ldg(&sc.perlin_rf[__ldg(&sc.perlin_perm[a]) ^ __ldg(&sc.perlin_perm[256 + b]) ^ __ldg(&sc.perlin_perm[512 + c])]);
+                            att = f3(nz, nz, nz);
+                        }
+                    }
+                }
+                thr.x *= att.x; thr.y *= att.y; thr.z *= att.z;
+                cont = ok && ((thr.x != 0.f) || (thr.y != 0.f) || (thr.z != 0.f));
+                if (cont) {
+                    w.ray_o[pid] = make_float4(point.x, point.y, point.z, __int_as_float(prim));
+                    w.ray_d[pid] = make_float4(wi.x, wi.y, wi.z, (float)MFX_SKY_TMAX);
+                    w.thr[pid] = thr;
+                }
+            }
+        }
+        const unsigned mc = __ballot_sync(0xffffffffu, cont);
+        if (lane == 0) s_cnt[par][warp] = __popc(mc);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int tot = 0;
+            for (int j = 0; j < SHADE_BLOCK / 32; j++) { const int c = s_cnt[par][j]; s_cnt[par][j] = tot; tot += c; }
+            s_base[par] = tot ? atomicAdd(&w.counts[bounce + 1], tot) : 0;
+        }
+        __syncthreads();
+        if (cont) qout[s_base[par] + s_cnt[par][warp] + __popc(mc & ((1u << lane) - 1u))] = pid;
+    }
+}
+
 __global__ void __launch_bounds__(256) k_f_resolve(SceneF sc, WaveF w, TileMap tm, int pix0, int npix, int S, double *pixsum)
 {
     for (int pl = blockIdx.x * blockDim.x + threadIdx.x; pl < npix; pl += gridDim.x * blockDim.x) {
@@ -877,6 +1040,10 @@ __global__ void __launch_bounds__(256) k_f_seam_setup(SceneF sc, WaveF w, int n,
         if (d) {
             oo = f3((float)o[3 * r], (float)o[3 * r + 1], (float)o[3 * r + 2]);
             dd = f3((float)d[3 * r], (float)d[3 * r + 1], (float)d[3 * r + 2]);
+            if (sc.mode == MFX_MODE_SKY) {      // Ray(origin, direc) normalises (RayTracing.fs:14-16)
+                const double l = sqrt(d[3 * r] * d[3 * r] + d[3 * r + 1] * d[3 * r + 1] + d[3 * r + 2] * d[3 * r + 2]);
+                dd = f3((float)(d[3 * r] / l), (float)(d[3 * r + 1] / l), (float)(d[3 * r + 2] / l));
+            }
         } else {
             double u, v;
             if (uv) { u = uv[2 * r]; v = uv[2 * r + 1]; }
@@ -1058,6 +1225,11 @@ void mfx_f_shade(const LaunchCfg &c, const SceneF &sc, const WaveF &w, TileMap t
 {
     if (c.reference_stream) k_f_shade<false><<<persistent_blocks(k_f_shade<false>, SHADE_BLOCK, c.blocks), SHADE_BLOCK, 0, c.stream>>>(sc, w, tm, pix0, npix, s0, bounce, seed);
     else k_f_shade<true><<<persistent_blocks(k_f_shade<true>, SHADE_BLOCK, c.blocks), SHADE_BLOCK, 0, c.stream>>>(sc, w, tm, pix0, npix, s0, bounce, seed);
+}
+void mfx_f_shade_sky(const LaunchCfg &c, const SceneF &sc, const WaveF &w, TileMap tm, int pix0, int npix, int s0, int bounce, uint64_t seed)
+{
+    if (c.reference_stream) k_f_shade_sky<false><<<persistent_blocks(k_f_shade_sky<false>, SHADE_BLOCK, c.blocks), SHADE_BLOCK, 0, c.stream>>>(sc, w, tm, pix0, npix, s0, bounce, seed);
+    else k_f_shade_sky<true><<<persistent_blocks(k_f_shade_sky<true>, SHADE_BLOCK, c.blocks), SHADE_BLOCK, 0, c.stream>>>(sc, w, tm, pix0, npix, s0, bounce, seed);
 }
 void mfx_f_shadow(const LaunchCfg &c, const SceneF &sc, const WaveF &w, int bounce, TravCounters *ctr)
 {

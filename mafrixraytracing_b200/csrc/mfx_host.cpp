@@ -117,6 +117,28 @@ extern "C" int mfx_camera_pinhole(const double pos[3], const double dir[3], doub
     return MFX_OK;
 }
 
+// RayTraceCamera(lookfrom, lookat, vup, vfov, aspect, aperture, focus_dist, t0, t1): RenderTest/Sample/RayTracing.fs:335-358
+extern "C" int mfx_camera_lens(const double lookfrom[3], const double lookat[3], const double vup[3], double vfov,
+                               double aspect, double aperture, double focus_dist, MfxLensCamera *out)
+{
+    if (!lookfrom || !lookat || !vup || !out) return fail(MFX_ERR_INVALID_ARGUMENT, "mfx_camera_lens: null argument");
+    const double PI = 3.14159265358979323846;
+    out->lens_radius = aperture / 2.0;                                   // :347
+    const double theta = vfov * PI / 180.;
+    const double half_height = std::tan(theta / 2.);
+    const double half_width = aspect * half_height;
+    const H3 origin = hld(lookfrom);
+    const H3 w = hnorm(hsub(hld(lookfrom), hld(lookat)));                // :352-354
+    const H3 u = hnorm(hcross(hld(vup), w));
+    const H3 v = hnorm(hcross(w, u));
+    // origin - focus_dist*half_width*u - focus_dist*half_height*v - focus_dist*w, :355
+    const H3 p = hsub(hsub(hsub(origin, hmul(u, focus_dist * half_width)), hmul(v, focus_dist * half_height)), hmul(w, focus_dist));
+    hst(out->origin, origin); hst(out->lower_left, p);
+    hst(out->horizontal, hmul(u, 2. * focus_dist * half_width));         // :357-358
+    hst(out->vertical, hmul(v, 2. * focus_dist * half_height));
+    hst(out->u, u); hst(out->v, v);
+    return MFX_OK;
+}
 
 // ------------------------------------------------------------------ scene
 struct MfxScene {
@@ -129,6 +151,9 @@ struct MfxScene {
     std::vector<int32_t> indices;
     MfxAreaLight light;
     MfxCamera camera;
+    MfxLensCamera lens;                      // MFX_SKY_TRACER
+    std::vector<double> perlin_rf;           // MFX_SKY_TRACER: 256 or empty
+    std::vector<int32_t> perlin_perm;        //                 768 or empty
     int width = 0, height = 0, max_depth = 0, integrator = 0;
 
     std::vector<std::pair<void *, size_t>> allocs;   // every device buffer of this scene
@@ -136,6 +161,7 @@ struct MfxScene {
     SceneX sx; SceneF sf; SceneF sf_ref; WaveX wx; WaveF wf;     // sf: own SAH tree; sf_ref: reference-tree layout
     uint64_t x_bytes = 0, f_bytes = 0, fr_bytes = 0;
     MatF *d_matf = nullptr;
+    float *d_perlin_rf = nullptr; int *d_perlin_perm = nullptr;
     double *d_pixsum = nullptr;          // [w*h][4] row-major sums
     double *d_color_wh = nullptr;        // Color[w,h]
     float4 *d_rgba = nullptr;            // row-major float4 (internal, when the caller gives none)
@@ -232,8 +258,25 @@ extern "C" int mfx_scene_create(const MfxSceneDesc *d, MfxScene **out)
     if (!d->materials || d->n_materials <= 0) return fail(MFX_ERR_INVALID_ARGUMENT, "scene has no materials");
     if (d->width <= 0 || d->height <= 0) return fail(MFX_ERR_INVALID_ARGUMENT, "bad film size %dx%d", d->width, d->height);
     if (d->max_depth < 0 || d->max_depth >= MFX_MAX_VERTS) return fail(MFX_ERR_UNSUPPORTED, "max_depth %d outside 0..%d", d->max_depth, MFX_MAX_VERTS - 1);
-    if (d->integrator != MFX_PATH_INTEGRATOR && d->integrator != MFX_NEW_PATH_TRACER) return fail(MFX_ERR_INVALID_ARGUMENT, "unknown integrator %d", d->integrator);
+    if (d->integrator != MFX_PATH_INTEGRATOR && d->integrator != MFX_NEW_PATH_TRACER && d->integrator != MFX_SKY_TRACER)
+        return fail(MFX_ERR_INVALID_ARGUMENT, "unknown integrator %d", d->integrator);
+    const bool sky = (d->integrator == MFX_SKY_TRACER);
+    if (sky && !d->sky) return fail(MFX_ERR_INVALID_ARGUMENT, "MFX_SKY_TRACER needs MfxSceneDesc.sky (lens camera)");
+    for (int i = 0; i < d->n_materials; i++) {
+        const int k = d->materials[i].kind;
+        if (k < 0 || k > MFX_LAMBERT_NOISE) return fail(MFX_ERR_INVALID_ARGUMENT, "material %d: unknown kind %d", i, k);
+        if (sky && k == MFX_SPECTRANS) return fail(MFX_ERR_INVALID_ARGUMENT, "material %d: SpecularTransmission does not exist in the sphere sample (use MFX_DIELECTRIC)", i);
+        if (!sky && k > MFX_SPECTRANS) return fail(MFX_ERR_INVALID_ARGUMENT, "material %d: kind %d only exists under MFX_SKY_TRACER", i, k);
+        if (k == MFX_LAMBERT_NOISE && (!d->sky->perlin_ranfloat || !d->sky->perlin_perm))
+            return fail(MFX_ERR_INVALID_ARGUMENT, "material %d: MFX_LAMBERT_NOISE needs the Perlin tables", i);
+    }
+    if (sky && d->sky->perlin_perm)
+        for (int i = 0; i < 768; i++)
+            if (d->sky->perlin_perm[i] < 0 || d->sky->perlin_perm[i] > 255) return fail(MFX_ERR_INVALID_ARGUMENT, "perlin_perm[%d] = %d outside 0..255", i, d->sky->perlin_perm[i]);
     for (int i = 0; i < d->n_prims; i++) {
+        // the sphere sample's IHitAble list holds spheres only (RayTracing.fs:176-253; MovingSphere is not carried over)
+        if (sky && (d->prims[i].kind != MFX_SPHERE || !(d->prims[i].v[3] > 0.)))
+            return fail(MFX_ERR_UNSUPPORTED, "primitive %d: MFX_SKY_TRACER takes spheres with a positive radius only", i);
         if (d->prims[i].kind < 0 || d->prims[i].kind > 2) return fail(MFX_ERR_INVALID_ARGUMENT, "primitive %d: unknown kind %d", i, d->prims[i].kind);
         if (d->prims[i].material < 0 || d->prims[i].material >= d->n_materials)
             return fail(MFX_ERR_INVALID_ARGUMENT, "primitive %d: material %d outside the table of %d", i, d->prims[i].material, d->n_materials);
@@ -255,6 +298,16 @@ extern "C" int mfx_scene_create(const MfxSceneDesc *d, MfxScene **out)
     s->prims.assign(d->prims, d->prims + d->n_prims);
     s->mats.assign(d->materials, d->materials + d->n_materials);
     s->light = d->light; s->camera = d->camera;
+    memset(&s->lens, 0, sizeof(s->lens));
+    if (sky) {
+        s->lens = d->sky->camera;
+        // the lens camera rides in the pinhole slots (see LensX): the seams and the kernels share one ray formula
+        memcpy(s->camera.pos, s->lens.origin, 24); memcpy(s->camera.topleft, s->lens.lower_left, 24);
+        memcpy(s->camera.right, s->lens.horizontal, 24); memcpy(s->camera.down, s->lens.vertical, 24);
+        memset(&s->light, 0, sizeof(s->light));
+        if (d->sky->perlin_ranfloat) s->perlin_rf.assign(d->sky->perlin_ranfloat, d->sky->perlin_ranfloat + 256);
+        if (d->sky->perlin_perm) s->perlin_perm.assign(d->sky->perlin_perm, d->sky->perlin_perm + 768);
+    }
     s->width = d->width; s->height = d->height; s->max_depth = d->max_depth; s->integrator = d->integrator;
     const int n_slots = 2 * d->n_prims - 1;
     s->nodes.resize(n_slots); s->indices.resize(d->n_prims);
@@ -310,6 +363,14 @@ static int flatten_exact(MfxScene *s)
         memset(&nodes[i], 0, sizeof(NodeX));
         for (int a = 0; a < 3; a++) { nodes[i].pmin[a] = s->nodes[i].pmin[a]; nodes[i].pmax[a] = s->nodes[i].pmax[a]; }
         nodes[i].first = s->nodes[i].first; nodes[i].count = s->nodes[i].count;
+        if (s->integrator == MFX_SKY_TRACER) {
+            // ListHit tests no boxes (RayTracing.fs:256-258): the tree must only ever skip spheres the formula would
+            // reject, so every box is padded far beyond the rounding of `center -+ radius` and of the slab divisions
+            for (int a = 0; a < 3; a++) {
+                const double pad = 1e-7 * std::max(1.0, std::max(std::fabs(nodes[i].pmin[a]), std::fabs(nodes[i].pmax[a])));
+                nodes[i].pmin[a] -= pad; nodes[i].pmax[a] += pad;
+            }
+        }
     }
     std::vector<PrimX> prims(n);
     std::vector<int> ref(n);
@@ -345,6 +406,13 @@ static int flatten_exact(MfxScene *s)
     for (int a = 0; a < 3; a++) { sx.light.normal[a] = s->light.normal[a]; sx.light.color[a] = s->light.color[a]; }
     memcpy(sx.cam.pos, s->camera.pos, 24); memcpy(sx.cam.topleft, s->camera.topleft, 24);
     memcpy(sx.cam.right, s->camera.right, 24); memcpy(sx.cam.down, s->camera.down, 24);
+    memcpy(sx.lens.u, s->lens.u, 24); memcpy(sx.lens.v, s->lens.v, 24); sx.lens.radius = s->lens.lens_radius;
+    if (!s->perlin_rf.empty() && !s->perlin_perm.empty()) {
+        double *drf; int *dpm;
+        std::vector<int> pm(s->perlin_perm.begin(), s->perlin_perm.end());
+        MFX_TRY(upload(s, &drf, s->perlin_rf)); MFX_TRY(upload(s, &dpm, pm));
+        sx.perlin_rf = drf; sx.perlin_perm = dpm;
+    }
     sx.width = s->width; sx.height = s->height; sx.max_depth = s->max_depth; sx.mode = s->integrator; sx.n_prims = n;
     s->x_ready = true;
     return MFX_OK;
@@ -395,6 +463,15 @@ static int fill_fast_common(MfxScene *s, SceneF &sf)
     }
     memcpy(sf.camx.pos, s->camera.pos, 24); memcpy(sf.camx.topleft, s->camera.topleft, 24);
     memcpy(sf.camx.right, s->camera.right, 24); memcpy(sf.camx.down, s->camera.down, 24);
+    memcpy(sf.lens.u, s->lens.u, 24); memcpy(sf.lens.v, s->lens.v, 24); sf.lens.radius = s->lens.lens_radius;
+    if (!s->perlin_rf.empty() && !s->perlin_perm.empty()) {
+        if (!s->d_perlin_rf) {
+            std::vector<float> rf(s->perlin_rf.begin(), s->perlin_rf.end());
+            std::vector<int> pm(s->perlin_perm.begin(), s->perlin_perm.end());
+            MFX_TRY(upload(s, &s->d_perlin_rf, rf)); MFX_TRY(upload(s, &s->d_perlin_perm, pm));
+        }
+        sf.perlin_rf = s->d_perlin_rf; sf.perlin_perm = s->d_perlin_perm;
+    }
     sf.width = s->width; sf.height = s->height; sf.max_depth = s->max_depth; sf.mode = s->integrator;
     return MFX_OK;
 }
@@ -669,8 +746,9 @@ static int ensure_wave_exact(MfxScene *s)
     MFX_TRY(dev_alloc_t(s, &w.ray_o, 3 * P)); MFX_TRY(dev_alloc_t(s, &w.ray_d, 3 * P));
     MFX_TRY(dev_alloc_t(s, &w.hit_t, P)); MFX_TRY(dev_alloc_t(s, &w.hit_slot, P));
     MFX_TRY(dev_alloc_t(s, &w.sh_d, 3 * P)); MFX_TRY(dev_alloc_t(s, &w.sh_dist, P));
-    MFX_TRY(dev_alloc_t(s, &w.v_l, V * 3 * P)); MFX_TRY(dev_alloc_t(s, &w.v_col, V * 3 * P));
-    MFX_TRY(dev_alloc_t(s, &w.v_ei, V * P)); MFX_TRY(dev_alloc_t(s, &w.v_kind, V * P));
+    const bool sky = (s->integrator == MFX_SKY_TRACER);      // keeps one terminal colour and the attenuations only
+    MFX_TRY(dev_alloc_t(s, &w.v_l, (sky ? 1 : V) * 3 * P)); MFX_TRY(dev_alloc_t(s, &w.v_col, V * 3 * P));
+    MFX_TRY(dev_alloc_t(s, &w.v_ei, (sky ? 1 : V) * P)); MFX_TRY(dev_alloc_t(s, &w.v_kind, (sky ? 1 : V) * P));
     MFX_TRY(dev_alloc_t(s, &w.nv, P));
     MFX_TRY(dev_alloc_t(s, &w.queue[0], P)); MFX_TRY(dev_alloc_t(s, &w.queue[1], P));
     MFX_TRY(dev_alloc_t(s, &w.counts, MFX_COUNTS_LEN));
@@ -699,7 +777,7 @@ static int ensure_wave_fast(MfxScene *s, size_t want)
     for (;;) {
         memset(&w, 0, sizeof(w));
         w.P = (int)P;
-        w.tmin = 1e-6f;
+        w.tmin = (s->integrator == MFX_SKY_TRACER) ? (float)MFX_SKY_TMIN : 1e-6f;
         auto all = [&]() -> int {
             MFX_TRY(dev_alloc_t(s, &w.ray_o, P)); MFX_TRY(dev_alloc_t(s, &w.ray_d, P));
             MFX_TRY(dev_alloc_t(s, &w.hit, P)); MFX_TRY(dev_alloc_t(s, &w.thr, P)); MFX_TRY(dev_alloc_t(s, &w.rad, P));
@@ -807,7 +885,8 @@ static int run_sample(MfxScene *s, const MfxSampleParams *p, double *d_color_wh,
     MFX_TRY(get_tilemap(s, p->tile_size, p->rank, p->world, &tm));
     if (!exact) MFX_TRY(ensure_wave_fast(s, (size_t)tm.n_pix * (size_t)p->spp));
     TravCounters *ctr = counting ? s->d_ctr : nullptr;
-    if (!exact) s->wf.cam_origin = (sfp->own_tree && !counting) ? 1 : 0;
+    const bool sky = (s->integrator == MFX_SKY_TRACER);
+    if (!exact) s->wf.cam_origin = (sfp->own_tree && !counting && !(sky && s->lens.lens_radius != 0.0)) ? 1 : 0;
     const size_t npx = (size_t)s->width * s->height;
     cudaStream_t st = s->stream;
     LaunchCfg cfg{ s->sm_count, 128, st, variant, (p->flags & MFX_SAMPLE_REFERENCE_STREAM) ? 1 : 0 };
@@ -855,6 +934,12 @@ static int run_sample(MfxScene *s, const MfxSampleParams *p, double *d_color_wh,
                 MFX_TRY(timed(0));
                 if (exact) mfx_x_extend(cfg, s->sx, s->wx, b, ctr); else mfx_f_extend(cfg, *sfp, s->wf, b, ctr);
                 MFX_TRY(timed_end());
+                if (sky) {      // GetColor (RayTracing.fs:367-382): no light, no shadow query
+                    if (exact) mfx_x_shade_sky(cfg, s->sx, s->wx, tm, pix0, np, sabs, b, p->seed);
+                    else mfx_f_shade_sky(cfg, *sfp, s->wf, tm, pix0, np, sabs, b, p->seed);
+                    launches += 2; l_ext++;
+                    continue;
+                }
                 if (exact) mfx_x_shade(cfg, s->sx, s->wx, tm, pix0, np, sabs, b, p->seed);
                 else mfx_f_shade(cfg, *sfp, s->wf, tm, pix0, np, sabs, b, p->seed);
                 MFX_TRY(timed(1));
@@ -866,7 +951,8 @@ static int run_sample(MfxScene *s, const MfxSampleParams *p, double *d_color_wh,
             else mfx_f_resolve(cfg, *sfp, s->wf, tm, pix0, np, S, s->d_pixsum);
             // rays traced: exact: closest = counts[0..D], shadow = counts[1..D+1];
             //              fast : closest = counts[0..D], shadow = counts[V+2 .. V+2+D]
-            if (exact) mfx_accum_ray_totals(st, counts, 0, D + 1, 1, D + 1, s->d_totals);
+            if (sky) mfx_accum_ray_totals(st, counts, 0, D + 1, 0, 0, s->d_totals);
+            else if (exact) mfx_accum_ray_totals(st, counts, 0, D + 1, 1, D + 1, s->d_totals);
             else mfx_accum_ray_totals(st, counts, 0, D + 1, MFX_MAX_VERTS + 2, D + 1, s->d_totals);
             launches += 2;
         }
@@ -1056,7 +1142,8 @@ extern "C" int mfx_trace_primary(MfxScene *s, int32_t precision, int64_t n, cons
         MFX_TRY(fast_layout(s, false, cfg.variant, &sfp));
         MFX_TRY(ensure_wave_fast(s, (size_t)n));
         return with_ray_buffers(s, n, uv, 2, nullptr, 0, prim, nullptr, t, [&](double *u, double *, int *p, int *, double *tt) {
-            fast_seam(s, sfp, cfg, 0, n, nullptr, nullptr, u, 1e-6f, 99999999.f, p, nullptr, tt);
+            const bool sky = (s->integrator == MFX_SKY_TRACER);      // ListHit(ray, 0.00001, 10000000), RayTracing.fs:368
+            fast_seam(s, sfp, cfg, 0, n, nullptr, nullptr, u, sky ? (float)MFX_SKY_TMIN : 1e-6f, sky ? (float)MFX_SKY_TMAX : 99999999.f, p, nullptr, tt);
         });
     }
     return fail(MFX_ERR_INVALID_ARGUMENT, "unknown precision %d", precision);

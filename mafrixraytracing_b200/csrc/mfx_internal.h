@@ -7,7 +7,10 @@
 
 #define MFX_LEAF_NODE_COUNT 3      // Bvh.LeafNodeCount, BvhNode.fs:39
 #define MFX_REJECTION_CAP 128      // cap of the GetRandomInUnitSphere loop (Material.fs:12), see DESIGN.md
-#define MFX_MAX_VERTS 16           // max_depth + 1 shaded vertices per path (max_depth <= 15)
+#define MFX_MAX_VERTS 64           // max_depth + 1 shaded vertices per path (max_depth <= 63; the sphere sample uses 50)
+#define MFX_MODE_SKY 2             // MFX_SKY_TRACER: GetColor of RenderTest/Sample/RayTracing.fs:367-382
+#define MFX_SKY_TMIN 0.00001       // ListHit(hitable, ray, 0.00001, 10000000), RayTracing.fs:368
+#define MFX_SKY_TMAX 10000000.
 
 // ------------------------------------------------------------------ exact (f64) device layout
 // One BvhNode, heap-indexed like the reference (children 2i+1 / 2i+2).  64 B.
@@ -45,6 +48,10 @@ struct LightX {
     double color[3];
 };
 struct CamX { double pos[3], topleft[3], right[3], down[3]; };
+// MFX_SKY_TRACER: RayTraceCamera (RayTracing.fs:335-364) rides in CamX as pos = origin, topleft = lowerLeftCorner,
+// right = horizontal, down = vertical -- GetRay's `lowerLeftCorner + s*horizontal + t*vertical - origin` has the
+// shape of the pinhole's `topleft + u*right + v*down - pos` -- plus the lens basis and radius.
+struct LensX { double u[3], v[3], radius; };
 
 struct SceneX {
     const NodeX *nodes;
@@ -53,6 +60,9 @@ struct SceneX {
     const MatX  *mats;
     LightX light;
     CamX   cam;
+    LensX  lens;                    // MFX_SKY_TRACER
+    const double *perlin_rf;        // MFX_SKY_TRACER: Perlin.ranfloat[256] (RayTracing.fs:82) or null
+    const int    *perlin_perm;      //                 perm_x | perm_y | perm_z [3*256] (:83-85) or null
     int    width, height, max_depth, mode;
     int    n_prims;
 };
@@ -66,7 +76,8 @@ struct WaveX {
     int    *hit_slot;       // [P]  slot | sub<<30, or -1
     double *sh_d;           // [3][P] unit direction to the light sample
     double *sh_dist;        // [P]
-    double *v_l;            // [V][3][P]  l_k   (direct term, zeroed by the shadow kernel when occluded)
+    double *v_l;            // [V][3][P]  l_k   (direct term, zeroed by the shadow kernel when occluded);
+                            //            MFX_SKY_TRACER: [3][P] the colour the recursion bottoms out with
     double *v_col;          // [V][3][P]  col_k
     double *v_ei;           // [V][P]     Lambertian.Shade cosine (mode B)
     int    *v_kind;         // [V][P]     material kind at vertex k (mode B)
@@ -122,6 +133,9 @@ struct SceneF {
     LightF light;
     CamF   cam;
     CamX   camx;            // f64 camera: primary rays are generated in f64 and rounded once
+    LensX  lens;            // MFX_SKY_TRACER (see SceneX)
+    const float *perlin_rf; // MFX_SKY_TRACER: noise tables (f32 view) or null
+    const int   *perlin_perm;
     float  root_min[3], root_max[3];
     int    root_meta;       // leaf meta if the whole tree is one leaf, else -1
     int    width, height, max_depth, mode;
@@ -181,6 +195,8 @@ void mfx_x_resolve(const LaunchCfg &, const SceneX &, const WaveX &, TileMap tm,
 void mfx_x_bvh_hit(const LaunchCfg &, const SceneX &, int any_hit, long long n, const double *o, const double *d,
                    double tmin, double tmax, int *prim, int *sub, double *t);
 void mfx_x_primary(const LaunchCfg &, const SceneX &, long long n, const double *uv, int *prim, double *t);
+void mfx_x_shade_sky(const LaunchCfg &, const SceneX &, const WaveX &, TileMap tm, int pix0, int npix, int s0,
+                     int bounce, uint64_t seed);
 void mfx_x_finalize(const LaunchCfg &, const double *pixsum, int width, int height, double inv_unused, int spp,
                     TileMap tm, double *color_wh /* x-major Color[w,h] or null */, float4 *rgba_f32 /* row-major or null */);
 
@@ -191,6 +207,8 @@ void mfx_f_extend(const LaunchCfg &, const SceneF &, const WaveF &, int bounce, 
 void mfx_f_shade(const LaunchCfg &, const SceneF &, const WaveF &, TileMap tm, int pix0, int npix, int s0,
                  int bounce, uint64_t seed);
 void mfx_f_shadow(const LaunchCfg &, const SceneF &, const WaveF &, int bounce, TravCounters *ctr);
+void mfx_f_shade_sky(const LaunchCfg &, const SceneF &, const WaveF &, TileMap tm, int pix0, int npix, int s0,
+                     int bounce, uint64_t seed);
 void mfx_f_resolve(const LaunchCfg &, const SceneF &, const WaveF &, TileMap tm, int pix0, int npix, int S,
                    double *pixsum);
 void mfx_f_seam_setup(const LaunchCfg &, const SceneF &, const WaveF &, int n, const double *o, const double *d, const double *uv,

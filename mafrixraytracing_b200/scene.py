@@ -9,6 +9,7 @@ Names and argument meaning follow the F# types they stand in for (paths under
   Scene(desc) / Scene.Hit / TracePrimary      Scene/Scene.fs:298-313, BvhNode.fs:83
   CudaPixelIntegrator.Sample(n)               Core/Integrator/Integrators.fs:143-172 (IPixelIntegrator)
   Film.GetFrame(integrator, samples)          Core/Film.fs:13-34
+  RayTraceCamera(lookfrom, lookat, vup, ...)  RenderTest/Sample/RayTracing.fs:335-364 (the sphere sample, SKY_TRACER)
 
 All compute goes through libmafrix_cuda; nothing here renders on the CPU.
 """
@@ -30,7 +31,8 @@ assert PRIM_DTYPE.itemsize == 104 and MATERIAL_DTYPE.itemsize == 56 and NODE_DTY
 
 TRIANGLE, RECT, SPHERE = 0, 1, 2
 LAMBERT, METAL, SPECTRANS = 0, 1, 2
-PATH_INTEGRATOR, NEW_PATH_TRACER = 0, 1
+DIELECTRIC, LAMBERT_CHECKER, LAMBERT_NOISE = 3, 4, 5      # SKY_TRACER only (RayTracing.fs:300-325, :54-61, :96-99)
+PATH_INTEGRATOR, NEW_PATH_TRACER, SKY_TRACER = 0, 1, 2
 EXACT_F64, FAST_F32 = 0, 1
 
 
@@ -65,6 +67,45 @@ class PinholeCamera:
         d = target - self.position
         l = np.sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2])
         return self.position.copy(), d / l
+
+
+class RayTraceCamera:
+    """RayTraceCamera(lookfrom, lookat, vup, vfov, aspect, aperture, focus_dist, t0, t1) of the sphere sample
+    (RenderTest/Sample/RayTracing.fs:335-358), derived on the host by the library; t0/t1 only feed MovingSphere,
+    which is not carried over."""
+
+    def __init__(self, lookfrom, lookat, vup, vfov, aspect, aperture=0.0, focus_dist=None):
+        self.lookfrom, self.lookat, self.vup = _vec3(lookfrom), _vec3(lookat), _vec3(vup)
+        self.vfov, self.aspect, self.aperture = float(vfov), float(aspect), float(aperture)
+        if focus_dist is None:                                   # dist_to_focus = (lookfrom-lookat).Length, :431
+            d = self.lookfrom - self.lookat
+            focus_dist = np.sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2])
+        self.focus_dist = float(focus_dist)
+        cam = _lib.MfxLensCamera()
+        _lib.check(_lib.load().mfx_camera_lens(_lib.ptr(self.lookfrom), _lib.ptr(self.lookat), _lib.ptr(self.vup),
+                                               self.vfov, self.aspect, self.aperture, self.focus_dist, C.byref(cam)))
+        self._c = cam
+
+    def derived(self):
+        """origin, lower_left, horizontal, vertical, u, v, lens_radius as one (19,) f64 array."""
+        c = self._c
+        return np.array(list(c.origin) + list(c.lower_left) + list(c.horizontal) + list(c.vertical) + list(c.u) +
+                        list(c.v) + [c.lens_radius])
+
+
+@dataclass
+class SkyTracer:
+    """What the sphere sample needs beyond shapes and materials: its camera and Perlin's static tables
+    (RayTracing.fs:81-85; ranfloat[256], perm = perm_x|perm_y|perm_z [3*256]; None without a noise material)."""
+    camera: RayTraceCamera
+    ranfloat: np.ndarray = None
+    perm: np.ndarray = None
+
+    def __post_init__(self):
+        if self.ranfloat is not None:
+            self.ranfloat = np.ascontiguousarray(self.ranfloat, dtype=np.float64).reshape(256)
+        if self.perm is not None:
+            self.perm = np.ascontiguousarray(self.perm, dtype=np.int32).reshape(768)
 
 
 @dataclass
@@ -119,16 +160,27 @@ def sphere_prims(centers, radii, materials):
 
 
 def make_materials(specs):
-    """specs: list of ("lambert", (r,g,b)) | ("metal", (r,g,b), fuzz) | ("spectrans", (r,g,b), ei, et)."""
+    """specs: list of ("lambert", (r,g,b)) | ("metal", (r,g,b), fuzz) | ("spectrans", (r,g,b), ei, et); SKY_TRACER
+    adds ("dielectric", ri) | ("checker", even_rgb, odd_rgb) | ("noise",)."""
     m = np.zeros(len(specs), dtype=MATERIAL_DTYPE)
     for i, s in enumerate(specs):
-        kind = {"lambert": LAMBERT, "metal": METAL, "spectrans": SPECTRANS}[s[0]]
+        kind = {"lambert": LAMBERT, "metal": METAL, "spectrans": SPECTRANS, "dielectric": DIELECTRIC,
+                "checker": LAMBERT_CHECKER, "noise": LAMBERT_NOISE}[s[0]]
         m[i]["kind"] = kind
+        if kind == DIELECTRIC:
+            m[i]["albedo"] = (1., 1., 1.)
+            m[i]["ei"] = s[1]
+            continue
+        if kind == LAMBERT_NOISE:
+            m[i]["albedo"] = (1., 1., 1.)
+            continue
         m[i]["albedo"] = s[1]
         if kind == METAL:
             m[i]["fuzz"] = s[2]
         if kind == SPECTRANS:
             m[i]["ei"], m[i]["et"] = s[2], s[3]
+        if kind == LAMBERT_CHECKER:                      # odd colour rides in (fuzz, ei, et), see MfxMaterial
+            m[i]["fuzz"], m[i]["ei"], m[i]["et"] = s[2]
     return m
 
 
@@ -146,6 +198,7 @@ class SceneDesc:
     integrator: int = PATH_INTEGRATOR
     name: str = ""
     meta: dict = field(default_factory=dict)
+    sky: SkyTracer = None               # SKY_TRACER: light and camera are ignored (pass None)
 
     def __post_init__(self):
         self.prims = np.ascontiguousarray(self.prims, dtype=PRIM_DTYPE)
@@ -189,10 +242,18 @@ class Scene:
             d.indices = _lib.ptr(bvh.indices)
         else:
             d.nodes, d.n_node_slots, d.indices = None, 0, None
-        d.light.p[:] = desc.light.p.reshape(-1).tolist()
-        d.light.normal[:] = desc.light.normal.tolist()
-        d.light.color[:] = desc.light.color.tolist()
-        d.camera = desc.camera._c
+        if desc.light is not None:
+            d.light.p[:] = desc.light.p.reshape(-1).tolist()
+            d.light.normal[:] = desc.light.normal.tolist()
+            d.light.color[:] = desc.light.color.tolist()
+        if desc.camera is not None:
+            d.camera = desc.camera._c
+        if desc.sky is not None:
+            self._sky = _lib.MfxSkyTracer()
+            self._sky.camera = desc.sky.camera._c
+            self._sky.perlin_ranfloat = _lib.ptr(desc.sky.ranfloat)
+            self._sky.perlin_perm = _lib.ptr(desc.sky.perm)
+            d.sky = C.pointer(self._sky)
         d.width, d.height = self.width, self.height
         d.max_depth, d.integrator = int(desc.max_depth), int(desc.integrator)
         h = C.c_void_p()

@@ -10,6 +10,8 @@ never read at run time.
   c3_renault()C3: Renault12TL, mixed materials, NewPathTracer, 1920x1080, 256 spp
   c4_spheres()C4: ~100k spheres (RayTracing.fs:384-415 recipe scaled), 3840x2160, 128 spp
   c5_soup()   C5: spot instanced 1708x (10.0M triangles), 3840x2160, 64 spp
+  random_scene()  the sphere sample itself (RenderTest/Sample/RayTracing.fs:384-436): RandomScene + RayTraceCamera,
+              400x200, 9 spp, depth 50, rendered by GetColor (SKY_TRACER)
 
 Surfaces are oriented deliberately: the reference never flips normals toward the ray
 (quirk Q4), so rooms face inward and objects outward.
@@ -18,8 +20,9 @@ import os
 
 import numpy as np
 
-from .scene import (AreaLight, PinholeCamera, SceneDesc, make_materials, make_prims, rect_prim,
-                    sphere_prims, triangles_from_mesh, NEW_PATH_TRACER, PATH_INTEGRATOR, RECT, TRIANGLE)
+from .scene import (AreaLight, PinholeCamera, RayTraceCamera, SceneDesc, SkyTracer, make_materials, make_prims,
+                    rect_prim, sphere_prims, triangles_from_mesh, NEW_PATH_TRACER, PATH_INTEGRATOR, SKY_TRACER, RECT,
+                    TRIANGLE)
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 MESH_DIR = os.environ.get("MFX_MESH_DIR", os.path.join(_HERE, "..", "tests", "golden", "meshes"))
@@ -194,5 +197,56 @@ def c5_soup(width=3840, height=2160, max_depth=5, instances=1708, cols=42, spaci
                      meta={"spp": 64})
 
 
+def perlin_tables(seed=7):
+    """Perlin's static tables (RayTracing.fs:64-85): ranfloat = 256 uniforms, perm_x/y/z = Permute([0..255]) --
+    the reference fills them from Random.Shared, here numpy PCG64(seed) with the same shuffle loop (:69-75)."""
+    rng = np.random.default_rng(seed)
+    ranfloat = rng.random(256)
+    perm = np.zeros((3, 256), np.int32)
+    for a in range(3):
+        p = np.arange(256, dtype=np.int32)
+        for i in range(255, -1, -1):
+            targ = int(rng.random() * float(i + 1))
+            p[i], p[targ] = p[targ], p[i]
+        perm[a] = p
+    return ranfloat, perm.reshape(-1)
+
+
+def random_scene(width=400, height=200, max_depth=50, seed=42, ground="noise", aperture=0.0, cells=range(-1, 12)):
+    """RandomScene (RenderTest/Sample/RayTracing.fs:384-415) behind the camera of DoRayTrace (:426-432): one small
+    sphere per (a, b) cell -- 80 % Lambertian(ConstantTexture(xi*xi)), 15 % Metal(0.5(1+xi), fuzz 0.5 xi), 5 %
+    Dielectric(1.5), skipped within 0.9 of (4, 0.2, 0) -- then the ground sphere r = 1000 (NoiseTexture; "checker" and
+    "grey" are the two alternatives commented out at :410-411) and the three big spheres.  numpy PCG64(seed) stands
+    in for `new System.Random()`, drawn in the reference's order."""
+    rng = np.random.default_rng(seed)
+    centers, radii, specs = [], [], []
+    for a in cells:                                  # Array.allPairs [|-1..11|] [|-1..11|]: a-major
+        for b in cells:
+            choose_mat = rng.random()
+            center = np.array([a + 0.9 * rng.random(), 0.2, b + rng.random()])
+            if np.sqrt(((center - np.array([4, 0.2, 0])) ** 2).sum()) > 0.9:
+                if choose_mat < 0.8:
+                    specs.append(("lambert", (rng.random() * rng.random(), rng.random() * rng.random(), rng.random() * rng.random())))
+                elif choose_mat < 0.95:
+                    alb = (0.5 * (1. + rng.random()), 0.5 * (1. + rng.random()), 0.5 * (1. + rng.random()))
+                    specs.append(("metal", alb, 0.5 * rng.random()))
+                else:
+                    specs.append(("dielectric", 1.5))
+                centers.append(center)
+                radii.append(0.2)
+    specs.append({"noise": ("noise",), "checker": ("checker", (0.2, 0.3, 0.1), (0.9, 0.9, 0.9)),
+                  "grey": ("lambert", (0.5, 0.5, 0.5))}[ground])
+    centers.append((0., -1000., 0.)); radii.append(1000.)
+    specs.append(("dielectric", 1.5)); centers.append((0., 1., 0.)); radii.append(1.0)
+    specs.append(("lambert", (0.4, 0.2, 0.1))); centers.append((-4., 1., 0.)); radii.append(1.0)
+    specs.append(("metal", (0.7, 0.6, 0.5), 0.0)); centers.append((4., 1., 0.)); radii.append(1.0)
+    prims = sphere_prims(np.array(centers, float), np.array(radii, float), np.arange(len(specs), dtype=np.int32))
+    mats = make_materials(specs)
+    cam = RayTraceCamera((13, 2, 3), (0, 0, 0), (0, 1, 0), 20.0, width / height, aperture)
+    rf, pm = perlin_tables(seed + 1)
+    return SceneDesc(prims, mats, None, None, width, height, max_depth, SKY_TRACER, name="random_scene",
+                     meta={"spp": 9}, sky=SkyTracer(cam, rf, pm))
+
+
 WORKLOADS = {"cornell": cornell, "c1_cube": c1_cube, "c2_spot": c2_spot, "c3_renault": c3_renault,
-             "c4_spheres": c4_spheres, "c5_soup": c5_soup}
+             "c4_spheres": c4_spheres, "c5_soup": c5_soup, "random_scene": random_scene}

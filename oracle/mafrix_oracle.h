@@ -22,7 +22,9 @@ extern "C" {
 #endif
 
 enum { ORC_TRIANGLE = 0, ORC_RECT = 1, ORC_SPHERE = 2 };
-enum { ORC_LAMBERT = 0, ORC_METAL = 1, ORC_SPECTRANS = 2 };
+enum { ORC_LAMBERT = 0, ORC_METAL = 1, ORC_SPECTRANS = 2,
+       /* sphere sample only (RenderTest/Sample/RayTracing.fs:300-325, :54-61, :96-99) */
+       ORC_DIELECTRIC = 3, ORC_LAMBERT_CHECKER = 4, ORC_LAMBERT_NOISE = 5 };
 enum { ORC_MODE_A = 0 /* PathIntegrator, Integrators.fs:96-141 */,
        ORC_MODE_B = 1 /* NewPathTracer,  PathTracer.fs:13-46   */ };
 
@@ -122,6 +124,32 @@ void orc_tonemap_rgba8(const double *texture, int width, int height, uint8_t *rg
 void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
 
 int orc_max_threads(void);
+
+/* ---- the sphere sample's integrator (mafrix_oracle_sky.c): GetColor, RenderTest/Sample/RayTracing.fs:367-382 ---- */
+/* RayTraceCamera, derived (RayTracing.fs:335-358) */
+typedef struct {
+    double origin[3], lower_left[3], horizontal[3], vertical[3], u[3], v[3];
+    double lens_radius;
+} OrcLensCamera;
+typedef struct OrcSkyScene OrcSkyScene;
+void orc_camera_lens(const double lookfrom[3], const double lookat[3], const double vup[3], double vfov,
+                     double aspect, double aperture, double focus_dist, OrcLensCamera *out);
+/* spheres: OrcPrim of kind ORC_SPHERE.  Materials: ORC_LAMBERT (ConstantTexture albedo), ORC_METAL (albedo, fuzz),
+ * ORC_DIELECTRIC (ri = ei), ORC_LAMBERT_CHECKER (even = albedo, odd = (fuzz, ei, et)), ORC_LAMBERT_NOISE.
+ * ranfloat[256] / perm[3*256] = Perlin's tables (may be NULL without a noise material).  max_depth = the 50 of :373. */
+OrcSkyScene *orc_sky_create(const OrcPrim *spheres, int n, const OrcMaterial *mats, int n_mats,
+                            const OrcLensCamera *cam, const double *ranfloat, const int32_t *perm,
+                            int width, int height, int max_depth);
+void orc_sky_destroy(OrcSkyScene *s);
+/* ListHit(items, Ray(origin, dir), tmin, tmax), RayTracing.fs:256-258 (the Ray constructor normalises dir) */
+void orc_sky_list_hit(const OrcSkyScene *s, int n, const double *origins, const double *dirs, double tmin, double tmax,
+                      int32_t *prim, double *t);
+/* cam.GetRay(u, v) without a lens sample + ListHit(ray, 0.00001, 10000000); uv == NULL: pixel centres */
+void orc_sky_trace_primary(const OrcSkyScene *s, int n, const double *uv, int32_t *prim, double *t);
+void orc_sky_trace_path(const OrcSkyScene *s, int px, int py, int sample, uint64_t seed, double *rgb_out, uint64_t *rays);
+/* the pixel loop of DoRayTrace (RayTracing.fs:444-455) -> Color[w,h], element [i,j] at (i*h+j)*4 */
+void orc_sky_sample(const OrcSkyScene *s, int n, uint64_t seed, int first_sample, int threads, double *texture,
+                    uint64_t *rays_out);
 
 #ifdef __cplusplus
 }

@@ -31,8 +31,9 @@ class OrcStats(C.Structure):
 
 
 def build(force=False):
+    srcs = ["mafrix_oracle.c", "mafrix_oracle_sky.c", "mafrix_oracle.h"]
     if force or not os.path.exists(LIB_PATH) or \
-            os.path.getmtime(LIB_PATH) < os.path.getmtime(os.path.join(_HERE, "mafrix_oracle.c")):
+            os.path.getmtime(LIB_PATH) < max(os.path.getmtime(os.path.join(_HERE, f)) for f in srcs):
         subprocess.check_call(["make", "-C", _HERE, "-s"])
     return LIB_PATH
 
@@ -62,6 +63,14 @@ def lib():
         L.orc_tonemap_rgba8.argtypes = [P, C.c_int, C.c_int, P]
         L.orc_philox4x32_10.argtypes = [P, P, P]
         L.orc_max_threads.restype = C.c_int
+        L.orc_camera_lens.argtypes = [P, P, P, C.c_double, C.c_double, C.c_double, C.c_double, P]
+        L.orc_sky_create.restype = P
+        L.orc_sky_create.argtypes = [P, C.c_int, P, C.c_int, P, P, P, C.c_int, C.c_int, C.c_int]
+        L.orc_sky_destroy.argtypes = [P]
+        L.orc_sky_list_hit.argtypes = [P, C.c_int, P, P, C.c_double, C.c_double, P, P]
+        L.orc_sky_trace_primary.argtypes = [P, C.c_int, P, P, P]
+        L.orc_sky_trace_path.argtypes = [P, C.c_int, C.c_int, C.c_int, C.c_uint64, P, P]
+        L.orc_sky_sample.argtypes = [P, C.c_int, C.c_uint64, C.c_int, C.c_int, P, P]
         _lib = L
     return _lib
 
@@ -168,6 +177,76 @@ class OracleScene:
     def trace_path(self, px, py, sample, seed=1):
         rgb = np.zeros(3)
         lib().orc_trace_path(self._h, int(px), int(py), int(sample), int(seed), _p(rgb))
+        return rgb
+
+
+def camera_lens(lookfrom, lookat, vup, vfov, aspect, aperture, focus_dist):
+    """RayTraceCamera constructor (RayTracing.fs:335-358) -> 19 doubles: origin, lower_left, horizontal, vertical,
+    u, v, lens_radius."""
+    out = np.zeros(19)
+    a = [np.ascontiguousarray(x, np.float64) for x in (lookfrom, lookat, vup)]
+    lib().orc_camera_lens(_p(a[0]), _p(a[1]), _p(a[2]), float(vfov), float(aspect), float(aperture), float(focus_dist), _p(out))
+    return out
+
+
+class OracleSkyScene:
+    """The sphere sample (RenderTest/Sample/RayTracing.fs): built from a SceneDesc whose integrator is the sky
+    tracer -- prims (spheres), materials, sky.camera (a RayTraceCamera mirror with its constructor arguments),
+    sky.ranfloat / sky.perm, width, height, max_depth.  The camera is re-derived by the oracle's own restatement."""
+
+    def __init__(self, desc, cam19=None):
+        self.desc = desc
+        self.width, self.height = int(desc.width), int(desc.height)
+        self.prims = np.ascontiguousarray(desc.prims).view(PRIM_DTYPE)
+        self.mats = np.ascontiguousarray(desc.materials).view(MATERIAL_DTYPE)
+        c = desc.sky.camera
+        self.cam = camera_lens(c.lookfrom, c.lookat, c.vup, c.vfov, c.aspect, c.aperture, c.focus_dist) \
+            if cam19 is None else np.ascontiguousarray(cam19, np.float64)
+        rf = None if desc.sky.ranfloat is None else np.ascontiguousarray(desc.sky.ranfloat, np.float64)
+        pm = None if desc.sky.perm is None else np.ascontiguousarray(desc.sky.perm, np.int32)
+        self._h = lib().orc_sky_create(_p(self.prims), len(self.prims), _p(self.mats), len(self.mats), _p(self.cam),
+                                       _p(rf), _p(pm), self.width, self.height, int(desc.max_depth))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().orc_sky_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def hit(self, origins, dirs, tmin=0.00001, tmax=10000000.):
+        o = np.ascontiguousarray(origins, np.float64).reshape(-1, 3)
+        d = np.ascontiguousarray(dirs, np.float64).reshape(-1, 3)
+        prim = np.zeros(len(o), np.int32)
+        t = np.zeros(len(o))
+        lib().orc_sky_list_hit(self._h, len(o), _p(o), _p(d), float(tmin), float(tmax), _p(prim), _p(t))
+        return prim, t
+
+    def trace_primary(self, uv=None):
+        if uv is None:
+            n = self.width * self.height
+        else:
+            uv = np.ascontiguousarray(uv, np.float64).reshape(-1, 2)
+            n = len(uv)
+        prim = np.zeros(n, np.int32)
+        t = np.zeros(n)
+        lib().orc_sky_trace_primary(self._h, n, _p(uv), _p(prim), _p(t))
+        return prim, t
+
+    def sample(self, n, seed=1, first_sample=0, threads=0, stats=False):
+        tex = np.zeros((self.width, self.height, 4))
+        rays = C.c_uint64()
+        lib().orc_sky_sample(self._h, int(n), int(seed), int(first_sample), int(threads), _p(tex), C.byref(rays))
+        return (tex, {"closest_rays": rays.value}) if stats else tex
+
+    def trace_path(self, px, py, sample, seed=1):
+        rgb = np.zeros(3)
+        rays = C.c_uint64()
+        lib().orc_sky_trace_path(self._h, int(px), int(py), int(sample), int(seed), _p(rgb), C.byref(rays))
         return rgb
 
 

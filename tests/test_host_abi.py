@@ -36,9 +36,10 @@ def test_ctypes_layouts_match_the_header():
 #include <stddef.h>
 #include "mafrix_cuda.h"
 int main(void) {
-  printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(MfxPrim), sizeof(MfxMaterial), sizeof(MfxBvhNode),
+  printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(MfxPrim), sizeof(MfxMaterial), sizeof(MfxBvhNode),
          sizeof(MfxAreaLight), sizeof(MfxCamera), sizeof(MfxSceneDesc), sizeof(MfxSampleParams), sizeof(MfxStats),
-         offsetof(MfxSceneDesc, light), offsetof(MfxStats, ms_total));
+         offsetof(MfxSceneDesc, light), offsetof(MfxStats, ms_total), sizeof(MfxLensCamera), sizeof(MfxSkyTracer),
+         offsetof(MfxSkyTracer, perlin_perm), offsetof(MfxSceneDesc, sky));
   return 0; }
 '''
     with tempfile.TemporaryDirectory() as td:
@@ -48,7 +49,8 @@ int main(void) {
     from mafrixraytracing_b200.scene import PRIM_DTYPE, MATERIAL_DTYPE
     want = [PRIM_DTYPE.itemsize, MATERIAL_DTYPE.itemsize, NODE_DTYPE.itemsize, C.sizeof(_lib.MfxAreaLight),
             C.sizeof(_lib.MfxCamera), C.sizeof(_lib.MfxSceneDesc), C.sizeof(_lib.MfxSampleParams), C.sizeof(_lib.MfxStats),
-            _lib.MfxSceneDesc.light.offset, _lib.MfxStats.ms_total.offset]
+            _lib.MfxSceneDesc.light.offset, _lib.MfxStats.ms_total.offset, C.sizeof(_lib.MfxLensCamera),
+            C.sizeof(_lib.MfxSkyTracer), _lib.MfxSkyTracer.perlin_perm.offset, _lib.MfxSceneDesc.sky.offset]
     assert got == want
 
 
@@ -73,7 +75,7 @@ def test_fsharp_shim_offsets_match_the_header():
               ("MfxSceneDesc", "n_prims"), ("MfxSceneDesc", "materials"), ("MfxSceneDesc", "n_materials"), ("MfxSceneDesc", "nodes"),
               ("MfxSceneDesc", "n_node_slots"), ("MfxSceneDesc", "indices"), ("MfxSceneDesc", "light"), ("MfxSceneDesc", "camera"),
               ("MfxSceneDesc", "width"), ("MfxSceneDesc", "height"), ("MfxSceneDesc", "max_depth"), ("MfxSceneDesc", "integrator"),
-              ("MfxAreaLight", "normal"), ("MfxAreaLight", "color"), ("MfxCamera", "topleft"), ("MfxCamera", "right"), ("MfxCamera", "down"),
+              ("MfxSceneDesc", "sky"), ("MfxAreaLight", "normal"), ("MfxAreaLight", "color"), ("MfxCamera", "topleft"), ("MfxCamera", "right"), ("MfxCamera", "down"),
               ("MfxSampleParams", "seed"), ("MfxSampleParams", "first_sample"), ("MfxSampleParams", "flags")]
     body = "".join(f'  printf("%zu\\n", offsetof({t}, {f}));\n' for t, f in fields)
     src = '#include <stdio.h>\n#include <stddef.h>\n#include "mafrix_cuda.h"\nint main(void) {\n' + body + \
@@ -84,18 +86,18 @@ def test_fsharp_shim_offsets_match_the_header():
         out = subprocess.check_output([os.path.join(td, "s")]).split()
     off = {tf: int(v) for tf, v in zip(fields, out)}
     sizes = [int(v) for v in out[len(fields):]]
-    assert sizes == [104, 56, 56, 312, 40]
+    assert sizes == [104, 56, 56, 320, 40]
     want = {("MfxPrim", "kind"): 0, ("MfxPrim", "material"): 4, ("MfxPrim", "v"): 8, ("MfxMaterial", "albedo"): 8, ("MfxMaterial", "fuzz"): 32,
             ("MfxMaterial", "ei"): 40, ("MfxMaterial", "et"): 48, ("MfxBvhNode", "pmax"): 24, ("MfxBvhNode", "first"): 48, ("MfxBvhNode", "count"): 52,
             ("MfxSceneDesc", "n_prims"): 8, ("MfxSceneDesc", "materials"): 16, ("MfxSceneDesc", "n_materials"): 24, ("MfxSceneDesc", "nodes"): 32,
             ("MfxSceneDesc", "n_node_slots"): 40, ("MfxSceneDesc", "indices"): 48, ("MfxSceneDesc", "light"): 56, ("MfxSceneDesc", "camera"): 200,
             ("MfxSceneDesc", "width"): 296, ("MfxSceneDesc", "height"): 300, ("MfxSceneDesc", "max_depth"): 304, ("MfxSceneDesc", "integrator"): 308,
-            ("MfxAreaLight", "normal"): 96, ("MfxAreaLight", "color"): 120, ("MfxCamera", "topleft"): 24, ("MfxCamera", "right"): 48, ("MfxCamera", "down"): 72,
+            ("MfxSceneDesc", "sky"): 312, ("MfxAreaLight", "normal"): 96, ("MfxAreaLight", "color"): 120, ("MfxCamera", "topleft"): 24, ("MfxCamera", "right"): 48, ("MfxCamera", "down"): 72,
             ("MfxSampleParams", "seed"): 8, ("MfxSampleParams", "first_sample"): 16, ("MfxSampleParams", "flags"): 32}
     assert off == want
     # ... and the shim really uses those numbers (the table above is what its comments and writes state)
     fs = open(os.path.join(ROOT, "host", "fsharp", "MafrixCuda.fs")).read()
-    for needle in ("AllocHGlobal(104 * hs.Length)", "AllocHGlobal 312", "WriteInt32(d, 296, width)", "WriteInt32(d, 300, height)",
+    for needle in ("AllocHGlobal(104 * hs.Length)", "AllocHGlobal 320", "WriteIntPtr(d, 312, 0n)", "WriteInt32(d, 296, width)", "WriteInt32(d, 300, height)",
                    "WriteInt32(d, 304, maxDepth)", "WriteInt32(d, 308,", "Interop.wpt d 200 cam.position", "Interop.wpt d 224 cam.topleft",
                    "Interop.wd d 248 cam.coord.right.x", "Interop.wd d 272 cam.coord.down.x", "Interop.wd d 152 light.normal.x",
                    "Interop.wd d 176 light.color.r", "WriteIntPtr(d, 48, pIdx)", "WriteInt32(mem, b + 48, n.first)", "wd mem (b + 32) fuzz"):
@@ -160,10 +162,33 @@ def test_scene_create_validates_before_touching_the_device():
         Scene(d)
     assert e.value.code == -1 and "material" in str(e.value)
     d2 = scenes.cornell(width=8, height=8)
-    d2.max_depth = 40
+    d2.max_depth = 64
     with pytest.raises(MafrixError) as e:
         Scene(d2)
     assert e.value.code == -5
+    # the sphere sample (MFX_SKY_TRACER): spheres only, its own material kinds, the noise tables when a material needs them
+    d3 = scenes.random_scene(width=8, height=8)
+    d3.prims = d3.prims.copy()
+    d3.prims["kind"][0] = 0
+    with pytest.raises(MafrixError) as e:
+        Scene(d3)
+    assert e.value.code == -5 and "spheres" in str(e.value)
+    d4 = scenes.random_scene(width=8, height=8)
+    d4.sky.ranfloat = None
+    with pytest.raises(MafrixError) as e:
+        Scene(d4)
+    assert e.value.code == -1 and "Perlin" in str(e.value)
+    d5 = scenes.random_scene(width=8, height=8)
+    d5.sky = None
+    with pytest.raises(MafrixError) as e:
+        Scene(d5)
+    assert e.value.code == -1 and "sky" in str(e.value)
+    d6 = scenes.cornell(width=8, height=8)
+    d6.materials = d6.materials.copy()
+    d6.materials["kind"][0] = 3                     # Dielectric only exists under the sky tracer
+    with pytest.raises(MafrixError) as e:
+        Scene(d6)
+    assert e.value.code == -1
 
 
 @pytest.mark.skipif(have_gpu(), reason="a CUDA device is present")

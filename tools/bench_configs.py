@@ -6,17 +6,20 @@ import json, os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from mafrixraytracing_b200 import scenes, Scene, CudaPixelIntegrator, Bvh, EXACT_F64, FAST_F32
 
-RUNS = [("cornell", 256, 16), ("c1_cube", 64, 16), ("c2_spot", 64, 2), ("c3_renault", 64, 2), ("c4_spheres", 8, 1), ("c5_soup", 8, 1)]
+RUNS = [("cornell", 256, 16), ("c1_cube", 64, 16), ("c2_spot", 64, 2), ("c3_renault", 64, 2), ("c4_spheres", 8, 1), ("c5_soup", 8, 1),
+        ("random_scene", 4096, 64), ("random_scene_1080p", 64, 2)]      # the sphere sample (MFX_SKY_TRACER), as shipped and at 1080p
 out = []
 only = sys.argv[2].split(",") if len(sys.argv) > 2 else None
 for name, spp_fast, spp_exact in RUNS:
     if only and name not in only:
         continue
-    t0 = time.time(); desc = scenes.WORKLOADS[name](); t_scene = time.time() - t0
+    t0 = time.time()
+    desc = scenes.random_scene(width=1920, height=1080) if name == "random_scene_1080p" else scenes.WORKLOADS[name]()
+    t_scene = time.time() - t0
     t0 = time.time(); bvh = Bvh.Build(desc.prims); t_bvh = time.time() - t0
     s = Scene(desc, bvh=bvh)
     row = {"config": name, "prims": int(len(desc.prims)), "size": [desc.width, desc.height], "max_depth": desc.max_depth,
-           "integrator": "PathIntegrator" if desc.integrator == 0 else "NewPathTracer", "host_bvh_build_s": round(t_bvh, 2)}
+           "integrator": ["PathIntegrator", "NewPathTracer", "GetColor (sky tracer)"][desc.integrator], "host_bvh_build_s": round(t_bvh, 2)}
     for prec, label, spp in ((FAST_F32, "fast_f32", spp_fast), (EXACT_F64, "exact_f64", spp_exact)):
         if name == "c5_soup" and prec == EXACT_F64:
             continue
