@@ -211,16 +211,14 @@ __global__ void __launch_bounds__(256) k_f_raygen(SceneF sc, WaveF w, TileMap tm
             const double tz = (c.topleft[2] + c.right[2] * u) + c.down[2] * v - c.pos[2] - oz;
             const double l = sqrt(tx * tx + ty * ty + tz * tz);
             d = f3((float)(tx / l), (float)(ty / l), (float)(tz / l));
-            w.ray_o[pid] = make_float4((float)(c.pos[0] + ox), (float)(c.pos[1] + oy), (float)(c.pos[2] + oz), __int_as_float(-1));
+            w.ray_o[0][pid] = make_float4((float)(c.pos[0] + ox), (float)(c.pos[1] + oy), (float)(c.pos[2] + oz), __int_as_float(-1));
         } else {
             d = camera_dir_f64(sc.camx, u, v);
-            if (!w.cam_origin) w.ray_o[pid] = make_float4(sc.cam.pos[0], sc.cam.pos[1], sc.cam.pos[2], __int_as_float(-1));
+            if (!w.cam_origin) w.ray_o[0][pid] = make_float4(sc.cam.pos[0], sc.cam.pos[1], sc.cam.pos[2], __int_as_float(-1));
         }
-        // w = tMax of the closest query: Integrators.fs:108 / RayTracing.fs:368
-        w.ray_d[pid] = make_float4(d.x, d.y, d.z, sc.mode == MFX_MODE_SKY ? (float)MFX_SKY_TMAX : 99999999.f);
+        w.ray_d[0][pid] = make_float4(d.x, d.y, d.z, __int_as_float((int)pid));     // bounce 0: queue position == path id
         // throughput starts at 1: vertex 0 of k_f_shade knows that and the 16 B per path are neither written nor read
         w.rad[pid] = make_float4(0.f, 0.f, 0.f, 0.f);
-        w.q_ext[0][pid] = (int)pid;
         if (pid == 0) w.counts[0] = (int)total;
     }
 }
@@ -252,7 +250,7 @@ __global__ void __launch_bounds__(FAST_BLOCK) k_f_trace4(SceneF sc, WaveF w, int
     const unsigned FULL = 0xffffffffu;
     const unsigned lane = threadIdx.x & 31u;
     const int n = ANY ? w.counts[CNT_SH(bounce)] : w.counts[bounce];
-    const int *q = ANY ? w.q_sh : w.q_ext[bounce & 1];
+    const float4 *ro = ANY ? w.sh_o : w.ray_o[bounce & 1], *rd = ANY ? w.sh_d : w.ray_d[bounce & 1];
     int *cursor = &w.counts[ANY ? CUR_SH(bounce) : CUR_EXT(bounce)];
     unsigned long long local[3] = { 0, 0, 0 };
 
@@ -278,11 +276,11 @@ __global__ void __launch_bounds__(FAST_BLOCK) k_f_trace4(SceneF sc, WaveF w, int
             if (pid < 0) {
                 const int idx = base + __popc(idle & ((1u << lane) - 1u));
                 if (idx < n) {
-                    pid = q[idx];
-                    const float4 o = w.ray_o[pid];
-                    const float4 d = ANY ? w.sh_d[pid] : w.ray_d[pid];
+                    pid = idx;                                          // the ray lives at its queue position
+                    const float4 o = ro[pid];
+                    const float4 d = rd[pid];
                     r = make_ray_fast(f3(o.x, o.y, o.z), f3(d.x, d.y, d.z), w.tmin, __float_as_int(o.w));
-                    best_t = ANY ? d.w - 1e-6f : d.w;                   // shadow: dist - 1e-6 (Integrators.fs:44); closest: tMax (:108)
+                    best_t = ANY ? d.w - 1e-6f : w.tmax;                // shadow: dist - 1e-6 (Integrators.fs:44); closest: tMax (:108)
                     best_slot = -1; pend = 0u; leafA = leafB = -1; h = 1u; depth = 0u;
                     float e;
                     if (COUNT) local[0]++;
@@ -353,7 +351,7 @@ __global__ void __launch_bounds__(FAST_BLOCK) k_f_trace4(SceneF sc, WaveF w, int
         }
         if (finished) {
             if (!ANY) w.hit[pid] = make_float2(best_t, __int_as_float(best_slot));
-            else if (best_slot < 0) { const float4 c = w.sh_c[pid]; float4 a = w.rad[pid]; a.x += c.x; a.y += c.y; a.z += c.z; w.rad[pid] = a; }
+            else if (best_slot < 0) { const float4 c = w.sh_c[pid]; float4 *ap = w.rad + __float_as_int(c.w); float4 a = *ap; a.x += c.x; a.y += c.y; a.z += c.z; *ap = a; }
             pid = -1;
         }
     }
@@ -406,7 +404,7 @@ __global__ void __launch_bounds__(FAST_BLOCK) k_f_trace5(SceneF sc, WaveF w, int
     const unsigned FULL = 0xffffffffu;
     const unsigned lane = threadIdx.x & 31u;
     const int n = ANY ? w.counts[CNT_SH(bounce)] : w.counts[bounce];
-    const int *q = ANY ? w.q_sh : w.q_ext[bounce & 1];
+    const float4 *ro = ANY ? w.sh_o : w.ray_o[bounce & 1], *rd = ANY ? w.sh_d : w.ray_d[bounce & 1];
     int *cursor = &w.counts[ANY ? CUR_SH(bounce) : CUR_EXT(bounce)];
 
     int pid = -1;
@@ -432,11 +430,11 @@ __global__ void __launch_bounds__(FAST_BLOCK) k_f_trace5(SceneF sc, WaveF w, int
             if (pid < 0) {
                 const int idx = base + __popc(idle & ((1u << lane) - 1u));
                 if (idx < n) {
-                    pid = q[idx];
-                    const float4 o = w.ray_o[pid];
-                    const float4 d = ANY ? w.sh_d[pid] : w.ray_d[pid];
+                    pid = idx;                                          // the ray lives at its queue position
+                    const float4 o = ro[pid];
+                    const float4 d = rd[pid];
                     r = make_ray_fast(f3(o.x, o.y, o.z), f3(d.x, d.y, d.z), w.tmin, __float_as_int(o.w));
-                    best_t = ANY ? d.w - 1e-6f : d.w;                   // shadow: dist - 1e-6 (Integrators.fs:44); closest: tMax (:108)
+                    best_t = ANY ? d.w - 1e-6f : w.tmax;                // shadow: dist - 1e-6 (Integrators.fs:44); closest: tMax (:108)
                     // no root-box test: the root quad's four boxes lie inside it, a ray that misses the scene simply
                     // finds no hit slot in its first node step and pops an empty trail (one-leaf trees never get here)
                     best_slot = -1; trail = 0ull; leafA = leafB = -1; h = 1u; depth = 0u; needPop = false;
@@ -524,7 +522,7 @@ __global__ void __launch_bounds__(FAST_BLOCK) k_f_trace5(SceneF sc, WaveF w, int
         }
         if (finished) {
             if (!ANY) w.hit[pid] = make_float2(best_t, __int_as_float(best_slot));
-            else if (best_slot < 0) { const float4 c = w.sh_c[pid]; float4 a = w.rad[pid]; a.x += c.x; a.y += c.y; a.z += c.z; w.rad[pid] = a; }
+            else if (best_slot < 0) { const float4 c = w.sh_c[pid]; float4 *ap = w.rad + __float_as_int(c.w); float4 a = *ap; a.x += c.x; a.y += c.y; a.z += c.z; *ap = a; }
             pid = -1;
         }
     }
@@ -548,7 +546,7 @@ __global__ void __launch_bounds__(FAST_BLOCK, MINB) k_f_trace6(SceneF sc, WaveF 
     const unsigned FULL = 0xffffffffu;
     const unsigned lane = threadIdx.x & 31u;
     const int n = ANY ? w.counts[CNT_SH(bounce)] : w.counts[bounce];
-    const int *q = ANY ? w.q_sh : w.q_ext[bounce & 1];
+    const float4 *ro = ANY ? w.sh_o : w.ray_o[bounce & 1], *rd = ANY ? w.sh_d : w.ray_d[bounce & 1];
     int *cursor = &w.counts[ANY ? CUR_SH(bounce) : CUR_EXT(bounce)];
     const bool cam0 = !ANY && bounce == 0 && w.cam_origin;      // primary rays of a pinhole frame: the origin is a constant
 
@@ -575,12 +573,12 @@ __global__ void __launch_bounds__(FAST_BLOCK, MINB) k_f_trace6(SceneF sc, WaveF 
             if (pid < 0) {
                 const int idx = base + __popc(idle & ((1u << lane) - 1u));
                 if (idx < n) {
-                    pid = q[idx];
+                    pid = idx;                                          // the ray lives at its queue position
                     float4 o = make_float4(sc.cam.pos[0], sc.cam.pos[1], sc.cam.pos[2], __int_as_float(-1));
-                    if (!cam0) o = w.ray_o[pid];
-                    const float4 d = ANY ? w.sh_d[pid] : w.ray_d[pid];
+                    if (!cam0) o = ro[pid];
+                    const float4 d = rd[pid];
                     r = make_ray_fast(f3(o.x, o.y, o.z), f3(d.x, d.y, d.z), w.tmin, __float_as_int(o.w));
-                    best_t = ANY ? d.w - 1e-6f : d.w;                   // shadow: dist - 1e-6 (Integrators.fs:44); closest: tMax (:108)
+                    best_t = ANY ? d.w - 1e-6f : w.tmax;                // shadow: dist - 1e-6 (Integrators.fs:44); closest: tMax (:108)
                     best_slot = -1; sp = 0; leafA = leafB = -1; node = 0; needPop = false;
                 }
             }
@@ -662,7 +660,7 @@ __global__ void __launch_bounds__(FAST_BLOCK, MINB) k_f_trace6(SceneF sc, WaveF 
         }
         if (finished) {
             if (!ANY) w.hit[pid] = make_float2(best_t, __int_as_float(best_slot));
-            else if (best_slot < 0) { const float4 c = w.sh_c[pid]; float4 a = w.rad[pid]; a.x += c.x; a.y += c.y; a.z += c.z; w.rad[pid] = a; }
+            else if (best_slot < 0) { const float4 c = w.sh_c[pid]; float4 *ap = w.rad + __float_as_int(c.w); float4 a = *ap; a.x += c.x; a.y += c.y; a.z += c.z; *ap = a; }
             pid = -1;
         }
     }
@@ -726,44 +724,45 @@ __device__ __forceinline__ float fresnel_f(float eta_i, float eta_t, float cosi)
 //   mode 1 (PathTracer.fs:40-41): L += T * l * col          ;  T *= col * shadeFactor
 #define SHADE_BLOCK 256
 template <bool DIRECT>
-__global__ void __launch_bounds__(SHADE_BLOCK, 5) k_f_shade(SceneF sc, WaveF w, TileMap tm, int pix0, int npix, int s0, int bounce, uint64_t seed)
+__global__ void __launch_bounds__(SHADE_BLOCK, 4) k_f_shade(SceneF sc, WaveF w, TileMap tm, int pix0, int npix, int s0, int bounce, uint64_t seed)
 {
     // Queue appends are aggregated per block: 5 000 resident warps hammering two counters with one atomic each per
     // iteration made the kernel wait on same-address atomics (72 % of its stall samples, profiles/); one atomic per
     // 256 paths and queue keeps the order inside a block.  Double-buffered by iteration parity: two barriers per pass.
+    // The survivors' state is kept in registers across the barriers and written at the claimed positions, so the
+    // next bounce's buffers are dense (see WaveF).
     __shared__ int s_cnt[2][2][SHADE_BLOCK / 32];
     __shared__ int s_base[2][2];
     const int n = w.counts[bounce];
-    const int *qin = w.q_ext[bounce & 1];
-    int *qout = w.q_ext[(bounce + 1) & 1];
+    const int cur = bounce & 1, nxt = cur ^ 1;
+    const float4 *in_o = w.ray_o[cur], *in_d = w.ray_d[cur], *in_thr = w.thr[cur];
+    float4 *out_o = w.ray_o[nxt], *out_d = w.ray_d[nxt], *out_thr = w.thr[nxt];
     const int k = bounce;
     const bool last = (bounce >= sc.max_depth);
     const int nblock_iters = (n + SHADE_BLOCK - 1) / SHADE_BLOCK;
-    // The kernel is bound by the latency of a chain of dependent loads (queue -> hit -> path state -> slot), so the
-    // first two links are software-pipelined: the path id is fetched two iterations ahead, its hit one ahead.
     const int stride = gridDim.x;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     int it = blockIdx.x, par = 0;
-    auto queue_at = [&](int iter) { const int i = iter * SHADE_BLOCK + threadIdx.x; return (iter < nblock_iters && i < n) ? qin[i] : -1; };
-    int pid_n = queue_at(it), pid_nn = queue_at(it + stride);
-    float2 hit_n = make_float2(0.f, __int_as_float(-1));
-    if (pid_n >= 0) hit_n = w.hit[pid_n];
+    // the hit of the next iteration's entry is fetched one iteration ahead (the loads are consecutive now, this
+    // only hides the first round trip)
+    auto hit_at = [&](int iter) { const int i = iter * SHADE_BLOCK + threadIdx.x; return (iter < nblock_iters && i < n) ? w.hit[i] : make_float2(0.f, __int_as_float(-1)); };
+    float2 hit_n = hit_at(it);
     for (; it < nblock_iters; it += stride, par ^= 1) {
         bool cont = false, shadow = false;
-        const int pid = pid_n;
+        const int i = it * SHADE_BLOCK + threadIdx.x;
         const float2 hr = hit_n;
-        pid_n = pid_nn;
-        pid_nn = queue_at(it + 2 * stride);
-        if (pid_n >= 0) hit_n = w.hit[pid_n];
-        if (pid >= 0) {
+        hit_n = hit_at(it + stride);
+        float4 st_o = make_float4(0.f, 0.f, 0.f, 0.f), st_d = st_o, st_thr = st_o, st_shd = st_o, st_shc = st_o;
+        if (i < n) {
             const int fs = __float_as_int(hr.y);
             if (fs >= 0) {
                 const float t = hr.x;
                 float4 o4 = make_float4(sc.cam.pos[0], sc.cam.pos[1], sc.cam.pos[2], __int_as_float(-1));
-                if (!(bounce == 0 && w.cam_origin)) o4 = w.ray_o[pid];
-                const float4 d4 = w.ray_d[pid];
+                if (!(bounce == 0 && w.cam_origin)) o4 = in_o[i];
+                const float4 d4 = in_d[i];
+                const int pid = __float_as_int(d4.w);                          // path id: RNG stream, slot of rad
                 float4 thr = make_float4(1.f, 1.f, 1.f, 0.f);
-                if (bounce > 0) thr = w.thr[pid];
+                if (bounce > 0) thr = in_thr[i];
                 const F3 o = f3(o4.x, o4.y, o4.z), d = f3(d4.x, d4.y, d4.z);
                 const F3 point = o + d * t;
                 const float4 sa = ldg4(&sc.slots[fs].a);
@@ -845,17 +844,16 @@ __global__ void __launch_bounds__(SHADE_BLOCK, 5) k_f_shade(SceneF sc, WaveF w, 
                 float lscale = 0.f;
                 if (cos_o < 0.f) lscale = dot(unit, normal) * (fabsf(cos_o) * sc.light.area / d2);
                 if (sc.mode == 0) lscale *= sc.light.inv_pdf;                // l / pdf_li
-                const float4 c = make_float4(thr.x * cr * lscale * sc.light.color[0], thr.y * cg * lscale * sc.light.color[1],
-                                             thr.z * cb * lscale * sc.light.color[2], 0.f);
-                shadow = (c.x != 0.f) || (c.y != 0.f) || (c.z != 0.f);
+                st_shc = make_float4(thr.x * cr * lscale * sc.light.color[0], thr.y * cg * lscale * sc.light.color[1],
+                                     thr.z * cb * lscale * sc.light.color[2], __int_as_float(pid));
+                shadow = (st_shc.x != 0.f) || (st_shc.y != 0.f) || (st_shc.z != 0.f);
                 thr.x *= cr * sf; thr.y *= cg * sf; thr.z *= cb * sf;
                 cont = !last && ((thr.x != 0.f) || (thr.y != 0.f) || (thr.z != 0.f));
-                if (shadow) { w.sh_d[pid] = make_float4(unit.x, unit.y, unit.z, dist); w.sh_c[pid] = c; }
-                if (shadow || cont) {
-                    // planar sources are never re-hit; spheres keep themselves as source (far root / none)
-                    w.ray_o[pid] = make_float4(point.x, point.y, point.z, __int_as_float(prim));
-                }
-                if (cont) { w.ray_d[pid] = make_float4(wi.x, wi.y, wi.z, 99999999.f); w.thr[pid] = thr; }
+                // planar sources are never re-hit; spheres keep themselves as source (far root / none)
+                st_o = make_float4(point.x, point.y, point.z, __int_as_float(prim));
+                st_d = make_float4(wi.x, wi.y, wi.z, __int_as_float(pid));
+                st_thr = thr;
+                st_shd = make_float4(unit.x, unit.y, unit.z, dist);
             }
         }
         const unsigned mc = __ballot_sync(0xffffffffu, cont), ms = __ballot_sync(0xffffffffu, shadow);
@@ -869,8 +867,14 @@ __global__ void __launch_bounds__(SHADE_BLOCK, 5) k_f_shade(SceneF sc, WaveF w, 
         }
         __syncthreads();
         const unsigned below = (1u << lane) - 1u;
-        if (cont) qout[s_base[par][0] + s_cnt[par][0][warp] + __popc(mc & below)] = pid;
-        if (shadow) w.q_sh[s_base[par][1] + s_cnt[par][1][warp] + __popc(ms & below)] = pid;
+        if (cont) {
+            const int pos = s_base[par][0] + s_cnt[par][0][warp] + __popc(mc & below);
+            out_o[pos] = st_o; out_d[pos] = st_d; out_thr[pos] = st_thr;
+        }
+        if (shadow) {
+            const int pos = s_base[par][1] + s_cnt[par][1][warp] + __popc(ms & below);
+            w.sh_o[pos] = st_o; w.sh_d[pos] = st_shd; w.sh_c[pos] = st_shc;
+        }
     }
 }
 
@@ -899,8 +903,7 @@ __global__ void __launch_bounds__(SHADE_BLOCK, 4) k_f_shade_sky(SceneF sc, WaveF
     __shared__ int s_cnt[2][SHADE_BLOCK / 32];
     __shared__ int s_base[2];
     const int n = w.counts[bounce];
-    const int *qin = w.q_ext[bounce & 1];
-    int *qout = w.q_ext[(bounce + 1) & 1];
+    const int cur = bounce & 1, nxt = cur ^ 1;
     const int k = bounce;
     const bool last = (bounce >= sc.max_depth);          // `depth < 50`, :373
     const int nblock_iters = (n + SHADE_BLOCK - 1) / SHADE_BLOCK;
@@ -909,21 +912,21 @@ __global__ void __launch_bounds__(SHADE_BLOCK, 4) k_f_shade_sky(SceneF sc, WaveF
     for (int it = blockIdx.x; it < nblock_iters; it += gridDim.x, par ^= 1) {
         const int i = it * SHADE_BLOCK + threadIdx.x;
         bool cont = false;
-        int pid = -1;
+        float4 st_o = make_float4(0.f, 0.f, 0.f, 0.f), st_d = st_o, st_thr = st_o;
         if (i < n) {
-            pid = qin[i];
-            const float2 hr = w.hit[pid];
+            const float2 hr = w.hit[i];
             const int fs = __float_as_int(hr.y);
-            const float4 d4 = w.ray_d[pid];
+            const float4 d4 = w.ray_d[cur][i];
+            const int pid = __float_as_int(d4.w);                                  // path id: RNG stream, slot of rad
             float4 thr = make_float4(1.f, 1.f, 1.f, 0.f);
-            if (bounce > 0) thr = w.thr[pid];
+            if (bounce > 0) thr = w.thr[cur][i];
             const F3 d = f3(d4.x, d4.y, d4.z);
             if (fs < 0) {
                 const float t = 0.5f * (d.y + 1.0f);                               // :378-381 (d is unit)
                 w.rad[pid] = make_float4(thr.x * ((1.f - t) + t * 0.5f), thr.y * ((1.f - t) + t * 0.7f), thr.z * ((1.f - t) + t), 0.f);
             } else if (!last) {
                 float4 o4 = make_float4(sc.cam.pos[0], sc.cam.pos[1], sc.cam.pos[2], __int_as_float(-1));
-                if (!(bounce == 0 && w.cam_origin)) o4 = w.ray_o[pid];
+                if (!(bounce == 0 && w.cam_origin)) o4 = w.ray_o[cur][i];
                 const F3 point = f3(o4.x, o4.y, o4.z) + d * hr.x;
                 const float4 sa = ldg4(&sc.slots[fs].a);
                 const float4 sb = ldg4(&sc.slots[fs].b);
@@ -994,11 +997,9 @@ __global__ void __launch_bounds__(SHADE_BLOCK, 4) k_f_shade_sky(SceneF sc, WaveF
                 }
                 thr.x *= att.x; thr.y *= att.y; thr.z *= att.z;
                 cont = ok && ((thr.x != 0.f) || (thr.y != 0.f) || (thr.z != 0.f));
-                if (cont) {
-                    w.ray_o[pid] = make_float4(point.x, point.y, point.z, __int_as_float(prim));
-                    w.ray_d[pid] = make_float4(wi.x, wi.y, wi.z, (float)MFX_SKY_TMAX);
-                    w.thr[pid] = thr;
-                }
+                st_o = make_float4(point.x, point.y, point.z, __int_as_float(prim));
+                st_d = make_float4(wi.x, wi.y, wi.z, __int_as_float(pid));
+                st_thr = thr;
             }
         }
         const unsigned mc = __ballot_sync(0xffffffffu, cont);
@@ -1010,7 +1011,10 @@ __global__ void __launch_bounds__(SHADE_BLOCK, 4) k_f_shade_sky(SceneF sc, WaveF
             s_base[par] = tot ? atomicAdd(&w.counts[bounce + 1], tot) : 0;
         }
         __syncthreads();
-        if (cont) qout[s_base[par] + s_cnt[par][warp] + __popc(mc & ((1u << lane) - 1u))] = pid;
+        if (cont) {
+            const int pos = s_base[par] + s_cnt[par][warp] + __popc(mc & ((1u << lane) - 1u));
+            w.ray_o[nxt][pos] = st_o; w.ray_d[nxt][pos] = st_d; w.thr[nxt][pos] = st_thr;
+        }
     }
 }
 
@@ -1055,13 +1059,13 @@ __global__ void __launch_bounds__(256) k_f_seam_setup(SceneF sc, WaveF w, int n,
             oo = f3(sc.cam.pos[0], sc.cam.pos[1], sc.cam.pos[2]);
             dd = camera_dir_f64(sc.camx, u, v);
         }
-        w.ray_o[i] = make_float4(oo.x, oo.y, oo.z, __int_as_float(-1));
-        w.ray_d[i] = make_float4(dd.x, dd.y, dd.z, tmax);
+        w.ray_o[0][i] = make_float4(oo.x, oo.y, oo.z, __int_as_float(-1));
+        w.ray_d[0][i] = make_float4(dd.x, dd.y, dd.z, __int_as_float(i));   // tMax of the closest query is w.tmax
+        w.sh_o[i] = make_float4(oo.x, oo.y, oo.z, __int_as_float(-1));
         w.sh_d[i] = make_float4(dd.x, dd.y, dd.z, tmax + 1e-6f);      // the shadow kernel subtracts 1e-6 (Integrators.fs:44)
-        w.sh_c[i] = make_float4(1.f, 0.f, 0.f, 0.f);                  // unoccluded rays add this to rad
+        w.sh_c[i] = make_float4(1.f, 0.f, 0.f, __int_as_float(i));    // unoccluded rays add this to rad[i]
         w.rad[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         w.hit[i] = make_float2(0.f, __int_as_float(-1));
-        w.q_ext[0][i] = i; w.q_sh[i] = i;
         if (i == 0) { w.counts[0] = any_hit ? 0 : n; w.counts[CNT_SH(0)] = any_hit ? n : 0; }
     }
 }

@@ -758,7 +758,7 @@ static int ensure_wave_exact(MfxScene *s)
 
 // Path state of one wave, fast precision.  Bigger waves mean fewer, longer launches: on C2 a 4 Mi-path wave (2 spp of
 // 1080p) costs 25 % against 32-64 Mi because every persistent launch pays its ramp-up and its tail (profiles/), so
-// the wave is sized for the call at hand -- pixels x spp -- up to MFX_WAVE_PATHS (default 64 Mi paths = 7.8 GB of
+// the wave is sized for the call at hand -- pixels x spp -- up to MFX_WAVE_PATHS (default 64 Mi paths = 12.3 GB of
 // the 180 GB) and only ever grows.
 static int ensure_wave_fast(MfxScene *s, size_t want)
 {
@@ -768,7 +768,7 @@ static int ensure_wave_fast(MfxScene *s, size_t want)
     WaveF &w = s->wf;
     if (s->wf_ready) {
         CUDA_TRY(cudaStreamSynchronize(s->stream));
-        void *old[] = { w.ray_o, w.ray_d, w.hit, w.thr, w.rad, w.sh_d, w.sh_c, w.q_ext[0], w.q_ext[1], w.q_sh, w.counts };
+        void *old[] = { w.ray_o[0], w.ray_o[1], w.ray_d[0], w.ray_d[1], w.thr[0], w.thr[1], w.hit, w.rad, w.sh_o, w.sh_d, w.sh_c, w.counts };
         for (void *q : old) dev_free_one(s, q);
         s->wf_ready = false;
     }
@@ -778,17 +778,19 @@ static int ensure_wave_fast(MfxScene *s, size_t want)
         memset(&w, 0, sizeof(w));
         w.P = (int)P;
         w.tmin = (s->integrator == MFX_SKY_TRACER) ? (float)MFX_SKY_TMIN : 1e-6f;
+        w.tmax = (s->integrator == MFX_SKY_TRACER) ? (float)MFX_SKY_TMAX : 99999999.f;
         auto all = [&]() -> int {
-            MFX_TRY(dev_alloc_t(s, &w.ray_o, P)); MFX_TRY(dev_alloc_t(s, &w.ray_d, P));
-            MFX_TRY(dev_alloc_t(s, &w.hit, P)); MFX_TRY(dev_alloc_t(s, &w.thr, P)); MFX_TRY(dev_alloc_t(s, &w.rad, P));
-            MFX_TRY(dev_alloc_t(s, &w.sh_d, P)); MFX_TRY(dev_alloc_t(s, &w.sh_c, P));
-            MFX_TRY(dev_alloc_t(s, &w.q_ext[0], P)); MFX_TRY(dev_alloc_t(s, &w.q_ext[1], P)); MFX_TRY(dev_alloc_t(s, &w.q_sh, P));
+            for (int b = 0; b < 2; b++) {
+                MFX_TRY(dev_alloc_t(s, &w.ray_o[b], P)); MFX_TRY(dev_alloc_t(s, &w.ray_d[b], P)); MFX_TRY(dev_alloc_t(s, &w.thr[b], P));
+            }
+            MFX_TRY(dev_alloc_t(s, &w.hit, P)); MFX_TRY(dev_alloc_t(s, &w.rad, P));
+            MFX_TRY(dev_alloc_t(s, &w.sh_o, P)); MFX_TRY(dev_alloc_t(s, &w.sh_d, P)); MFX_TRY(dev_alloc_t(s, &w.sh_c, P));
             MFX_TRY(dev_alloc_t(s, &w.counts, MFX_COUNTS_LEN));
             return MFX_OK;
         };
         const int rc = all();
         if (rc == MFX_OK) break;
-        void *part[] = { w.ray_o, w.ray_d, w.hit, w.thr, w.rad, w.sh_d, w.sh_c, w.q_ext[0], w.q_ext[1], w.q_sh, w.counts };
+        void *part[] = { w.ray_o[0], w.ray_o[1], w.ray_d[0], w.ray_d[1], w.thr[0], w.thr[1], w.hit, w.rad, w.sh_o, w.sh_d, w.sh_c, w.counts };
         for (void *q : part) dev_free_one(s, q, false);
         if (rc != MFX_ERR_OUT_OF_MEMORY || P <= ((size_t)1 << 20)) return rc;
         cudaGetLastError();                                       // clear the allocation error
@@ -1092,6 +1094,7 @@ static void fast_seam(MfxScene *s, const SceneF *sfp, const LaunchCfg &cfg, int 
 {
     WaveF w = s->wf;
     w.tmin = tmin;
+    w.tmax = tmax;
     w.cam_origin = 0;
     for (int64_t first = 0; first < n; first += w.P) {
         const int m = (int)std::min<int64_t>(w.P, n - first);

@@ -151,18 +151,22 @@ struct SceneF {
     int    spill_threads;
 };
 
+// Path state lives at QUEUE POSITIONS, not at path ids: the shade kernel of bounce b reads entry i of buffer b&1 and
+// writes the survivors densely into buffer (b+1)&1 (and the shadow rays densely into sh_*), so every kernel of the
+// next bounce reads consecutive entries -- no queue of path ids, no gather.  The path id (pixel/sample for the RNG,
+// slot of `rad`) rides in ray_d.w / sh_c.w.
 struct WaveF {
     int     P;
-    float4 *ray_o;          // [P] o.xyz, w = source fast slot as int bits (-1: camera)
-    float4 *ray_d;          // [P] d.xyz, w unused
-    float2 *hit;            // [P] (t, slot as int bits)
-    float4 *thr;            // [P] throughput rgb
-    float4 *rad;            // [P] accumulated radiance rgb
+    float4 *ray_o[2];       // [P] o.xyz, w = source fast slot as int bits (-1: camera)
+    float4 *ray_d[2];       // [P] d.xyz, w = path id as int bits
+    float4 *thr[2];         // [P] throughput rgb (not stored for bounce 0: it is 1)
+    float2 *hit;            // [P] (t, slot as int bits) of the extend-queue entry
+    float4 *rad;            // [P] accumulated radiance rgb, indexed by PATH ID
+    float4 *sh_o;           // [P] shadow ray origin.xyz, w = source fast slot
     float4 *sh_d;           // [P] shadow dir.xyz, w = dist
-    float4 *sh_c;           // [P] contribution rgb if unoccluded
-    int    *q_ext[2];       // ping-pong extend queues of path ids
-    int    *q_sh;           // shadow queue of the current bounce
+    float4 *sh_c;           // [P] contribution rgb if unoccluded, w = path id as int bits
     float   tmin;           // tMin of every query (1e-6, Integrators.fs:44,108; the Bvh.Hit seam may pass another)
+    float   tmax;           // tMax of the closest-hit queries (99999999., Integrators.fs:108; 1e7 for the sky tracer)
     int     cam_origin;     // 1: every bounce-0 ray starts at the camera position (pinhole): ray_o is neither written by
                             //    raygen nor read by the bounce-0 extend / shade (own-tree frames only; 0 for the seams)
     int    *counts;         // [0 .. MFX_MAX_VERTS+1] extend queue sizes per bounce,
