@@ -758,11 +758,11 @@ static int ensure_wave_exact(MfxScene *s)
 
 // Path state of one wave, fast precision.  Bigger waves mean fewer, longer launches: on C2 a 4 Mi-path wave (2 spp of
 // 1080p) costs 25 % against 32-64 Mi because every persistent launch pays its ramp-up and its tail (profiles/), so
-// the wave is sized for the call at hand -- pixels x spp -- up to MFX_WAVE_PATHS (default 64 Mi paths = 12.3 GB of
+// the wave is sized for the call at hand -- pixels x spp -- up to MFX_WAVE_PATHS (default 128 Mi paths = 24.6 GB of
 // the 180 GB) and only ever grows.
 static int ensure_wave_fast(MfxScene *s, size_t want)
 {
-    const size_t cap = (size_t)std::max(1024L, env_long("MFX_WAVE_PATHS", 1L << 26));
+    const size_t cap = (size_t)std::max(1024L, env_long("MFX_WAVE_PATHS", 1L << 27));
     size_t P = std::min(cap, std::max(want, (size_t)1 << 16));
     if (s->wf_ready && (size_t)s->wf.P >= P) return MFX_OK;
     WaveF &w = s->wf;
