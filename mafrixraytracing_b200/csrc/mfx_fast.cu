@@ -1210,7 +1210,7 @@ static void launch_trace_variant(const LaunchCfg &c, const SceneF &sc, const Wav
         case 65: launch_trace6<ANY, 8, 12, 2, 1>(c, sc, w, bounce); break;
         case 84: launch_trace6<ANY, 12, 12, 2, 1>(c, sc, w, bounce); break;
         case 85: launch_trace6<ANY, 16, 8, 2, 1>(c, sc, w, bounce); break;
-        default: launch_trace6<ANY, 16, 10, 2, 1>(c, sc, w, bounce); break;
+        default: launch_trace6<ANY, 16, 10, 2, 1, 8>(c, sc, w, bounce); break;    // 8 blocks/SM: 64 registers
         }
         return;
     }
