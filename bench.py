@@ -350,7 +350,7 @@ def main():
                 "dtype": "f32" if prec == FAST_F32 else "f64", "data": "synthetic",
                 "config": {"workload": WORKLOAD if args.workload == "c2_spot" else args.workload, "spp": args.spp,
                            "parallelism": f"tiles{mdist.TILE}x{mdist.TILE} interleaved over {world} GPU(s), scene replicated, 1 NCCL sum-reduce per frame",
-                           "l2": "256 MB buffer written between timed iterations (L2 flush); path state (116 B/path, one wave = pixels x spp up to 64 Mi paths = 7.8 GB) exceeds L2, scene is L2 resident by nature",
+                           "l2": "256 MB buffer written between timed iterations (L2 flush); path state (184 B/path, one wave = pixels x spp up to 128 Mi paths = 24.6 GB) exceeds L2, scene is L2 resident by nature",
                            "rays_per_step": rays_all / args.steps, "paths_per_step": desc.width * desc.height * args.spp},
                 "spp_per_s": args.spp * args.steps / (t_all * 1e-3), "wall_s_timed_region": wall,
                 "e2e": e2e, "gpu_launches": int(launches), "clocks": clk, "roofline": roof, "cpu_baseline": cpu}

@@ -253,7 +253,8 @@ MFX_API int mfx_film_reset(MfxFilm *film);                                   /* 
  * target = sum / frameCount; texture (Color[w,h], may be NULL) receives target. */
 MFX_API int mfx_film_get_frame(MfxFilm *film, const MfxSampleParams *params, double *texture);
 /* ACESFilmToneMapping + sqrt + int(255.99 c) -> RGBA8 at x*4 + y*width*4 (Scene.fs:273-289,315-330)
- * applied on the device to the film's current target. */
+ * applied on the device to the film's current target.  Under MFX_SKY_TRACER: the sphere sample's own display
+ * transform instead -- sqrt, int(255.99 c), row j of the texture on screen row height-1-j (RayTracing.fs:456-460). */
 MFX_API int mfx_film_post_process(MfxFilm *film, uint8_t *rgba8);
 MFX_API int mfx_film_frame_count(const MfxFilm *film, double *out);
 /* Checkpoint / resume of the only state the reference's renderer carries between frames: Film.texture (the

@@ -1140,6 +1140,23 @@ __global__ void __launch_bounds__(256) k_film_tonemap(const double *target, int 
     }
 }
 
+// The sphere sample's display transform (RenderTest/Sample/RayTracing.fs:456-460): sqrt, int(255.99 c), and
+// screen[i, (ny-1)-j]: row j of the texture (v grows upwards from lowerLeftCorner) lands on screen row ny-1-j.
+__global__ void __launch_bounds__(256) k_film_display_sky(const double *target, int width, int height, uint8_t *rgba8)
+{
+    const long long n = (long long)width * height;
+    for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += (long long)gridDim.x * blockDim.x) {
+        const int y = (int)(p / width), x = (int)(p - (long long)y * width);
+        const double *px = target + ((size_t)x * height + (height - 1 - y)) * 4;
+        uint8_t out[3];
+        for (int c = 0; c < 3; c++) {
+            const double v = __dmul_rn(255.99, sqrt(px[c]));
+            out[c] = (v == v) ? (uint8_t)(int)v : 0;
+        }
+        *reinterpret_cast<uchar4 *>(rgba8 + 4 * p) = make_uchar4(out[0], out[1], out[2], 255);
+    }
+}
+
 __global__ void __launch_bounds__(256) k_fill_zero(double *p, long long n)
 {
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) p[i] = 0.;
@@ -1263,6 +1280,10 @@ void mfx_film_add(cudaStream_t s, double *sum, const double *frame, double *targ
 void mfx_film_tonemap(cudaStream_t s, const double *target_wh, int width, int height, uint8_t *rgba8)
 {
     k_film_tonemap<<<592, 256, 0, s>>>(target_wh, width, height, rgba8);
+}
+void mfx_film_display_sky(cudaStream_t s, const double *target_wh, int width, int height, uint8_t *rgba8)
+{
+    k_film_display_sky<<<592, 256, 0, s>>>(target_wh, width, height, rgba8);
 }
 void mfx_fill_zero_f64(cudaStream_t s, double *p, long long n)
 {

@@ -1218,7 +1218,9 @@ extern "C" int mfx_film_post_process(MfxFilm *f, uint8_t *rgba8)   // Scene.fs:3
     if (!f || !rgba8) return fail(MFX_ERR_INVALID_ARGUMENT, "null argument");
     MfxScene *s = f->scene;
     MFX_TRY(ensure_device());
-    mfx_film_tonemap(s->stream, f->d_target, s->width, s->height, f->d_rgba8);
+    // MFX_SKY_TRACER: the sphere sample shows sqrt(c) flipped vertically (RayTracing.fs:456-460), no ACES curve
+    if (s->integrator == MFX_SKY_TRACER) mfx_film_display_sky(s->stream, f->d_target, s->width, s->height, f->d_rgba8);
+    else mfx_film_tonemap(s->stream, f->d_target, s->width, s->height, f->d_rgba8);
     CUDA_TRY(cudaGetLastError());
     return copy_out(s, rgba8, f->d_rgba8, (size_t)s->width * s->height * 4);
 }

@@ -225,4 +225,5 @@ void mfx_accum_ray_totals(cudaStream_t, const int *counts, int ext_lo, int ext_n
                           unsigned long long *totals);
 void mfx_film_add(cudaStream_t, double *sum, const double *frame, double *target, long long n_pixels, double frame_count);
 void mfx_film_tonemap(cudaStream_t, const double *target_wh, int width, int height, uint8_t *rgba8);
+void mfx_film_display_sky(cudaStream_t, const double *target_wh, int width, int height, uint8_t *rgba8);
 void mfx_fill_zero_f64(cudaStream_t, double *p, long long n);

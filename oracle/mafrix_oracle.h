@@ -150,6 +150,8 @@ void orc_sky_trace_path(const OrcSkyScene *s, int px, int py, int sample, uint64
 /* the pixel loop of DoRayTrace (RayTracing.fs:444-455) -> Color[w,h], element [i,j] at (i*h+j)*4 */
 void orc_sky_sample(const OrcSkyScene *s, int n, uint64_t seed, int first_sample, int threads, double *texture,
                     uint64_t *rays_out);
+/* sqrt + int(255.99 c) + vertical flip (RayTracing.fs:456-460): Color[w,h] -> RGBA8 row-major */
+void orc_sky_display_rgba8(const double *texture, int width, int height, uint8_t *rgba8);
 
 #ifdef __cplusplus
 }

@@ -348,3 +348,20 @@ void orc_sky_sample(const OrcSkyScene *s, int n, uint64_t seed, int first_sample
     }
     if (rays_out) *rays_out = rays;
 }
+
+/* What the pixel loop of DoRayTrace does with the mean colour before it reaches the window (RayTracing.fs:456-460):
+ * col = (sqrt r, sqrt g, sqrt b); ir = int(255.99*col.r) ..; screen[i, (ny-1)-j] <- (ir, ig, ib).  texture is
+ * Color[w,h] ([i,j] at (i*h+j)*4); rgba8 is row-major like Scene.PostProcessAndToScreenBuffer: x*4 + y*w*4, a = 255. */
+void orc_sky_display_rgba8(const double *texture, int width, int height, uint8_t *rgba8)
+{
+    for (int i = 0; i < width; i++)
+        for (int j = 0; j < height; j++) {
+            const double *c = texture + ((size_t)i * height + j) * 4;
+            uint8_t *o = rgba8 + ((size_t)(height - 1 - j) * width + i) * 4;
+            for (int k = 0; k < 3; k++) {
+                double v = 255.99 * sqrt(c[k]);
+                o[k] = (v == v) ? (uint8_t)(int)v : 0;
+            }
+            o[3] = 255;
+        }
+}

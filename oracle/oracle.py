@@ -71,6 +71,7 @@ def lib():
         L.orc_sky_trace_primary.argtypes = [P, C.c_int, P, P, P]
         L.orc_sky_trace_path.argtypes = [P, C.c_int, C.c_int, C.c_int, C.c_uint64, P, P]
         L.orc_sky_sample.argtypes = [P, C.c_int, C.c_uint64, C.c_int, C.c_int, P, P]
+        L.orc_sky_display_rgba8.argtypes = [P, C.c_int, C.c_int, P]
         _lib = L
     return _lib
 
@@ -254,6 +255,14 @@ def film_add_sample(sum_, frame, frame_count):
     target = np.zeros_like(sum_)
     lib().orc_film_add_sample(_p(sum_), _p(np.ascontiguousarray(frame)), _p(target), sum_.size // 4, float(frame_count))
     return target
+
+
+def sky_display_rgba8(texture_wh):
+    """sqrt + int(255.99 c) + vertical flip of the sphere sample (RayTracing.fs:456-460) -> (height, width, 4) uint8."""
+    w, h = texture_wh.shape[0], texture_wh.shape[1]
+    out = np.zeros((h, w, 4), np.uint8)
+    lib().orc_sky_display_rgba8(_p(np.ascontiguousarray(texture_wh)), w, h, _p(out))
+    return out
 
 
 def tonemap_rgba8(texture_wh):

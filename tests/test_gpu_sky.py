@@ -144,3 +144,24 @@ def test_tile_sharding_and_film_in_sky_mode(precision):
     f2 = film.GetFrame(integ, 2).copy()
     assert np.allclose(f2[:, :, :3], (f1[:, :, :3] + integ.Sample(2, first_sample=2)[:, :, :3]) / 2, rtol=1e-6, atol=1e-7)
     film.close()
+
+
+@pytest.mark.parametrize("name", ["random_scene", "mixed"])
+def test_exact_matches_the_committed_sky_goldens_and_display_transform(name):
+    """The committed vectors (tests/golden/sky_goldens.npz) and the sphere sample's display transform
+    (sqrt, int(255.99 c), vertical flip -- RayTracing.fs:456-460) through Film.PostProcess."""
+    import hashlib
+    from .test_oracle_sky import _sky_goldens, golden_sky_scenes
+    g = _sky_goldens()
+    full, small = golden_sky_scenes()[name]
+    prim, t = Scene(full).TracePrimary(precision=EXACT_F64)
+    assert np.array_equal(prim, g[f"primary/{name}/prim"]) and np.array_equal(t[::97], g[f"primary/{name}/t_stride97"])
+    s = Scene(small)
+    integ = CudaPixelIntegrator(s, precision=EXACT_F64, seed=7)
+    film = Film(s)
+    tex = film.GetFrame(integ, 2, first_sample=0).copy()
+    assert np.array_equal(tex[:, :, :3], g[f"image/{name}/rgb"])
+    disp = film.PostProcess()
+    assert np.array_equal(disp, oracle.sky_display_rgba8(tex))
+    assert np.array_equal(np.frombuffer(hashlib.sha256(disp.tobytes()).digest(), dtype=np.uint8), g[f"image/{name}/display_sha"])
+    film.close()

@@ -149,3 +149,41 @@ def test_random_scene_recipe():
     assert all(sorted(p) == list(range(256)) for p in pm) and 0.0 <= rf.min() and rf.max() < 1.0
     img = oracle.OracleSkyScene(d).sample(2, seed=1)
     assert img[:, :, :3].min() >= 0.0 and 0.2 < img[:, :, :3].mean() < 0.9
+
+
+def _sky_goldens():
+    import os
+    return np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "sky_goldens.npz"))
+
+
+def golden_sky_scenes():
+    rf, pm = scenes.perlin_tables(3)
+    cam = RayTraceCamera((0.2, 0.6, 2.5), (0, 0, -1), (0, 1, 0), 45.0, 1.5, 0.4, 3.4)
+    return {"random_scene": (scenes.random_scene(), scenes.random_scene(width=120, height=60)),
+            "mixed": (sky_desc(MIXED["centers"], MIXED["radii"], MIXED["specs"], width=96, height=64, cam=cam, tables=(rf, pm)),) * 2}
+
+
+@pytest.mark.parametrize("name", ["random_scene", "mixed"])
+def test_oracle_matches_the_committed_sky_goldens(name):
+    """tests/golden/sky_goldens.npz (minted by tests/golden/make_goldens.py sky) guards the restatement against drift."""
+    import hashlib
+    g = _sky_goldens()
+    full, small = golden_sky_scenes()[name]
+    prim, t = oracle.OracleSkyScene(full).trace_primary()
+    assert np.array_equal(prim, g[f"primary/{name}/prim"]) and np.array_equal(t[::97], g[f"primary/{name}/t_stride97"])
+    assert np.array_equal(np.frombuffer(hashlib.sha256(t.tobytes()).digest(), dtype=np.uint8), g[f"primary/{name}/sha_t"])
+    tex = oracle.OracleSkyScene(small).sample(2, seed=7)
+    assert np.array_equal(tex[:, :, :3], g[f"image/{name}/rgb"])
+    disp = oracle.sky_display_rgba8(tex)
+    assert np.array_equal(np.frombuffer(hashlib.sha256(disp.tobytes()).digest(), dtype=np.uint8), g[f"image/{name}/display_sha"])
+
+
+def test_display_transform_known_answers():
+    # sqrt, int(255.99 c) (truncation), row j of the texture on screen row h-1-j (RayTracing.fs:456-460)
+    tex = np.zeros((2, 3, 4))
+    tex[0, 0, :3] = (1.0, 0.25, 0.0)
+    tex[1, 2, :3] = (0.5, 0.04, 1.0 / 255.99 ** 2)
+    out = oracle.sky_display_rgba8(tex)
+    assert out.shape == (3, 2, 4)
+    assert tuple(out[2, 0]) == (255, 127, 0, 255)                    # texture [0,0] -> bottom-left
+    assert tuple(out[0, 1][:2]) == (int(255.99 * math.sqrt(0.5)), int(255.99 * 0.2)) and out[0, 1, 2] in (0, 1)
