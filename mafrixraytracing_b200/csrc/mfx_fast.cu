@@ -12,6 +12,7 @@
 //   k_f_trace4  reference tree, binary, stackless (1 bit per level); also the COUNT-instrumented kernel
 // Shading: k_f_shade (BSDF + light sample, block-aggregated queue appends); k_f_raygen / k_f_resolve bracket a wave.
 #include "mfx_device.cuh"
+#include <algorithm>
 
 typedef V3<float> F3;
 
@@ -1204,6 +1205,7 @@ static void launch_trace6b(const LaunchCfg &c, const SceneF &sc, const WaveF &w,
     // the spill columns were sized for spill_threads: never launch more threads than that
     int blocks = persistent_blocks(k_f_trace6<ANY, BIG, RT, LT, NS, NL, MB, CNT>, FAST_BLOCK, c.blocks, smem);
     if (sc.stack_spill && blocks * FAST_BLOCK > sc.spill_threads) blocks = sc.spill_threads / FAST_BLOCK;
+    if (c.max_items > 0) blocks = std::max(1, std::min(blocks, (c.max_items + FAST_BLOCK - 1) / FAST_BLOCK));
     k_f_trace6<ANY, BIG, RT, LT, NS, NL, MB, CNT><<<blocks, FAST_BLOCK, smem, c.stream>>>(sc, w, bounce, ctr);
 }
 template <bool ANY, int RT, int LT, int NS, int NL = 2, int MB = 1>
@@ -1249,8 +1251,10 @@ void mfx_f_shade(const LaunchCfg &c, const SceneF &sc, const WaveF &w, TileMap t
 }
 void mfx_f_shade_sky(const LaunchCfg &c, const SceneF &sc, const WaveF &w, TileMap tm, int pix0, int npix, int s0, int bounce, uint64_t seed)
 {
-    if (c.reference_stream) k_f_shade_sky<false><<<persistent_blocks(k_f_shade_sky<false>, SHADE_BLOCK, c.blocks), SHADE_BLOCK, 0, c.stream>>>(sc, w, tm, pix0, npix, s0, bounce, seed);
-    else k_f_shade_sky<true><<<persistent_blocks(k_f_shade_sky<true>, SHADE_BLOCK, c.blocks), SHADE_BLOCK, 0, c.stream>>>(sc, w, tm, pix0, npix, s0, bounce, seed);
+    int blocks = c.reference_stream ? persistent_blocks(k_f_shade_sky<false>, SHADE_BLOCK, c.blocks) : persistent_blocks(k_f_shade_sky<true>, SHADE_BLOCK, c.blocks);
+    if (c.max_items > 0) blocks = std::max(1, std::min(blocks, (c.max_items + SHADE_BLOCK - 1) / SHADE_BLOCK));
+    if (c.reference_stream) k_f_shade_sky<false><<<blocks, SHADE_BLOCK, 0, c.stream>>>(sc, w, tm, pix0, npix, s0, bounce, seed);
+    else k_f_shade_sky<true><<<blocks, SHADE_BLOCK, 0, c.stream>>>(sc, w, tm, pix0, npix, s0, bounce, seed);
 }
 void mfx_f_shadow(const LaunchCfg &c, const SceneF &sc, const WaveF &w, int bounce, TravCounters *ctr)
 {

@@ -929,6 +929,7 @@ static int run_sample(MfxScene *s, const MfxSampleParams *p, double *d_color_wh,
             const int S = std::min(S_wave, p->spp - s0);
             const int sabs = p->first_sample + s0;
             CUDA_TRY(cudaMemsetAsync(counts, 0, MFX_COUNTS_LEN * sizeof(int), st));
+            cfg.max_items = 0;
             if (exact) mfx_x_raygen(cfg, s->sx, s->wx, tm, pix0, np, sabs, S, p->seed);
             else mfx_f_raygen(cfg, *sfp, s->wf, tm, pix0, np, sabs, S, p->seed);
             launches++;
@@ -940,6 +941,17 @@ static int run_sample(MfxScene *s, const MfxSampleParams *p, double *d_color_wh,
                     if (exact) mfx_x_shade_sky(cfg, s->sx, s->wx, tm, pix0, np, sabs, b, p->seed);
                     else mfx_f_shade_sky(cfg, *sfp, s->wf, tm, pix0, np, sabs, b, p->seed);
                     launches += 2; l_ext++;
+                    // `depth < 50`: the late bounces hold a few rays at most (paths caught inside glass spheres), and a
+                    // full persistent grid that finds a tiny queue still costs ~30 us per bounce (profiles/).  A queue
+                    // never grows from one bounce to the next, so the host looks at the device-side count now and then
+                    // and sizes the following grids for it -- or leaves the loop when nothing is left.
+                    if (b >= 8 && (b % 6) == 2 && b < D) {
+                        int next_n = 0;
+                        CUDA_TRY(cudaMemcpyAsync(&next_n, counts + b + 1, sizeof(int), cudaMemcpyDeviceToHost, st));
+                        CUDA_TRY(cudaStreamSynchronize(st));
+                        if (next_n == 0) break;
+                        cfg.max_items = next_n;
+                    }
                     continue;
                 }
                 if (exact) mfx_x_shade(cfg, s->sx, s->wx, tm, pix0, np, sabs, b, p->seed);

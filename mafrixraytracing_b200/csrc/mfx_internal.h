@@ -185,7 +185,9 @@ struct TileMap {
 };
 
 // ------------------------------------------------------------------ launchers (defined in the .cu TUs)
-struct LaunchCfg { int blocks; int threads; cudaStream_t stream; int variant; int reference_stream; };
+// max_items > 0: the host knows an upper bound of the queue this launch works on (sky tracer, late bounces): the
+// persistent grid is clamped to the blocks that many entries can occupy
+struct LaunchCfg { int blocks; int threads; cudaStream_t stream; int variant; int reference_stream; int max_items; };
 
 // exact
 void mfx_x_raygen(const LaunchCfg &, const SceneX &, const WaveX &, TileMap tm, int pix0, int npix, int s0, int S,

@@ -10,7 +10,7 @@ never read at run time.
   c3_renault()C3: Renault12TL, mixed materials, NewPathTracer, 1920x1080, 256 spp
   c4_spheres()C4: ~100k spheres (RayTracing.fs:384-415 recipe scaled), 3840x2160, 128 spp
   c5_soup()   C5: spot instanced 1708x (10.0M triangles), 3840x2160, 64 spp
-  random_scene()  the sphere sample itself (RenderTest/Sample/RayTracing.fs:384-436): RandomScene + RayTraceCamera,
+  random_scene()  the sphere sample itself (RenderTest/Sample/RayTracing.fs:384-433): RandomScene + RayTraceCamera,
               400x200, 9 spp, depth 50, rendered by GetColor (SKY_TRACER)
 
 Surfaces are oriented deliberately: the reference never flips normals toward the ray
@@ -213,7 +213,7 @@ def perlin_tables(seed=7):
 
 
 def random_scene(width=400, height=200, max_depth=50, seed=42, ground="noise", aperture=0.0, cells=range(-1, 12)):
-    """RandomScene (RenderTest/Sample/RayTracing.fs:384-415) behind the camera of DoRayTrace (:426-432): one small
+    """RandomScene (RenderTest/Sample/RayTracing.fs:384-415) behind the camera of DoRayTrace (:427-433): one small
     sphere per (a, b) cell -- 80 % Lambertian(ConstantTexture(xi*xi)), 15 % Metal(0.5(1+xi), fuzz 0.5 xi), 5 %
     Dielectric(1.5), skipped within 0.9 of (4, 0.2, 0) -- then the ground sphere r = 1000 (NoiseTexture; "checker" and
     "grey" are the two alternatives commented out at :410-411) and the three big spheres.  numpy PCG64(seed) stands
