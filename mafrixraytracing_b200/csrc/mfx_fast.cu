@@ -10,7 +10,11 @@
 //   k_f_trace6  own tree, sorted 4-wide node step, stack of (key, record) entries in shared memory   <- shipped
 //   k_f_trace5  reference tree, two levels per fetch, stackless (2 bits per level trail + heap index)
 //   k_f_trace4  reference tree, binary, stackless (1 bit per level); also the COUNT-instrumented kernel
-// Shading: k_f_shade (BSDF + light sample, block-aggregated queue appends); k_f_raygen / k_f_resolve bracket a wave.
+// Path state lives at QUEUE POSITIONS (WaveF, mfx_internal.h): entry i of buffer b & 1 is the i-th ray of bounce b, the
+// shade kernel writes its survivors densely into the other buffer and its shadow rays densely into sh_*; no queue of
+// path ids, no gathers.
+// Shading: k_f_shade (BSDF + light sample, block-aggregated position claims), k_f_shade_sky (the sphere sample's
+// GetColor, MFX_SKY_TRACER); k_f_raygen / k_f_resolve bracket a wave.
 #include "mfx_device.cuh"
 #include <algorithm>
 

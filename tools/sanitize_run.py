@@ -1,19 +1,21 @@
-"""Small end-to-end run for compute-sanitizer: every fast/exact kernel, both integrators, spheres incl. the f64 big one,
-own-tree counters, reference-tree variants, Film + tone map, seams."""
+"""Small end-to-end run for compute-sanitizer: every fast/exact kernel, all three integrators, spheres incl. the f64 big
+one, own-tree counters, reference-tree variants, Film + tone map / sky display, seams."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 from mafrixraytracing_b200 import scenes, Scene, CudaPixelIntegrator, Film, EXACT_F64, FAST_F32, _lib
 for name, kw in [("cornell", dict(width=64, height=48)), ("c2_spot", dict(width=96, height=54)), ("c3_renault", dict(width=64, height=36)),
-                 ("c4_spheres", dict(width=64, height=36, grid=20))]:
+                 ("c4_spheres", dict(width=64, height=36, grid=20)), ("random_scene", dict(width=64, height=32, aperture=0.2)),
+                 ("random_scene", dict(width=64, height=32, ground="checker"))]:
     desc = scenes.WORKLOADS[name](**kw)
+    sky = (name == "random_scene")
     s = Scene(desc)
     for prec in (FAST_F32, EXACT_F64):
         integ = CudaPixelIntegrator(s, precision=prec, seed=1)
         a = integ.Sample(2)
         assert np.isfinite(a).all()
     integ = CudaPixelIntegrator(s, precision=FAST_F32, seed=1)
-    for fl in (_lib.SAMPLE_REFERENCE_STREAM, _lib.SAMPLE_COUNT_OWN_TREE, _lib.SAMPLE_COUNT_TRAVERSAL):
+    for fl in (_lib.SAMPLE_REFERENCE_STREAM, _lib.SAMPLE_COUNT_OWN_TREE) + (() if sky else (_lib.SAMPLE_COUNT_TRAVERSAL,)):
         integ.Sample(1, flags=fl)
     uv = np.random.default_rng(0).random((5000, 2))
     s.TracePrimary(uv, precision=FAST_F32); s.TracePrimary(uv, precision=EXACT_F64)
