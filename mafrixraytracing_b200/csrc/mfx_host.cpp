@@ -179,7 +179,7 @@ struct MfxScene {
 static std::mutex g_pool_mu;
 static std::multimap<std::pair<int, size_t>, void *> g_pool;
 static size_t g_pool_bytes = 0;
-static const size_t POOL_MIN = 1u << 20, POOL_MAX = (size_t)24 << 30;
+static const size_t POOL_MIN = 1u << 20, POOL_MAX = (size_t)32 << 30;    // holds one full 128 Mi-path wave (24.6 GB)
 
 static int dev_alloc(MfxScene *s, void **p, size_t bytes)
 {
