@@ -413,11 +413,11 @@ def test_wave_grows_with_the_call_and_frames_do_not_depend_on_it():
 
 
 def test_wave_shrinks_when_the_gpu_is_nearly_full():
-    """Another tenant holds almost all HBM: the path-state wave (3.9 GB wanted here) must fall back to a smaller one
+    """Another tenant holds almost all HBM: the path-state wave (6.5 GB wanted here) must fall back to a smaller one
     -- more launches, same frame -- instead of failing."""
     import torch
     desc = _desc("c2_spot", width=1920, height=1080)
-    spp = 17                                        # 35 M paths = 4.1 GB of path state, a size no other test leaves pooled
+    spp = 17                                        # 35 M paths x 184 B = 6.5 GB of path state, a size no other test leaves pooled
     torch.cuda.synchronize()
     free, _total = torch.cuda.mem_get_info()
     hog = torch.empty(max(free - (3 << 30), 1 << 20), dtype=torch.uint8, device="cuda")
