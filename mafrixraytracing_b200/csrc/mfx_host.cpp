@@ -815,10 +815,22 @@ static int ensure_frame_buffers(MfxScene *s)
 static void tile_pixels(int width, int height, int tile, int rank, int world, std::vector<int> &pix)
 {
     const int tx = (width + tile - 1) / tile, ty = (height + tile - 1) / tile;
+    // sized once and filled row by row: a host that rebuilds its Scene per frame pays this per frame (1 M ids at 2 GPUs)
+    size_t total = 0;
     for (int t = rank; t < tx * ty; t += world) {
         const int x0 = (t % tx) * tile, y0 = (t / tx) * tile;
-        for (int y = y0; y < std::min(y0 + tile, height); y++)
-            for (int x = x0; x < std::min(x0 + tile, width); x++) pix.push_back(y * width + x);
+        total += (size_t)(std::min(x0 + tile, width) - x0) * (size_t)(std::min(y0 + tile, height) - y0);
+    }
+    const size_t base = pix.size();
+    pix.resize(base + total);
+    int *out = pix.data() + base;
+    for (int t = rank; t < tx * ty; t += world) {
+        const int x0 = (t % tx) * tile, y0 = (t / tx) * tile;
+        const int x1 = std::min(x0 + tile, width), y1 = std::min(y0 + tile, height);
+        for (int y = y0; y < y1; y++) {
+            const int row = y * width;
+            for (int x = x0; x < x1; x++) *out++ = row + x;
+        }
     }
 }
 
