@@ -47,6 +47,8 @@ module Native =
     [<DllImport(Lib)>] extern int mfx_film_destroy(nativeint film)
     [<DllImport(Lib)>] extern int mfx_film_get_frame(nativeint film, MfxSampleParams& p, nativeint texture)
     [<DllImport(Lib)>] extern int mfx_film_post_process(nativeint film, nativeint rgba8)
+    // the sphere sample (RenderTest/Sample/RayTracing.fs, MFX_SKY_TRACER): RayTraceCamera's constructor -> MfxLensCamera (152 B)
+    [<DllImport(Lib)>] extern int mfx_camera_lens(double[] lookfrom, double[] lookat, double[] vup, double vfov, double aspect, double aperture, double focusDist, nativeint out)
 
 let private check rc =
     if rc <> 0 then failwithf "libmafrix_cuda (%d): %s" rc (Marshal.PtrToStringAnsi(Native.mfx_last_error()))
