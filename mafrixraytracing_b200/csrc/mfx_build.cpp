@@ -4,6 +4,7 @@
 //   * mfx_build_own_tree: the fast path's own tree (binned SAH, four children per record).
 // Compiled with -ffp-contract=off like the rest of the host code.
 #include "mfx_build.h"
+#include <functional>
 
 #include <algorithm>
 #include <atomic>
@@ -306,6 +307,59 @@ void mfx_build_own_tree(const float *lo, const float *hi, int ns, int max_leaf, 
     sah_bound(c, nodes[0]);
     sah_build(c, 0, par_depth);
 
+    // Optional (MFX_COLLAPSE_DP = cost of one record step in percent of one primitive test, 0 = off, the default):
+    // choose the <= 4 slots of every record by dynamic programming over the binary tree instead of greedily --
+    //   slot(n)   = min( area(n) * prims(n)                          if prims(n) <= max_leaf: n becomes ONE leaf,
+    //                    area(n) * c_rec + min_k F(left, k) + F(right, 4 - k)          : n becomes a record )
+    //   F(n, j)   = min( F(n, j - 1), min_k F(left, k) + F(right, j - k) ),  F(n, 1) = slot(n)
+    // (the wide-BVH construction of Ylitie, Karras, Laine 2017, four wide).  Evaluated with tools/own_tree_sim.cpp.
+    const float dp_rec = (float)env_long("MFX_COLLAPSE_DP", 0) * 0.01f;
+    const bool dp = dp_rec > 0.f && nodes[0].count == 0;
+    const int nn = c.next.load();
+    std::vector<int> np;                    // prims below a binary node
+    std::vector<float> fcost;               // F(n, j), j = 1..4 at [4n + j - 1]
+    std::vector<unsigned char> as_leaf, fsplit;     // slot(n) is a leaf; fsplit[4n + j - 1] = k (0: take F(n, j - 1))
+    if (dp) {
+        np.assign(nn, 0); fcost.assign((size_t)4 * nn, 0.f); as_leaf.assign(nn, 0); fsplit.assign((size_t)4 * nn, 0);
+        // children are allocated after their parent (fetch_add), so a descending index order is a post-order
+        std::vector<int> orderv; orderv.reserve(nn);
+        { std::vector<int> st{ 0 }; while (!st.empty()) { const int i = st.back(); st.pop_back(); orderv.push_back(i); if (nodes[i].count == 0) { st.push_back(nodes[i].left); st.push_back(nodes[i].right); } } }
+        for (size_t r = orderv.size(); r-- > 0;) {
+            const int i = orderv[r];
+            const SahNode &nd = nodes[i];
+            const float ar = half_area(nd.lo, nd.hi);
+            float *F = &fcost[(size_t)4 * i];
+            if (nd.count > 0) {
+                np[i] = nd.count; as_leaf[i] = 1;
+                for (int j = 0; j < 4; j++) F[j] = ar * (float)nd.count;
+                continue;
+            }
+            const int L = nd.left, R = nd.right;
+            np[i] = np[L] + np[R];
+            const float *FL = &fcost[(size_t)4 * L], *FR = &fcost[(size_t)4 * R];
+            // as a record: the best way to spend four slots on the two subtrees
+            float rec = SAH_INF;
+            for (int k = 1; k <= 3; k++) rec = std::min(rec, FL[k - 1] + FR[3 - k]);
+            rec += ar * dp_rec;
+            const float leaf = np[i] <= max_leaf ? ar * (float)np[i] : SAH_INF;
+            as_leaf[i] = leaf <= rec;
+            F[0] = std::min(leaf, rec);
+            for (int j = 2; j <= 4; j++) {
+                float best = F[j - 2]; int bk = 0;
+                for (int k = 1; k < j; k++) { const float v = FL[k - 1] + FR[j - k - 1]; if (v < best) { best = v; bk = k; } }
+                F[j - 1] = best; fsplit[(size_t)4 * i + j - 1] = (unsigned char)bk;
+            }
+        }
+    }
+    // the slots the DP gives subtree n when it may use up to j of them
+    std::function<void(int, int, int *, int &)> dp_expand = [&](int n, int j, int *kids, int &nk) {
+        while (j > 1 && fsplit[(size_t)4 * n + j - 1] == 0) j--;
+        if (j == 1 || nodes[n].count > 0) { kids[nk++] = n; return; }
+        const int k = fsplit[(size_t)4 * n + j - 1];
+        dp_expand(nodes[n].left, k, kids, nk); dp_expand(nodes[n].right, j - k, kids, nk);
+    };
+    auto slot_prims = [&](int b) { return dp ? (as_leaf[b] ? np[b] : 0) : nodes[b].count; };   // > 0: the slot is a leaf
+
     // collapse to four children per record, depth-first; leaves of a record get consecutive slots
     std::vector<QuadF> &quads = out.quads;
     quads.clear();
@@ -323,8 +377,14 @@ void mfx_build_own_tree(const float *lo, const float *hi, int ns, int max_leaf, 
         own_depth = std::max(own_depth, it.level + 1);
         int kids[4], nk = 0;
         if (nodes[it.bnode].count > 0) kids[nk++] = it.bnode;           // a one-leaf tree: the root record holds it
+        else if (dp) {
+            const float *FL = &fcost[(size_t)4 * nodes[it.bnode].left], *FR = &fcost[(size_t)4 * nodes[it.bnode].right];
+            int bk = 1; float best = SAH_INF;
+            for (int k = 1; k <= 3; k++) { const float v = FL[k - 1] + FR[3 - k]; if (v < best) { best = v; bk = k; } }
+            dp_expand(nodes[it.bnode].left, bk, kids, nk); dp_expand(nodes[it.bnode].right, 4 - bk, kids, nk);
+        }
         else { kids[nk++] = nodes[it.bnode].left; kids[nk++] = nodes[it.bnode].right; }
-        while (nk < 4) {
+        while (!dp && nk < 4) {
             int pick = -1; float pa = -1.f;
             for (int k = 0; k < nk; k++) if (nodes[kids[k]].count == 0) { const float ar = half_area(nodes[kids[k]].lo, nodes[kids[k]].hi); if (ar > pa) { pa = ar; pick = k; } }
             if (pick < 0) break;
@@ -337,9 +397,10 @@ void mfx_build_own_tree(const float *lo, const float *hi, int ns, int max_leaf, 
         for (int k = 0; k < nk; k++) {
             const SahNode &nd = nodes[kids[k]];
             for (int a = 0; a < 3; a++) { lo[a][k] = nd.lo[a]; hi[a][k] = nd.hi[a]; }
-            if (nd.count > 0) {
-                meta[k] = ((int)order.size() << 3) | nd.count;
-                for (int j = 0; j < nd.count; j++) order.push_back(idx[nd.first + j]);
+            const int cnt = slot_prims(kids[k]);
+            if (cnt > 0) {
+                meta[k] = ((int)order.size() << 3) | cnt;
+                for (int j = 0; j < cnt; j++) order.push_back(idx[nd.first + j]);
             }
         }
         q.lox = make_float4(lo[0][0], lo[0][1], lo[0][2], lo[0][3]); q.hix = make_float4(hi[0][0], hi[0][1], hi[0][2], hi[0][3]);
@@ -347,7 +408,7 @@ void mfx_build_own_tree(const float *lo, const float *hi, int ns, int max_leaf, 
         q.loz = make_float4(lo[2][0], lo[2][1], lo[2][2], lo[2][3]); q.hiz = make_float4(hi[2][0], hi[2][1], hi[2][2], hi[2][3]);
         q.meta = make_float4(int_bits(meta[0]), int_bits(meta[1]), int_bits(meta[2]), int_bits(meta[3]));
         quads.push_back(q);
-        for (int k = nk - 1; k >= 0; k--) if (nodes[kids[k]].count == 0) todo.push_back({ kids[k], it.level + 1, qi, k });
+        for (int k = nk - 1; k >= 0; k--) if (slot_prims(kids[k]) == 0) todo.push_back({ kids[k], it.level + 1, qi, k });
     }
     out.depth = own_depth;
 }
