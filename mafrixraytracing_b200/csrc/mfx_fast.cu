@@ -607,7 +607,12 @@ __global__ void __launch_bounds__(FAST_BLOCK, MINB) k_f_trace6(SceneF sc, WaveF 
                 const float tn = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fmaxf(fminf(z0, z1), r.tmin));           \
                 const float tf = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fminf(fmaxf(z0, z1), best_t));           \
                 const int mt = __float_as_int(m4.C);                                                                 \
-                key[S_] = (tn <= tf && mt != MFX_QUAD_EMPTY) ? ((__float_as_uint(tn) & ~7u) | (mt >= 0 ? 4u : 0u) | (unsigned)S_) : KEY_INF; \
+                /* closest hit: nearest child first.  Shadow query: FARTHEST first -- any hit will do, the ray starts   \
+                   inside the geometry it leaves (an occluded ray from the unlit side of a mesh walks the whole         \
+                   interior nearest-first) and ends in the open near the light: tools/own_tree_sim.cpp, DESIGN.md 7.  \
+                   Keys stay below KEY_INF (tn is finite and >= tMin > 0). */                                          \
+                const unsigned ord = ANY ? (0x7f7ffff8u - (__float_as_uint(tn) & ~7u)) : (__float_as_uint(tn) & ~7u);   \
+                key[S_] = (tn <= tf && mt != MFX_QUAD_EMPTY) ? (ord | (mt >= 0 ? 4u : 0u) | (unsigned)S_) : KEY_INF;   \
             }
             QUAD_SLOT(0, x) QUAD_SLOT(1, y) QUAD_SLOT(2, z) QUAD_SLOT(3, w)
 #undef QUAD_SLOT
@@ -644,7 +649,8 @@ __global__ void __launch_bounds__(FAST_BLOCK, MINB) k_f_trace6(SceneF sc, WaveF 
             if (__popc(lp) >= LEAF_T || nd == 0u) {
                 if (pid >= 0 && leafA >= 0) {
                     bool found = leaf_f3<COUNT, BIG>(sc, r, leafA, best_t, best_slot, local);
-                    if (NLEAF > 1 && leafB >= 0 && !(ANY && found) && eB <= best_t) found |= leaf_f3<COUNT, BIG>(sc, r, leafB, best_t, best_slot, local);
+                    // (a shadow query's keys are not distances and its best_t never shrinks: no cull for it)
+                    if (NLEAF > 1 && leafB >= 0 && !(ANY && found) && (ANY || eB <= best_t)) found |= leaf_f3<COUNT, BIG>(sc, r, leafB, best_t, best_slot, local);
                     leafA = leafB = -1;
                     if (ANY && found) finished = true;
                 }

@@ -1,15 +1,18 @@
 // CPU model of the shipped traversal (k_f_trace6, csrc/mfx_fast.cu) over the library's own tree (csrc/mfx_build.cpp):
 // counts 128-byte records fetched and triangle tests per ray for a C2-like path population (primary rays, uniform
 // hemisphere bounces to depth 5, one shadow ray per vertex towards the quad light), with the kernel's rules -- sorted
-// 4-wide node step, nearest first, deferred hits culled by their entry distance at pop time, leaves of the nearest hit
-// tested at once, first hit ends a shadow ray, a ray never re-hits the triangle it starts on.  One thread, f32.
+// 4-wide node step, nearest child first (shadow queries: farthest first), deferred hits culled by their entry distance
+// at pop time, leaves of the chosen child tested at once, first hit ends a shadow ray, a ray never re-hits the triangle
+// it starts on.  One thread, f32.
 // The GPU's own counters (MFX_SAMPLE_COUNT_OWN_TREE, bench.py `own_tree`) are what validates this model: C2 measures
-// 3.35 records + 2.07 triangle tests per closest-hit ray and 4.19 + 1.65 per shadow ray.
+// 3.35 records + 2.07 triangle tests per closest-hit ray and, with shadow queries still nearest-first
+// (SIM_ANY_NEAREST=1 here), 4.19 + 1.65 per shadow ray.
 //
 // build:  g++ -O2 -std=c++17 -pthread -I /usr/local/cuda/include -I mafrixraytracing_b200/csrc -o /tmp/own_tree_sim \
 //             tools/own_tree_sim.cpp mafrixraytracing_b200/csrc/mfx_build.cpp
 // usage:  own_tree_sim tris.bin n [width height]      tris.bin = n x 9 doubles (tools/own_tree_sim.py writes C2's)
 // env:    MFX_COLLAPSE_DP / MFX_SAH_MAX_LEAF / MFX_SAH_TRAV_COST_PCT   the builder's knobs
+//         SIM_ANY_NEAREST=1         shadow queries visit the nearest child first (the kernel up to the last GPU run of round 1)
 //         SIM_SHADOW_FROM_LIGHT=1   trace every shadow ray from the light sample towards the surface point instead (same
 //                                   segment, same answer); the run always prints both directions split by outcome
 #include "mfx_build.h"
@@ -37,6 +40,7 @@ static int as_int(float f) { int i; memcpy(&i, &f, 4); return i; }
 static unsigned as_uint(float f) { unsigned i; memcpy(&i, &f, 4); return i; }
 static float as_float(unsigned u) { float f; memcpy(&f, &u, 4); return f; }
 
+static bool g_any_nearest = false;
 struct Tri { V v0, e1, e2, n; };
 struct Counts { double rays = 0, records = 0, tris = 0, leaf_visits = 0; };
 
@@ -88,7 +92,9 @@ struct Sim {
                     const float tn = std::max(std::max(std::min(x0, x1), std::min(y0, y1)), std::max(std::min(z0, z1), tmin));
                     const float tf = std::min(std::min(std::max(x0, x1), std::max(y0, y1)), std::min(std::max(z0, z1), best));
                     const int mt = as_int((&q.meta.x)[s]);
-                    key[s] = (tn <= tf && mt != MFX_QUAD_EMPTY) ? ((as_uint(tn) & ~7u) | (mt >= 0 ? 4u : 0u) | (unsigned)s) : 0x7f800000u;
+                    // closest hit: nearest child first; shadow query: farthest first (as shipped; SIM_ANY_NEAREST=1: the old order)
+                    const unsigned ord = (any && !g_any_nearest) ? (0x7f7ffff8u - (as_uint(tn) & ~7u)) : (as_uint(tn) & ~7u);
+                    key[s] = (tn <= tf && mt != MFX_QUAD_EMPTY) ? (ord | (mt >= 0 ? 4u : 0u) | (unsigned)s) : 0x7f800000u;
                 }
                 std::sort(key, key + 4);
                 for (int k = 3; k >= 1; k--) if (key[k] != 0x7f800000u) stack[sp++] = { key[k], node };      // nearest on top
@@ -127,6 +133,7 @@ int main(int argc, char **argv)
 {
     if (argc < 3) { fprintf(stderr, "usage: own_tree_sim tris.bin n [width height]\n"); return 2; }
     const int n = atoi(argv[2]);
+    g_any_nearest = getenv("SIM_ANY_NEAREST") != nullptr;
     const int W = argc > 3 ? atoi(argv[3]) : 480, H = argc > 4 ? atoi(argv[4]) : 270;
     FILE *f = fopen(argv[1], "rb");
     if (!f) { fprintf(stderr, "cannot open %s\n", argv[1]); return 2; }
@@ -207,7 +214,7 @@ int main(int argc, char **argv)
                cl[b].records / std::max(cl[b].rays, 1.0), cl[b].tris / std::max(cl[b].rays, 1.0), sh[b].rays, sh[b].records / std::max(sh[b].rays, 1.0), sh[b].tris / std::max(sh[b].rays, 1.0));
         C.rays += cl[b].rays; C.records += cl[b].records; C.tris += cl[b].tris; S.rays += sh[b].rays; S.records += sh[b].records; S.tris += sh[b].tris;
     }
-    printf("all: closest %.3f records + %.3f tris per ray (GPU counters on C2: 3.35 + 2.07); shadow %.3f + %.3f (GPU: 4.19 + 1.65)\n",
+    printf("all: closest %.3f records + %.3f tris per ray (GPU counters on C2: 3.35 + 2.07); shadow %.3f + %.3f (GPU, nearest-first shadow queries: 4.19 + 1.65)\n",
            C.records / C.rays, C.tris / C.rays, S.records / S.rays, S.tris / S.rays);
     return 0;
 }
