@@ -10,7 +10,7 @@
 //
 // build:  g++ -O2 -std=c++17 -pthread -I /usr/local/cuda/include -I mafrixraytracing_b200/csrc -o /tmp/own_tree_sim \
 //             tools/own_tree_sim.cpp mafrixraytracing_b200/csrc/mfx_build.cpp
-// usage:  own_tree_sim tris.bin n [width height]      tris.bin = n x 9 doubles (tools/own_tree_sim.py writes C2's)
+// usage:  own_tree_sim tris.bin n [width height [camera and light, see main]]      tris.bin = n x 9 doubles (tools/own_tree_sim.py)
 // env:    MFX_COLLAPSE_DP / MFX_SAH_MAX_LEAF / MFX_SAH_TRAV_COST_PCT   the builder's knobs
 //         SIM_ANY_NEAREST=1         shadow queries visit the nearest child first (the kernel up to the last GPU run of round 1)
 //         SIM_SHADOW_FROM_LIGHT=1   trace every shadow ray from the light sample towards the surface point instead (same
@@ -165,12 +165,17 @@ int main(int argc, char **argv)
     printf("tree: %zu records, depth %d; children per record 1..4: %ld %ld %ld %ld; leaf sizes 1..4: %ld %ld %ld %ld\n", tree.quads.size(), tree.depth,
            kids_hist[1], kids_hist[2], kids_hist[3], kids_hist[4], leaf_hist[1], leaf_hist[2], leaf_hist[3], leaf_hist[4]);
 
-    // C2: PinholeCamera((0, 0.1, -2.6), (0, 0, 1), fov 120 -> effective 60 deg, aspect 16/9), light quad 1x1 at y = 2.5
-    const V pos = { 0.f, 0.1f, -2.6f };
-    const float hs = std::tan(0.5f * 120.f * 3.14159265f / 360.f), vs = hs / (16.f / 9.f);
-    const V fwd = { 0, 0, 1 }, hori = cross(fwd, V{ 0, 1, 0 }), vert = cross(hori, fwd);
+    // camera and light: C2's by default -- PinholeCamera((0, 0.1, -2.6), (0, 0, 1), fov 120 -> effective 60 deg, aspect 16/9),
+    // light quad 1x1 at y = 2.5 -- or 19 numbers after width/height: pos(3) dir(3) fov aspect, light p0(3) p1(3) p3(3), max_depth
+    float cv[19] = { 0.f, 0.1f, -2.6f, 0.f, 0.f, 1.f, 120.f, 16.f / 9.f, -0.5f, 2.5f, 0.5f, -0.5f, 2.5f, -0.5f, 0.5f, 2.5f, 0.5f, 5.f, 0.f };
+    for (int k = 0; k < 18 && 5 + k < argc; k++) cv[k] = (float)atof(argv[5 + k]);
+    const int D = (int)cv[17];
+    const V pos = { cv[0], cv[1], cv[2] };
+    const float hs = std::tan(0.5f * cv[6] * 3.14159265f / 360.f), vs = hs / cv[7];
+    const V fwd = norm(V{ cv[3], cv[4], cv[5] }), hori = cross(fwd, V{ 0, 1, 0 }), vert = cross(hori, fwd);
     const V right = hori * hs, up = vert * vs, down = up * -1.f;
     const V tl = pos + fwd * 0.5f - right * 0.5f + up * 0.5f;
+    const V l0 = { cv[8], cv[9], cv[10] }, le1 = V{ cv[11], cv[12], cv[13] } - l0, le3 = V{ cv[14], cv[15], cv[16] } - l0;
     std::mt19937 rng(12345);
     std::uniform_real_distribution<float> U(0.f, 1.f);
     Counts cl[6], sh[6];
@@ -178,13 +183,13 @@ int main(int argc, char **argv)
         const float u = (i + U(rng)) / W, v = (j + U(rng)) / H;
         V o = pos, d = norm(tl + right * u + down * v - pos);
         int src = -1;
-        for (int b = 0; b <= 5; b++) {
+        for (int b = 0; b <= D && b <= 5; b++) {
             float t;
             const int slot = sim.trace(o, d, 1e-6f, 99999999.f, src, false, t, cl[b]);
             if (slot < 0) break;
             const V p = o + d * t, nm = sim.tri[slot].n;
             // light sample (uniform on the quad is close enough for a count), shadow ray unless the contribution is zero
-            const V lp = { -0.5f + U(rng), 2.5f, -0.5f + U(rng) };
+            const V lp = l0 + le1 * U(rng) + le3 * U(rng);
             const V toL = lp - p;
             const float dist = std::sqrt(dot(toL, toL));
             if (dot(toL, V{ 0, -1, 0 }) < 0.f && dot(toL, nm) != 0.f) {

@@ -24,4 +24,7 @@ exe = os.path.join(td, "own_tree_sim")
 csrc = os.path.join(ROOT, "mafrixraytracing_b200", "csrc")
 subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++17", "-pthread", "-I", "/usr/local/cuda/include", "-I", csrc, "-o", exe,
                        os.path.join(ROOT, "tools", "own_tree_sim.cpp"), os.path.join(csrc, "mfx_build.cpp")])
-subprocess.check_call([exe, os.path.join(td, "tris.bin"), str(len(t))] + sys.argv[2:4])
+wh = sys.argv[2:4] if len(sys.argv) > 3 else ["480", "270"]
+cam, lp = desc.camera, desc.light.p
+view = [*cam.pos_arg, *cam.dir_arg, cam.fov, cam.aspect, *lp[0], *lp[1], *lp[3], min(desc.max_depth, 5)]
+subprocess.check_call([exe, os.path.join(td, "tris.bin"), str(len(t))] + wh + [repr(float(x)) for x in view])
