@@ -43,3 +43,31 @@ def test_warp_model_shadow_queries_terminate():
     op, _, _ = o.hit([r[0] for r in rays], [r[1] for r in rays], 1e-6, 2.5)
     occl = np.array([out[r][1] >= 0 for r in range(len(rays))])
     assert (occl != (op >= 0)).mean() <= 0.02
+
+
+def _own_tree_sim(workload, env=None, size=("96", "54")):
+    import re
+    import subprocess
+    out = subprocess.check_output([sys.executable, os.path.join(ROOT, "tools", "own_tree_sim.py"), workload, *size],
+                                  text=True, env=dict(os.environ, **(env or {})))
+    occ = re.search(r"shadow rays, occluded: (\d+) rays; from the surface ([\d.]+) records ([\d.]+) tris \| from the light "
+                    r"([\d.]+) records ([\d.]+) tris\s+\(answers that differ: (\d+)\)", out)
+    tot = re.search(r"all: closest ([\d.]+) records \+ ([\d.]+) tris per ray.*?; shadow ([\d.]+) \+ ([\d.]+)", out)
+    return [float(x) for x in occ.groups()], [float(x) for x in tot.groups()]
+
+
+@pytest.mark.parametrize("workload", ["c2_spot", "cornell"])
+def test_shadow_query_order_is_answer_invariant_and_cheaper_in_the_cpu_model(workload):
+    """tools/own_tree_sim.cpp models the shipped own-tree traversal (it reproduces the GPU's record / triangle counters
+    on C2).  A shadow query may visit its children in any order: the answers of the shipped farthest-first order, of
+    the old nearest-first order and of the same rays traced from the light must be identical, and farthest-first must
+    not fetch more records per shadow ray than nearest-first did."""
+    occ_far, tot_far = _own_tree_sim(workload)
+    occ_near, tot_near = _own_tree_sim(workload, {"SIM_ANY_NEAREST": "1"})
+    assert occ_far[0] == occ_near[0] > 100              # the same rays are occluded whichever order finds the occluder
+    assert occ_far[5] == 0 and occ_near[5] == 0         # ... and whichever end the ray is traced from
+    assert tot_far[:2] == tot_near[:2]                  # closest-hit queries are untouched
+    assert tot_far[2] <= tot_near[2] and tot_far[3] <= tot_near[3] * 1.02
+    if workload == "c2_spot":
+        assert 3.0 < tot_near[0] < 3.7 and 3.6 < tot_near[2] < 4.7     # the GPU measures 3.35 and 4.19 records per ray
+        assert tot_far[2] < 0.9 * tot_near[2]
