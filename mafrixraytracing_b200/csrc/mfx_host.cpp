@@ -155,6 +155,8 @@ struct MfxScene {
     std::vector<double> perlin_rf;           // MFX_SKY_TRACER: 256 or empty
     std::vector<int32_t> perlin_perm;        //                 768 or empty
     int width = 0, height = 0, max_depth = 0, integrator = 0;
+    int host_share = 1;                      // ranks known to share this host (MfxSampleParams.world): the tree builder
+                                             // forks over hardware threads / host_share
 
     std::vector<std::pair<void *, size_t>> allocs;   // every device buffer of this scene
     bool x_ready = false, f_ready = false, fr_ready = false, wx_ready = false, wf_ready = false;
@@ -176,6 +178,7 @@ struct MfxScene {
 // Scene every frame (the e2e path of bench.py) must not pay cudaMalloc/cudaFree for ~0.5 GB of
 // path state each time.  Bounded; everything beyond the bound is really freed.
 #include <mutex>
+#include <thread>
 static std::mutex g_pool_mu;
 static std::multimap<std::pair<int, size_t>, void *> g_pool;
 static size_t g_pool_bytes = 0;
@@ -680,8 +683,14 @@ static int flatten_fast(MfxScene *s)
     lap("slots");
     if ((size_t)ns > ((size_t)1 << 28)) return fail(MFX_ERR_INVALID_ARGUMENT, "too many fast slots (%d)", ns);
     MfxOwnTree tree;
+    // The builder forks its top levels over threads (identical tree for any fork depth).  One process per GPU means
+    // `world` builders on one host at the same time: eight of them forking 32 ways each on a 16-thread host take longer
+    // than eight serial ones, so the fork depth follows the threads this rank can expect for itself.
+    int par_depth = 0;
+    for (unsigned share = std::max(1u, std::thread::hardware_concurrency()) / (unsigned)std::max(1, s->host_share); share > 1 && par_depth < 5; share >>= 1) par_depth++;
+    par_depth = (int)env_long("MFX_BVH_BUILD_PAR_DEPTH", par_depth);
     mfx_build_own_tree(blo.data(), bhi.data(), ns, (int)std::min(7L, std::max(1L, env_long("MFX_SAH_MAX_LEAF", 4))),
-                       (float)env_long("MFX_SAH_TRAV_COST_PCT", 100) * 0.01f, (int)env_long("MFX_BVH_BUILD_PAR_DEPTH", 5), tree);
+                       (float)env_long("MFX_SAH_TRAV_COST_PCT", 100) * 0.01f, par_depth, tree);
     lap("own tree");
     const std::vector<QuadF> &quads = tree.quads;
     const std::vector<int> &order = tree.order;
@@ -888,6 +897,7 @@ static int run_sample(MfxScene *s, const MfxSampleParams *p, double *d_color_wh,
     if (p->world > 1 && p->tile_size <= 0) return fail(MFX_ERR_INVALID_ARGUMENT, "world > 1 needs a positive tile_size");
     MFX_TRY(ensure_device());
     const bool exact = (p->precision == MFX_EXACT_F64);
+    s->host_share = std::max(1, p->world);
     if (exact) { MFX_TRY(flatten_exact(s)); MFX_TRY(ensure_wave_exact(s)); }
     const bool count_ref = (p->flags & MFX_SAMPLE_COUNT_TRAVERSAL) != 0;
     const bool counting = count_ref || (p->flags & MFX_SAMPLE_COUNT_OWN_TREE) != 0;
