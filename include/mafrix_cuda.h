@@ -161,6 +161,11 @@ typedef struct {
 /* MFX_FAST_F32 only: instrumented run on the library's own tree (what the shipped kernel really fetches):
  * MfxStats.nodes counts 128-byte four-child records, tris / spheres count primitive tests. */
 #define MFX_SAMPLE_COUNT_OWN_TREE 4
+/* MFX_FAST_F32 only.  By default the closest hits of bounce 0 (the primary rays) are ID-EXACT: same primitive and the
+ * same f64 t as Bvh.Hit (BvhNode.fs:62-83) finds, tie rules included -- f32 box tests over conservatively padded boxes
+ * of the library's own tree, f64 primitive tests, mfx_hybrid.cu.  With this bit bounce 0 uses f32 primitive tests like
+ * the deeper bounces (primary ids then differ from the reference on <= 2e-4 of the rays). */
+#define MFX_SAMPLE_F32_PRIMARY 8
 
 typedef struct {
     uint64_t closest_rays;       /* closest-hit queries traced by the last Sample call             */
@@ -176,7 +181,7 @@ typedef struct {
     uint32_t launches;           /* kernels launched by the call                                   */
     uint32_t launches_extend;
     uint32_t launches_shadow;
-    uint32_t pad;
+    uint32_t hybrid_fixups;      /* id-exact bounce 0 / seams: rays the hybrid kernel handed to the exact walk */
 } MfxStats;
 
 typedef struct MfxScene MfxScene;

@@ -56,12 +56,13 @@ class MfxStats(C.Structure):
                 ("ms_total", C.c_double), ("ms_extend", C.c_double), ("ms_shadow", C.c_double),
                 ("ms_shade", C.c_double),
                 ("launches", C.c_uint32), ("launches_extend", C.c_uint32),
-                ("launches_shadow", C.c_uint32), ("pad", C.c_uint32)]
+                ("launches_shadow", C.c_uint32), ("hybrid_fixups", C.c_uint32)]
 
 
 SAMPLE_COUNT_TRAVERSAL = 1
 SAMPLE_REFERENCE_STREAM = 2
 SAMPLE_COUNT_OWN_TREE = 4
+SAMPLE_F32_PRIMARY = 8
 
 # every symbol include/mafrix_cuda.h declares: name -> (restype, argtypes)
 _P = C.c_void_p

@@ -161,7 +161,10 @@ struct MfxScene {
     std::vector<std::pair<void *, size_t>> allocs;   // every device buffer of this scene
     bool x_ready = false, f_ready = false, fr_ready = false, wx_ready = false, wf_ready = false;
     SceneX sx; SceneF sf; SceneF sf_ref; WaveX wx; WaveF wf;     // sf: own SAH tree; sf_ref: reference-tree layout
-    uint64_t x_bytes = 0, f_bytes = 0, fr_bytes = 0;
+    uint64_t x_bytes = 0, f_bytes = 0, fr_bytes = 0, h_bytes = 0;
+    bool h_ready = false, wh_ready = false;  // hybrid (id-exact closest hit on the own tree): tables, f64 ray queue
+    SceneH sh; WaveH wh; int wh_P = 0;
+    std::vector<int> f_slot_prim;            // own-tree fast slot -> caller's primitive index, bit 30 = second half of a Rect
     MatF *d_matf = nullptr;
     float *d_perlin_rf = nullptr; int *d_perlin_perm = nullptr;
     double *d_pixsum = nullptr;          // [w*h][4] row-major sums
@@ -697,6 +700,11 @@ static int flatten_fast(MfxScene *s)
     const int own_depth = tree.depth;
     std::vector<SlotF> slots(ns); std::vector<float4> nrm(ns);
     for (int k = 0; k < ns; k++) { slots[k] = raw[order[k]]; nrm[k] = raw_nrm[order[k]]; }
+    s->f_slot_prim.resize(ns);
+    for (int k = 0; k < ns; k++) {      // bit 30: the second triangle of a Rect (raw slots of one primitive are adjacent)
+        const int raw_k = order[k];
+        s->f_slot_prim[k] = owner[raw_k] | ((raw_k > 0 && owner[raw_k - 1] == owner[raw_k]) ? (1 << 30) : 0);
+    }
 
     SceneF &sf = s->sf;
     memset(&sf, 0, sizeof(sf));
@@ -729,6 +737,74 @@ static int fast_layout(MfxScene *s, bool counting, int variant, const SceneF **o
     const bool ref = counting || variant == 4 || variant == 5 || variant == 51 || variant == 52;
     if (ref) { MFX_TRY(flatten_fast_ref(s)); *out = &s->sf_ref; }
     else { MFX_TRY(flatten_fast(s)); *out = &s->sf; }
+    return MFX_OK;
+}
+
+// ---- flatten: the tables of the id-exact hybrid traversal (mfx_hybrid.cu) on top of the exact and the own-tree layouts
+static int flatten_hybrid(MfxScene *s)
+{
+    if (s->h_ready) return MFX_OK;
+    MFX_TRY(flatten_exact(s)); MFX_TRY(flatten_fast(s));
+    const int n = (int)s->prims.size(), ns = (int)s->f_slot_prim.size();
+    std::vector<int> ref_of_prim(n), leaf_of_ref(n, 0);
+    std::vector<PrimH> ph(ns);
+    std::vector<int2> ref_fslot(n, make_int2(-1, -1));
+    for (int slot = 0; slot < n; slot++) ref_of_prim[s->indices[slot]] = slot;
+    for (int k = 0; k < ns; k++) {
+        const int prim = s->f_slot_prim[k] & 0x3fffffff, half = s->f_slot_prim[k] >> 30;
+        const int ref = ref_of_prim[prim];
+        if (half) ref_fslot[ref].y = k; else ref_fslot[ref].x = k;
+        const MfxPrim &p = s->prims[prim];
+        PrimH &x = ph[k];
+        memset(&x, 0, sizeof(PrimH));
+        x.ref = ref;
+        if (p.kind == MFX_SPHERE) { x.kind = 2; hst(x.v0, hld(p.v)); x.e1[0] = p.v[3]; }
+        else {      // the same subtractions as flatten_exact: bit-identical edge vectors
+            H3 v0 = hld(p.v), v1 = hld(p.v + 3), v2 = hld(p.v + 6);
+            hst(x.v0, v0); hst(x.e1, hsub(v1, v0)); hst(x.e2, hsub(v2, v0));
+            x.kind = half ? 1 : 0;
+            if (p.kind == MFX_RECT) hst(x.e3, hsub(hld(p.v + 9), v0));
+        }
+    }
+    // reference tree: depth-first walk from the root, leaf iff count <= LeafNodeCount (BvhNode.fs:39,44)
+    {
+        std::vector<int> todo{ 0 };
+        while (!todo.empty()) {
+            const int i = todo.back(); todo.pop_back();
+            const MfxBvhNode &nd = s->nodes[i];
+            if (nd.count > MFX_LEAF_NODE_COUNT) { todo.push_back(2 * i + 2); todo.push_back(2 * i + 1); continue; }
+            for (int k = 0; k < nd.count; k++) leaf_of_ref[nd.first + k] = i;
+        }
+    }
+    SceneH &sh = s->sh;
+    memset(&sh, 0, sizeof(sh));
+    int *d_leaf; int2 *d_fslot; PrimH *d_ph;
+    MFX_TRY(upload(s, &d_ph, ph)); MFX_TRY(upload(s, &d_leaf, leaf_of_ref)); MFX_TRY(upload(s, &d_fslot, ref_fslot));
+    sh.prims_h = d_ph; sh.leaf_of_ref = d_leaf; sh.ref_fslot = d_fslot;
+    double m = 0.;
+    for (int a = 0; a < 3; a++) m = std::max(m, std::max(std::fabs(s->nodes[0].pmin[a]), std::fabs(s->nodes[0].pmax[a])));
+    sh.max_abs = round_up(m);
+    s->h_bytes = (uint64_t)ns * sizeof(PrimH) + (uint64_t)n * 12;
+    s->h_ready = true;
+    return MFX_OK;
+}
+
+// the hybrid's per-wave buffers follow the fast wave's capacity (they are only allocated once the hybrid is used)
+static int ensure_wave_hybrid(MfxScene *s)
+{
+    if (s->wh_ready && s->wh_P == s->wf.P) return MFX_OK;
+    WaveH &w = s->wh;
+    if (s->wh_ready) {
+        CUDA_TRY(cudaStreamSynchronize(s->stream));
+        void *old[] = { w.dir64, w.org64, w.t, w.ref, w.fix_q, w.fix_n };
+        for (void *q : old) dev_free_one(s, q);
+        s->wh_ready = false;
+    }
+    memset(&w, 0, sizeof(w));
+    const size_t P = (size_t)s->wf.P;
+    MFX_TRY(dev_alloc_t(s, &w.dir64, 3 * P)); MFX_TRY(dev_alloc_t(s, &w.org64, 3 * P)); MFX_TRY(dev_alloc_t(s, &w.t, P)); MFX_TRY(dev_alloc_t(s, &w.ref, P));
+    MFX_TRY(dev_alloc_t(s, &w.fix_q, (size_t)MFX_HYB_FIX_CAP)); MFX_TRY(dev_alloc_t(s, &w.fix_n, 4));
+    s->wh_P = (int)P; s->wh_ready = true;
     return MFX_OK;
 }
 
@@ -815,7 +891,7 @@ static int ensure_frame_buffers(MfxScene *s)
     if (!s->d_pixsum) MFX_TRY(dev_alloc_t(s, &s->d_pixsum, 4 * npx));
     if (!s->d_color_wh) MFX_TRY(dev_alloc_t(s, &s->d_color_wh, 4 * npx));
     if (!s->d_rgba) MFX_TRY(dev_alloc_t(s, &s->d_rgba, npx));
-    if (!s->d_totals) MFX_TRY(dev_alloc_t(s, &s->d_totals, 4));
+    if (!s->d_totals) MFX_TRY(dev_alloc_t(s, &s->d_totals, 8));
     if (!s->d_ctr) MFX_TRY(dev_alloc_t(s, &s->d_ctr, 1));
     return MFX_OK;
 }
@@ -882,6 +958,13 @@ static int get_event(MfxScene *s, size_t idx, cudaEvent_t *e)
     return MFX_OK;
 }
 
+// MFX_FAST_F32 closest hits of bounce 0 and of the seams go through the id-exact hybrid traversal unless the caller
+// (MFX_SAMPLE_F32_PRIMARY) or the environment (MFX_F32_PRIMARY=1, A/B runs) asks for f32 leaf tests everywhere.
+static bool use_hybrid(int flags)
+{
+    return !(flags & MFX_SAMPLE_F32_PRIMARY) && env_long("MFX_F32_PRIMARY", 0) == 0;
+}
+
 // ------------------------------------------------------------------ the wavefront driver
 // One IPixelIntegrator.Sample(n) call (Integrators.fs:160-172): every (pixel, sample) of this
 // rank's tiles becomes one path; paths advance one vertex per bounce through
@@ -908,15 +991,18 @@ static int run_sample(MfxScene *s, const MfxSampleParams *p, double *d_color_wh,
     TileMap tm;
     MFX_TRY(get_tilemap(s, p->tile_size, p->rank, p->world, &tm));
     if (!exact) MFX_TRY(ensure_wave_fast(s, (size_t)tm.n_pix * (size_t)p->spp));
+    // bounce 0 of the throughput path is traced id-exactly (mfx_hybrid.cu) unless the caller opts out
+    const bool hyb = !exact && sfp->own_tree && !counting && use_hybrid(p->flags);
+    if (hyb) { MFX_TRY(flatten_hybrid(s)); MFX_TRY(ensure_wave_hybrid(s)); }
     TravCounters *ctr = counting ? s->d_ctr : nullptr;
     const bool sky = (s->integrator == MFX_SKY_TRACER);
     if (!exact) s->wf.cam_origin = (sfp->own_tree && !counting && !(sky && s->lens.lens_radius != 0.0)) ? 1 : 0;
     const size_t npx = (size_t)s->width * s->height;
     cudaStream_t st = s->stream;
-    LaunchCfg cfg{ s->sm_count, 128, st, variant, (p->flags & MFX_SAMPLE_REFERENCE_STREAM) ? 1 : 0 };
+    LaunchCfg cfg{ s->sm_count, 128, st, variant, (p->flags & MFX_SAMPLE_REFERENCE_STREAM) ? 1 : 0, 0, (int)env_long("MFX_HYB_VARIANT", 0) };
 
     CUDA_TRY(cudaMemsetAsync(s->d_pixsum, 0, 4 * npx * sizeof(double), st));
-    CUDA_TRY(cudaMemsetAsync(s->d_totals, 0, 4 * sizeof(unsigned long long), st));
+    CUDA_TRY(cudaMemsetAsync(s->d_totals, 0, 8 * sizeof(unsigned long long), st));
     CUDA_TRY(cudaMemsetAsync(s->d_ctr, 0, sizeof(TravCounters), st));
     if (tm.pix) {   // pixels of other ranks must read as zero
         if (d_color_wh) CUDA_TRY(cudaMemsetAsync(d_color_wh, 0, 4 * npx * sizeof(double), st));
@@ -953,11 +1039,18 @@ static int run_sample(MfxScene *s, const MfxSampleParams *p, double *d_color_wh,
             CUDA_TRY(cudaMemsetAsync(counts, 0, MFX_COUNTS_LEN * sizeof(int), st));
             cfg.max_items = 0;
             if (exact) mfx_x_raygen(cfg, s->sx, s->wx, tm, pix0, np, sabs, S, p->seed);
+            else if (hyb) mfx_h_raygen(cfg, *sfp, s->sx, s->wf, s->wh, tm, pix0, np, sabs, S, p->seed);
             else mfx_f_raygen(cfg, *sfp, s->wf, tm, pix0, np, sabs, S, p->seed);
             launches++;
             for (int b = 0; b <= D; b++) {
                 MFX_TRY(timed(0));
-                if (exact) mfx_x_extend(cfg, s->sx, s->wx, b, ctr); else mfx_f_extend(cfg, *sfp, s->wf, b, ctr);
+                if (exact) mfx_x_extend(cfg, s->sx, s->wx, b, ctr);
+                else if (hyb && b == 0) {
+                    const HybQuery q{ sky ? MFX_SKY_TMIN : 1e-6, sky ? MFX_SKY_TMAX : 99999999., sky ? 1 : 0 };   // Integrators.fs:108 / RayTracing.fs:368
+                    mfx_h_extend(cfg, *sfp, s->sx, s->sh, s->wf, s->wh, 0, q, 0);
+                    mfx_h_accum_fixups(st, s->wh, s->d_totals + 4);
+                    launches += 2;
+                } else mfx_f_extend(cfg, *sfp, s->wf, b, ctr);
                 MFX_TRY(timed_end());
                 if (sky) {      // GetColor (RayTracing.fs:367-382): no light, no shadow query
                     if (exact) mfx_x_shade_sky(cfg, s->sx, s->wx, tm, pix0, np, sabs, b, p->seed);
@@ -999,7 +1092,7 @@ static int run_sample(MfxScene *s, const MfxSampleParams *p, double *d_color_wh,
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaStreamSynchronize(st));
 
-    unsigned long long totals[4];
+    unsigned long long totals[8];
     TravCounters hc;
     CUDA_TRY(cudaMemcpy(totals, s->d_totals, sizeof(totals), cudaMemcpyDeviceToHost));
     CUDA_TRY(cudaMemcpy(&hc, s->d_ctr, sizeof(hc), cudaMemcpyDeviceToHost));
@@ -1018,6 +1111,7 @@ static int run_sample(MfxScene *s, const MfxSampleParams *p, double *d_color_wh,
     }
     stt.ms_extend = m_ext; stt.ms_shadow = m_sh; stt.ms_shade = stt.ms_total - m_ext - m_sh;
     stt.launches = launches; stt.launches_extend = l_ext; stt.launches_shadow = l_sh;
+    stt.hybrid_fixups = (uint32_t)std::min<unsigned long long>(totals[4], 0xffffffffull);
     return MFX_OK;
 }
 
@@ -1139,13 +1233,32 @@ static void fast_seam(MfxScene *s, const SceneF *sfp, const LaunchCfg &cfg, int 
     }
 }
 
+// The same seams through the id-exact hybrid kernel (closest-hit queries only): f64 rays into the wave's ray64 queue.
+static void hybrid_seam(MfxScene *s, const SceneF *sfp, const LaunchCfg &cfg, int64_t n, const double *o, const double *d, const double *uv,
+                        double tmin, double tmax, int *prim, int *sub, double *t)
+{
+    WaveF w = s->wf;
+    w.cam_origin = 0;
+    const HybQuery q{ tmin, tmax, s->integrator == MFX_SKY_TRACER ? 1 : 0 };
+    for (int64_t first = 0; first < n; first += w.P) {
+        const int m = (int)std::min<int64_t>(w.P, n - first);
+        cudaMemsetAsync(w.counts, 0, MFX_COUNTS_LEN * sizeof(int), s->stream);
+        mfx_h_seam_setup(cfg, s->sx, w, s->wh, m, o, d, uv, first);
+        mfx_h_extend(cfg, *sfp, s->sx, s->sh, w, s->wh, 0, q, 1);
+        mfx_h_seam_read(cfg, s->sx, s->wh, m, first, prim, sub, t);
+        int fx = 0;     // seam calls are synchronous anyway: keep the number of rays the exact walk had to settle
+        if (cudaMemcpyAsync(&fx, s->wh.fix_n, sizeof(int), cudaMemcpyDeviceToHost, s->stream) == cudaSuccess && cudaStreamSynchronize(s->stream) == cudaSuccess)
+            s->stats.hybrid_fixups = (first == 0 ? 0u : s->stats.hybrid_fixups) + (uint32_t)fx;
+    }
+}
+
 extern "C" int mfx_bvh_hit(MfxScene *s, int32_t precision, int32_t any_hit, int64_t n, const double *origins, const double *dirs,
                            double tmin, double tmax, int32_t *prim, int32_t *sub, double *t)
 {
     if (!s || !origins || !dirs || !prim || !t) return fail(MFX_ERR_INVALID_ARGUMENT, "mfx_bvh_hit: null argument");
     if (n <= 0) return MFX_OK;
     MFX_TRY(ensure_device());
-    LaunchCfg cfg{ s->sm_count, 128, s->stream, (int)env_long("MFX_TRACE_VARIANT", -1), 0 };
+    LaunchCfg cfg{ s->sm_count, 128, s->stream, (int)env_long("MFX_TRACE_VARIANT", -1), 0, 0, (int)env_long("MFX_HYB_VARIANT", 0) };
     if (precision == MFX_EXACT_F64) {
         MFX_TRY(flatten_exact(s));
         return with_ray_buffers(s, n, origins, 3, dirs, 3, prim, sub, t, [&](double *o, double *d, int *p, int *sb, double *tt) {
@@ -1155,8 +1268,11 @@ extern "C" int mfx_bvh_hit(MfxScene *s, int32_t precision, int32_t any_hit, int6
         const SceneF *sfp = nullptr;
         MFX_TRY(fast_layout(s, false, cfg.variant, &sfp));
         MFX_TRY(ensure_wave_fast(s, (size_t)n));
+        const bool hyb = !any_hit && sfp->own_tree && use_hybrid(0);
+        if (hyb) { MFX_TRY(flatten_hybrid(s)); MFX_TRY(ensure_wave_hybrid(s)); }
         return with_ray_buffers(s, n, origins, 3, dirs, 3, prim, sub, t, [&](double *o, double *d, int *p, int *sb, double *tt) {
-            fast_seam(s, sfp, cfg, any_hit, n, o, d, nullptr, (float)tmin, (float)tmax, p, sb, tt);
+            if (hyb) hybrid_seam(s, sfp, cfg, n, o, d, nullptr, tmin, tmax, p, sb, tt);
+            else fast_seam(s, sfp, cfg, any_hit, n, o, d, nullptr, (float)tmin, (float)tmax, p, sb, tt);
         });
     }
     return fail(MFX_ERR_INVALID_ARGUMENT, "unknown precision %d", precision);
@@ -1168,7 +1284,7 @@ extern "C" int mfx_trace_primary(MfxScene *s, int32_t precision, int64_t n, cons
     if (!uv && n != (int64_t)s->width * s->height) return fail(MFX_ERR_INVALID_ARGUMENT, "uv == NULL needs n == width*height");
     if (n <= 0) return MFX_OK;
     MFX_TRY(ensure_device());
-    LaunchCfg cfg{ s->sm_count, 128, s->stream, (int)env_long("MFX_TRACE_VARIANT", -1), 0 };
+    LaunchCfg cfg{ s->sm_count, 128, s->stream, (int)env_long("MFX_TRACE_VARIANT", -1), 0, 0, (int)env_long("MFX_HYB_VARIANT", 0) };
     if (precision == MFX_EXACT_F64) {
         MFX_TRY(flatten_exact(s));
         return with_ray_buffers(s, n, uv, 2, nullptr, 0, prim, nullptr, t, [&](double *u, double *, int *p, int *, double *tt) {
@@ -1178,8 +1294,11 @@ extern "C" int mfx_trace_primary(MfxScene *s, int32_t precision, int64_t n, cons
         const SceneF *sfp = nullptr;
         MFX_TRY(fast_layout(s, false, cfg.variant, &sfp));
         MFX_TRY(ensure_wave_fast(s, (size_t)n));
+        const bool hyb = sfp->own_tree && use_hybrid(0);
+        if (hyb) { MFX_TRY(flatten_hybrid(s)); MFX_TRY(ensure_wave_hybrid(s)); }
         return with_ray_buffers(s, n, uv, 2, nullptr, 0, prim, nullptr, t, [&](double *u, double *, int *p, int *, double *tt) {
             const bool sky = (s->integrator == MFX_SKY_TRACER);      // ListHit(ray, 0.00001, 10000000), RayTracing.fs:368
+            if (hyb) { hybrid_seam(s, sfp, cfg, n, nullptr, nullptr, u, sky ? MFX_SKY_TMIN : 1e-6, sky ? MFX_SKY_TMAX : 99999999., p, nullptr, tt); return; }
             fast_seam(s, sfp, cfg, 0, n, nullptr, nullptr, u, sky ? (float)MFX_SKY_TMIN : 1e-6f, sky ? (float)MFX_SKY_TMAX : 99999999.f, p, nullptr, tt);
         });
     }

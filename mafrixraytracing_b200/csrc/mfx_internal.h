@@ -176,6 +176,44 @@ struct WaveF {
 // the last entry is the traversal watchdog flag
 #define MFX_COUNTS_LEN (4 * (MFX_MAX_VERTS + 2))
 
+// ------------------------------------------------------------------ hybrid (id-exact closest hit, mfx_hybrid.cu)
+// The closest-hit query of the reference has ONE answer (BvhNode.fs:62-83): the smallest t over every primitive the
+// exhaustive walk tests, ties to the later leaf in depth-first order, then to the earlier slot of that leaf.  The
+// hybrid kernel finds it on the library's own SAH tree: f32 slab tests over boxes padded per ray (conservative
+// against every rounding between the f64 ray and the f32 arithmetic), candidate primitives tested with the exact
+// kernel's f64 functions on the exact layout's PrimX records, the tie rule applied from the reference tree's leaf
+// table, and the winner's reference leaf box re-tested with AABB.hit verbatim (the reference only ever tests a
+// primitive whose boxes all pass; child boxes nest, so the leaf's own test decides).  Anything that check does not
+// clear goes to the exact kernel's traversal (k_h_fixup).
+// One own-tree slot in f64: the PrimX arithmetic inputs (v0, e1 = v1-v0, e2 = v2-v0, e3 = v3-v0: the single subtractions
+// Triangle.PreCalcu does per call, Trangle.fs:124-125) in the own tree's slot order, so a leaf's records are adjacent.
+//   kind 0: Triangle, or first triangle of a Rect;  kind 1: second triangle of a Rect (e1, e2, e3 all present: Rect.Hit
+//   tries (v0,e1,e2) first, Rect.fs:26-31);  kind 2: Sphere (v0 = center, e1[0] = radius).  ref = exact leaf-order slot.
+struct __align__(16) PrimH {
+    double v0[3];
+    double e1[3];
+    double e2[3];
+    double e3[3];
+    int    kind;
+    int    ref;
+    double pad;
+};
+struct SceneH {
+    const PrimH *prims_h;       // [own-tree fast slots]
+    const int  *leaf_of_ref;    // exact slot -> heap index of the reference-tree leaf holding it (BvhNode.fs:40-41)
+    const int2 *ref_fslot;      // exact slot -> own-tree fast slots of (first, second) triangle; .y = -1 unless a Rect
+    float max_abs;              // largest |coordinate| of the scene bound: scale of the per-ray box pad
+};
+#define MFX_HYB_FIX_CAP (1 << 20)
+struct WaveH {
+    double *dir64;              // [P][3] f64 direction of the queued closest-hit rays (bounce 0 / the seams)
+    double *org64;              // [P][3] f64 origin; not touched by pinhole frames (WaveF.cam_origin: the camera position)
+    double *t;                  // [P] exact hit distance
+    int    *ref;                // [P] exact slot | sub << 30, -1 = miss, -2 = waiting for k_h_fixup
+    int    *fix_q;              // [MFX_HYB_FIX_CAP] queue positions waiting for k_h_fixup
+    int    *fix_n;              // [1] how many were flagged (may exceed the capacity: then k_h_fixup scans `ref`)
+};
+
 // Traversal counters (instrumented runs only): [class][nodes,tris,spheres]
 struct TravCounters { unsigned long long v[2][3]; };
 
@@ -187,7 +225,7 @@ struct TileMap {
 // ------------------------------------------------------------------ launchers (defined in the .cu TUs)
 // max_items > 0: the host knows an upper bound of the queue this launch works on (sky tracer, late bounces): the
 // persistent grid is clamped to the blocks that many entries can occupy
-struct LaunchCfg { int blocks; int threads; cudaStream_t stream; int variant; int reference_stream; int max_items; };
+struct LaunchCfg { int blocks; int threads; cudaStream_t stream; int variant; int reference_stream; int max_items; int hyb_variant; };
 
 // exact
 void mfx_x_raygen(const LaunchCfg &, const SceneX &, const WaveX &, TileMap tm, int pix0, int npix, int s0, int S,
@@ -220,6 +258,16 @@ void mfx_f_resolve(const LaunchCfg &, const SceneF &, const WaveF &, TileMap tm,
 void mfx_f_seam_setup(const LaunchCfg &, const SceneF &, const WaveF &, int n, const double *o, const double *d, const double *uv,
                       long long first, float tmax, int any_hit);
 void mfx_f_seam_read(const LaunchCfg &, const SceneF &, const WaveF &, int n, long long first, int any_hit, int *prim, int *sub, double *t);
+
+// hybrid (mfx_hybrid.cu, --fmad=false): id-exact closest hits on the own tree
+struct HybQuery { double tmin, tmax; int sky; };
+void mfx_h_raygen(const LaunchCfg &, const SceneF &, const SceneX &, const WaveF &, const WaveH &, TileMap tm, int pix0, int npix,
+                  int s0, int S, uint64_t seed);
+void mfx_h_seam_setup(const LaunchCfg &, const SceneX &, const WaveF &, const WaveH &, int n, const double *o, const double *d,
+                      const double *uv, long long first);
+void mfx_h_extend(const LaunchCfg &, const SceneF &, const SceneX &, const SceneH &, const WaveF &, const WaveH &, int bounce, HybQuery q, int seam);
+void mfx_h_seam_read(const LaunchCfg &, const SceneX &, const WaveH &, int n, long long first, int *prim, int *sub, double *t);
+void mfx_h_accum_fixups(cudaStream_t, const WaveH &, unsigned long long *total);
 
 // misc (mfx_fast.cu)
 // totals[0] += sum counts[ext_lo..+ext_n), totals[1] += sum counts[sh_lo..+sh_n), totals[2] += counts[0]

@@ -75,21 +75,28 @@ def test_exact_depth_limit_and_progressive_frames():
 
 
 @pytest.mark.parametrize("make", [lambda: scenes.random_scene(width=640, height=320), lambda: mixed(width=480, height=320)])
-def test_fast_primary_ids_and_t_tolerance(make):
+def test_fast_primary_is_bit_exact_and_f32_tests_within_tolerance(monkeypatch, make):
+    """Default: the id-exact hybrid kernel (own tree, f32 boxes, f64 Sphere.Hit, ListHit's tie rule) -- ids and t equal
+    the oracle's.  MFX_F32_PRIMARY=1: the f32 sphere tests of the deeper bounces -- ids within 2e-4, t within 1e-4."""
     desc = make()
     s = Scene(desc)
+    o = oracle.OracleSkyScene(desc)
+    oprim, ot = o.trace_primary()
+    rng = np.random.default_rng(2)
+    org = rng.uniform(-6, 6, (20000, 3)) * [1, 0.2, 1] + [0, 1.5, 0]      # arbitrary rays, origins off every surface
+    dirs = rng.normal(0, 1, (20000, 3)) * 3.0
+    p0, t0 = o.hit(org, dirs)
     prim, t = s.TracePrimary(precision=FAST_F32)
-    oprim, ot = oracle.OracleSkyScene(desc).trace_primary()
+    assert np.array_equal(prim, oprim) and np.array_equal(t, ot)
+    p1, _, t1 = s.Hit(org, dirs, 0.00001, 10000000., precision=FAST_F32)
+    assert np.array_equal(p1, p0) and np.array_equal(t1[p0 >= 0], t0[p0 >= 0])
+    monkeypatch.setenv("MFX_F32_PRIMARY", "1")
+    prim, t = s.TracePrimary(precision=FAST_F32)
     differ = prim != oprim
     assert differ.mean() <= 2e-4, f"{differ.sum()} of {differ.size} sphere ids differ"
     both = (~differ) & (oprim >= 0)
     assert np.max(np.abs(t[both] - ot[both]) / ot[both]) <= 1e-4
-    # the wavefront seam for arbitrary rays, origins off every surface
-    rng = np.random.default_rng(2)
-    org = rng.uniform(-6, 6, (20000, 3)) * [1, 0.2, 1] + [0, 1.5, 0]
-    dirs = rng.normal(0, 1, (20000, 3)) * 3.0
     p1, _, t1 = s.Hit(org, dirs, 0.00001, 10000000., precision=FAST_F32)
-    p0, t0 = oracle.OracleSkyScene(desc).hit(org, dirs)
     assert (p1 != p0).mean() <= 2e-4
     ok = (p1 == p0) & (p0 >= 0)
     assert np.max(np.abs(t1[ok] - t0[ok]) / t0[ok]) <= 1e-4
