@@ -4,16 +4,23 @@ path on BASELINE.json configs[1]: spot (cow OBJ) 1920x1080, 64 spp, max depth 5,
 light (SURVEY.md 8(d) "C2"), one step = one IPixelIntegrator.Sample(64) of the whole frame.
 
   python bench.py --gpus 1 --steps K --warmup W          this repo's CUDA path (libmafrix_cuda)
-  torchrun ... bench.py --gpus N ...                     frame tile-sharded over N GPUs + NCCL reduce
+  torchrun ... bench.py --gpus N ...                     frame stripe-sharded over N GPUs (one process each) + NCCL gather
   python bench.py --impl reference ...                   the reference's CPU algorithm (the oracle
                                                          restatement; .NET is not in this image)
 
 value   : whole-job Mrays/s, scene + path state resident in HBM, result left in HBM (device timed)
-e2e     : same metric through the reference-facing call with HOST buffers -- scene upload
-          (mfx_scene_create) + Sample -> Color[w,h] on the host, copies inside the timed region
-roofline: closest-hit traversal kernel, algorithmic bytes (32 B/node + 48 B/tri +
-          16 B/sphere + 64 B queue traffic per ray, counted by an instrumented run) / CUDA-event
-          time, against the measured HBM copy bandwidth in MEASURED_PEAKS.json
+e2e     : same metric through the reference-facing call with HOST buffers -- scene upload + Sample -> Color[w,h] on the
+          host, copies inside the timed region.  N = 1: mfx_scene_create + mfx_pixel_integrator_sample; N > 1: what a
+          single-threaded host (the reference's shape) calls: mfx_multi_create + mfx_multi_sample over the N GPUs, from
+          rank 0 alone while the other ranks wait on a CPU barrier
+roofline: closest-hit traversal kernel.  The scene of this workload is cache resident, so the bound is the rate at which
+          the L1 turns divergent 32-byte sectors around: achieved = bytes of records + primitives the kernel requests per
+          ray (instrumented run on its own tree) x rays / CUDA-event time, peak = the same access pattern measured live on
+          this GPU by tools/peaks_cache.  `hbm_definition` keeps SURVEY 8(d)'s figure (reference-tree records against the
+          HBM copy bandwidth) -- labelled: it exceeds 1 because those bytes never leave the caches; `dram` is the DRAM
+          traffic ncu measured for the whole step against the 64 B/ray queue budget and the HBM peak
+configs : BASELINE configs[2..4] at their stated size through the same device-timed path
+primary : the id-exact bounce-0 kernel (hybrid: f32 boxes, f64 primitive tests) against f32 primitive tests, primary rays alone
 """
 import argparse
 import json
@@ -45,6 +52,8 @@ def parse():
     ap.add_argument("--precision", default="fast", choices=["fast", "exact"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the C3/C4/C5 table (about a minute at N=1)")
+    ap.add_argument("--no-primary", action="store_true")
     return ap.parse_args()
 
 
@@ -165,6 +174,30 @@ def cpu_baseline(desc):
             "spp_per_s": n / dt, "ref_nodes_per_ray": st["ref_nodes"] / rays_per_spp, "ref_prims_per_ray": st["ref_prims"] / rays_per_spp}
 
 
+def cache_peaks():
+    """On-chip bandwidth of THIS GPU for the traversal kernel's access pattern (divergent 256-bit record loads), measured
+    live by tools/peaks_cache (built by __graft_entry__.build())."""
+    exe = os.path.join(ROOT, "tools", "peaks_cache")
+    if not os.path.exists(exe):
+        return None
+    try:
+        out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+        return json.loads(out.stdout.strip().splitlines()[-1]) if out.returncode == 0 else None
+    except Exception:
+        return None
+
+
+def load_traffic():
+    """DRAM bytes per launch / per step of the bench configuration, from the committed ncu capture (profiles/)."""
+    for name in ("r02_traffic.json", "roofline_traffic.json"):
+        p = os.path.join(ROOT, "profiles", name)
+        if os.path.exists(p):
+            d = json.load(open(p))
+            d["file"] = "profiles/" + name
+            return d
+    return {}
+
+
 def main():
     args = parse()
     rank = int(os.environ.get("RANK", "0"))
@@ -176,18 +209,20 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from mafrixraytracing_b200 import scenes, Scene, CudaPixelIntegrator, Bvh, EXACT_F64, FAST_F32, _lib
+    from mafrixraytracing_b200 import scenes, Scene, CudaPixelIntegrator, MultiGpuPixelIntegrator, Bvh, EXACT_F64, FAST_F32, _lib
     from mafrixraytracing_b200 import dist as mdist
 
     torch.cuda.set_device(local_rank)
+    cpu_group = None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local_rank))
+        cpu_group = dist.new_group(backend="gloo")       # waits that must not occupy a GPU (rank 0 drives all of them in the e2e leg)
     prec = FAST_F32 if args.precision == "fast" else EXACT_F64
     desc = scenes.WORKLOADS[args.workload]()
     bvh = Bvh.Build(desc.prims)                                 # host, one-off (kept on the host by the north star)
     scene = Scene(desc, bvh=bvh, device=local_rank)
-    sharded = mdist.ShardedPixelIntegrator(scene, rank, world, precision=prec, seed=1, tile=mdist.TILE)
+    sharded = mdist.ShardedPixelIntegrator(scene, rank, world, precision=prec, seed=1, stripe=mdist.STRIPE)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")           # > 126 MB L2
 
     def sync_all():
@@ -196,15 +231,22 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
-    def step(k):
+    def cpu_barrier():
+        if world > 1:
+            dist.barrier(group=cpu_group)
+
+    def timed_step(integ, spp, k=0):
         flush.fill_(k & 0xff)                                   # L2 flush between iterations
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize()
         e0.record()
-        sharded.Sample(args.spp, first_sample=0, reduce=True)   # render this rank's tiles + NCCL sum-reduce to rank 0
+        integ.Sample(spp, first_sample=0)                       # render this rank's stripes + NCCL gather of the owned stripes to rank 0
         e1.record()
         torch.cuda.synchronize()
-        return e0.elapsed_time(e1), dict(sharded.stats)
+        return e0.elapsed_time(e1), dict(integ.stats)
+
+    def step(k):
+        return timed_step(sharded, args.spp, k)
 
     clocks = ClockSampler(local_rank)
     if rank == 0:
@@ -235,70 +277,63 @@ def main():
     if clk is not None:
         clk["window"] = "timed region" if extra == 0 else f"timed region + {extra} identical untimed steps (region shorter than the sampling period)"
 
-    rays_rank = sum(s["closest_rays"] + s["shadow_rays"] for s in stats)
-    t_rank = sum(ms_steps)
-    if world > 1:
-        tt = torch.tensor([t_rank], dtype=torch.float64, device="cuda")
-        rr = torch.tensor([float(rays_rank)], dtype=torch.float64, device="cuda")
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        dist.all_reduce(rr, op=dist.ReduceOp.SUM)
-        t_all, rays_all = tt.item(), rr.item()
-    else:
-        t_all, rays_all = t_rank, float(rays_rank)
+    def aggregate(rays_rank, t_rank):
+        if world > 1:
+            tt = torch.tensor([t_rank], dtype=torch.float64, device="cuda")
+            rr = torch.tensor([float(rays_rank)], dtype=torch.float64, device="cuda")
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            dist.all_reduce(rr, op=dist.ReduceOp.SUM)
+            return rr.item(), tt.item()
+        return float(rays_rank), t_rank
+
+    rays_all, t_all = aggregate(sum(s["closest_rays"] + s["shadow_rays"] for s in stats), sum(ms_steps))
     value = rays_all / t_all / 1e3                               # rays / ms / 1e3 = Mrays/s
 
     # ---- end to end through the reference-facing call, host buffers
     e2e = None
     if not args.no_e2e:
-        tex = np.zeros((desc.width, desc.height, 4), dtype=np.float64)
-        # the host keeps ONE Texture2D<Color> for its lifetime (Integrators.fs:147): pin it once so the
-        # per-frame download is a direct DMA (mfx_host_register)
-        _lib.check(_lib.load().mfx_host_register(_lib.ptr(tex), tex.nbytes))
-        host_frame = torch.empty((desc.height, desc.width, 4), dtype=torch.float32).pin_memory()
         h2d = desc.prims.nbytes + desc.materials.nbytes + bvh.nodes.nbytes + bvh.indices.nbytes + 12 * 8 + 18 * 8
-        rays_e2e, t_e2e = 0.0, 0.0
-        for k in range(args.steps + 1):
-            sync_all()
-            t0 = time.perf_counter()
-            sc = Scene(desc, bvh=bvh, device=local_rank)         # H2D: flattened scene (prims, tree, materials)
-            if world == 1:
-                integ = CudaPixelIntegrator(sc, precision=prec, seed=1)
-                integ.Sample(args.spp, out=tex)                  # D2H: Color[w,h] f64 = the reference's Texture2D
-                d2h = tex.nbytes
+        rays_e2e, t_e2e, d2h = 0.0, 0.0, 0
+        if rank == 0:
+            tex = np.zeros((desc.width, desc.height, 4), dtype=np.float64)
+            # the host keeps ONE Texture2D<Color> for its lifetime (Integrators.fs:147): pin it once so the
+            # per-frame download is a direct DMA (mfx_host_register)
+            _lib.check(_lib.load().mfx_host_register(_lib.ptr(tex), tex.nbytes))
+            d2h = tex.nbytes
+        cpu_barrier()                                            # N > 1: ranks 1.. hold no GPU work while rank 0 drives every device
+        if rank == 0:
+            for k in range(args.steps + 1):
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                if world == 1:
+                    sc = Scene(desc, bvh=bvh, device=local_rank)     # H2D: flattened scene (prims, tree, materials)
+                    integ = CudaPixelIntegrator(sc, precision=prec, seed=1)
+                    integ.Sample(args.spp, out=tex)                  # D2H: Color[w,h] f64 = the reference's Texture2D
+                else:
+                    sc = integ = MultiGpuPixelIntegrator(desc, devices=list(range(world)), bvh=bvh, precision=prec, seed=1)
+                    integ.Sample(args.spp, out=tex)                  # every device DMAs its stripes into the one host texture
+                dt = time.perf_counter() - t0
                 st = integ.stats
-            else:
-                sh = mdist.ShardedPixelIntegrator(sc, rank, world, precision=prec, seed=1, tile=mdist.TILE)
-                fr = sh.Sample(args.spp)
-                if rank == 0:
-                    host_frame.copy_(fr, non_blocking=False)     # D2H: assembled float4 frame on rank 0
-                d2h = host_frame.numel() * 4
-                st = sh.stats
-            sync_all()
-            dt = time.perf_counter() - t0
-            sc.close()
-            if k == 0:
-                continue                                         # first call allocates the path state
-            rr = torch.tensor([float(st["closest_rays"] + st["shadow_rays"]), dt], dtype=torch.float64, device="cuda")
-            if world > 1:
-                r2 = rr.clone()
-                dist.all_reduce(rr, op=dist.ReduceOp.SUM)
-                dist.all_reduce(r2, op=dist.ReduceOp.MAX)
-                rays_e2e += rr[0].item()
-                t_e2e += r2[1].item()
-            else:
-                rays_e2e += rr[0].item()
+                sc.close()
+                if k == 0:
+                    continue                                         # first call allocates the path state
+                rays_e2e += st["closest_rays"] + st["shadow_rays"]
                 t_e2e += dt
-        _lib.load().mfx_host_unregister(_lib.ptr(tex))
-        e2e = {"value": rays_e2e / t_e2e / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-               "ms_per_step": t_e2e / args.steps * 1e3,
-               "call": "mfx_scene_create + mfx_pixel_integrator_sample (Color[w,h] f64 to host)" if world == 1 else
-                       "mfx_scene_create + mfx_pixel_integrator_sample_device + NCCL reduce + D2H on rank 0"}
+            _lib.load().mfx_host_unregister(_lib.ptr(tex))
+        cpu_barrier()
+        if rank == 0:
+            e2e = {"value": rays_e2e / t_e2e / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": int(h2d * world), "d2h_bytes_per_step": int(d2h),
+                   "ms_per_step": t_e2e / args.steps * 1e3,
+                   "call": "mfx_scene_create + mfx_pixel_integrator_sample (Color[w,h] f64 to the pinned host texture)" if world == 1 else
+                           f"mfx_multi_create + mfx_multi_sample from ONE host thread over {world} GPUs (scene replicated per device, every device "
+                           "DMAs its column stripes into the pinned host texture; ranks 1.. idle on a CPU barrier)"}
 
     # ---- roofline of the dominant kernel (closest-hit traversal), rank 0's share
-    roof, cpu = None, None
+    roof, cpu, primary = None, None, None
     if rank == 0:
         integ = sharded.integ
-        integ.SampleDevice(2, sharded.frame.data_ptr(), flags=_lib.SAMPLE_COUNT_TRAVERSAL)     # instrumented, untimed
+        fl = sharded.flags
+        integ.SampleDeviceColor(2, sharded.frame.data_ptr(), flags=fl | _lib.SAMPLE_COUNT_TRAVERSAL)     # instrumented, untimed
         cs = integ.stats
         bc = b_ray(cs["nodes"][0], cs["tris"][0], cs["spheres"][0], cs["closest_rays"])
         bs = b_ray(cs["nodes"][1], cs["tris"][1], cs["spheres"][1], cs["shadow_rays"])
@@ -307,41 +342,115 @@ def main():
         ext_launches = sum(s["launches_extend"] for s in stats)
         sh_ms = sum(s["ms_shadow"] for s in stats)
         sh_rays = sum(s["shadow_rays"] for s in stats)
-        peak, how = peaks()
-        achieved = ext_rays * bc / (ext_ms * 1e-3) / 1e9
-        traffic = None
-        tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
-        if os.path.exists(tp):
-            traffic = json.load(open(tp)).get("extend_dram_bytes_per_launch")
-        roof = {"bound": "hbm", "kernel": "k_f_extend (closest-hit BVH traversal)" if prec == FAST_F32 else "k_x_extend",
-                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": how,
-                "bytes_per_ray_closest": bc, "bytes_per_ray_shadow": bs,
-                "nodes_per_ray": [cs["nodes"][0] / max(cs["closest_rays"], 1), cs["nodes"][1] / max(cs["shadow_rays"], 1)],
-                "tris_per_ray": [cs["tris"][0] / max(cs["closest_rays"], 1), cs["tris"][1] / max(cs["shadow_rays"], 1)],
-                "algorithmic_bytes_per_launch": ext_rays * bc / max(ext_launches, 1),
-                "avg_launch_ms": ext_ms / max(ext_launches, 1), "launches": ext_launches,
-                "share_of_step": ext_ms / max(sum(s["ms_total"] for s in stats), 1e-9),
+        step_ms = sum(s["ms_total"] for s in stats)
+        hbm_peak, how = peaks()
+        traffic = load_traffic()
+        dev_bytes = scene.device_bytes()
+        hbm_def = {"bytes_per_ray_closest": bc, "bytes_per_ray_shadow": bs,
+                   "nodes_per_ray": [cs["nodes"][0] / max(cs["closest_rays"], 1), cs["nodes"][1] / max(cs["shadow_rays"], 1)],
+                   "tris_per_ray": [cs["tris"][0] / max(cs["closest_rays"], 1), cs["tris"][1] / max(cs["shadow_rays"], 1)],
+                   "achieved": ext_rays * bc / (ext_ms * 1e-3) / 1e9, "peak": hbm_peak, "peak_source": how,
+                   "frac": ext_rays * bc / (ext_ms * 1e-3) / 1e9 / hbm_peak,
+                   "whole_step_achieved_gbs": (ext_rays * bc + sh_rays * bs) / (step_ms * 1e-3) / 1e9,
+                   "note": "SURVEY 8(d) / north star definition: 32 B/node + 48 B/tri + 16 B/sphere + 64 B of records an ordered, t-shrinking "
+                           "traversal of the REFERENCE's median-split tree touches, against the HBM copy bandwidth.  NOT a roofline of the "
+                           "shipped kernel: it walks its own SAH tree (a quarter of those records) and the scene never leaves the caches, "
+                           "so the figure exceeds 1; kept for comparability with round 1"}
+        roof = {"kernel": "k_f_trace6<closest> (BVH traversal of the extend queue)" if prec == FAST_F32 else "k_x_extend",
+                "avg_launch_ms": ext_ms / max(ext_launches, 1), "launches": ext_launches, "share_of_step": ext_ms / max(step_ms, 1e-9),
                 "extend_mrays_s": ext_rays / ext_ms / 1e3, "shadow_mrays_s": sh_rays / max(sh_ms, 1e-9) / 1e3,
-                "shadow_achieved_gbs": sh_rays * bs / max(sh_ms * 1e-3, 1e-12) / 1e9,
-                "whole_step_achieved_gbs": (ext_rays * bc + sh_rays * bs) / (sum(s["ms_total"] for s in stats) * 1e-3) / 1e9,
-                "note": "algorithmic bytes are counted on the REFERENCE tree (north star's definition: ordered, t-shrinking "
-                        "traversal of the reference's median-split BVH); the shipped kernel walks its own SAH tree, see own_tree; "
-                        "scene is L2 resident (fast layout %.2f MB incl. stack spill columns): the HBM figure is the stated "
-                        "denominator, the kernel itself is instruction-issue bound" % (scene.device_bytes()["fast"] / 1e6)}
+                "scene_fast_bytes": dev_bytes["fast"], "hbm_definition": hbm_def}
         if prec == FAST_F32:
-            # what the shipped kernel really fetches: 128 B four-child records + 48 B triangles of its own tree
-            integ.SampleDevice(2, sharded.frame.data_ptr(), flags=_lib.SAMPLE_COUNT_OWN_TREE)
+            # what the shipped kernel really requests: 128 B four-child records + 48 B triangle slots of its own tree
+            integ.SampleDeviceColor(2, sharded.frame.data_ptr(), flags=fl | _lib.SAMPLE_COUNT_OWN_TREE)
             os_ = integ.stats
             rec = [os_["nodes"][0] / max(os_["closest_rays"], 1), os_["nodes"][1] / max(os_["shadow_rays"], 1)]
             tri = [os_["tris"][0] / max(os_["closest_rays"], 1), os_["tris"][1] / max(os_["shadow_rays"], 1)]
             sph = [os_["spheres"][0] / max(os_["closest_rays"], 1), os_["spheres"][1] / max(os_["shadow_rays"], 1)]
-            own_bc = 128.0 * rec[0] + 48.0 * tri[0] + 16.0 * sph[0] + 64.0
-            own_ach = ext_rays * own_bc / (ext_ms * 1e-3) / 1e9
-            roof["own_tree"] = {"records_per_ray": rec, "tris_per_ray": tri, "bytes_per_ray_closest": own_bc,
-                                "achieved": own_ach, "frac": own_ach / peak,
-                                "note": "requested bytes of the shipped kernel (cache hits included), same launch times"}
+            own_bc = 128.0 * rec[0] + 48.0 * tri[0] + 16.0 * sph[0]
+            own_bs = 128.0 * rec[1] + 48.0 * tri[1] + 16.0 * sph[1]
+            ach = ext_rays * own_bc / (ext_ms * 1e-3) / 1e9
+            cp = cache_peaks() if world == 1 else None
+            roof.update({"records_per_ray": rec, "tris_per_ray": tri, "spheres_per_ray": sph,
+                         "bytes_per_ray_closest": own_bc, "bytes_per_ray_shadow": own_bs,
+                         "algorithmic_bytes_per_launch": ext_rays * own_bc / max(ext_launches, 1),
+                         "achieved": ach, "unit": "GB/s",
+                         "shadow_achieved": sh_rays * own_bs / max(sh_ms * 1e-3, 1e-12) / 1e9})
+            if cp:
+                # the scene (records + slots) is far below L2 size; the part of it a block keeps in its L1 is served at the
+                # 64 KB figure, the rest at the L2 figure: the L1-resident figure is the ceiling of this access pattern
+                l1, l2 = cp["divergent_64KB"], cp["divergent_4MB"]
+                roof.update({"bound": "l1", "peak": l1, "frac": ach / l1, "frac_of_l2_resident_peak": ach / l2,
+                             "peak_source": "measured live on this GPU by tools/peaks_cache: divergent 4 x 256-bit loads per 128-byte record, one "
+                                            "record per lane, table resident in L1 (64 KB); l2 = same pattern over a 4 MB table",
+                             "cache_peaks": cp})
+            else:
+                roof.update({"bound": "l1", "peak": None, "frac": None,
+                             "peak_source": "tools/peaks_cache not run (N > 1 or binary missing): see the N = 1 line"})
+        else:
+            roof.update({"bound": "hbm", "achieved": hbm_def["achieved"], "peak": hbm_peak, "unit": "GB/s", "frac": hbm_def["frac"], "peak_source": how})
+        roof["traffic"] = traffic.get("extend_dram_bytes_per_launch")
+        if traffic.get("whole_step_dram_bytes"):
+            rays_step = traffic.get("whole_step_rays") or (rays_all / args.steps)
+            roof["dram"] = {"bytes_per_ray_whole_step": traffic["whole_step_dram_bytes"] / rays_step, "budget_bytes_per_ray": 64,
+                            "whole_step_dram_bytes": traffic["whole_step_dram_bytes"],
+                            "whole_step_gbs": traffic["whole_step_dram_bytes"] / (t_all / args.steps * 1e-3) / 1e9 if world == 1 else None,
+                            "hbm_peak": hbm_peak, "source": traffic.get("file"),
+                            "note": "dram__bytes_read.sum + dram__bytes_write.sum of every launch of one step (ncu --set full, committed capture)"}
         if world == 1 and not args.no_cpu_baseline:
             cpu = cpu_baseline(desc)
+
+    # ---- the id-exact bounce-0 kernel against f32 primitive tests, primary rays alone (same scene, max_depth 0)
+    if rank == 0 and world == 1 and prec == FAST_F32 and not args.no_primary:
+        d0 = scenes.WORKLOADS[args.workload]()
+        d0.max_depth = 0
+        s0 = Scene(d0, bvh=bvh, device=local_rank)
+        i0 = CudaPixelIntegrator(s0, precision=FAST_F32, seed=1)
+        primary = {"workload": "same scene and frame, max_depth 0: every closest-hit ray is a primary ray", "spp": 16}
+        for label, flags in (("id_exact_hybrid", 0), ("f32_primitive_tests", _lib.SAMPLE_F32_PRIMARY)):
+            best = None
+            for _ in range(3):
+                i0.SampleF32(16, flags=flags)
+                if best is None or i0.stats["ms_extend"] < best["ms_extend"]:
+                    best = dict(i0.stats)
+            primary[label] = {"primary_mrays_s": best["closest_rays"] / best["ms_extend"] / 1e3, "ms_extend": best["ms_extend"],
+                              "fixups": best["hybrid_fixups"]}
+        primary["note"] = ("bounce 0 of every frame in this file uses the id-exact kernel (mfx_hybrid.cu): primary-hit ids and t equal the "
+                           "oracle's bit for bit (tests/test_gpu_parity.py::test_fast_primary_is_bit_exact)")
+        s0.close()
+
+    # ---- BASELINE configs[2..4] at their stated size through the same path (device timed, one full-size step each)
+    configs = None
+    if not args.no_configs and prec == FAST_F32:
+        configs = []
+        for name, spp in (("c3_renault", 256), ("c4_spheres", 128), ("c5_soup", 64)):
+            cdesc = scenes.WORKLOADS[name]()
+            t0 = time.perf_counter()
+            cbvh = Bvh.Build(cdesc.prims)
+            t_bvh = time.perf_counter() - t0
+            csc = Scene(cdesc, bvh=cbvh, device=local_rank)
+            csh = mdist.ShardedPixelIntegrator(csc, rank, world, precision=prec, seed=1, stripe=mdist.STRIPE)
+            t0 = time.perf_counter()
+            csh.Sample(1)                                        # builds the layouts (own SAH tree, hybrid tables), untimed
+            t_first = time.perf_counter() - t0
+            sync_all()
+            ms, st = timed_step(csh, spp)
+            r_all, t_cfg = aggregate(st["closest_rays"] + st["shadow_rays"], ms)
+            row = {"config": name, "prims": int(len(cdesc.prims)), "size": [cdesc.width, cdesc.height], "spp": spp, "max_depth": cdesc.max_depth,
+                   "integrator": ["PathIntegrator", "NewPathTracer", "GetColor"][cdesc.integrator], "n_gpus": world,
+                   "rays": r_all, "ms": t_cfg, "mrays_s": r_all / t_cfg / 1e3, "spp_per_s": spp / (t_cfg * 1e-3),
+                   "rank0": {"extend_mrays_s": st["closest_rays"] / max(st["ms_extend"], 1e-9) / 1e3,
+                             "shadow_mrays_s": st["shadow_rays"] / max(st["ms_shadow"], 1e-9) / 1e3, "launches": st["launches"],
+                             "hybrid_fixups": st["hybrid_fixups"]},
+                   "host_bvh_build_s": t_bvh, "first_call_s": t_first, "scene_bytes": csc.device_bytes() if rank == 0 else None}
+            if name == "c5_soup" and rank == 0:
+                tr = load_traffic().get("c5")
+                if tr:      # the one config whose scene leaves L2: HBM roofline from the committed ncu capture
+                    row["hbm"] = tr
+            configs.append(row)
+            del csh
+            csc.close()
+            sync_all()
 
     if rank == 0:
         launches = sum(s["launches"] for s in stats)
@@ -349,11 +458,14 @@ def main():
                 "ms_per_step": t_all / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                 "dtype": "f32" if prec == FAST_F32 else "f64", "data": "synthetic",
                 "config": {"workload": WORKLOAD if args.workload == "c2_spot" else args.workload, "spp": args.spp,
-                           "parallelism": f"tiles{mdist.TILE}x{mdist.TILE} interleaved over {world} GPU(s), scene replicated, 1 NCCL sum-reduce per frame",
+                           "parallelism": f"column stripes of {mdist.STRIPE} px interleaved over {world} GPU(s), scene replicated, "
+                                          "1 NCCL gather of the owned stripes per frame" if world > 1 else "1 GPU, whole frame",
                            "l2": "256 MB buffer written between timed iterations (L2 flush); path state (184 B/path, one wave = pixels x spp up to 128 Mi paths = 24.6 GB) exceeds L2, scene is L2 resident by nature",
+                           "primary_rays": "id-exact (hybrid kernel: f32 boxes, f64 primitive tests)" if prec == FAST_F32 else "exact f64",
                            "rays_per_step": rays_all / args.steps, "paths_per_step": desc.width * desc.height * args.spp},
                 "spp_per_s": args.spp * args.steps / (t_all * 1e-3), "wall_s_timed_region": wall,
-                "e2e": e2e, "gpu_launches": int(launches), "clocks": clk, "roofline": roof, "cpu_baseline": cpu}
+                "e2e": e2e, "gpu_launches": int(launches), "clocks": clk, "roofline": roof, "cpu_baseline": cpu,
+                "primary": primary, "configs": configs}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

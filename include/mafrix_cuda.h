@@ -166,6 +166,13 @@ typedef struct {
  * of the library's own tree, f64 primitive tests, mfx_hybrid.cu.  With this bit bounce 0 uses f32 primitive tests like
  * the deeper bounces (primary ids then differ from the reference on <= 2e-4 of the rays). */
 #define MFX_SAMPLE_F32_PRIMARY 8
+/* Multi-GPU ownership by COLUMN STRIPES instead of square tiles: columns [c*tile_size, (c+1)*tile_size) belong to rank
+ * c % world.  In the reference's x-major Color[w,h] a stripe is one contiguous block, ownership is arithmetic (no pixel
+ * table is built or uploaded).  mfx_multi_sample uses it. */
+#define MFX_SAMPLE_STRIPES 16
+/* With world > 1: leave the pixels of the other ranks in the output untouched instead of zeroing them (the caller
+ * assembles the frame from the owned pixels only). */
+#define MFX_SAMPLE_NO_CLEAR 32
 
 typedef struct {
     uint64_t closest_rays;       /* closest-hit queries traced by the last Sample call             */
@@ -213,6 +220,11 @@ MFX_API int mfx_bvh_build(const MfxPrim *prims, int32_t n, MfxBvhNode *nodes_out
 MFX_API int mfx_tile_map(int32_t width, int32_t height, int32_t tile_size, int32_t rank, int32_t world,
                          int32_t *pixels_out, int32_t *n_out);
 
+/* Column-stripe ownership (MFX_SAMPLE_STRIPES) as a table, in the order the kernels enumerate it: this rank's stripes one
+ * after the other, row-major inside a stripe.  pixels_out may be NULL to query the count. */
+MFX_API int mfx_stripe_map(int32_t width, int32_t height, int32_t stripe, int32_t rank, int32_t world,
+                           int32_t *pixels_out, int32_t *n_out);
+
 /* ---- scene: replaces `new Scene(state)`'s Bvh + PathIntegrator + PixelIntegrator ------------ */
 MFX_API int mfx_scene_create(const MfxSceneDesc *desc, MfxScene **out);
 MFX_API int mfx_scene_destroy(MfxScene *scene);
@@ -242,12 +254,38 @@ MFX_API int mfx_pixel_integrator_sample(MfxScene *scene, const MfxSampleParams *
  * mean over spp, zero outside this rank's tiles (so a sum-reduce over ranks assembles the frame). */
 MFX_API int mfx_pixel_integrator_sample_device(MfxScene *scene, const MfxSampleParams *params,
                                                void *d_rgba_f32);
+/* Same, result left on the device in the reference's own layout: d_color_wh = Color[w,h], width*height*4 doubles,
+ * x-major.  With MFX_SAMPLE_STRIPES a rank's share is a set of contiguous blocks: what a multi-process host gathers. */
+MFX_API int mfx_pixel_integrator_sample_device_color(MfxScene *scene, const MfxSampleParams *params,
+                                                     void *d_color_wh_f64);
 /* Same, host output as float RGBA row-major (PFM/PNG writers). */
 MFX_API int mfx_pixel_integrator_sample_f32(MfxScene *scene, const MfxSampleParams *params, float *rgba);
 MFX_API int mfx_get_stats(const MfxScene *scene, MfxStats *out);
 /* Pin (cudaHostRegister) / unpin a caller buffer that will receive textures repeatedly. */
 MFX_API int mfx_host_register(void *ptr, uint64_t bytes);
 MFX_API int mfx_host_unregister(void *ptr);
+
+/* ---- multi-GPU behind the same seam ------------------------------------------------------------
+ * The reference host is one process with one render thread (Film.fs:67-73 -> Scene.Render -> Integrators.fs:160-172);
+ * its only parallelism is Array.Parallel.iter over pixels (:164).  mfx_multi_* is that loop over GPUs: the scene is
+ * replicated on every listed device, one worker thread per device lives inside the library, and the caller's single
+ * thread gets IPixelIntegrator.Sample back with the whole frame.  Ownership: column stripes of 16 pixels, stripe c ->
+ * devices[c % n]; every device writes its stripes straight into the caller's texture over its own PCIe link (no
+ * collective: the path has no exchange step).  The frame is bit-identical to the one-GPU frame. */
+typedef struct MfxMulti MfxMulti;
+/* devices == NULL: the first n_devices CUDA devices (n_devices <= 0: all of them).  desc->nodes == NULL: Bvh.Build runs
+ * once on the host and every replica takes that tree. */
+MFX_API int mfx_multi_create(const MfxSceneDesc *desc, const int32_t *devices, int32_t n_devices, MfxMulti **out);
+MFX_API int mfx_multi_destroy(MfxMulti *multi);
+MFX_API int mfx_multi_device_count(const MfxMulti *multi, int32_t *n_out);
+/* IPixelIntegrator.Sample over all devices -> Color[w,h] (pin it once with mfx_host_register: direct DMA from every
+ * device).  params->rank / world / tile_size are ignored (the library shards), every other field as in
+ * mfx_pixel_integrator_sample. */
+MFX_API int mfx_multi_sample(MfxMulti *multi, const MfxSampleParams *params, double *texture);
+/* Same, float RGBA row-major. */
+MFX_API int mfx_multi_sample_f32(MfxMulti *multi, const MfxSampleParams *params, float *rgba);
+/* total: rays / paths / launches summed over the devices, ms_* of the slowest one; per_device: n entries or NULL. */
+MFX_API int mfx_multi_get_stats(const MfxMulti *multi, MfxStats *total, MfxStats *per_device);
 
 /* ---- Film (Film.fs:13-34): progressive accumulation, state kept in HBM ----------------------- */
 /* Lifetime: a film borrows its scene's stream -- destroy every film BEFORE mfx_scene_destroy of its scene. */

@@ -7,17 +7,17 @@ Only what the hot path needs lives here:
   scene.py     PinholeCamera / Bvh / Scene / CudaPixelIntegrator / Film -- the reference's names
   scenes.py    the BASELINE workload builders (C1..C5) and the sphere sample's RandomScene
   imageio.py   headless PFM / PNG writers (replace the reference's ImGui window)
-  dist.py      tile sharding over ranks + the NCCL reduce of the accumulation buffers
+  dist.py      one-process-per-GPU sharding (torchrun): stripes per rank + the NCCL gather of the owned stripes
 There is no CPU fallback: without the CUDA library or a GPU every compute call raises.
 """
 from .scene import (PRIM_DTYPE, MATERIAL_DTYPE, NODE_DTYPE, TRIANGLE, RECT, SPHERE, LAMBERT, METAL,
                     SPECTRANS, DIELECTRIC, LAMBERT_CHECKER, LAMBERT_NOISE, PATH_INTEGRATOR, NEW_PATH_TRACER,
                     SKY_TRACER, EXACT_F64, FAST_F32,
                     PinholeCamera, RayTraceCamera, SkyTracer, AreaLight, SceneDesc, Bvh, Scene, CudaPixelIntegrator,
-                    Film, MafrixError)
+                    MultiGpuPixelIntegrator, Film, MafrixError)
 
 __all__ = ["PRIM_DTYPE", "MATERIAL_DTYPE", "NODE_DTYPE", "TRIANGLE", "RECT", "SPHERE", "LAMBERT",
            "METAL", "SPECTRANS", "DIELECTRIC", "LAMBERT_CHECKER", "LAMBERT_NOISE", "PATH_INTEGRATOR",
            "NEW_PATH_TRACER", "SKY_TRACER", "EXACT_F64", "FAST_F32",
-           "PinholeCamera", "RayTraceCamera", "SkyTracer", "AreaLight", "SceneDesc", "Bvh", "Scene", "CudaPixelIntegrator", "Film",
-           "MafrixError"]
+           "PinholeCamera", "RayTraceCamera", "SkyTracer", "AreaLight", "SceneDesc", "Bvh", "Scene", "CudaPixelIntegrator",
+           "MultiGpuPixelIntegrator", "Film", "MafrixError"]

@@ -63,6 +63,8 @@ SAMPLE_COUNT_TRAVERSAL = 1
 SAMPLE_REFERENCE_STREAM = 2
 SAMPLE_COUNT_OWN_TREE = 4
 SAMPLE_F32_PRIMARY = 8
+SAMPLE_STRIPES = 16
+SAMPLE_NO_CLEAR = 32
 
 # every symbol include/mafrix_cuda.h declares: name -> (restype, argtypes)
 _P = C.c_void_p
@@ -75,6 +77,7 @@ SYMBOLS = {
     "mfx_camera_lens": (C.c_int, [_P, _P, _P, C.c_double, C.c_double, C.c_double, C.c_double, C.POINTER(MfxLensCamera)]),
     "mfx_bvh_build": (C.c_int, [_P, C.c_int32, _P, C.c_int32, _P]),
     "mfx_tile_map": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, C.POINTER(C.c_int32)]),
+    "mfx_stripe_map": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, C.POINTER(C.c_int32)]),
     "mfx_scene_create": (C.c_int, [C.POINTER(MfxSceneDesc), C.POINTER(_P)]),
     "mfx_scene_destroy": (C.c_int, [_P]),
     "mfx_scene_get_bvh": (C.c_int, [_P, _P, _P]),
@@ -83,10 +86,17 @@ SYMBOLS = {
     "mfx_trace_primary": (C.c_int, [_P, C.c_int32, C.c_int64, _P, _P, _P]),
     "mfx_pixel_integrator_sample": (C.c_int, [_P, C.POINTER(MfxSampleParams), _P]),
     "mfx_pixel_integrator_sample_device": (C.c_int, [_P, C.POINTER(MfxSampleParams), _P]),
+    "mfx_pixel_integrator_sample_device_color": (C.c_int, [_P, C.POINTER(MfxSampleParams), _P]),
     "mfx_pixel_integrator_sample_f32": (C.c_int, [_P, C.POINTER(MfxSampleParams), _P]),
     "mfx_get_stats": (C.c_int, [_P, C.POINTER(MfxStats)]),
     "mfx_host_register": (C.c_int, [_P, C.c_uint64]),
     "mfx_host_unregister": (C.c_int, [_P]),
+    "mfx_multi_create": (C.c_int, [C.POINTER(MfxSceneDesc), _P, C.c_int32, C.POINTER(_P)]),
+    "mfx_multi_destroy": (C.c_int, [_P]),
+    "mfx_multi_device_count": (C.c_int, [_P, C.POINTER(C.c_int32)]),
+    "mfx_multi_sample": (C.c_int, [_P, C.POINTER(MfxSampleParams), _P]),
+    "mfx_multi_sample_f32": (C.c_int, [_P, C.POINTER(MfxSampleParams), _P]),
+    "mfx_multi_get_stats": (C.c_int, [_P, C.POINTER(MfxStats), _P]),
     "mfx_film_create": (C.c_int, [_P, C.POINTER(_P)]),
     "mfx_film_destroy": (C.c_int, [_P]),
     "mfx_film_reset": (C.c_int, [_P]),

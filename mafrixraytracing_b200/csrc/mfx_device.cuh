@@ -68,18 +68,36 @@ __device__ __forceinline__ int warp_append(bool pred, int *counter)
 
 __device__ __forceinline__ void pixel_of(const TileMap &tm, int width, int pl, int &pix, int &px, int &py)
 {
+    if (tm.stripe > 0) {
+        // every owned stripe but possibly the last one is full, so the local stripe index is a plain division
+        const int per = tm.stripe * tm.height;
+        const int ls = pl / per, rem = pl - ls * per;
+        const int x0 = (ls * tm.world + tm.rank) * tm.stripe;
+        const int wl = min(tm.stripe, width - x0);
+        py = rem / wl;
+        px = x0 + (rem - py * wl);
+        pix = py * width + px;
+        return;
+    }
     pix = tm.pix ? tm.pix[pl] : pl;
     py = pix / width;
     px = pix - py * width;
 }
 
-// Persistent grids: SM count x resident blocks per SM for this kernel (cached per kernel).
+// Persistent grids: SM count x resident blocks per SM for this kernel (cached per kernel, dynamic shared memory and
+// device; guarded: distinct handles may launch from distinct host threads, one per GPU).
 #include <map>
+#include <mutex>
+#include <tuple>
 template <typename K>
 static inline int persistent_blocks(K kernel, int threads, int sms, size_t dyn_smem = 0)
 {
-    static std::map<std::pair<const void *, size_t>, int> cache;
-    const std::pair<const void *, size_t> key((const void *)kernel, dyn_smem);
+    static std::mutex mu;
+    static std::map<std::tuple<const void *, size_t, int>, int> cache;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const std::tuple<const void *, size_t, int> key((const void *)kernel, dyn_smem, dev);
+    std::lock_guard<std::mutex> g(mu);
     auto it = cache.find(key);
     if (it == cache.end()) {
         int occ = 0;

@@ -388,7 +388,7 @@ __global__ void __launch_bounds__(128) k_x_primary(SceneX sc, long long n, const
 __global__ void __launch_bounds__(256) k_finalize(const double *pixsum, int width, int height, int spp, TileMap tm,
                                                   double *color_wh, float4 *rgba_f32)
 {
-    const int n = tm.pix ? tm.n_pix : width * height;
+    const int n = tm.n_pix;
     const double dn = (double)spp;
     for (int pl = blockIdx.x * blockDim.x + threadIdx.x; pl < n; pl += gridDim.x * blockDim.x) {
         int pix, px, py;

@@ -955,13 +955,15 @@ __global__ void __launch_bounds__(256) k_f_resolve(SceneF sc, WaveF w, TileMap t
     for (int pl = blockIdx.x * blockDim.x + threadIdx.x; pl < npix; pl += gridDim.x * blockDim.x) {
         int pix, px, py;
         pixel_of(tm, sc.width, pix0 + pl, pix, px, py);
-        float r = 0.f, g = 0.f, b = 0.f;
+        // f64 running sums in absolute sample order: the frame does not depend on how spp was cut into waves
+        // (world size, MFX_WAVE_PATHS, the out-of-memory halving)
+        double *p = pixsum + 4 * (size_t)pix;
+        double r = p[0], g = p[1], b = p[2];
         for (int sl = 0; sl < S; sl++) {
             const float4 a = w.rad[(size_t)sl * npix + pl];
-            r += a.x; g += a.y; b += a.z;
+            r += (double)a.x; g += (double)a.y; b += (double)a.z;
         }
-        double *p = pixsum + 4 * (size_t)pix;
-        p[0] += (double)r; p[1] += (double)g; p[2] += (double)b; p[3] = 1.0;
+        p[0] = r; p[1] = g; p[2] = b; p[3] = 1.0;
     }
 }
 

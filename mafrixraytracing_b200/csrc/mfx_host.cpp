@@ -18,6 +18,7 @@
 #include <cstring>
 #include <future>
 #include <map>
+#include <memory>
 #include <string>
 #include <tuple>
 #include <vector>
@@ -74,10 +75,18 @@ extern "C" int mfx_init(int device)
     return MFX_OK;
 }
 
+// mfx_scene_create runs on the device the calling thread chose with mfx_init (default 0) ...
 static int ensure_device()
 {
     if (g_device >= 0) { CUDA_TRY(cudaSetDevice(g_device)); return MFX_OK; }
     return mfx_init(0);
+}
+// ... every other entry point takes a handle and runs on the device THAT HANDLE lives on, whichever thread calls
+// (a .NET thread-pool or render-callback thread never called mfx_init: its thread-local default must not win).
+static int bind_device(int device)
+{
+    CUDA_TRY(cudaSetDevice(device));
+    return MFX_OK;
 }
 
 // ------------------------------------------------------------------ host math (f64, reference order)
@@ -155,6 +164,7 @@ struct MfxScene {
     std::vector<double> perlin_rf;           // MFX_SKY_TRACER: 256 or empty
     std::vector<int32_t> perlin_perm;        //                 768 or empty
     int width = 0, height = 0, max_depth = 0, integrator = 0;
+    bool in_process_replica = false;         // one of mfx_multi_create's replicas: the workers share one process and one tree cache
     int host_share = 1;                      // ranks known to share this host (MfxSampleParams.world): the tree builder
                                              // forks over hardware threads / host_share
 
@@ -185,8 +195,15 @@ struct MfxScene {
 static std::mutex g_pool_mu;
 static std::multimap<std::pair<int, size_t>, void *> g_pool;
 static size_t g_pool_bytes = 0;
-static const size_t POOL_MIN = 1u << 20, POOL_MAX = (size_t)32 << 30;    // holds one full 128 Mi-path wave (24.6 GB)
+static const size_t POOL_MIN = 1u << 20;
+static size_t pool_max()      // a third of the device (B200: 60 GB -- holds one full 128 Mi-path wave with its hybrid buffers), at most 64 GB
+{
+    static size_t v = 0;
+    if (!v) { size_t fr = 0, tot = 0; v = (cudaMemGetInfo(&fr, &tot) == cudaSuccess && tot) ? std::min(tot / 3, (size_t)64 << 30) : ((size_t)32 << 30); }
+    return v;
+}
 
+static void pool_trim(int device);
 static int dev_alloc(MfxScene *s, void **p, size_t bytes)
 {
     bytes = bytes ? bytes : 16;
@@ -199,7 +216,16 @@ static int dev_alloc(MfxScene *s, void **p, size_t bytes)
             return MFX_OK;
         }
     }
-    CUDA_TRY(cudaMalloc(p, bytes));
+    cudaError_t e = cudaMalloc(p, bytes);
+    if (e == cudaErrorMemoryAllocation) {       // memory parked in the pool is not "in use": give it back and retry once
+        cudaGetLastError();
+        pool_trim(s->device);
+        e = cudaMalloc(p, bytes);
+    }
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(e == cudaErrorMemoryAllocation ? MFX_ERR_OUT_OF_MEMORY : MFX_ERR_CUDA, "cudaMalloc(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
+    }
     s->allocs.push_back({ *p, bytes });
     return MFX_OK;
 }
@@ -208,7 +234,7 @@ static void dev_release(int device, void *p, size_t bytes)
 {
     if (bytes >= POOL_MIN) {
         std::lock_guard<std::mutex> g(g_pool_mu);
-        if (g_pool_bytes + bytes <= POOL_MAX) { g_pool.insert({ { device, bytes }, p }); g_pool_bytes += bytes; return; }
+        if (g_pool_bytes + bytes <= pool_max()) { g_pool.insert({ { device, bytes }, p }); g_pool_bytes += bytes; return; }
     }
     cudaFree(p);
 }
@@ -255,6 +281,32 @@ long mfx_env_long(const char *name, long dflt)
     return atol(v);
 }
 
+// A caller-supplied Bvh (nodes + indices) is indexed by the flatteners and by the kernels: reject anything that is not
+// a permutation / a well-formed heap-indexed tree instead of reading out of bounds.
+static int validate_tree(const std::vector<MfxBvhNode> &nodes, const std::vector<int32_t> &indices)
+{
+    const int n = (int)indices.size();
+    std::vector<char> seen((size_t)n, 0);
+    for (int i = 0; i < n; i++) {
+        const int v = indices[i];
+        if (v < 0 || v >= n || seen[v]) return fail(MFX_ERR_INVALID_ARGUMENT, "supplied tree: indices[%d] = %d is not part of a permutation of 0..%d", i, v, n - 1);
+        seen[v] = 1;
+    }
+    std::vector<int> todo{ 0 };
+    long covered = 0;
+    while (!todo.empty()) {
+        const int i = todo.back(); todo.pop_back();
+        const MfxBvhNode &nd = nodes[i];
+        if (nd.count <= 0 || nd.first < 0 || (long)nd.first + nd.count > n)
+            return fail(MFX_ERR_INVALID_ARGUMENT, "supplied tree: node %d covers [%d, %d + %d) outside 0..%d", i, nd.first, nd.first, nd.count, n);
+        if (nd.count <= MFX_LEAF_NODE_COUNT) { covered += nd.count; continue; }
+        if ((size_t)(2 * (long)i + 2) >= nodes.size()) return fail(MFX_ERR_INVALID_ARGUMENT, "supplied tree: interior node %d has no child slots", i);
+        todo.push_back(2 * i + 1); todo.push_back(2 * i + 2);
+    }
+    if (covered != n) return fail(MFX_ERR_INVALID_ARGUMENT, "supplied tree: its leaves cover %ld of %d primitives", covered, n);
+    return MFX_OK;
+}
+
 extern "C" int mfx_scene_create(const MfxSceneDesc *d, MfxScene **out)
 {
     if (!d || !out) return fail(MFX_ERR_INVALID_ARGUMENT, "mfx_scene_create: null argument");
@@ -286,6 +338,12 @@ extern "C" int mfx_scene_create(const MfxSceneDesc *d, MfxScene **out)
         if (d->prims[i].kind < 0 || d->prims[i].kind > 2) return fail(MFX_ERR_INVALID_ARGUMENT, "primitive %d: unknown kind %d", i, d->prims[i].kind);
         if (d->prims[i].material < 0 || d->prims[i].material >= d->n_materials)
             return fail(MFX_ERR_INVALID_ARGUMENT, "primitive %d: material %d outside the table of %d", i, d->prims[i].material, d->n_materials);
+    }
+    const int n_slots_in = 2 * d->n_prims - 1;
+    if (d->nodes) {     // argument errors come before the device check (and need no GPU to be reported)
+        if (d->n_node_slots != n_slots_in || !d->indices)
+            return fail(MFX_ERR_INVALID_ARGUMENT, "supplied tree needs 2n-1 = %d node slots and an index array", n_slots_in);
+        MFX_TRY(validate_tree(std::vector<MfxBvhNode>(d->nodes, d->nodes + n_slots_in), std::vector<int32_t>(d->indices, d->indices + d->n_prims)));
     }
     MFX_TRY(ensure_device());
     MfxScene *s = new MfxScene();
@@ -649,14 +707,46 @@ static int flatten_fast_ref(MfxScene *s)
 }
 
 // ---- flatten: fast layout over the library's own tree (mfx_build.cpp: binned SAH, collapsed to four children per record)
-static int flatten_fast(MfxScene *s)
+// The host half (slots, bounds, tree build, reordering) depends on the primitives alone, so it is cached by content:
+// the replicas of a multi-GPU scene (mfx_multi_create) and a host that re-creates its Scene every frame (Scene.fs
+// builds a new Bvh per `new Scene(state)`) pay for it once.  Two independent 64-bit hashes over the primitive bytes
+// key the cache; a handful of entries, bounded in bytes, least recently used goes first.
+struct OwnTreeHost {
+    std::vector<QuadF> quads;
+    std::vector<SlotF> slots;
+    std::vector<float4> nrm;
+    std::vector<int> slot_prim;         // own-tree fast slot -> primitive index, bit 30 = second triangle of a Rect
+    int depth = 0, has_big = 0;
+    size_t bytes() const { return quads.size() * sizeof(QuadF) + slots.size() * sizeof(SlotF) + nrm.size() * 16 + slot_prim.size() * 4; }
+};
+struct TreeKey {
+    uint64_t h1, h2; size_t n; long max_leaf, trav;
+    bool operator==(const TreeKey &o) const { return h1 == o.h1 && h2 == o.h2 && n == o.n && max_leaf == o.max_leaf && trav == o.trav; }
+};
+static std::mutex g_tree_mu;
+static std::vector<std::pair<TreeKey, std::shared_ptr<OwnTreeHost>>> g_tree_cache;    // most recently used last
+static const size_t TREE_CACHE_BYTES = (size_t)6 << 30, TREE_CACHE_ENTRIES = 8;
+
+static TreeKey tree_key(const std::vector<MfxPrim> &prims, long max_leaf, long trav)
 {
-    if (s->f_ready) return MFX_OK;
+    const uint64_t *w = reinterpret_cast<const uint64_t *>(prims.data());
+    const size_t nw = prims.size() * sizeof(MfxPrim) / 8;
+    uint64_t a = 0x9E3779B97F4A7C15ull, b = 0xC2B2AE3D27D4EB4Full;
+    for (size_t i = 0; i < nw; i++) {
+        a = (a ^ w[i]) * 0x100000001B3ull; a ^= a >> 29;
+        b = (b + w[i]) * 0xFF51AFD7ED558CCDull; b ^= b >> 32;
+    }
+    return TreeKey{ a, b, prims.size(), max_leaf, trav };
+}
+
+static std::shared_ptr<OwnTreeHost> build_own_tree_host(MfxScene *s, long max_leaf, long trav)
+{
     const auto t_begin = std::chrono::steady_clock::now();
     auto lap = [&](const char *what) {
         if (env_long("MFX_DEBUG", 0))
             fprintf(stderr, "[mfx] flatten_fast %-10s %8.2f ms\n", what, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count());
     };
+    auto out = std::make_shared<OwnTreeHost>();
     const int n = (int)s->prims.size();
     std::vector<SlotF> raw; std::vector<float4> raw_nrm;
     int has_big = 0;
@@ -684,7 +774,6 @@ static int flatten_fast(MfxScene *s)
         for (int a = 0; a < 3; a++) { blo[(size_t)k * 3 + a] = round_down(lo[a]); bhi[(size_t)k * 3 + a] = round_up(hi[a]); }
     }
     lap("slots");
-    if ((size_t)ns > ((size_t)1 << 28)) return fail(MFX_ERR_INVALID_ARGUMENT, "too many fast slots (%d)", ns);
     MfxOwnTree tree;
     // The builder forks its top levels over threads (identical tree for any fork depth).  One process per GPU means
     // `world` builders on one host at the same time: eight of them forking 32 ways each on a 16-thread host take longer
@@ -692,31 +781,62 @@ static int flatten_fast(MfxScene *s)
     int par_depth = 0;
     for (unsigned share = std::max(1u, std::thread::hardware_concurrency()) / (unsigned)std::max(1, s->host_share); share > 1 && par_depth < 5; share >>= 1) par_depth++;
     par_depth = (int)env_long("MFX_BVH_BUILD_PAR_DEPTH", par_depth);
-    mfx_build_own_tree(blo.data(), bhi.data(), ns, (int)std::min(7L, std::max(1L, env_long("MFX_SAH_MAX_LEAF", 4))),
-                       (float)env_long("MFX_SAH_TRAV_COST_PCT", 100) * 0.01f, par_depth, tree);
+    mfx_build_own_tree(blo.data(), bhi.data(), ns, (int)max_leaf, (float)trav * 0.01f, par_depth, tree);
     lap("own tree");
-    const std::vector<QuadF> &quads = tree.quads;
     const std::vector<int> &order = tree.order;
-    const int own_depth = tree.depth;
-    std::vector<SlotF> slots(ns); std::vector<float4> nrm(ns);
-    for (int k = 0; k < ns; k++) { slots[k] = raw[order[k]]; nrm[k] = raw_nrm[order[k]]; }
-    s->f_slot_prim.resize(ns);
+    out->depth = tree.depth; out->has_big = has_big;
+    out->slots.resize(ns); out->nrm.resize(ns); out->slot_prim.resize(ns);
     for (int k = 0; k < ns; k++) {      // bit 30: the second triangle of a Rect (raw slots of one primitive are adjacent)
         const int raw_k = order[k];
-        s->f_slot_prim[k] = owner[raw_k] | ((raw_k > 0 && owner[raw_k - 1] == owner[raw_k]) ? (1 << 30) : 0);
+        out->slots[k] = raw[raw_k]; out->nrm[k] = raw_nrm[raw_k];
+        out->slot_prim[k] = owner[raw_k] | ((raw_k > 0 && owner[raw_k - 1] == owner[raw_k]) ? (1 << 30) : 0);
     }
+    out->quads = std::move(tree.quads);
+    lap("reorder");
+    return out;
+}
+
+static int flatten_fast(MfxScene *s)
+{
+    if (s->f_ready) return MFX_OK;
+    if (s->prims.size() > ((size_t)1 << 27)) return fail(MFX_ERR_INVALID_ARGUMENT, "too many primitives (%zu)", s->prims.size());
+    const long max_leaf = std::min(7L, std::max(1L, env_long("MFX_SAH_MAX_LEAF", 4))), trav = env_long("MFX_SAH_TRAV_COST_PCT", 100);
+    std::shared_ptr<OwnTreeHost> host;
+    {
+        // one builder at a time: the replicas of one scene arrive together, the first one builds, the others find it
+        std::lock_guard<std::mutex> g(g_tree_mu);
+        const TreeKey key = tree_key(s->prims, max_leaf, trav);
+        const bool use_cache = env_long("MFX_TREE_CACHE", 1) != 0;
+        for (size_t i = 0; use_cache && i < g_tree_cache.size(); i++)
+            if (g_tree_cache[i].first == key) {
+                host = g_tree_cache[i].second;
+                std::rotate(g_tree_cache.begin() + (long)i, g_tree_cache.begin() + (long)i + 1, g_tree_cache.end());
+                break;
+            }
+        if (!host) {
+            host = build_own_tree_host(s, max_leaf, trav);
+            if (use_cache && host->bytes() <= TREE_CACHE_BYTES) {
+                g_tree_cache.push_back({ key, host });
+                size_t total = 0;
+                for (auto &e : g_tree_cache) total += e.second->bytes();
+                while (g_tree_cache.size() > TREE_CACHE_ENTRIES || total > TREE_CACHE_BYTES) { total -= g_tree_cache.front().second->bytes(); g_tree_cache.erase(g_tree_cache.begin()); }
+            }
+        }
+    }
+    const std::vector<QuadF> &quads = host->quads;
+    const int ns = (int)host->slots.size();
+    s->f_slot_prim = host->slot_prim;
 
     SceneF &sf = s->sf;
     memset(&sf, 0, sizeof(sf));
     SlotF *dslots; float4 *dnrm; QuadF *dquads;
-    MFX_TRY(upload(s, &dquads, quads)); MFX_TRY(upload(s, &dslots, slots)); MFX_TRY(upload(s, &dnrm, nrm));
-    lap("upload");
-    s->f_bytes = quads.size() * sizeof(QuadF) + slots.size() * sizeof(SlotF) + nrm.size() * 16 + s->mats.size() * sizeof(MatF);
+    MFX_TRY(upload(s, &dquads, quads)); MFX_TRY(upload(s, &dslots, host->slots)); MFX_TRY(upload(s, &dnrm, host->nrm));
+    s->f_bytes = quads.size() * sizeof(QuadF) + host->slots.size() * sizeof(SlotF) + host->nrm.size() * 16 + s->mats.size() * sizeof(MatF);
     sf.quads = dquads; sf.slots = dslots; sf.slot_nrm = dnrm;
     sf.ref_id = nullptr;                                        // b.w already holds the caller's primitive index
     sf.root_meta = -1;
-    sf.own_tree = 1; sf.own_depth = own_depth;
-    const int need = 3 * own_depth;
+    sf.own_tree = 1; sf.own_depth = host->depth;
+    const int need = 3 * host->depth;
     sf.stack_smem = (int)std::min((long)need, std::max(1L, env_long("MFX_STACK_SMEM", 12)));
     sf.spill_threads = s->sm_count * 16 * 128;                  // most threads a persistent 128-thread grid can hold
     if (need > sf.stack_smem) {
@@ -725,7 +845,7 @@ static int flatten_fast(MfxScene *s)
     }
     MFX_TRY(fill_fast_common(s, sf));
     sf.n_slots = ns;
-    sf.has_big_sphere = has_big;
+    sf.has_big_sphere = host->has_big;
     s->f_ready = true;
     return MFX_OK;
 }
@@ -812,7 +932,7 @@ extern "C" int mfx_scene_device_bytes(const MfxScene *sc, uint64_t *exact_bytes,
 {
     if (!sc) return fail(MFX_ERR_INVALID_ARGUMENT, "null scene");
     MfxScene *s = const_cast<MfxScene *>(sc);
-    MFX_TRY(ensure_device());
+    MFX_TRY(bind_device(s->device));
     MFX_TRY(flatten_exact(s)); MFX_TRY(flatten_fast(s));
     if (exact_bytes) *exact_bytes = s->x_bytes;
     if (fast_bytes) *fast_bytes = s->f_bytes;
@@ -931,9 +1051,42 @@ extern "C" int mfx_tile_map(int32_t width, int32_t height, int32_t tile_size, in
     return MFX_OK;
 }
 
-static int get_tilemap(MfxScene *s, int tile, int rank, int world, TileMap *tm)
+// pixels of rank `rank` under column-stripe ownership (TileMap)
+static int stripe_pixels(int width, int height, int stripe, int rank, int world)
 {
+    long n = 0;
+    for (int x0 = rank * stripe; x0 < width; x0 += world * stripe) n += (long)std::min(stripe, width - x0) * height;
+    return (int)n;
+}
+
+// The stripe rule as a table (same local order as pixel_of computes on the device): for hosts and tests.
+extern "C" int mfx_stripe_map(int32_t width, int32_t height, int32_t stripe, int32_t rank, int32_t world,
+                              int32_t *pixels_out, int32_t *n_out)
+{
+    if (width <= 0 || height <= 0 || stripe <= 0 || world <= 0 || rank < 0 || rank >= world || !n_out)
+        return fail(MFX_ERR_INVALID_ARGUMENT, "mfx_stripe_map: bad arguments (w=%d h=%d stripe=%d rank=%d world=%d)", width, height, stripe, rank, world);
+    *n_out = stripe_pixels(width, height, stripe, rank, world);
+    if (pixels_out) {
+        int32_t *out = pixels_out;
+        for (int x0 = rank * stripe; x0 < width; x0 += world * stripe) {
+            const int wl = std::min(stripe, width - x0);
+            for (int y = 0; y < height; y++)
+                for (int x = x0; x < x0 + wl; x++) *out++ = y * width + x;
+        }
+    }
+    return MFX_OK;
+}
+
+static int get_tilemap(MfxScene *s, int tile, int rank, int world, bool stripes, TileMap *tm)
+{
+    memset(tm, 0, sizeof(*tm));
+    tm->height = s->height;
     if (world <= 1 || tile <= 0) { tm->pix = nullptr; tm->n_pix = s->width * s->height; return MFX_OK; }
+    if (stripes) {
+        tm->stripe = tile; tm->rank = rank; tm->world = world;
+        tm->n_pix = stripe_pixels(s->width, s->height, tile, rank, world);
+        return MFX_OK;
+    }
     auto key = std::make_tuple(tile, rank, world);
     auto it = s->tilemaps.find(key);
     if (it == s->tilemaps.end()) {
@@ -978,9 +1131,9 @@ static int run_sample(MfxScene *s, const MfxSampleParams *p, double *d_color_wh,
     if (p->precision != MFX_EXACT_F64 && p->precision != MFX_FAST_F32) return fail(MFX_ERR_INVALID_ARGUMENT, "unknown precision %d", p->precision);
     if (p->world > 1 && (p->rank < 0 || p->rank >= p->world)) return fail(MFX_ERR_INVALID_ARGUMENT, "rank %d outside world %d", p->rank, p->world);
     if (p->world > 1 && p->tile_size <= 0) return fail(MFX_ERR_INVALID_ARGUMENT, "world > 1 needs a positive tile_size");
-    MFX_TRY(ensure_device());
+    MFX_TRY(bind_device(s->device));
     const bool exact = (p->precision == MFX_EXACT_F64);
-    s->host_share = std::max(1, p->world);
+    s->host_share = s->in_process_replica ? 1 : std::max(1, p->world);
     if (exact) { MFX_TRY(flatten_exact(s)); MFX_TRY(ensure_wave_exact(s)); }
     const bool count_ref = (p->flags & MFX_SAMPLE_COUNT_TRAVERSAL) != 0;
     const bool counting = count_ref || (p->flags & MFX_SAMPLE_COUNT_OWN_TREE) != 0;
@@ -989,7 +1142,7 @@ static int run_sample(MfxScene *s, const MfxSampleParams *p, double *d_color_wh,
     if (!exact) MFX_TRY(fast_layout(s, count_ref, variant, &sfp));
     MFX_TRY(ensure_frame_buffers(s));
     TileMap tm;
-    MFX_TRY(get_tilemap(s, p->tile_size, p->rank, p->world, &tm));
+    MFX_TRY(get_tilemap(s, p->tile_size, p->rank, p->world, (p->flags & MFX_SAMPLE_STRIPES) != 0, &tm));
     if (!exact) MFX_TRY(ensure_wave_fast(s, (size_t)tm.n_pix * (size_t)p->spp));
     // bounce 0 of the throughput path is traced id-exactly (mfx_hybrid.cu) unless the caller opts out
     const bool hyb = !exact && sfp->own_tree && !counting && use_hybrid(p->flags);
@@ -1004,7 +1157,7 @@ static int run_sample(MfxScene *s, const MfxSampleParams *p, double *d_color_wh,
     CUDA_TRY(cudaMemsetAsync(s->d_pixsum, 0, 4 * npx * sizeof(double), st));
     CUDA_TRY(cudaMemsetAsync(s->d_totals, 0, 8 * sizeof(unsigned long long), st));
     CUDA_TRY(cudaMemsetAsync(s->d_ctr, 0, sizeof(TravCounters), st));
-    if (tm.pix) {   // pixels of other ranks must read as zero
+    if ((tm.pix || tm.stripe) && !(p->flags & MFX_SAMPLE_NO_CLEAR)) {   // pixels of other ranks must read as zero
         if (d_color_wh) CUDA_TRY(cudaMemsetAsync(d_color_wh, 0, 4 * npx * sizeof(double), st));
         if (d_rgba) CUDA_TRY(cudaMemsetAsync(d_rgba, 0, npx * sizeof(float4), st));
     }
@@ -1148,7 +1301,7 @@ extern "C" int mfx_pixel_integrator_sample(MfxScene *s, const MfxSampleParams *p
 {
     if (!texture) return fail(MFX_ERR_INVALID_ARGUMENT, "null texture");
     if (!s) return fail(MFX_ERR_INVALID_ARGUMENT, "null scene");
-    MFX_TRY(ensure_device()); MFX_TRY(ensure_frame_buffers(s));
+    MFX_TRY(bind_device(s->device)); MFX_TRY(ensure_frame_buffers(s));
     MFX_TRY(run_sample(s, p, s->d_color_wh, nullptr));
     return copy_out(s, texture, s->d_color_wh, (size_t)s->width * s->height * 4 * sizeof(double));
 }
@@ -1160,11 +1313,18 @@ extern "C" int mfx_pixel_integrator_sample_device(MfxScene *s, const MfxSamplePa
     return run_sample(s, p, nullptr, (float4 *)d_rgba_f32);
 }
 
+extern "C" int mfx_pixel_integrator_sample_device_color(MfxScene *s, const MfxSampleParams *p, void *d_color_wh_f64)
+{
+    if (!d_color_wh_f64) return fail(MFX_ERR_INVALID_ARGUMENT, "null device buffer");
+    if (!s) return fail(MFX_ERR_INVALID_ARGUMENT, "null scene");
+    return run_sample(s, p, (double *)d_color_wh_f64, nullptr);
+}
+
 extern "C" int mfx_pixel_integrator_sample_f32(MfxScene *s, const MfxSampleParams *p, float *rgba)
 {
     if (!rgba) return fail(MFX_ERR_INVALID_ARGUMENT, "null output");
     if (!s) return fail(MFX_ERR_INVALID_ARGUMENT, "null scene");
-    MFX_TRY(ensure_device()); MFX_TRY(ensure_frame_buffers(s));
+    MFX_TRY(bind_device(s->device)); MFX_TRY(ensure_frame_buffers(s));
     MFX_TRY(run_sample(s, p, nullptr, s->d_rgba));
     return copy_out(s, rgba, s->d_rgba, (size_t)s->width * s->height * sizeof(float4));
 }
@@ -1180,7 +1340,7 @@ extern "C" int mfx_host_register(void *ptr, uint64_t bytes)
 {
     if (!ptr || !bytes) return fail(MFX_ERR_INVALID_ARGUMENT, "null buffer");
     MFX_TRY(ensure_device());
-    CUDA_TRY(cudaHostRegister(ptr, bytes, cudaHostRegisterDefault));
+    CUDA_TRY(cudaHostRegister(ptr, bytes, cudaHostRegisterPortable));     // pinned for every device: mfx_multi_sample DMAs from all of them
     return MFX_OK;
 }
 extern "C" int mfx_host_unregister(void *ptr)
@@ -1200,16 +1360,17 @@ static int with_ray_buffers(MfxScene *s, int64_t n, const double *a, size_t a_pe
     int rc = MFX_OK;
     auto cleanup = [&]() { cudaFree(da); cudaFree(db); cudaFree(dt); cudaFree(dp); cudaFree(ds); };
 #define WRB_TRY(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { cleanup(); return fail(MFX_ERR_CUDA, "%s failed: %s", #x, cudaGetErrorString(e_)); } } while (0)
-    if (a) { WRB_TRY(cudaMalloc(&da, n * a_per * sizeof(double))); WRB_TRY(cudaMemcpy(da, a, n * a_per * sizeof(double), cudaMemcpyHostToDevice)); }
-    if (b) { WRB_TRY(cudaMalloc(&db, n * b_per * sizeof(double))); WRB_TRY(cudaMemcpy(db, b, n * b_per * sizeof(double), cudaMemcpyHostToDevice)); }
+    // every copy rides on the scene's stream (created non-blocking: the legacy default stream orders nothing against it)
+    if (a) { WRB_TRY(cudaMalloc(&da, n * a_per * sizeof(double))); WRB_TRY(cudaMemcpyAsync(da, a, n * a_per * sizeof(double), cudaMemcpyHostToDevice, s->stream)); }
+    if (b) { WRB_TRY(cudaMalloc(&db, n * b_per * sizeof(double))); WRB_TRY(cudaMemcpyAsync(db, b, n * b_per * sizeof(double), cudaMemcpyHostToDevice, s->stream)); }
     WRB_TRY(cudaMalloc(&dt, n * sizeof(double))); WRB_TRY(cudaMalloc(&dp, n * sizeof(int)));
     if (sub) WRB_TRY(cudaMalloc(&ds, n * sizeof(int)));
     launch(da, db, dp, ds, dt);
     WRB_TRY(cudaGetLastError());
+    WRB_TRY(cudaMemcpyAsync(prim, dp, n * sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+    WRB_TRY(cudaMemcpyAsync(t, dt, n * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    if (sub) WRB_TRY(cudaMemcpyAsync(sub, ds, n * sizeof(int), cudaMemcpyDeviceToHost, s->stream));
     WRB_TRY(cudaStreamSynchronize(s->stream));
-    WRB_TRY(cudaMemcpy(prim, dp, n * sizeof(int), cudaMemcpyDeviceToHost));
-    WRB_TRY(cudaMemcpy(t, dt, n * sizeof(double), cudaMemcpyDeviceToHost));
-    if (sub) WRB_TRY(cudaMemcpy(sub, ds, n * sizeof(int), cudaMemcpyDeviceToHost));
 #undef WRB_TRY
     cleanup();
     return rc;
@@ -1257,7 +1418,7 @@ extern "C" int mfx_bvh_hit(MfxScene *s, int32_t precision, int32_t any_hit, int6
 {
     if (!s || !origins || !dirs || !prim || !t) return fail(MFX_ERR_INVALID_ARGUMENT, "mfx_bvh_hit: null argument");
     if (n <= 0) return MFX_OK;
-    MFX_TRY(ensure_device());
+    MFX_TRY(bind_device(s->device));
     LaunchCfg cfg{ s->sm_count, 128, s->stream, (int)env_long("MFX_TRACE_VARIANT", -1), 0, 0, (int)env_long("MFX_HYB_VARIANT", 0) };
     if (precision == MFX_EXACT_F64) {
         MFX_TRY(flatten_exact(s));
@@ -1283,7 +1444,7 @@ extern "C" int mfx_trace_primary(MfxScene *s, int32_t precision, int64_t n, cons
     if (!s || !prim || !t) return fail(MFX_ERR_INVALID_ARGUMENT, "mfx_trace_primary: null argument");
     if (!uv && n != (int64_t)s->width * s->height) return fail(MFX_ERR_INVALID_ARGUMENT, "uv == NULL needs n == width*height");
     if (n <= 0) return MFX_OK;
-    MFX_TRY(ensure_device());
+    MFX_TRY(bind_device(s->device));
     LaunchCfg cfg{ s->sm_count, 128, s->stream, (int)env_long("MFX_TRACE_VARIANT", -1), 0, 0, (int)env_long("MFX_HYB_VARIANT", 0) };
     if (precision == MFX_EXACT_F64) {
         MFX_TRY(flatten_exact(s));
@@ -1316,12 +1477,23 @@ struct MfxFilm {
 extern "C" int mfx_film_create(MfxScene *s, MfxFilm **out)
 {
     if (!s || !out) return fail(MFX_ERR_INVALID_ARGUMENT, "null argument");
-    MFX_TRY(ensure_device());
+    MFX_TRY(bind_device(s->device));
     MfxFilm *f = new MfxFilm();
     f->scene = s;
     const size_t npx = (size_t)s->width * s->height;
-    if (cudaMalloc(&f->d_sum, 4 * npx * sizeof(double)) != cudaSuccess || cudaMalloc(&f->d_target, 4 * npx * sizeof(double)) != cudaSuccess ||
-        cudaMalloc(&f->d_rgba8, 4 * npx) != cudaSuccess) {
+    auto alloc3 = [&]() {
+        return cudaMalloc(&f->d_sum, 4 * npx * sizeof(double)) == cudaSuccess && cudaMalloc(&f->d_target, 4 * npx * sizeof(double)) == cudaSuccess &&
+               cudaMalloc(&f->d_rgba8, 4 * npx) == cudaSuccess;
+    };
+    bool ok = alloc3();
+    if (!ok) {      // memory parked in the buffer pool is not in use: give it back and retry once
+        cudaGetLastError();
+        cudaFree(f->d_sum); cudaFree(f->d_target); cudaFree(f->d_rgba8); f->d_sum = f->d_target = nullptr; f->d_rgba8 = nullptr;
+        pool_trim(s->device);
+        ok = alloc3();
+    }
+    if (!ok) {
+        cudaGetLastError();
         cudaFree(f->d_sum); cudaFree(f->d_target); cudaFree(f->d_rgba8); delete f;
         return fail(MFX_ERR_OUT_OF_MEMORY, "film allocation failed");
     }
@@ -1342,7 +1514,7 @@ extern "C" int mfx_film_destroy(MfxFilm *f)
 extern "C" int mfx_film_reset(MfxFilm *f)                      // Film.Reset, Film.fs:26-30
 {
     if (!f) return fail(MFX_ERR_INVALID_ARGUMENT, "null film");
-    MFX_TRY(ensure_device());
+    MFX_TRY(bind_device(f->scene->device));
     const size_t npx = (size_t)f->scene->width * f->scene->height;
     f->frame_count = 0.;
     CUDA_TRY(cudaMemsetAsync(f->d_sum, 0, 4 * npx * sizeof(double), f->scene->stream));
@@ -1355,7 +1527,7 @@ extern "C" int mfx_film_get_frame(MfxFilm *f, const MfxSampleParams *p, double *
 {
     if (!f || !p) return fail(MFX_ERR_INVALID_ARGUMENT, "null argument");
     MfxScene *s = f->scene;
-    MFX_TRY(ensure_device()); MFX_TRY(ensure_frame_buffers(s));
+    MFX_TRY(bind_device(f->scene->device)); MFX_TRY(ensure_frame_buffers(s));
     MFX_TRY(run_sample(s, p, s->d_color_wh, nullptr));
     f->frame_count += 1.;
     const size_t npx = (size_t)s->width * s->height;
@@ -1370,7 +1542,7 @@ extern "C" int mfx_film_post_process(MfxFilm *f, uint8_t *rgba8)   // Scene.fs:3
 {
     if (!f || !rgba8) return fail(MFX_ERR_INVALID_ARGUMENT, "null argument");
     MfxScene *s = f->scene;
-    MFX_TRY(ensure_device());
+    MFX_TRY(bind_device(f->scene->device));
     // MFX_SKY_TRACER: the sphere sample shows sqrt(c) flipped vertically (RayTracing.fs:456-460), no ACES curve
     if (s->integrator == MFX_SKY_TRACER) mfx_film_display_sky(s->stream, f->d_target, s->width, s->height, f->d_rgba8);
     else mfx_film_tonemap(s->stream, f->d_target, s->width, s->height, f->d_rgba8);
@@ -1388,7 +1560,7 @@ extern "C" int mfx_film_frame_count(const MfxFilm *f, double *out)
 extern "C" int mfx_film_export(MfxFilm *f, double *sum, double *frame_count)
 {
     if (!f || !sum || !frame_count) return fail(MFX_ERR_INVALID_ARGUMENT, "null argument");
-    MFX_TRY(ensure_device());
+    MFX_TRY(bind_device(f->scene->device));
     *frame_count = f->frame_count;
     return copy_out(f->scene, sum, f->d_sum, (size_t)f->scene->width * f->scene->height * 4 * sizeof(double));
 }
@@ -1396,7 +1568,7 @@ extern "C" int mfx_film_export(MfxFilm *f, double *sum, double *frame_count)
 extern "C" int mfx_film_import(MfxFilm *f, const double *sum, double frame_count)
 {
     if (!f || !sum || frame_count < 0.) return fail(MFX_ERR_INVALID_ARGUMENT, "bad argument");
-    MFX_TRY(ensure_device());
+    MFX_TRY(bind_device(f->scene->device));
     MfxScene *s = f->scene;
     const size_t npx = (size_t)s->width * s->height;
     CUDA_TRY(cudaMemcpyAsync(f->d_sum, sum, npx * 4 * sizeof(double), cudaMemcpyHostToDevice, s->stream));
@@ -1412,3 +1584,5 @@ extern "C" int mfx_film_import(MfxFilm *f, const double *sum, double frame_count
     }
     return MFX_OK;
 }
+
+#include "mfx_multi.inl"

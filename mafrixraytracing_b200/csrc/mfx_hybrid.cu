@@ -118,14 +118,40 @@ __device__ __noinline__ HybBest hyb_leaf(const PrimH *ph, const int *leaf_of_ref
     return best;
 }
 
-// Does the reference's walk reach the winner?  AABB.hit verbatim on its leaf box (see the header).
+// Does the reference's walk reach the winner?  AABB.hit on its leaf box (see the header) -- decided WITHOUT the six
+// divisions whenever the hit point p = o + t d sits robustly inside the box: then on every axis the slab's entry parameter
+// is below t and its exit parameter above t by far more than the rounding of `(plane - o) / d` (2^-53 relative; the
+// margin here is 1e-10 of the summed magnitudes involved), so every comparison AABB.hit makes between an entry and an exit of
+// two DIFFERENT axes (IHitable.fs:38-52 never compares an axis with itself) comes out "overlap", and tmin < tMax,
+// tmax > tMin follow from tMin < t < tMax.  One axis may be flat (an axis-aligned quad's box has no thickness: entry and
+// exit are then the SAME expression, both within rounding of t).  Anything less clear-cut -- the point within the margin
+// of a face, two flat axes, t within the margin of tMin -- runs AABB.hit verbatim.
 __device__ __noinline__ bool hyb_verify(const NodeX *nodes, const int *leaf_of_ref, D3 o, const double *dir, int ref, double tMin, double tMax, double t)
 {
     const D3 d = mk3<double>(dir[0], dir[1], dir[2]);
     if (d.x == 0. || d.y == 0. || d.z == 0.) return false;
     if (!(t < tMax)) return false;
+    const NodeX *nd = nodes + leaf_of_ref[ref & HYB_REF_MASK];
+    const double lo[3] = { nd->pmin[0], nd->pmin[1], nd->pmin[2] }, hi[3] = { nd->pmax[0], nd->pmax[1], nd->pmax[2] };
+    const double oo[3] = { o.x, o.y, o.z }, dd[3] = { d.x, d.y, d.z };
+    // S bounds every magnitude that enters the slab expressions; inside-margin 1e-10 S in space is >= 1e-10 S in t (|d| <= 1),
+    // a flat axis is pinned to 1e-13 S in space and needs |d_a| >= 1e-3, i.e. to 1e-10 S in t: below every other margin
+    double S = fabs(t) + fabs(tMin);
+#pragma unroll
+    for (int a = 0; a < 3; a++) S += fabs(oo[a]) + fabs(lo[a]) + fabs(hi[a]);
+    const double m_in = 1e-10 * S, m_flat = 1e-13 * S;
+    int flat = 0; bool clear = (t > tMin + m_in) && (t < tMax - 1e-10 * fabs(tMax));
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+        const double p = oo[a] + t * dd[a];
+        const bool inside = (p >= lo[a] + m_in) && (p <= hi[a] - m_in);
+        const bool on_flat = (hi[a] == lo[a]) && (fabs(p - lo[a]) <= m_flat) && (fabs(dd[a]) >= 1e-3);
+        flat += on_flat ? 1 : 0;
+        clear = clear && (inside || on_flat);
+    }
+    if (clear && flat <= 1) return true;
     double e;
-    return aabb_hit_x(nodes[leaf_of_ref[ref & HYB_REF_MASK]], o, d, tMin, tMax, e);
+    return aabb_hit_x(*nd, o, d, tMin, tMax, e);
 }
 
 // the ray origin: one constant for a pinhole frame (the camera), per ray otherwise

@@ -217,9 +217,17 @@ struct WaveH {
 // Traversal counters (instrumented runs only): [class][nodes,tris,spheres]
 struct TravCounters { unsigned long long v[2][3]; };
 
+// Which pixels this rank renders, and in which order (local index pl -> pixel):
+//   pix != null : table of linear pixel ids (interleaved square tiles, mfx_tile_map);
+//   stripe > 0  : COLUMN STRIPES computed arithmetically -- stripe c (columns [c*stripe, (c+1)*stripe)) belongs to rank
+//                 c % world; local order = owned stripe after owned stripe, row-major inside a stripe.  In the reference's
+//                 x-major Color[w,h] (Texture.fs:21-28) a stripe is one contiguous block, so a GPU's share of the frame
+//                 goes to the host with one strided copy and nothing has to be uploaded or reduced (mfx_multi_sample);
+//   otherwise   : identity (the whole frame).
 struct TileMap {
-    const int *pix;         // linear pixel ids (y*width+x) rendered by this rank, or nullptr = identity
+    const int *pix;
     int  n_pix;
+    int  stripe, rank, world, height;
 };
 
 // ------------------------------------------------------------------ launchers (defined in the .cu TUs)

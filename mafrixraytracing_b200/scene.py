@@ -231,6 +231,14 @@ class Scene:
             _lib.check(lib.mfx_init(int(device)))
         self.desc = desc
         self.width, self.height = int(desc.width), int(desc.height)
+        d = self._c_desc(desc, bvh)
+        h = C.c_void_p()
+        _lib.check(lib.mfx_scene_create(C.byref(d), C.byref(h)))
+        self._h = h
+        self._films = weakref.WeakSet()
+
+    def _c_desc(self, desc, bvh):
+        """MfxSceneDesc over the arrays of `desc` (kept alive by it) -- what `new Scene(state)` consumes."""
         d = _lib.MfxSceneDesc()
         d.prims = _lib.ptr(desc.prims)
         d.n_prims = len(desc.prims)
@@ -254,12 +262,10 @@ class Scene:
             self._sky.perlin_ranfloat = _lib.ptr(desc.sky.ranfloat)
             self._sky.perlin_perm = _lib.ptr(desc.sky.perm)
             d.sky = C.pointer(self._sky)
-        d.width, d.height = self.width, self.height
+        d.width, d.height = int(desc.width), int(desc.height)
         d.max_depth, d.integrator = int(desc.max_depth), int(desc.integrator)
-        h = C.c_void_p()
-        _lib.check(lib.mfx_scene_create(C.byref(d), C.byref(h)))
-        self._h = h
-        self._films = weakref.WeakSet()
+        self._bvh_keep = bvh
+        return d
 
     def close(self):
         if getattr(self, "_h", None):
@@ -357,6 +363,67 @@ class CudaPixelIntegrator:
         self._after()
 
 
+    def SampleDeviceColor(self, n, device_ptr, first_sample=0, flags=0):
+        """Leaves Color[w,h] (width*height*4 f64, x-major: the reference's Texture2D layout) in caller-owned device memory."""
+        p = self._params(n, first_sample, flags)
+        _lib.check(_lib.load().mfx_pixel_integrator_sample_device_color(self.scene._h, C.byref(p), C.c_void_p(int(device_ptr))))
+        self._after()
+
+
+class MultiGpuPixelIntegrator:
+    """IPixelIntegrator over several GPUs behind ONE host thread (mfx_multi_*): the scene is replicated on every device,
+    the library shards the frame by column stripes and every device writes its stripes straight into `texture`."""
+
+    def __init__(self, desc: SceneDesc, devices=None, n_devices=0, bvh: Bvh = None, precision=FAST_F32, seed=1):
+        self._keep = Scene.__new__(Scene)                    # borrow Scene's descriptor marshalling without creating a scene
+        lib = _lib.load()
+        self.desc, self.precision, self.seed = desc, int(precision), int(seed)
+        self.width, self.height = int(desc.width), int(desc.height)
+        d = Scene._c_desc(self._keep, desc, bvh)
+        devs = None if devices is None else np.ascontiguousarray(devices, dtype=np.int32)
+        h = C.c_void_p()
+        _lib.check(lib.mfx_multi_create(C.byref(d), _lib.ptr(devs), len(devs) if devs is not None else int(n_devices), C.byref(h)))
+        self._h = h
+        n = C.c_int32()
+        _lib.check(lib.mfx_multi_device_count(self._h, C.byref(n)))
+        self.n_devices = n.value
+        self.texture = np.zeros((self.width, self.height, 4), dtype=np.float64)
+        self.stats = None
+
+    def close(self):
+        if getattr(self, "_h", None):
+            _lib.load().mfx_multi_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _after(self):
+        st = _lib.MfxStats()
+        per = (_lib.MfxStats * self.n_devices)()
+        _lib.check(_lib.load().mfx_multi_get_stats(self._h, C.byref(st), C.cast(per, C.c_void_p)))
+        conv = lambda x: {k: (list(getattr(x, k)) if k in ("nodes", "tris", "spheres") else getattr(x, k)) for k, _ in _lib.MfxStats._fields_}
+        self.stats = conv(st)
+        self.stats["per_device"] = [conv(x) for x in per]
+
+    def Sample(self, n, first_sample=0, flags=0, out=None):
+        tex = self.texture if out is None else out
+        p = _lib.MfxSampleParams(self.precision, int(n), self.seed, int(first_sample), 0, 0, 1, int(flags))
+        _lib.check(_lib.load().mfx_multi_sample(self._h, C.byref(p), _lib.ptr(tex)))
+        self._after()
+        return tex
+
+    def SampleF32(self, n, first_sample=0, flags=0):
+        img = np.zeros((self.height, self.width, 4), dtype=np.float32)
+        p = _lib.MfxSampleParams(self.precision, int(n), self.seed, int(first_sample), 0, 0, 1, int(flags))
+        _lib.check(_lib.load().mfx_multi_sample_f32(self._h, C.byref(p), _lib.ptr(img)))
+        self._after()
+        return img
+
+
 class Film:
     """Film (Film.fs:13-34): sum += frame; target = sum / frameCount -- kept in HBM."""
 
@@ -401,6 +468,9 @@ class Film:
 
     def Import(self, sum_wh, frame_count):
         sum_wh = np.ascontiguousarray(sum_wh, dtype=np.float64)
+        want = (self.scene.width, self.scene.height, 4)
+        if sum_wh.shape != want:
+            raise ValueError(f"Film.Import: running sum has shape {sum_wh.shape}, the film is Color[w,h] = {want}")
         _lib.check(_lib.load().mfx_film_import(self._h, _lib.ptr(sum_wh), float(frame_count)))
 
     def PostProcess(self):

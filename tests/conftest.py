@@ -33,3 +33,10 @@ def goldens():
 def have_gpu():
     from mafrixraytracing_b200 import _lib
     return _lib.load().mfx_device_count() > 0
+
+
+@pytest.fixture(scope="session")
+def big_goldens():
+    """Full-size primary-hit checksums of BASELINE configs[3] / [4] (tests/golden/make_goldens_big.py)."""
+    import numpy as np
+    return dict(np.load(os.path.join(ROOT, "tests", "golden", "big_goldens.npz")))

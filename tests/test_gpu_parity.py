@@ -320,6 +320,84 @@ def test_tile_sharding_sums_to_the_whole_frame(world):
         assert np.array_equal(acc, full)          # RNG keyed on absolute pixel/sample: bit-identical for any world
 
 
+@pytest.mark.parametrize("world,w,h", [(2, 200, 136), (3, 70, 33), (8, 300, 64), (5, 50, 7)])
+def test_stripe_sharding_assembles_the_whole_frame(world, w, h):
+    """Column stripes (MFX_SAMPLE_STRIPES, arithmetic ownership in the kernels -- no pixel table): the ranks' frames are
+    disjoint, cover the frame and sum to the one-GPU frame bit for bit; with MFX_SAMPLE_NO_CLEAR a rank touches only its
+    own stripes of the output."""
+    import torch
+    desc = _desc("c1_cube", width=w, height=h)
+    s = Scene(desc)
+    for prec in (EXACT_F64, FAST_F32):
+        full = CudaPixelIntegrator(s, precision=prec, seed=2).Sample(3).copy()
+        acc = np.zeros_like(full)
+        owned = np.zeros(full.shape[:2], int)
+        for r in range(world):
+            integ = CudaPixelIntegrator(s, precision=prec, seed=2, tile_size=16, rank=r, world=world)
+            part = integ.Sample(3, flags=_lib.SAMPLE_STRIPES).copy()
+            own = np.zeros(full.shape[:2], bool)
+            own[(np.arange(w) // 16) % world == r, :] = True
+            assert np.array_equal(part[:, :, 3] == 1.0, own)
+            owned += own
+            acc += part
+            dev = torch.full((w, h, 4), -7.0, dtype=torch.float64, device="cuda")
+            torch.cuda.synchronize()
+            integ.SampleDeviceColor(3, dev.data_ptr(), flags=_lib.SAMPLE_STRIPES | _lib.SAMPLE_NO_CLEAR)
+            got = dev.cpu().numpy()
+            assert np.array_equal(got[own], full[own]) and (got[~own] == -7.0).all()
+        assert (owned == 1).all()
+        assert np.array_equal(acc, full)
+
+
+def test_multi_gpu_api_on_the_devices_present():
+    """mfx_multi_*: the N-GPU path behind ONE host thread.  With every visible device (1 on the test box, 2..8 under
+    gpurun --gpus N) the assembled Color[w,h] and the float frame equal the single-GPU frame bit for bit."""
+    from mafrixraytracing_b200 import MultiGpuPixelIntegrator
+    n = _lib.load().mfx_device_count()
+    for name, kw in (("c1_cube", dict(width=333, height=120)), ("c2_spot", dict(width=480, height=270))):
+        desc = _desc(name, **kw)
+        single = CudaPixelIntegrator(Scene(desc), precision=FAST_F32, seed=3)
+        want = single.Sample(4).copy()
+        want32 = single.SampleF32(4)
+        for devs in ([0], list(range(n))) if n > 1 else ([0],):
+            m = MultiGpuPixelIntegrator(desc, devices=devs, precision=FAST_F32, seed=3)
+            assert m.n_devices == len(devs)
+            tex = np.full((desc.width, desc.height, 4), -1.0)
+            _lib.check(_lib.load().mfx_host_register(_lib.ptr(tex), tex.nbytes))
+            try:
+                got = m.Sample(4, out=tex)
+            finally:
+                _lib.load().mfx_host_unregister(_lib.ptr(tex))
+            assert np.array_equal(got, want)
+            assert np.array_equal(m.SampleF32(4), want32)                 # pageable destination
+            st = m.stats
+            assert st["paths"] == desc.width * desc.height * 4 and len(st["per_device"]) == len(devs)
+            assert st["closest_rays"] == single.stats["closest_rays"] and st["shadow_rays"] == single.stats["shadow_rays"]
+            m.close()
+    with pytest.raises(MafrixError):
+        MultiGpuPixelIntegrator(_desc("cornell", width=16, height=16), devices=[0, 0])
+    with pytest.raises(MafrixError):
+        MultiGpuPixelIntegrator(_desc("cornell", width=16, height=16), devices=[n + 3])
+
+
+def test_cpp_host_drives_several_gpus_through_the_c_abi(tmp_path):
+    """host/render_test --gpus N: a single-threaded C++ host (the reference's shape) over mfx_multi_*; its PFM equals
+    the one-GPU run's.  Needs >= 2 devices (gpurun --gpus 2); the one-device box checks the refusal instead."""
+    import subprocess
+    from tests.conftest import ROOT
+    exe = os.path.join(ROOT, "host", "render_test")
+    subprocess.check_call(["make", "-C", os.path.join(ROOT, "host"), "-s"])
+    n = _lib.load().mfx_device_count()
+    if n < 2:
+        r = subprocess.run([exe, "--gpus", "2", "--frames", "1", "--size", "64x48", "--out", str(tmp_path / "x")], capture_output=True, text=True)
+        assert r.returncode == 1 and "device(s) visible" in r.stderr
+        return
+    a, b = str(tmp_path / "one"), str(tmp_path / "many")
+    subprocess.check_call([exe, "--frames", "3", "--spp", "2", "--size", "250x90", "--out", a])
+    subprocess.check_call([exe, "--frames", "3", "--spp", "2", "--size", "250x90", "--gpus", str(n), "--out", b])
+    assert open(a + ".pfm", "rb").read() == open(b + ".pfm", "rb").read()
+
+
 def test_f32_and_device_outputs_agree_with_color_wh():
     import torch
     desc = _desc("cornell", width=90, height=60)

@@ -194,6 +194,21 @@ def test_scene_create_validates_before_touching_the_device():
     with pytest.raises(MafrixError) as e:
         Scene(d6)
     assert e.value.code == -1
+    # a caller-supplied Bvh is indexed by the flatteners and the kernels: malformed ones are refused, not dereferenced
+    d7 = scenes.cornell(width=8, height=8)
+    good = Bvh.Build(d7.prims)
+    for what, breakit in (("permutation", lambda b: b.indices.__setitem__(2, b.indices[3])),
+                          ("permutation", lambda b: b.indices.__setitem__(0, len(d7.prims) + 5)),
+                          ("covers", lambda b: b.nodes["first"].__setitem__(1, -3)),
+                          ("cover", lambda b: b.nodes["count"].__setitem__(2, 1))):
+        bad = Bvh(good.nodes.copy(), good.indices.copy())
+        breakit(bad)
+        with pytest.raises(MafrixError) as e:
+            Scene(d7, bvh=bad)
+        assert e.value.code == -1 and what in str(e.value), str(e.value)
+    with pytest.raises(MafrixError) as e:
+        Scene(d7, bvh=Bvh(good.nodes[:-2].copy(), good.indices.copy()))
+    assert e.value.code == -1 and "2n-1" in str(e.value)
 
 
 @pytest.mark.skipif(have_gpu(), reason="a CUDA device is present")
@@ -222,6 +237,28 @@ def test_tile_map_partitions_the_frame(w, h, tile, world):
     lib = _lib.load()
     n = C.c_int32()
     assert lib.mfx_tile_map(w, h, tile, world, world, None, C.byref(n)) == -1
+
+
+@pytest.mark.parametrize("w,h,stripe,world", [(1920, 1080, 16, 8), (300, 300, 16, 3), (70, 33, 8, 2), (50, 7, 16, 5), (16, 4, 16, 4)])
+def test_stripe_map_partitions_the_frame(w, h, stripe, world):
+    """Column-stripe ownership (MFX_SAMPLE_STRIPES, what mfx_multi_sample and the torchrun path shard by): every pixel
+    has one owner, stripe c belongs to rank c % world, and the local order is stripe after stripe, row-major inside."""
+    seen = np.zeros(w * h, int)
+    for r in range(world):
+        pix = mdist.stripe_pixels(w, h, stripe, r, world)
+        seen[pix] += 1
+        x, y = pix % w, pix // w
+        assert ((x // stripe) % world == r).all()
+        # the arithmetic the kernels use (pixel_of in mfx_device.cuh), restated
+        pl = np.arange(len(pix))
+        per = stripe * h
+        ls, rem = pl // per, pl % per
+        x0 = (ls * world + r) * stripe
+        wl = np.minimum(stripe, w - x0)
+        assert np.array_equal(y, rem // wl) and np.array_equal(x, x0 + rem % wl)
+    assert (seen == 1).all()
+    n = C.c_int32()
+    assert _lib.load().mfx_stripe_map(w, h, stripe, world, world, None, C.byref(n)) == -1
 
 
 def test_workload_builders_match_the_configs():
