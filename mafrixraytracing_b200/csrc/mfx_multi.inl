@@ -82,7 +82,12 @@ static void multi_worker(MfxMulti *m, int i)
         p.flags |= MFX_SAMPLE_STRIPES | MFX_SAMPLE_NO_CLEAR;
         int rc = ensure_frame_buffers(s);
         if (rc == MFX_OK) rc = run_sample(s, &p, m->texture ? s->d_color_wh : nullptr, m->texture ? nullptr : s->d_rgba);
+        const auto t1 = std::chrono::steady_clock::now();
         if (rc == MFX_OK) rc = multi_copy_out(m, i);
+        if (env_long("MFX_DEBUG", 0))
+            fprintf(stderr, "[mfx] multi worker %d: run_sample %.2f ms (device %.2f ms), copy out %.2f ms\n", i,
+                    std::chrono::duration<double, std::milli>(t1 - t0).count(), s->stats.ms_total,
+                    std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t1).count());
         m->rc[(size_t)i] = rc;
         if (rc != MFX_OK) m->err[(size_t)i] = g_err;
         m->ms_wall[(size_t)i] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
@@ -111,23 +116,33 @@ extern "C" int mfx_multi_create(const MfxSceneDesc *d, const int32_t *devices, i
     m->devices = devs;
     m->width = d->width; m->height = d->height;
     m->stripe = (int)std::max(1L, env_long("MFX_MULTI_STRIPE", 16));
-    int rc = MFX_OK;
+    m->scenes.assign(devs.size(), nullptr);
+    // replica 0 on this thread (argument checks, and Bvh.Build -- BvhNode.fs:24-61 -- runs once: the others take its tree),
+    // the other replicas side by side on short-lived threads
     MfxSceneDesc dd = *d;
-    for (size_t i = 0; i < devs.size() && rc == MFX_OK; i++) {
-        rc = mfx_init(devs[i]);
-        MfxScene *s = nullptr;
-        if (rc == MFX_OK) rc = mfx_scene_create(&dd, &s);
-        if (rc != MFX_OK) break;
-        s->in_process_replica = true;     // the workers share one process: the tree cache lets one of them build, with every core
-        m->scenes.push_back(s);
-        if (i == 0 && !dd.nodes) {      // Bvh.Build ran once (BvhNode.fs:24-61 on the host): the replicas take that tree
-            dd.nodes = s->nodes.data(); dd.n_node_slots = (int32_t)s->nodes.size(); dd.indices = s->indices.data();
-        }
+    int rc = mfx_init(devs[0]);
+    if (rc == MFX_OK) rc = mfx_scene_create(&dd, &m->scenes[0]);
+    std::string why = g_err;
+    if (rc == MFX_OK) {
+        m->scenes[0]->in_process_replica = true;    // the workers share one process: the tree cache lets one of them build, with every core
+        if (!dd.nodes) { dd.nodes = m->scenes[0]->nodes.data(); dd.n_node_slots = (int32_t)m->scenes[0]->nodes.size(); dd.indices = m->scenes[0]->indices.data(); }
+        std::vector<int> rcs(devs.size(), MFX_OK);
+        std::vector<std::string> errs(devs.size());
+        std::vector<std::thread> makers;
+        for (size_t i = 1; i < devs.size(); i++)
+            makers.emplace_back([&, i] {
+                int r = mfx_init(devs[i]);
+                if (r == MFX_OK) r = mfx_scene_create(&dd, &m->scenes[i]);
+                if (r == MFX_OK) m->scenes[i]->in_process_replica = true;
+                rcs[i] = r;
+                if (r != MFX_OK) errs[i] = g_err;
+            });
+        for (std::thread &th : makers) th.join();
+        for (size_t i = 1; i < devs.size() && rc == MFX_OK; i++) if (rcs[i] != MFX_OK) { rc = rcs[i]; why = errs[i]; }
     }
     g_device = keep;                     // the calling thread keeps the device it had chosen (or none)
     if (keep >= 0) cudaSetDevice(keep);
     if (rc != MFX_OK) {
-        const std::string why = g_err;
         for (MfxScene *s : m->scenes) mfx_scene_destroy(s);
         delete m;
         g_err = why;

@@ -1,0 +1,23 @@
+#!/usr/bin/env python3
+"""Where does a mfx_multi_create + mfx_multi_sample + destroy step spend its host time?  usage: multi_probe.py [n_gpus] [spp]"""
+import os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+from mafrixraytracing_b200 import scenes, Bvh, MultiGpuPixelIntegrator, FAST_F32, _lib
+n = int(sys.argv[1]) if len(sys.argv) > 1 else _lib.load().mfx_device_count()
+spp = int(sys.argv[2]) if len(sys.argv) > 2 else 64
+desc = scenes.c2_spot(); bvh = Bvh.Build(desc.prims)
+tex = np.zeros((desc.width, desc.height, 4))
+_lib.check(_lib.load().mfx_host_register(_lib.ptr(tex), tex.nbytes))
+for k in range(4):
+    t0 = time.perf_counter()
+    m = MultiGpuPixelIntegrator(desc, devices=list(range(n)), bvh=bvh, precision=FAST_F32, seed=1)
+    t1 = time.perf_counter()
+    m.Sample(spp, out=tex)
+    t2 = time.perf_counter()
+    m.Sample(spp, out=tex)
+    t3 = time.perf_counter()
+    dev = max(p["ms_total"] for p in m.stats["per_device"])
+    m.close()
+    t4 = time.perf_counter()
+    print(f"iter {k}: create {1e3*(t1-t0):.2f} ms, first sample {1e3*(t2-t1):.2f} ms, second sample {1e3*(t3-t2):.2f} ms (slowest device {dev:.2f} ms), destroy {1e3*(t4-t3):.2f} ms", flush=True)
