@@ -250,6 +250,13 @@ MFX_API int mfx_trace_primary(MfxScene *scene, int32_t precision, int64_t n, con
  * doubles r,g,b,a; a = 1.  A blittable Array2D<Color> can be pinned and passed directly.
  * With world > 1 only this rank's tiles are written, every other pixel is 0. */
 MFX_API int mfx_pixel_integrator_sample(MfxScene *scene, const MfxSampleParams *params, double *texture);
+/* Sample without the wait (the reference's loop renders frame after frame, Scene.fs:331-333 from Film.fs:67-73): the
+ * kernels and the download are enqueued and the call returns; mfx_pixel_integrator_wait completes the OLDEST frame in
+ * flight (texture filled, mfx_get_stats describes it).  Up to two frames per scene may be in flight -- the download of
+ * frame k then runs beside the kernels of frame k+1; a third call completes the oldest first.  texture must be pinned
+ * (mfx_host_register) and stay untouched until its wait returns; use one texture per frame in flight. */
+MFX_API int mfx_pixel_integrator_sample_async(MfxScene *scene, const MfxSampleParams *params, double *texture);
+MFX_API int mfx_pixel_integrator_wait(MfxScene *scene);
 /* Same call, result left on the device: d_rgba = width*height float4, row-major (y*width+x),
  * mean over spp, zero outside this rank's tiles (so a sum-reduce over ranks assembles the frame). */
 MFX_API int mfx_pixel_integrator_sample_device(MfxScene *scene, const MfxSampleParams *params,

@@ -85,6 +85,8 @@ SYMBOLS = {
     "mfx_bvh_hit": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int64, _P, _P, C.c_double, C.c_double, _P, _P, _P]),
     "mfx_trace_primary": (C.c_int, [_P, C.c_int32, C.c_int64, _P, _P, _P]),
     "mfx_pixel_integrator_sample": (C.c_int, [_P, C.POINTER(MfxSampleParams), _P]),
+    "mfx_pixel_integrator_sample_async": (C.c_int, [_P, C.POINTER(MfxSampleParams), _P]),
+    "mfx_pixel_integrator_wait": (C.c_int, [_P]),
     "mfx_pixel_integrator_sample_device": (C.c_int, [_P, C.POINTER(MfxSampleParams), _P]),
     "mfx_pixel_integrator_sample_device_color": (C.c_int, [_P, C.POINTER(MfxSampleParams), _P]),
     "mfx_pixel_integrator_sample_f32": (C.c_int, [_P, C.POINTER(MfxSampleParams), _P]),

@@ -150,6 +150,24 @@ extern "C" int mfx_camera_lens(const double lookfrom[3], const double lookat[3],
 }
 
 // ------------------------------------------------------------------ scene
+// One Sample call in flight: what launch_sample enqueued and finish_sample needs to turn into MfxStats.  Two slots, so
+// the download of frame k (copy stream) runs beside the kernels of frame k+1 (mfx_pixel_integrator_sample_async).
+struct Span { size_t a, b; int cls; };
+struct FrameJob {
+    bool active = false;
+    std::vector<cudaEvent_t> events;         // timing + dependency events of this job (grown on demand, reused)
+    std::vector<Span> spans;
+    size_t e_begin = 0, e_end = 1;
+    uint32_t launches = 0, l_ext = 0, l_sh = 0;
+    unsigned long long *d_totals = nullptr;  // [8] rays / paths / watchdog / hybrid fixups
+    TravCounters *d_ctr = nullptr;
+    unsigned long long *h_totals = nullptr;  // pinned host mirrors, filled by async copies behind the kernels
+    TravCounters *h_ctr = nullptr;
+    cudaEvent_t done = nullptr;              // kernels + stat copies of the job finished (main stream)
+    cudaEvent_t copied = nullptr;            // async only: the texture download finished (copy stream)
+    bool has_copy = false;
+};
+
 struct MfxScene {
     int device = 0;
     int sm_count = 148;
@@ -181,10 +199,11 @@ struct MfxScene {
     double *d_pixsum = nullptr;          // [w*h][4] row-major sums
     double *d_color_wh = nullptr;        // Color[w,h]
     float4 *d_rgba = nullptr;            // row-major float4 (internal, when the caller gives none)
-    unsigned long long *d_totals = nullptr;   // [3]
-    TravCounters *d_ctr = nullptr;
+    FrameJob jobs[2];
+    int job_head = 0, job_count = 0;         // outstanding async frames: jobs[job_head], jobs[(job_head + 1) % 2]
+    cudaStream_t copy_stream = nullptr;      // texture downloads of async frames
+    double *d_color_async[2] = { nullptr, nullptr };   // Color[w,h] per async slot
     std::map<std::tuple<int, int, int>, std::pair<int *, int>> tilemaps;
-    std::vector<cudaEvent_t> events;
     MfxStats stats;
 };
 
@@ -395,8 +414,15 @@ extern "C" int mfx_scene_destroy(MfxScene *s)
     if (!s) return MFX_OK;
     cudaSetDevice(s->device);
     if (s->stream) cudaStreamSynchronize(s->stream);
+    if (s->copy_stream) { cudaStreamSynchronize(s->copy_stream); cudaStreamDestroy(s->copy_stream); }
     for (auto &a : s->allocs) dev_release(s->device, a.first, a.second);
-    for (cudaEvent_t e : s->events) cudaEventDestroy(e);
+    for (FrameJob &j : s->jobs) {
+        for (cudaEvent_t e : j.events) cudaEventDestroy(e);
+        if (j.done) cudaEventDestroy(j.done);
+        if (j.copied) cudaEventDestroy(j.copied);
+        if (j.h_totals) cudaFreeHost(j.h_totals);
+        if (j.h_ctr) cudaFreeHost(j.h_ctr);
+    }
     if (s->stream2) { cudaStreamSynchronize(s->stream2); cudaStreamDestroy(s->stream2); }
     if (s->stream) cudaStreamDestroy(s->stream);
     delete s;
@@ -1014,8 +1040,6 @@ static int ensure_frame_buffers(MfxScene *s)
     if (!s->d_pixsum) MFX_TRY(dev_alloc_t(s, &s->d_pixsum, 4 * npx));
     if (!s->d_color_wh) MFX_TRY(dev_alloc_t(s, &s->d_color_wh, 4 * npx));
     if (!s->d_rgba) MFX_TRY(dev_alloc_t(s, &s->d_rgba, npx));
-    if (!s->d_totals) MFX_TRY(dev_alloc_t(s, &s->d_totals, 8));
-    if (!s->d_ctr) MFX_TRY(dev_alloc_t(s, &s->d_ctr, 1));
     return MFX_OK;
 }
 
@@ -1103,14 +1127,25 @@ static int get_tilemap(MfxScene *s, int tile, int rank, int world, bool stripes,
     return MFX_OK;
 }
 
-static int get_event(MfxScene *s, size_t idx, cudaEvent_t *e)
+static int get_event(FrameJob &j, size_t idx, cudaEvent_t *e)
 {
-    while (s->events.size() <= idx) {
+    while (j.events.size() <= idx) {
         cudaEvent_t ev;
         CUDA_TRY(cudaEventCreate(&ev));
-        s->events.push_back(ev);
+        j.events.push_back(ev);
     }
-    *e = s->events[idx];
+    *e = j.events[idx];
+    return MFX_OK;
+}
+
+static int ensure_job(MfxScene *s, FrameJob &j)
+{
+    if (!j.d_totals) MFX_TRY(dev_alloc_t(s, &j.d_totals, 8));
+    if (!j.d_ctr) MFX_TRY(dev_alloc_t(s, &j.d_ctr, 1));
+    if (!j.h_totals) CUDA_TRY(cudaMallocHost(&j.h_totals, 8 * sizeof(unsigned long long)));
+    if (!j.h_ctr) CUDA_TRY(cudaMallocHost(&j.h_ctr, sizeof(TravCounters)));
+    if (!j.done) CUDA_TRY(cudaEventCreateWithFlags(&j.done, cudaEventDisableTiming));
+    if (!j.copied) CUDA_TRY(cudaEventCreateWithFlags(&j.copied, cudaEventDisableTiming));
     return MFX_OK;
 }
 
@@ -1127,7 +1162,11 @@ static bool use_hybrid(int flags)
 //   extend (closest hit) -> shade (BSDF + light sample, queue compaction) -> shadow (occlusion)
 // and are resolved into per-pixel sums.  No host synchronisation inside: queue sizes stay on
 // the device and every kernel is a persistent grid-stride loop over `counts[bounce]`.
-static int run_sample(MfxScene *s, const MfxSampleParams *p, double *d_color_wh, float4 *d_rgba)
+static int finish_sample(MfxScene *s, FrameJob &job);
+static int finish_oldest(MfxScene *s);
+
+// Enqueues one Sample call on the scene's stream and returns without waiting for it.
+static int launch_sample(MfxScene *s, const MfxSampleParams *p, double *d_color_wh, float4 *d_rgba, FrameJob &job)
 {
     if (!s || !p) return fail(MFX_ERR_INVALID_ARGUMENT, "null scene/params");
     if (p->spp <= 0) return fail(MFX_ERR_INVALID_ARGUMENT, "spp must be positive, got %d", p->spp);
@@ -1150,7 +1189,8 @@ static int run_sample(MfxScene *s, const MfxSampleParams *p, double *d_color_wh,
     // bounce 0 of the throughput path is traced id-exactly (mfx_hybrid.cu) unless the caller opts out
     const bool hyb = !exact && sfp->own_tree && !counting && use_hybrid(p->flags);
     if (hyb) { MFX_TRY(flatten_hybrid(s)); MFX_TRY(ensure_wave_hybrid(s)); }
-    TravCounters *ctr = counting ? s->d_ctr : nullptr;
+    MFX_TRY(ensure_job(s, job));
+    TravCounters *ctr = counting ? job.d_ctr : nullptr;
     const bool sky = (s->integrator == MFX_SKY_TRACER);
     if (!exact) s->wf.cam_origin = (sfp->own_tree && !counting && !(sky && s->lens.lens_radius != 0.0)) ? 1 : 0;
     const size_t npx = (size_t)s->width * s->height;
@@ -1158,27 +1198,28 @@ static int run_sample(MfxScene *s, const MfxSampleParams *p, double *d_color_wh,
     LaunchCfg cfg{ s->sm_count, 128, st, variant, (p->flags & MFX_SAMPLE_REFERENCE_STREAM) ? 1 : 0, 0, (int)env_long("MFX_HYB_VARIANT", 0) };
 
     CUDA_TRY(cudaMemsetAsync(s->d_pixsum, 0, 4 * npx * sizeof(double), st));
-    CUDA_TRY(cudaMemsetAsync(s->d_totals, 0, 8 * sizeof(unsigned long long), st));
-    CUDA_TRY(cudaMemsetAsync(s->d_ctr, 0, sizeof(TravCounters), st));
+    CUDA_TRY(cudaMemsetAsync(job.d_totals, 0, 8 * sizeof(unsigned long long), st));
+    CUDA_TRY(cudaMemsetAsync(job.d_ctr, 0, sizeof(TravCounters), st));
     if ((tm.pix || tm.stripe) && !(p->flags & MFX_SAMPLE_NO_CLEAR)) {   // pixels of other ranks must read as zero
         if (d_color_wh) CUDA_TRY(cudaMemsetAsync(d_color_wh, 0, 4 * npx * sizeof(double), st));
         if (d_rgba) CUDA_TRY(cudaMemsetAsync(d_rgba, 0, npx * sizeof(float4), st));
     }
     size_t ev = 0;
     cudaEvent_t e_begin, e_end;
-    MFX_TRY(get_event(s, ev++, &e_begin)); MFX_TRY(get_event(s, ev++, &e_end));
+    MFX_TRY(get_event(job, ev++, &e_begin)); MFX_TRY(get_event(job, ev++, &e_end));
+    job.e_begin = 0; job.e_end = 1;
     CUDA_TRY(cudaEventRecord(e_begin, st));
-    struct Span { size_t a, b; int cls; };
-    std::vector<Span> spans;
+    std::vector<Span> &spans = job.spans;
+    spans.clear();
     auto timed = [&](int cls, cudaStream_t on) -> int {      // returns via spans the event pair bracketing the next launch
         cudaEvent_t a, b;
-        MFX_TRY(get_event(s, ev, &a)); MFX_TRY(get_event(s, ev + 1, &b));
+        MFX_TRY(get_event(job, ev, &a)); MFX_TRY(get_event(job, ev + 1, &b));
         spans.push_back(Span{ ev, ev + 1, cls });
         ev += 2;
         CUDA_TRY(cudaEventRecord(a, on));
         return MFX_OK;
     };
-    auto timed_end = [&](cudaStream_t on) -> int { CUDA_TRY(cudaEventRecord(s->events[spans.back().b], on)); return MFX_OK; };
+    auto timed_end = [&](cudaStream_t on) -> int { CUDA_TRY(cudaEventRecord(job.events[spans.back().b], on)); return MFX_OK; };
     // Two streams (fast precision, light-sampling integrators): the shadow queries of bounce b touch sh_* and rad only,
     // the closest hits of bounce b+1 the ray queue and hit[] only -- side by side, the head of one persistent grid fills
     // the SMs the tail of the other one leaves idle.  shade(b+1) rewrites sh_*: it waits for shadow(b).
@@ -1216,7 +1257,7 @@ static int run_sample(MfxScene *s, const MfxSampleParams *p, double *d_color_wh,
                 else if (hyb && b == 0) {
                     const HybQuery q{ sky ? MFX_SKY_TMIN : 1e-6, sky ? MFX_SKY_TMAX : 99999999., sky ? 1 : 0 };   // Integrators.fs:108 / RayTracing.fs:368
                     mfx_h_extend(cfg, *sfp, s->sx, s->sh, s->wf, s->wh, 0, q, 0);
-                    mfx_h_accum_fixups(st, s->wh, s->d_totals + 4);
+                    mfx_h_accum_fixups(st, s->wh, job.d_totals + 4);
                     launches += 2;
                 } else mfx_f_extend(cfg, *sfp, s->wf, b, ctr);
                 MFX_TRY(timed_end(st));
@@ -1242,7 +1283,7 @@ static int run_sample(MfxScene *s, const MfxSampleParams *p, double *d_color_wh,
                 else mfx_f_shade(cfg, *sfp, s->wf, tm, pix0, np, sabs, b, p->seed);
                 if (two) {
                     cudaEvent_t e_shaded;
-                    MFX_TRY(get_event(s, ev++, &e_shaded));
+                    MFX_TRY(get_event(job, ev++, &e_shaded));
                     CUDA_TRY(cudaEventRecord(e_shaded, st));
                     CUDA_TRY(cudaStreamWaitEvent(st2, e_shaded, 0));
                 }
@@ -1250,7 +1291,7 @@ static int run_sample(MfxScene *s, const MfxSampleParams *p, double *d_color_wh,
                 if (exact) mfx_x_shadow(cfg, s->sx, s->wx, b, ctr); else mfx_f_shadow(cfg2, *sfp, s->wf, b, ctr);
                 MFX_TRY(timed_end(st2));
                 if (two) {
-                    MFX_TRY(get_event(s, ev++, &e_shadow_done));
+                    MFX_TRY(get_event(job, ev++, &e_shadow_done));
                     CUDA_TRY(cudaEventRecord(e_shadow_done, st2));
                 }
                 launches += 3; l_ext++; l_sh++;
@@ -1260,9 +1301,9 @@ static int run_sample(MfxScene *s, const MfxSampleParams *p, double *d_color_wh,
             else mfx_f_resolve(cfg, *sfp, s->wf, tm, pix0, np, S, s->d_pixsum);
             // rays traced: exact: closest = counts[0..D], shadow = counts[1..D+1];
             //              fast : closest = counts[0..D], shadow = counts[V+2 .. V+2+D]
-            if (sky) mfx_accum_ray_totals(st, counts, 0, D + 1, 0, 0, s->d_totals);
-            else if (exact) mfx_accum_ray_totals(st, counts, 0, D + 1, 1, D + 1, s->d_totals);
-            else mfx_accum_ray_totals(st, counts, 0, D + 1, MFX_MAX_VERTS + 2, D + 1, s->d_totals);
+            if (sky) mfx_accum_ray_totals(st, counts, 0, D + 1, 0, 0, job.d_totals);
+            else if (exact) mfx_accum_ray_totals(st, counts, 0, D + 1, 1, D + 1, job.d_totals);
+            else mfx_accum_ray_totals(st, counts, 0, D + 1, MFX_MAX_VERTS + 2, D + 1, job.d_totals);
             launches += 2;
         }
     }
@@ -1270,29 +1311,60 @@ static int run_sample(MfxScene *s, const MfxSampleParams *p, double *d_color_wh,
     launches++;
     CUDA_TRY(cudaEventRecord(e_end, st));
     CUDA_TRY(cudaGetLastError());
-    CUDA_TRY(cudaStreamSynchronize(st));
+    // the statistics follow the kernels down the stream into pinned host memory: nobody has to block for them
+    CUDA_TRY(cudaMemcpyAsync(job.h_totals, job.d_totals, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(job.h_ctr, job.d_ctr, sizeof(TravCounters), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaEventRecord(job.done, st));
+    job.launches = launches; job.l_ext = l_ext; job.l_sh = l_sh;
+    job.active = true; job.has_copy = false;
+    return MFX_OK;
+}
 
-    unsigned long long totals[8];
-    TravCounters hc;
-    CUDA_TRY(cudaMemcpy(totals, s->d_totals, sizeof(totals), cudaMemcpyDeviceToHost));
-    CUDA_TRY(cudaMemcpy(&hc, s->d_ctr, sizeof(hc), cudaMemcpyDeviceToHost));
+// Waits for a launched Sample call (and its texture download, if it has one) and publishes its MfxStats.
+static int finish_sample(MfxScene *s, FrameJob &job)
+{
+    if (!job.active) return MFX_OK;
+    job.active = false;
+    CUDA_TRY(cudaEventSynchronize(job.done));
+    if (job.has_copy) CUDA_TRY(cudaEventSynchronize(job.copied));
+    const unsigned long long *totals = job.h_totals;
+    const TravCounters &hc = *job.h_ctr;
     MfxStats &stt = s->stats;
     memset(&stt, 0, sizeof(stt));
     stt.closest_rays = totals[0]; stt.shadow_rays = totals[1]; stt.paths = totals[2];
     if (totals[3]) return fail(MFX_ERR_CUDA, "traversal watchdog tripped in %llu warp(s): the frame is incomplete", totals[3]);
     for (int c = 0; c < 2; c++) { stt.nodes[c] = hc.v[c][0]; stt.tris[c] = hc.v[c][1]; stt.spheres[c] = hc.v[c][2]; }
     float ms = 0.f;
-    CUDA_TRY(cudaEventElapsedTime(&ms, e_begin, e_end));
+    CUDA_TRY(cudaEventElapsedTime(&ms, job.events[job.e_begin], job.events[job.e_end]));
     stt.ms_total = ms;
     double m_ext = 0., m_sh = 0.;
-    for (const Span &sp : spans) {
-        CUDA_TRY(cudaEventElapsedTime(&ms, s->events[sp.a], s->events[sp.b]));
+    for (const Span &sp : job.spans) {
+        CUDA_TRY(cudaEventElapsedTime(&ms, job.events[sp.a], job.events[sp.b]));
         if (sp.cls == 0) m_ext += ms; else m_sh += ms;
     }
     stt.ms_extend = m_ext; stt.ms_shadow = m_sh; stt.ms_shade = stt.ms_total - m_ext - m_sh;
-    stt.launches = launches; stt.launches_extend = l_ext; stt.launches_shadow = l_sh;
+    stt.launches = job.launches; stt.launches_extend = job.l_ext; stt.launches_shadow = job.l_sh;
     stt.hybrid_fixups = (uint32_t)std::min<unsigned long long>(totals[4], 0xffffffffull);
     return MFX_OK;
+}
+
+static int finish_oldest(MfxScene *s)
+{
+    if (s->job_count == 0) return MFX_OK;
+    FrameJob &j = s->jobs[s->job_head];
+    s->job_head = (s->job_head + 1) % 2;
+    s->job_count--;
+    return finish_sample(s, j);
+}
+
+// The synchronous call: one Sample, finished before it returns.  Frames still in flight from the async entry point are
+// completed first (their textures fill, their statistics are superseded).
+static int run_sample(MfxScene *s, const MfxSampleParams *p, double *d_color_wh, float4 *d_rgba)
+{
+    if (!s || !p) return fail(MFX_ERR_INVALID_ARGUMENT, "null scene/params");
+    while (s->job_count > 0) MFX_TRY(finish_oldest(s));
+    MFX_TRY(launch_sample(s, p, d_color_wh, d_rgba, s->jobs[0]));
+    return finish_sample(s, s->jobs[0]);
 }
 
 static int ensure_pinned(MfxScene *, size_t bytes)
@@ -1338,6 +1410,42 @@ extern "C" int mfx_pixel_integrator_sample_device(MfxScene *s, const MfxSamplePa
     if (!d_rgba_f32) return fail(MFX_ERR_INVALID_ARGUMENT, "null device buffer");
     if (!s) return fail(MFX_ERR_INVALID_ARGUMENT, "null scene");
     return run_sample(s, p, nullptr, (float4 *)d_rgba_f32);
+}
+
+// IPixelIntegrator.Sample without the wait: the kernels and the download of Color[w,h] are enqueued and the call returns.
+// Up to two frames may be in flight per scene -- the download of frame k (copy stream, its own device buffer) then runs
+// beside the kernels of frame k+1; a third call first completes the oldest frame.
+extern "C" int mfx_pixel_integrator_sample_async(MfxScene *s, const MfxSampleParams *p, double *texture)
+{
+    if (!texture) return fail(MFX_ERR_INVALID_ARGUMENT, "null texture");
+    if (!s) return fail(MFX_ERR_INVALID_ARGUMENT, "null scene");
+    MFX_TRY(bind_device(s->device));
+    cudaPointerAttributes attr;
+    const bool pinned = (cudaPointerGetAttributes(&attr, texture) == cudaSuccess) && (attr.type == cudaMemoryTypeHost);
+    cudaGetLastError();
+    if (!pinned) return fail(MFX_ERR_INVALID_ARGUMENT, "mfx_pixel_integrator_sample_async needs a pinned texture: register it once with mfx_host_register");
+    MFX_TRY(ensure_frame_buffers(s));
+    if (s->job_count == 2) MFX_TRY(finish_oldest(s));
+    const int slot = (s->job_head + s->job_count) % 2;
+    const size_t bytes = (size_t)s->width * s->height * 4 * sizeof(double);
+    if (!s->d_color_async[slot]) MFX_TRY(dev_alloc(s, (void **)&s->d_color_async[slot], bytes));
+    if (!s->copy_stream) CUDA_TRY(cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking));
+    FrameJob &job = s->jobs[slot];
+    MFX_TRY(launch_sample(s, p, s->d_color_async[slot], nullptr, job));
+    CUDA_TRY(cudaStreamWaitEvent(s->copy_stream, job.done, 0));
+    CUDA_TRY(cudaMemcpyAsync(texture, s->d_color_async[slot], bytes, cudaMemcpyDeviceToHost, s->copy_stream));
+    CUDA_TRY(cudaEventRecord(job.copied, s->copy_stream));
+    job.has_copy = true;
+    s->job_count++;
+    return MFX_OK;
+}
+
+// Completes the OLDEST frame in flight: its texture is filled and mfx_get_stats describes it.  No frame in flight: no-op.
+extern "C" int mfx_pixel_integrator_wait(MfxScene *s)
+{
+    if (!s) return fail(MFX_ERR_INVALID_ARGUMENT, "null scene");
+    MFX_TRY(bind_device(s->device));
+    return finish_oldest(s);
 }
 
 extern "C" int mfx_pixel_integrator_sample_device_color(MfxScene *s, const MfxSampleParams *p, void *d_color_wh_f64)

@@ -347,6 +347,16 @@ class CudaPixelIntegrator:
         self._after()
         return tex
 
+    def SampleAsync(self, n, out, first_sample=0, flags=0):
+        """Enqueues Sample(n) into the PINNED texture `out` (mfx_host_register) and returns; Wait() completes the oldest
+        frame in flight (two at most: frame k downloads while frame k+1 renders)."""
+        p = self._params(n, first_sample, flags)
+        _lib.check(_lib.load().mfx_pixel_integrator_sample_async(self.scene._h, C.byref(p), _lib.ptr(out)))
+
+    def Wait(self):
+        _lib.check(_lib.load().mfx_pixel_integrator_wait(self.scene._h))
+        self._after()
+
     def SampleF32(self, n, first_sample=0, flags=0):
         """Row-major (height, width, 4) float32 image (PFM/PNG writers)."""
         img = np.zeros((self.scene.height, self.scene.width, 4), dtype=np.float32)

@@ -398,6 +398,41 @@ def test_cpp_host_drives_several_gpus_through_the_c_abi(tmp_path):
     assert open(a + ".pfm", "rb").read() == open(b + ".pfm", "rb").read()
 
 
+def test_async_sample_pipelines_frames_and_equals_the_blocking_call():
+    """mfx_pixel_integrator_sample_async / _wait: two frames in flight (frame k downloads while frame k+1 renders), every
+    texture equal to the blocking call's, statistics of the frame each wait completes, pageable textures refused."""
+    desc = _desc("c2_spot", width=480, height=270)
+    s = Scene(desc)
+    integ = CudaPixelIntegrator(s, precision=FAST_F32, seed=4)
+    want = [integ.Sample(2, first_sample=2 * k).copy() for k in range(5)]
+    rays = integ.stats["closest_rays"]
+    lib = _lib.load()
+    tex = [np.full((desc.width, desc.height, 4), -1.0) for _ in range(2)]
+    with pytest.raises(MafrixError):
+        integ.SampleAsync(2, tex[0])                                   # not pinned
+    for t in tex:
+        _lib.check(lib.mfx_host_register(_lib.ptr(t), t.nbytes))
+    try:
+        integ.Wait()                                                   # nothing in flight: no-op
+        integ.SampleAsync(2, tex[0], first_sample=0)
+        for k in range(1, 5):                                          # launch k, then complete k-1
+            integ.SampleAsync(2, tex[k % 2], first_sample=2 * k)
+            integ.Wait()
+            assert np.array_equal(tex[(k - 1) % 2], want[k - 1])
+            assert integ.stats["paths"] == desc.width * desc.height * 2
+        integ.Wait()
+        assert np.array_equal(tex[0], want[4]) and integ.stats["closest_rays"] == rays
+        # three launches without a wait: the third completes the first itself; a blocking call drains the rest
+        for k in range(3):
+            integ.SampleAsync(2, tex[k % 2], first_sample=2 * k)
+        assert np.array_equal(integ.Sample(2, first_sample=6), integ.Sample(2, first_sample=6))
+        assert np.array_equal(tex[1], want[1]) and np.array_equal(tex[0], want[2])
+    finally:
+        for t in tex:
+            lib.mfx_host_unregister(_lib.ptr(t))
+    s.close()
+
+
 def test_f32_and_device_outputs_agree_with_color_wh():
     import torch
     desc = _desc("cornell", width=90, height=60)
