@@ -294,37 +294,71 @@ def main():
     if not args.no_e2e:
         h2d = desc.prims.nbytes + desc.materials.nbytes + bvh.nodes.nbytes + bvh.indices.nbytes + 12 * 8 + 18 * 8
         rays_e2e, t_e2e, d2h = 0.0, 0.0, 0
+        texs = []
         if rank == 0:
-            tex = np.zeros((desc.width, desc.height, 4), dtype=np.float64)
-            # the host keeps ONE Texture2D<Color> for its lifetime (Integrators.fs:147): pin it once so the
-            # per-frame download is a direct DMA (mfx_host_register)
-            _lib.check(_lib.load().mfx_host_register(_lib.ptr(tex), tex.nbytes))
-            d2h = tex.nbytes
+            # the host keeps its Texture2D<Color> for its lifetime (Integrators.fs:147): pinned once so the per-frame
+            # download is a direct DMA (mfx_host_register).  Two of them: frame k downloads while frame k+1
+            # renders (mfx_pixel_integrator_sample_async), the pipelined form of the reference's frame-after-frame loop
+            for _ in range(2 if world == 1 else 1):
+                t = np.zeros((desc.width, desc.height, 4), dtype=np.float64)
+                _lib.check(_lib.load().mfx_host_register(_lib.ptr(t), t.nbytes))
+                texs.append(t)
+            d2h = texs[0].nbytes
         cpu_barrier()                                            # N > 1: ranks 1.. hold no GPU work while rank 0 drives every device
-        if rank == 0:
+        if rank == 0 and world == 1:
+            def pipelined(n_steps):
+                """n_steps frames, each through its own `new Scene(state)`: H2D of the flattened scene, Sample, D2H of Color[w,h]."""
+                rays, prev = 0.0, None
+                for k in range(n_steps):
+                    sc = Scene(desc, bvh=bvh, device=local_rank)     # H2D: prims, tree, materials -> flattened layouts
+                    integ = CudaPixelIntegrator(sc, precision=prec, seed=1)
+                    integ.SampleAsync(args.spp, texs[k % 2])         # kernels + D2H enqueued; returns at once
+                    if prev is not None:
+                        prev[1].Wait()                               # frame k-1 complete on the host
+                        rays += prev[1].stats["closest_rays"] + prev[1].stats["shadow_rays"]
+                        prev[0].close()
+                    prev = (sc, integ)
+                prev[1].Wait()
+                rays += prev[1].stats["closest_rays"] + prev[1].stats["shadow_rays"]
+                prev[0].close()
+                return rays
+            pipelined(2)                                             # untimed: allocates the path state of two frames in flight
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            rays_e2e = pipelined(args.steps)
+            t_e2e = time.perf_counter() - t0
+            # the same step without pipelining (one blocking call per frame), for reference
+            t0 = time.perf_counter()
+            for k in range(args.steps):
+                sc = Scene(desc, bvh=bvh, device=local_rank)
+                CudaPixelIntegrator(sc, precision=prec, seed=1).Sample(args.spp, out=texs[0])
+                sc.close()
+            t_block = time.perf_counter() - t0
+        elif rank == 0:
+            t_block = None
             for k in range(args.steps + 1):
                 torch.cuda.synchronize()
                 t0 = time.perf_counter()
-                if world == 1:
-                    sc = Scene(desc, bvh=bvh, device=local_rank)     # H2D: flattened scene (prims, tree, materials)
-                    integ = CudaPixelIntegrator(sc, precision=prec, seed=1)
-                    integ.Sample(args.spp, out=tex)                  # D2H: Color[w,h] f64 = the reference's Texture2D
-                else:
-                    sc = integ = MultiGpuPixelIntegrator(desc, devices=list(range(world)), bvh=bvh, precision=prec, seed=1)
-                    integ.Sample(args.spp, out=tex)                  # every device DMAs its stripes into the one host texture
+                integ = MultiGpuPixelIntegrator(desc, devices=list(range(world)), bvh=bvh, precision=prec, seed=1)
+                integ.Sample(args.spp, out=texs[0])                  # every device DMAs its stripes into the one host texture
                 dt = time.perf_counter() - t0
                 st = integ.stats
-                sc.close()
+                integ.close()
                 if k == 0:
                     continue                                         # first call allocates the path state
                 rays_e2e += st["closest_rays"] + st["shadow_rays"]
                 t_e2e += dt
-            _lib.load().mfx_host_unregister(_lib.ptr(tex))
+        if rank == 0:
+            for t in texs:
+                _lib.load().mfx_host_unregister(_lib.ptr(t))
         cpu_barrier()
         if rank == 0:
             e2e = {"value": rays_e2e / t_e2e / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": int(h2d * world), "d2h_bytes_per_step": int(d2h),
                    "ms_per_step": t_e2e / args.steps * 1e3,
-                   "call": "mfx_scene_create + mfx_pixel_integrator_sample (Color[w,h] f64 to the pinned host texture)" if world == 1 else
+                   "blocking_ms_per_step": t_block / args.steps * 1e3 if t_block else None,
+                   "call": "per frame: mfx_scene_create + mfx_pixel_integrator_sample_async -> pinned Color[w,h] f64, mfx_pixel_integrator_wait on the "
+                           "previous frame (two frames in flight: download k beside render k+1); blocking_ms_per_step = the same with "
+                           "mfx_pixel_integrator_sample" if world == 1 else
                            f"mfx_multi_create + mfx_multi_sample from ONE host thread over {world} GPUs (scene replicated per device, every device "
                            "DMAs its column stripes into the pinned host texture; ranks 1.. idle on a CPU barrier)"}
 

@@ -409,6 +409,8 @@ extern "C" int mfx_scene_create(const MfxSceneDesc *d, MfxScene **out)
     return MFX_OK;
 }
 
+static void stat_block_put(void *p);
+
 extern "C" int mfx_scene_destroy(MfxScene *s)
 {
     if (!s) return MFX_OK;
@@ -420,8 +422,7 @@ extern "C" int mfx_scene_destroy(MfxScene *s)
         for (cudaEvent_t e : j.events) cudaEventDestroy(e);
         if (j.done) cudaEventDestroy(j.done);
         if (j.copied) cudaEventDestroy(j.copied);
-        if (j.h_totals) cudaFreeHost(j.h_totals);
-        if (j.h_ctr) cudaFreeHost(j.h_ctr);
+        stat_block_put(j.h_totals);
     }
     if (s->stream2) { cudaStreamSynchronize(s->stream2); cudaStreamDestroy(s->stream2); }
     if (s->stream) cudaStreamDestroy(s->stream);
@@ -1138,12 +1139,35 @@ static int get_event(FrameJob &j, size_t idx, cudaEvent_t *e)
     return MFX_OK;
 }
 
+// Pinned 256-byte blocks for the per-frame statistics, recycled for the life of the process: cudaMallocHost and
+// cudaFreeHost synchronise the device, which a host that re-creates its Scene every frame would pay per frame.
+static std::vector<void *> g_stat_blocks;
+static int stat_block_get(void **p)
+{
+    {
+        std::lock_guard<std::mutex> g(g_pool_mu);
+        if (!g_stat_blocks.empty()) { *p = g_stat_blocks.back(); g_stat_blocks.pop_back(); return MFX_OK; }
+    }
+    CUDA_TRY(cudaHostAlloc(p, 256, cudaHostAllocPortable));
+    return MFX_OK;
+}
+static void stat_block_put(void *p)
+{
+    if (!p) return;
+    std::lock_guard<std::mutex> g(g_pool_mu);
+    g_stat_blocks.push_back(p);
+}
+
 static int ensure_job(MfxScene *s, FrameJob &j)
 {
     if (!j.d_totals) MFX_TRY(dev_alloc_t(s, &j.d_totals, 8));
     if (!j.d_ctr) MFX_TRY(dev_alloc_t(s, &j.d_ctr, 1));
-    if (!j.h_totals) CUDA_TRY(cudaMallocHost(&j.h_totals, 8 * sizeof(unsigned long long)));
-    if (!j.h_ctr) CUDA_TRY(cudaMallocHost(&j.h_ctr, sizeof(TravCounters)));
+    if (!j.h_totals) {      // one block: [0, 64) totals, [128, 176) traversal counters
+        void *blk = nullptr;
+        MFX_TRY(stat_block_get(&blk));
+        j.h_totals = (unsigned long long *)blk;
+        j.h_ctr = (TravCounters *)((char *)blk + 128);
+    }
     if (!j.done) CUDA_TRY(cudaEventCreateWithFlags(&j.done, cudaEventDisableTiming));
     if (!j.copied) CUDA_TRY(cudaEventCreateWithFlags(&j.copied, cudaEventDisableTiming));
     return MFX_OK;
