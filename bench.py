@@ -207,17 +207,21 @@ def main():
         run_reference(args, rank, world)
         return
 
+    dbg = (lambda *a: print(f"[bench rank {rank}]", *a, file=sys.stderr, flush=True)) if os.environ.get("BENCH_DEBUG") else (lambda *a: None)
+    dbg("start", sys.argv)
     import torch
     import torch.distributed as dist
     from mafrixraytracing_b200 import scenes, Scene, CudaPixelIntegrator, MultiGpuPixelIntegrator, Bvh, EXACT_F64, FAST_F32, _lib
     from mafrixraytracing_b200 import dist as mdist
 
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # a box that sets NCCL_DEBUG=VERSION must not write into the JSON stream
     torch.cuda.set_device(local_rank)
     cpu_group = None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local_rank))
         cpu_group = dist.new_group(backend="gloo")       # waits that must not occupy a GPU (rank 0 drives all of them in the e2e leg)
+    dbg("process group up")
     prec = FAST_F32 if args.precision == "fast" else EXACT_F64
     desc = scenes.WORKLOADS[args.workload]()
     bvh = Bvh.Build(desc.prims)                                 # host, one-off (kept on the host by the north star)
@@ -286,6 +290,7 @@ def main():
             return rr.item(), tt.item()
         return float(rays_rank), t_rank
 
+    dbg("timed region done")
     rays_all, t_all = aggregate(sum(s["closest_rays"] + s["shadow_rays"] for s in stats), sum(ms_steps))
     value = rays_all / t_all / 1e3                               # rays / ms / 1e3 = Mrays/s
 
@@ -362,6 +367,7 @@ def main():
                            f"mfx_multi_create + mfx_multi_sample from ONE host thread over {world} GPUs (scene replicated per device, every device "
                            "DMAs its column stripes into the pinned host texture; ranks 1.. idle on a CPU barrier)"}
 
+    dbg("e2e done")
     # ---- roofline of the dominant kernel (closest-hit traversal), rank 0's share
     roof, cpu, primary = None, None, None
     if rank == 0:
@@ -458,9 +464,11 @@ def main():
     if not args.no_configs and prec == FAST_F32:
         configs = []
         for name, spp in (("c3_renault", 256), ("c4_spheres", 128), ("c5_soup", 64)):
+            dbg("config", name)
             cdesc = scenes.WORKLOADS[name]()
             t0 = time.perf_counter()
             cbvh = Bvh.Build(cdesc.prims)
+            dbg("config", name, "tree built")
             t_bvh = time.perf_counter() - t0
             csc = Scene(cdesc, bvh=cbvh, device=local_rank)
             csh = mdist.ShardedPixelIntegrator(csc, rank, world, precision=prec, seed=1, stripe=mdist.STRIPE)
@@ -468,7 +476,9 @@ def main():
             csh.Sample(1)                                        # builds the layouts (own SAH tree, hybrid tables), untimed
             t_first = time.perf_counter() - t0
             sync_all()
+            dbg("config", name, "layouts built")
             ms, st = timed_step(csh, spp)
+            dbg("config", name, "timed")
             r_all, t_cfg = aggregate(st["closest_rays"] + st["shadow_rays"], ms)
             row = {"config": name, "prims": int(len(cdesc.prims)), "size": [cdesc.width, cdesc.height], "spp": spp, "max_depth": cdesc.max_depth,
                    "integrator": ["PathIntegrator", "NewPathTracer", "GetColor"][cdesc.integrator], "n_gpus": world,
@@ -486,6 +496,7 @@ def main():
             csc.close()
             sync_all()
 
+    dbg("configs done")
     if rank == 0:
         launches = sum(s["launches"] for s in stats)
         line = {"metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),

@@ -31,7 +31,8 @@ type MfxSampleParams =                       // 40 bytes, include/mafrix_cuda.h:
     val mutable tileSize : int
     val mutable rank : int
     val mutable world : int
-    val mutable flags : int                  // 2 = MFX_SAMPLE_REFERENCE_STREAM (rejection sampler on the exact stream)
+    val mutable flags : int                  // 2 = MFX_SAMPLE_REFERENCE_STREAM (rejection sampler on the exact stream),
+                                             // 8 = MFX_SAMPLE_F32_PRIMARY (bounce 0 with f32 primitive tests instead of the id-exact kernel)
 
 module Native =
     [<Literal>]
@@ -41,6 +42,13 @@ module Native =
     [<DllImport(Lib)>] extern int mfx_scene_create(nativeint desc, nativeint& scene)
     [<DllImport(Lib)>] extern int mfx_scene_destroy(nativeint scene)
     [<DllImport(Lib)>] extern int mfx_pixel_integrator_sample(nativeint scene, MfxSampleParams& p, nativeint texture)
+    // Sample without the wait: frame k downloads while frame k+1 renders (two pinned textures, Film.fs:67-73's loop pipelined)
+    [<DllImport(Lib)>] extern int mfx_pixel_integrator_sample_async(nativeint scene, MfxSampleParams& p, nativeint texture)
+    [<DllImport(Lib)>] extern int mfx_pixel_integrator_wait(nativeint scene)
+    // N GPUs behind this one render thread: the library replicates the scene and shards the frame by column stripes
+    [<DllImport(Lib)>] extern int mfx_multi_create(nativeint desc, nativeint devices, int nDevices, nativeint& multi)
+    [<DllImport(Lib)>] extern int mfx_multi_destroy(nativeint multi)
+    [<DllImport(Lib)>] extern int mfx_multi_sample(nativeint multi, MfxSampleParams& p, nativeint texture)
     [<DllImport(Lib)>] extern int mfx_host_register(nativeint ptr, uint64 bytes)
     [<DllImport(Lib)>] extern int mfx_host_unregister(nativeint ptr)
     [<DllImport(Lib)>] extern int mfx_film_create(nativeint scene, nativeint& film)
@@ -110,11 +118,12 @@ module private Interop =
 
 /// IPixelIntegrator over the GPU, built from the very objects Scene's constructor already has (Scene.fs:298-313).
 type CudaPixelIntegrator(width:int, height:int, cam:PinholeCamera, bvh:Bvh, light:NewAreaLight, maxDepth:int,
-                         materialProps:IMaterial -> int * float * float * float, ?newPathTracer:bool, ?fast:bool, ?seed:uint64) =
+                         materialProps:IMaterial -> int * float * float * float, ?newPathTracer:bool, ?fast:bool, ?seed:uint64, ?gpus:int) =
     let texture = Array2D.zeroCreate<Color> width height       // Color = 4 x float64, blittable; [x,y] at (x*h+y)*4
     let tex2d = new Texture2D<Color>(texture, width, height)
     let pin = GCHandle.Alloc(texture, GCHandleType.Pinned)      // pinned once + registered: the download is one DMA
     let mutable frame = 0
+    let nGpus = defaultArg gpus 1                                // > 1: mfx_multi_* (devices 0 .. gpus-1), same single-threaded caller
     let scene =
         let mats = MaterialManager.GetManager().materials
         let pPrims, pMats = Interop.prims bvh.primitives, Interop.materials mats materialProps
@@ -139,7 +148,8 @@ type CudaPixelIntegrator(width:int, height:int, cam:PinholeCamera, bvh:Bvh, ligh
             Marshal.WriteIntPtr(d, 312, 0n)                      // MfxSceneDesc.sky: only MFX_SKY_TRACER reads it
             check (Native.mfx_init 0)
             let mutable h = 0n
-            check (Native.mfx_scene_create(d, &h))               // copies everything: the buffers die right here
+            if nGpus > 1 then check (Native.mfx_multi_create(d, 0n, nGpus, &h))   // one replica per device, Bvh shared
+            else check (Native.mfx_scene_create(d, &h))          // copies everything: the buffers die right here
             check (Native.mfx_host_register(pin.AddrOfPinnedObject(), uint64 (width * height * 32)))
             h
         finally
@@ -151,10 +161,11 @@ type CudaPixelIntegrator(width:int, height:int, cam:PinholeCamera, bvh:Bvh, ligh
             p.spp <- n; p.seed <- defaultArg seed 1UL
             p.firstSample <- frame; p.world <- 1
             frame <- frame + n                                   // fresh samples every displayed frame
-            check (Native.mfx_pixel_integrator_sample(scene, &p, pin.AddrOfPinnedObject()))
+            if nGpus > 1 then check (Native.mfx_multi_sample(scene, &p, pin.AddrOfPinnedObject()))   // every device DMAs its stripes
+            else check (Native.mfx_pixel_integrator_sample(scene, &p, pin.AddrOfPinnedObject()))
             tex2d
     interface IDisposable with
         member this.Dispose() =
             Native.mfx_host_unregister(pin.AddrOfPinnedObject()) |> ignore
-            Native.mfx_scene_destroy scene |> ignore
+            (if nGpus > 1 then Native.mfx_multi_destroy scene else Native.mfx_scene_destroy scene) |> ignore
             pin.Free()

@@ -72,7 +72,7 @@ static void multi_worker(MfxMulti *m, int i)
         {
             std::unique_lock<std::mutex> lk(m->mu);
             m->cv_job.wait(lk, [&] { return m->quit || m->job != seen; });
-            if (m->quit) return;
+            if (m->quit) break;
             seen = m->job;
         }
         const auto t0 = std::chrono::steady_clock::now();
@@ -96,6 +96,9 @@ static void multi_worker(MfxMulti *m, int i)
             if (--m->pending == 0) m->cv_done.notify_all();
         }
     }
+    // every worker takes its own replica down (stream sync, ~60 buffers back to the pool, events): side by side
+    mfx_scene_destroy(m->scenes[(size_t)i]);
+    m->scenes[(size_t)i] = nullptr;
 }
 
 extern "C" int mfx_multi_create(const MfxSceneDesc *d, const int32_t *devices, int32_t n_devices, MfxMulti **out)
@@ -164,7 +167,7 @@ extern "C" int mfx_multi_destroy(MfxMulti *m)
     }
     m->cv_job.notify_all();
     for (std::thread &t : m->threads) t.join();
-    for (MfxScene *s : m->scenes) mfx_scene_destroy(s);
+    for (MfxScene *s : m->scenes) mfx_scene_destroy(s);          // whatever a worker did not take down itself
     delete m;
     return MFX_OK;
 }
