@@ -5,7 +5,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmafrix_cuda.so")
+# MFX_LIB: another build of the same ABI (the `make DEBUG=1` flavour with bounds checks, libmafrix_cuda_dbg.so)
+LIB_PATH = os.environ.get("MFX_LIB") or os.path.join(_HERE, "libmafrix_cuda.so")
 
 
 class MafrixError(RuntimeError):

@@ -50,6 +50,13 @@ __device__ __forceinline__ double u32_to_unit_f64(uint32_t x) { return (double)x
 // f32 uniform in [0,1): top 24 bits (differs from the f64 stream value by < 2^-24)
 __device__ __forceinline__ float u32_to_unit_f32(uint32_t x) { return (float)(x >> 8) * (1.0f / 16777216.0f); }
 
+// ---------------------------------------------------------------- debug build (make DEBUG=1)
+#ifdef MFX_DEBUG_CHECKS
+#define DBG_CHECK(cond, counts) do { if (!(cond)) atomicAdd(&(counts)[MFX_DBG_SLOT], 1); } while (0)
+#else
+#define DBG_CHECK(cond, counts) do { } while (0)
+#endif
+
 // ---------------------------------------------------------------- warp-aggregated append
 // Lanes with `pred` obtain consecutive positions in a queue with ONE atomic per warp:
 // ballot -> popc -> leader atomicAdd -> shuffle broadcast.  Must be called by the full warp

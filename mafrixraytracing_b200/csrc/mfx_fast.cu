@@ -553,6 +553,7 @@ __global__ void __launch_bounds__(FAST_BLOCK, MINB) k_f_trace6(SceneF sc, WaveF 
             const int m = (p0 != KEY_INF ? 1 : 0) + (p1 != KEY_INF ? 1 : 0) + (p2 != KEY_INF ? 1 : 0);
 #define STACK_PUT(I, K)                                                                                              \
             { const int i_ = (I); const uint2 v_ = make_uint2((K), (unsigned)node);                                  \
+              DBG_CHECK(i_ >= 0 && i_ < 3 * sc.own_depth, w.counts);                                                  \
               if (i_ < S) my_stack[(size_t)i_ * FAST_BLOCK] = v_; else my_spill[(size_t)(i_ - S) * spill_stride] = v_; }
             if (m >= 1) STACK_PUT(sp + m - 1, p0)
             if (m >= 2) STACK_PUT(sp + m - 2, p1)
@@ -562,6 +563,8 @@ __global__ void __launch_bounds__(FAST_BLOCK, MINB) k_f_trace6(SceneF sc, WaveF 
             const bool descend = any0 && !leaf0;
             needPop = !descend;
             if (descend) node = ~c0;
+            DBG_CHECK(!descend || (unsigned)node < (unsigned)sc.n_quads, w.counts);
+            DBG_CHECK(leafA < 0 || ((leafA >> 3) >= 0 && (leafA >> 3) + (leafA & 7) <= sc.n_slots), w.counts);
         }
         bool finished = false;
         const unsigned lp = __ballot_sync(FULL, pid >= 0 && leafA >= 0);
@@ -586,13 +589,19 @@ __global__ void __launch_bounds__(FAST_BLOCK, MINB) k_f_trace6(SceneF sc, WaveF 
                     const int link = __ldg(reinterpret_cast<const int *>(&sc.quads[e.y].meta) + (e.x & 3u));
                     if (e.x & 4u) { leafA = link; leafB = -1; }
                     else { node = ~link; needPop = false; }
+                    DBG_CHECK(e.y < (unsigned)sc.n_quads && ((e.x & 4u) ? (link >= 0 && (link >> 3) + (link & 7) <= sc.n_slots) : (unsigned)~link < (unsigned)sc.n_quads), w.counts);
                     break;
                 }
             }
         }
         if (finished) {
+            DBG_CHECK(pid >= 0 && pid < w.P && best_slot < sc.n_slots, w.counts);
             if (!ANY) w.hit[pid] = make_float2(best_t, __int_as_float(best_slot));
-            else if (best_slot < 0) { const float4 c = w.sh_c[pid]; float4 *ap = w.rad + __float_as_int(c.w); float4 a = *ap; a.x += c.x; a.y += c.y; a.z += c.z; *ap = a; }
+            else if (best_slot < 0) {
+                const float4 c = w.sh_c[pid];
+                DBG_CHECK(__float_as_int(c.w) >= 0 && __float_as_int(c.w) < w.P, w.counts);
+                float4 *ap = w.rad + __float_as_int(c.w); float4 a = *ap; a.x += c.x; a.y += c.y; a.z += c.z; *ap = a;
+            }
             pid = -1;
         }
     }
@@ -710,10 +719,12 @@ __global__ void __launch_bounds__(SHADE_BLOCK, 4) k_f_shade(SceneF sc, WaveF w, 
                     const double cz = __hiloint2double(__float_as_int(sc4.w), __float_as_int(sc4.z));
                     normal = normalize_f(f3((float)((double)point.x - cx), (float)((double)point.y - cy), (float)((double)point.z - cz)));
                 }
+                DBG_CHECK(fs < sc.n_slots && pid >= 0 && pid < w.P && (unsigned)__float_as_int(nm4.w) < (unsigned)sc.n_mats, w.counts);
                 const MatF m = sc.mats[__float_as_int(nm4.w)];
                 const int sl = pid / npix, pl = pid - sl * npix;
                 int pix, px, py;
                 pixel_of(tm, sc.width, pix0 + pl, pix, px, py);
+                DBG_CHECK(pix >= 0 && pix < sc.width * sc.height, w.counts);
                 RngF g; g.pixel = (uint32_t)pix; g.sample = (uint32_t)(s0 + sl); g.k0 = (uint32_t)seed; g.k1 = (uint32_t)(seed >> 32);
 
                 uint32_t dz[4] = { 0u, 0u, 0u, 0u };
@@ -801,10 +812,17 @@ __global__ void __launch_bounds__(SHADE_BLOCK, 4) k_f_shade(SceneF sc, WaveF w, 
         const unsigned below = (1u << lane) - 1u;
         if (cont) {
             const int pos = s_base[par][0] + s_cnt[par][0][warp] + __popc(mc & below);
+            DBG_CHECK(pos >= 0 && pos < w.P, w.counts);
             out_o[pos] = st_o; out_d[pos] = st_d; out_thr[pos] = st_thr;
         }
         if (shadow) {
             const int pos = s_base[par][1] + s_cnt[par][1][warp] + __popc(ms & below);
+            DBG_CHECK(pos >= 0 && pos < w.P, w.counts);
+#ifdef MFX_DEBUG_CHECKS
+            // the shadow kernel adds to rad[path] without an atomic: sound only while a path has at most ONE shadow ray in
+            // flight per bounce -- every path stamps the bounce that queued its ray, a second stamp of the same bounce trips
+            if (w.dbg_stamp) DBG_CHECK(atomicExch(&w.dbg_stamp[__float_as_int(st_shc.w)], bounce + 1) != bounce + 1, w.counts);
+#endif
             w.sh_o[pos] = st_o; w.sh_d[pos] = st_shd; w.sh_c[pos] = st_shc;
         }
     }
@@ -1034,6 +1052,7 @@ __global__ void k_accum_totals(const int *counts, int ext_lo, int ext_n, int sh_
     for (int i = 0; i < sh_n; i++) s += (unsigned)counts[sh_lo + i];
     totals[0] += e; totals[1] += s; totals[2] += (unsigned)counts[0];
     totals[3] += (unsigned)counts[MFX_COUNTS_LEN - 1];      // traversal watchdog trips
+    totals[5] += (unsigned)counts[MFX_DBG_SLOT];            // violations counted by a debug build (MFX_DEBUG_CHECKS)
 }
 
 // Film.AddSample (Film.fs:18-23): c = sum + frame; sum <- c; target <- c / frameCount

@@ -53,7 +53,11 @@ int mfx_fail(int code, const char *fmt, ...)
         if (r_ != MFX_OK) return r_; \
     } while (0)
 
-extern "C" const char *mfx_version(void) { return "mafrix_cuda 0.1 (sm_100a)"; }
+#ifdef MFX_DEBUG_CHECKS
+extern "C" const char *mfx_version(void) { return "mafrix_cuda 0.2 (sm_100a, DEBUG CHECKS)"; }
+#else
+extern "C" const char *mfx_version(void) { return "mafrix_cuda 0.2 (sm_100a)"; }
+#endif
 extern "C" const char *mfx_last_error(void) { return g_err.c_str(); }
 
 extern "C" int mfx_device_count(void)
@@ -567,6 +571,7 @@ static int fill_fast_common(MfxScene *s, SceneF &sf)
         sf.perlin_rf = s->d_perlin_rf; sf.perlin_perm = s->d_perlin_perm;
     }
     sf.width = s->width; sf.height = s->height; sf.max_depth = s->max_depth; sf.mode = s->integrator;
+    sf.n_mats = (int)s->mats.size();
     return MFX_OK;
 }
 
@@ -726,7 +731,7 @@ static int flatten_fast_ref(MfxScene *s)
     MFX_TRY(upload(s, &dpairs, pairs)); MFX_TRY(upload(s, &dslots, slots)); MFX_TRY(upload(s, &dnrm, nrm));
     MFX_TRY(upload(s, &dref, ref));
     s->fr_bytes = quads.size() * sizeof(QuadF) + pairs.size() * sizeof(PairF) + slots.size() * sizeof(SlotF) + nrm.size() * 16 + ref.size() * 4;
-    sf.quads = dquads; sf.qlevels = qlevels; sf.qpar = qpar;
+    sf.quads = dquads; sf.qlevels = qlevels; sf.qpar = qpar; sf.n_quads = (int)quads.size();
     sf.pairs = dpairs; sf.slots = dslots; sf.slot_nrm = dnrm; sf.ref_id = dref; sf.slot_prim = nullptr;
     MFX_TRY(fill_fast_common(s, sf));
     sf.n_slots = (int)slots.size();
@@ -875,6 +880,7 @@ static int flatten_fast(MfxScene *s)
     }
     MFX_TRY(fill_fast_common(s, sf));
     sf.n_slots = ns;
+    sf.n_quads = (int)quads.size();
     sf.has_big_sphere = host->has_big;
     s->f_ready = true;
     return MFX_OK;
@@ -934,6 +940,7 @@ static int flatten_hybrid(MfxScene *s)
     double m = 0.;
     for (int a = 0; a < 3; a++) m = std::max(m, std::max(std::fabs(s->nodes[0].pmin[a]), std::fabs(s->nodes[0].pmax[a])));
     sh.max_abs = round_up(m);
+    sh.n_ref = n;
     s->h_bytes = (uint64_t)ns * sizeof(PrimH) + (uint64_t)n * 12;
     s->h_ready = true;
     return MFX_OK;
@@ -1003,7 +1010,7 @@ static int ensure_wave_fast(MfxScene *s, size_t want)
     WaveF &w = s->wf;
     if (s->wf_ready) {
         CUDA_TRY(cudaStreamSynchronize(s->stream));
-        void *old[] = { w.ray_o[0], w.ray_o[1], w.ray_d[0], w.ray_d[1], w.thr[0], w.thr[1], w.hit, w.rad, w.sh_o, w.sh_d, w.sh_c, w.counts };
+        void *old[] = { w.ray_o[0], w.ray_o[1], w.ray_d[0], w.ray_d[1], w.thr[0], w.thr[1], w.hit, w.rad, w.sh_o, w.sh_d, w.sh_c, w.counts, w.dbg_stamp };
         for (void *q : old) dev_free_one(s, q);
         s->wf_ready = false;
     }
@@ -1021,11 +1028,15 @@ static int ensure_wave_fast(MfxScene *s, size_t want)
             MFX_TRY(dev_alloc_t(s, &w.hit, P)); MFX_TRY(dev_alloc_t(s, &w.rad, P));
             MFX_TRY(dev_alloc_t(s, &w.sh_o, P)); MFX_TRY(dev_alloc_t(s, &w.sh_d, P)); MFX_TRY(dev_alloc_t(s, &w.sh_c, P));
             MFX_TRY(dev_alloc_t(s, &w.counts, MFX_COUNTS_LEN));
+#ifdef MFX_DEBUG_CHECKS
+            MFX_TRY(dev_alloc_t(s, &w.dbg_stamp, P));
+            CUDA_TRY(cudaMemsetAsync(w.dbg_stamp, 0, P * sizeof(int), s->stream));
+#endif
             return MFX_OK;
         };
         const int rc = all();
         if (rc == MFX_OK) break;
-        void *part[] = { w.ray_o[0], w.ray_o[1], w.ray_d[0], w.ray_d[1], w.thr[0], w.thr[1], w.hit, w.rad, w.sh_o, w.sh_d, w.sh_c, w.counts };
+        void *part[] = { w.ray_o[0], w.ray_o[1], w.ray_d[0], w.ray_d[1], w.thr[0], w.thr[1], w.hit, w.rad, w.sh_o, w.sh_d, w.sh_c, w.counts, w.dbg_stamp };
         for (void *q : part) dev_free_one(s, q, false);
         if (rc != MFX_ERR_OUT_OF_MEMORY || P <= ((size_t)1 << 20)) return rc;
         cudaGetLastError();                                       // clear the allocation error
@@ -1270,6 +1281,11 @@ static int launch_sample(MfxScene *s, const MfxSampleParams *p, double *d_color_
             const int S = std::min(S_wave, p->spp - s0);
             const int sabs = p->first_sample + s0;
             CUDA_TRY(cudaMemsetAsync(counts, 0, MFX_COUNTS_LEN * sizeof(int), st));
+#ifdef MFX_DEBUG_CHECKS
+            // (MFX_DEBUG_FAULT=1 leaves the previous call's stamps in place: the next call's shadow rays then look like
+            //  second rays of their bounce and the check must trip -- the test that the assertion is alive)
+            if (!exact && s->wf.dbg_stamp && !env_long("MFX_DEBUG_FAULT", 0)) CUDA_TRY(cudaMemsetAsync(s->wf.dbg_stamp, 0, (size_t)s->wf.P * sizeof(int), st));
+#endif
             cfg.max_items = 0;
             if (exact) mfx_x_raygen(cfg, s->sx, s->wx, tm, pix0, np, sabs, S, p->seed);
             else if (hyb) mfx_h_raygen(cfg, *sfp, s->sx, s->wf, s->wh, tm, pix0, np, sabs, S, p->seed);
@@ -1357,6 +1373,7 @@ static int finish_sample(MfxScene *s, FrameJob &job)
     memset(&stt, 0, sizeof(stt));
     stt.closest_rays = totals[0]; stt.shadow_rays = totals[1]; stt.paths = totals[2];
     if (totals[3]) return fail(MFX_ERR_CUDA, "traversal watchdog tripped in %llu warp(s): the frame is incomplete", totals[3]);
+    if (totals[5]) return fail(MFX_ERR_CUDA, "debug build: %llu index / shadow-ray check(s) failed in the wavefront kernels", totals[5]);
     for (int c = 0; c < 2; c++) { stt.nodes[c] = hc.v[c][0]; stt.tris[c] = hc.v[c][1]; stt.spheres[c] = hc.v[c][2]; }
     float ms = 0.f;
     CUDA_TRY(cudaEventElapsedTime(&ms, job.events[job.e_begin], job.events[job.e_end]));

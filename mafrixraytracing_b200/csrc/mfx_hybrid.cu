@@ -252,6 +252,7 @@ __global__ void __launch_bounds__(FAST_BLOCK, MINB) k_h_trace(SceneF sc, const N
             const int m = (k1 != KEY_INF ? 1 : 0) + (k2 != KEY_INF ? 1 : 0) + (k3 != KEY_INF ? 1 : 0);
 #define STACK_PUT(I, K)                                                                                              \
             { const int i_ = (I); const uint2 v_ = make_uint2((K), (unsigned)node);                                  \
+              DBG_CHECK(i_ >= 0 && i_ < 3 * sc.own_depth, w.counts);                                                  \
               if (i_ < S) my_stack[(size_t)i_ * FAST_BLOCK] = v_; else my_spill[(size_t)(i_ - S) * spill_stride] = v_; }
             if (m >= 1) STACK_PUT(sp + m - 1, k1)
             if (m >= 2) STACK_PUT(sp + m - 2, k2)
@@ -261,6 +262,8 @@ __global__ void __launch_bounds__(FAST_BLOCK, MINB) k_h_trace(SceneF sc, const N
             const bool descend = any0 && !leaf0;
             needPop = !descend;
             if (descend) node = ~c0;
+            DBG_CHECK(!descend || (unsigned)node < (unsigned)sc.n_quads, w.counts);
+            DBG_CHECK(leafA < 0 || ((leafA >> 3) >= 0 && (leafA >> 3) + (leafA & 7) <= sc.n_slots), w.counts);
         }
         bool finished = false;
         const unsigned lp = __ballot_sync(FULL, pid >= 0 && leafA >= 0);
@@ -295,6 +298,7 @@ __global__ void __launch_bounds__(FAST_BLOCK, MINB) k_h_trace(SceneF sc, const N
                 const int at = atomicAdd(wh.fix_n, 1);
                 if (at < MFX_HYB_FIX_CAP) wh.fix_q[at] = pid;
             }
+            DBG_CHECK(pid >= 0 && pid < w.P && (ref < 0 || (ref & HYB_REF_MASK) < sh.n_ref), w.counts);
             if (seam) { wh.ref[pid] = ref; wh.t[pid] = best.t; }
             int fs = ref;                                   // -1 miss, -2 waiting for k_h_fixup
             if (ref >= 0) { const int2 f = __ldg(sh.ref_fslot + (ref & HYB_REF_MASK)); fs = (ref >> 30) ? f.y : f.x; }

@@ -140,6 +140,7 @@ struct SceneF {
     int    root_meta;       // leaf meta if the whole tree is one leaf, else -1
     int    width, height, max_depth, mode;
     int    n_slots;
+    int    n_quads, n_mats;     // record / material counts (bounds of the debug build's checks)
     int    levels;          // entries of the per-level entry-distance column (deepest child depth + 1)
     int    has_big_sphere;  // any kind-3 slot (selects the kernel variant with the f64 sphere branch)
     int    qlevels;         // number of quad levels
@@ -169,12 +170,16 @@ struct WaveF {
     float   tmax;           // tMax of the closest-hit queries (99999999., Integrators.fs:108; 1e7 for the sky tracer)
     int     cam_origin;     // 1: every bounce-0 ray starts at the camera position (pinhole): ray_o is neither written by
                             //    raygen nor read by the bounce-0 extend / shade (own-tree frames only; 0 for the seams)
+    int    *dbg_stamp;      // MFX_DEBUG_CHECKS: [P] last bounce that queued a shadow ray for the path (null otherwise)
     int    *counts;         // [0 .. MFX_MAX_VERTS+1] extend queue sizes per bounce,
                             // [MFX_MAX_VERTS+2 + bounce] shadow queue sizes
 };
 // + [2(V+2)+b] extend queue cursors, [3(V+2)+b] shadow queue cursors (persistent kernels);
 // the last entry is the traversal watchdog flag
 #define MFX_COUNTS_LEN (4 * (MFX_MAX_VERTS + 2))
+// one before the watchdog flag: violations counted by a `make DEBUG=1` build (MFX_DEBUG_CHECKS: bounds of every index the
+// wavefront kernels compute, one shadow ray per path and bounce) -- compute-sanitizer is closed on the GPU pool
+#define MFX_DBG_SLOT (MFX_COUNTS_LEN - 2)
 
 // ------------------------------------------------------------------ hybrid (id-exact closest hit, mfx_hybrid.cu)
 // The closest-hit query of the reference has ONE answer (BvhNode.fs:62-83): the smallest t over every primitive the
@@ -203,6 +208,7 @@ struct SceneH {
     const int  *leaf_of_ref;    // exact slot -> heap index of the reference-tree leaf holding it (BvhNode.fs:40-41)
     const int2 *ref_fslot;      // exact slot -> own-tree fast slots of (first, second) triangle; .y = -1 unless a Rect
     float max_abs;              // largest |coordinate| of the scene bound: scale of the per-ray box pad
+    int   n_ref;                // number of exact slots (= primitives)
 };
 #define MFX_HYB_FIX_CAP (1 << 20)
 struct WaveH {
