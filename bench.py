@@ -459,7 +459,7 @@ def main():
                            "oracle's bit for bit (tests/test_gpu_parity.py::test_fast_primary_is_bit_exact)")
         s0.close()
 
-    # ---- BASELINE configs[2..4] at their stated size through the same path (device timed, one full-size step each)
+    # ---- BASELINE configs[2..4] at their stated size through the same path (device timed, one warm + one timed full-size step each)
     configs = None
     if not args.no_configs and prec == FAST_F32:
         configs = []
@@ -477,6 +477,8 @@ def main():
             t_first = time.perf_counter() - t0
             sync_all()
             dbg("config", name, "layouts built")
+            timed_step(csh, spp)                                 # untimed: the path state of a full-size wave is allocated here
+            sync_all()
             ms, st = timed_step(csh, spp)
             dbg("config", name, "timed")
             r_all, t_cfg = aggregate(st["closest_rays"] + st["shadow_rays"], ms)
