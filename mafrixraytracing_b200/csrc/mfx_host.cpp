@@ -755,8 +755,8 @@ struct OwnTreeHost {
     size_t bytes() const { return quads.size() * sizeof(QuadF) + slots.size() * sizeof(SlotF) + nrm.size() * 16 + slot_prim.size() * 4; }
 };
 struct TreeKey {
-    uint64_t h1, h2; size_t n; long max_leaf, trav;
-    bool operator==(const TreeKey &o) const { return h1 == o.h1 && h2 == o.h2 && n == o.n && max_leaf == o.max_leaf && trav == o.trav; }
+    uint64_t h1, h2; size_t n; long max_leaf, trav, collapse;
+    bool operator==(const TreeKey &o) const { return h1 == o.h1 && h2 == o.h2 && n == o.n && max_leaf == o.max_leaf && trav == o.trav && collapse == o.collapse; }
 };
 static std::mutex g_tree_mu;
 static std::vector<std::pair<TreeKey, std::shared_ptr<OwnTreeHost>>> g_tree_cache;    // most recently used last
@@ -771,7 +771,7 @@ static TreeKey tree_key(const std::vector<MfxPrim> &prims, long max_leaf, long t
         a = (a ^ w[i]) * 0x100000001B3ull; a ^= a >> 29;
         b = (b + w[i]) * 0xFF51AFD7ED558CCDull; b ^= b >> 32;
     }
-    return TreeKey{ a, b, prims.size(), max_leaf, trav };
+    return TreeKey{ a, b, prims.size(), max_leaf, trav, env_long("MFX_COLLAPSE_DP", 100) };
 }
 
 static std::shared_ptr<OwnTreeHost> build_own_tree_host(MfxScene *s, long max_leaf, long trav)

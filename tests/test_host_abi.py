@@ -65,8 +65,8 @@ def test_own_tree_builder_is_a_valid_bvh(tmp_path):
     for n, mode in [(1, 0), (2, 0), (3, 0), (5, 0), (17, 0), (1000, 0), (150000, 0), (3000, 1), (5000, 2)]:
         out = subprocess.check_output([exe, str(n), str(mode)], text=True)
         assert out.startswith(f"ok n={n} mode={mode}"), out
-    # the optional dynamic-programming collapse (MFX_COLLAPSE_DP, off by default) must give valid trees too
-    for dp in ("100", "250"):
+    # the greedy collapse of round 1 (MFX_COLLAPSE_DP=0) and another record cost must give valid trees too
+    for dp in ("0", "250"):
         for n, mode in [(1, 0), (3, 0), (5, 0), (17, 0), (1000, 0), (40000, 0), (3000, 1), (5000, 2)]:
             out = subprocess.check_output([exe, str(n), str(mode)], text=True, env=dict(os.environ, MFX_COLLAPSE_DP=dp))
             assert out.startswith(f"ok n={n} mode={mode}"), (dp, out)

@@ -1,5 +1,6 @@
 #!/usr/bin/env python3
-"""A/B of an environment knob on whole frames.  usage: ab_env.py VAR v1,v2,.. workload spp[,spp..] [reps]"""
+"""A/B of an environment knob on whole frames.  usage: ab_env.py VAR v1,v2,.. workload spp[,spp..] [reps] [rebuild]
+rebuild: the knob is read when the scene's layouts are built (tree builder knobs): a fresh Scene per value, tree cache off."""
 import os, sys, json
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
@@ -7,6 +8,9 @@ from mafrixraytracing_b200 import scenes, Scene, CudaPixelIntegrator, FAST_F32
 var, vals, name = sys.argv[1], sys.argv[2].split(","), sys.argv[3]
 spps = [int(x) for x in sys.argv[4].split(",")]
 reps = int(sys.argv[5]) if len(sys.argv) > 5 else 5
+rebuild = len(sys.argv) > 6
+if rebuild:
+    os.environ["MFX_TREE_CACHE"] = "0"
 desc = scenes.WORKLOADS[name]()
 s = Scene(desc)
 integ = CudaPixelIntegrator(s, precision=FAST_F32, seed=1)
@@ -14,6 +18,10 @@ ref = {}
 for spp in spps:
     for v in vals:
         os.environ[var] = v
+        if rebuild:
+            s.close()
+            s = Scene(desc)
+            integ = CudaPixelIntegrator(s, precision=FAST_F32, seed=1)
         best = None
         for _ in range(reps):
             img = integ.SampleF32(spp)
