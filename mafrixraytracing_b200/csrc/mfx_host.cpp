@@ -941,6 +941,7 @@ static int flatten_hybrid(MfxScene *s)
     for (int a = 0; a < 3; a++) m = std::max(m, std::max(std::fabs(s->nodes[0].pmin[a]), std::fabs(s->nodes[0].pmax[a])));
     sh.max_abs = round_up(m);
     sh.n_ref = n;
+    sh.pad_factor = (float)env_long("MFX_HYB_PAD_PPB", 4000) * 1e-9f;
     s->h_bytes = (uint64_t)ns * sizeof(PrimH) + (uint64_t)n * 12;
     s->h_ready = true;
     return MFX_OK;

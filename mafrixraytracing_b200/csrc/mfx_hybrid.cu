@@ -208,7 +208,7 @@ __global__ void __launch_bounds__(FAST_BLOCK, MINB) k_h_trace(SceneF sc, const N
                     const RayF r = make_ray_fast(o, d, HYB_TMIN_BOX, -1);
                     idir = r.idir;
                     // per-ray pad: every box plane moves outward by `pad` in space = pad * |1/d| in t
-                    const float pad = 4e-6f * (sh.max_abs + fmaxf(fabsf(o.x), fmaxf(fabsf(o.y), fabsf(o.z))));
+                    const float pad = sh.pad_factor * (sh.max_abs + fmaxf(fabsf(o.x), fmaxf(fabsf(o.y), fabsf(o.z))));
                     const F3 pt = f3(pad * fabsf(idir.x), pad * fabsf(idir.y), pad * fabsf(idir.z));
                     ood_n = r.ood + pt; ood_f = r.ood - pt;
                     limit = 3.0e38f;                         // triangles ignore tMax (Trangle.fs:148): nothing is culled by it

@@ -209,6 +209,7 @@ struct SceneH {
     const int2 *ref_fslot;      // exact slot -> own-tree fast slots of (first, second) triangle; .y = -1 unless a Rect
     float max_abs;              // largest |coordinate| of the scene bound: scale of the per-ray box pad
     int   n_ref;                // number of exact slots (= primitives)
+    float pad_factor;           // 4e-6 (MFX_HYB_PAD_PPB = 4000 parts per billion): the margin experiment of tools/hyb_pad_margin.py
 };
 #define MFX_HYB_FIX_CAP (1 << 20)
 struct WaveH {
