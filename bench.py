@@ -304,7 +304,7 @@ def main():
             # the host keeps its Texture2D<Color> for its lifetime (Integrators.fs:147): pinned once so the per-frame
             # download is a direct DMA (mfx_host_register).  Two of them: frame k downloads while frame k+1
             # renders (mfx_pixel_integrator_sample_async), the pipelined form of the reference's frame-after-frame loop
-            for _ in range(2 if world == 1 else 1):
+            for _ in range(2):
                 t = np.zeros((desc.width, desc.height, 4), dtype=np.float64)
                 _lib.check(_lib.load().mfx_host_register(_lib.ptr(t), t.nbytes))
                 texs.append(t)
@@ -340,19 +340,38 @@ def main():
                 sc.close()
             t_block = time.perf_counter() - t0
         elif rank == 0:
-            t_block = None
-            for k in range(args.steps + 1):
-                torch.cuda.synchronize()
-                t0 = time.perf_counter()
-                integ = MultiGpuPixelIntegrator(desc, devices=list(range(world)), bvh=bvh, precision=prec, seed=1)
-                integ.Sample(args.spp, out=texs[0])                  # every device DMAs its stripes into the one host texture
-                dt = time.perf_counter() - t0
-                st = integ.stats
-                integ.close()
-                if k == 0:
-                    continue                                         # first call allocates the path state
-                rays_e2e += st["closest_rays"] + st["shadow_rays"]
-                t_e2e += dt
+            def one_blocking():
+                m = MultiGpuPixelIntegrator(desc, devices=list(range(world)), bvh=bvh, precision=prec, seed=1)
+                m.Sample(args.spp, out=texs[0])                  # every device DMAs its stripes into the one host texture
+                st = m.stats
+                m.close()
+                return st["closest_rays"] + st["shadow_rays"]
+
+            def pipelined_multi(n_steps):
+                """n_steps frames, each through its own mfx_multi_create: frame k renders and downloads while the host thread
+                creates the replicas of frame k+1 (mfx_multi_sample_async / mfx_multi_wait)."""
+                rays, prev = 0.0, None
+                for k in range(n_steps):
+                    m = MultiGpuPixelIntegrator(desc, devices=list(range(world)), bvh=bvh, precision=prec, seed=1)
+                    m.SampleAsync(args.spp, texs[k % 2])
+                    if prev is not None:
+                        prev.Wait()
+                        rays += prev.stats["closest_rays"] + prev.stats["shadow_rays"]
+                        prev.close()
+                    prev = m
+                prev.Wait()
+                rays += prev.stats["closest_rays"] + prev.stats["shadow_rays"]
+                prev.close()
+                return rays
+            one_blocking(); pipelined_multi(2)                       # untimed: contexts, path state of two frames in flight
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            rays_e2e = pipelined_multi(args.steps)
+            t_e2e = time.perf_counter() - t0
+            t0 = time.perf_counter()
+            for k in range(args.steps):
+                one_blocking()
+            t_block = time.perf_counter() - t0
         if rank == 0:
             for t in texs:
                 _lib.load().mfx_host_unregister(_lib.ptr(t))
@@ -364,8 +383,9 @@ def main():
                    "call": "per frame: mfx_scene_create + mfx_pixel_integrator_sample_async -> pinned Color[w,h] f64, mfx_pixel_integrator_wait on the "
                            "previous frame (two frames in flight: download k beside render k+1); blocking_ms_per_step = the same with "
                            "mfx_pixel_integrator_sample" if world == 1 else
-                           f"mfx_multi_create + mfx_multi_sample from ONE host thread over {world} GPUs (scene replicated per device, every device "
-                           "DMAs its column stripes into the pinned host texture; ranks 1.. idle on a CPU barrier)"}
+                           f"per frame: mfx_multi_create + mfx_multi_sample_async from ONE host thread over {world} GPUs (scene replicated per device, "
+                           "every device DMAs its column stripes into the pinned host texture), mfx_multi_wait on the previous frame; "
+                           "blocking_ms_per_step = the same with mfx_multi_sample; ranks 1.. idle on a CPU barrier"}
 
     dbg("e2e done")
     # ---- roofline of the dominant kernel (closest-hit traversal), rank 0's share

@@ -289,6 +289,10 @@ MFX_API int mfx_multi_device_count(const MfxMulti *multi, int32_t *n_out);
  * device).  params->rank / world / tile_size are ignored (the library shards), every other field as in
  * mfx_pixel_integrator_sample. */
 MFX_API int mfx_multi_sample(MfxMulti *multi, const MfxSampleParams *params, double *texture);
+/* The same call without the wait (one frame in flight per handle): the workers render and download while the caller goes
+ * on; mfx_multi_wait completes it.  texture must stay untouched until then. */
+MFX_API int mfx_multi_sample_async(MfxMulti *multi, const MfxSampleParams *params, double *texture);
+MFX_API int mfx_multi_wait(MfxMulti *multi);
 /* Same, float RGBA row-major. */
 MFX_API int mfx_multi_sample_f32(MfxMulti *multi, const MfxSampleParams *params, float *rgba);
 /* total: rays / paths / launches summed over the devices, ms_* of the slowest one; per_device: n entries or NULL. */

@@ -98,6 +98,8 @@ SYMBOLS = {
     "mfx_multi_destroy": (C.c_int, [_P]),
     "mfx_multi_device_count": (C.c_int, [_P, C.POINTER(C.c_int32)]),
     "mfx_multi_sample": (C.c_int, [_P, C.POINTER(MfxSampleParams), _P]),
+    "mfx_multi_sample_async": (C.c_int, [_P, C.POINTER(MfxSampleParams), _P]),
+    "mfx_multi_wait": (C.c_int, [_P]),
     "mfx_multi_sample_f32": (C.c_int, [_P, C.POINTER(MfxSampleParams), _P]),
     "mfx_multi_get_stats": (C.c_int, [_P, C.POINTER(MfxStats), _P]),
     "mfx_film_create": (C.c_int, [_P, C.POINTER(_P)]),

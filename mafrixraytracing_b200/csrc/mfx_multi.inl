@@ -32,6 +32,8 @@ struct MfxMulti {
     std::vector<std::string> err;
     std::vector<double> ms_wall;    // per device: run_sample + its D2H, host clock
     double ms_call = 0.;
+    bool posted = false;            // a job was handed to the workers and not yet waited for
+    std::chrono::steady_clock::time_point t_post;
 };
 
 // this device's stripes of the finished frame -> the caller's buffer
@@ -158,9 +160,12 @@ extern "C" int mfx_multi_create(const MfxSceneDesc *d, const int32_t *devices, i
     return MFX_OK;
 }
 
+static int multi_wait(MfxMulti *m);
+
 extern "C" int mfx_multi_destroy(MfxMulti *m)
 {
     if (!m) return MFX_OK;
+    multi_wait(m);                       // a frame still in flight finishes first
     {
         std::lock_guard<std::mutex> lk(m->mu);
         m->quit = true;
@@ -179,24 +184,33 @@ extern "C" int mfx_multi_device_count(const MfxMulti *m, int32_t *n_out)
     return MFX_OK;
 }
 
-static int multi_run(MfxMulti *m, const MfxSampleParams *p, double *texture, float *rgba)
+// Posts one Sample to the workers and returns; multi_wait completes it.  One job in flight per handle.
+static int multi_post(MfxMulti *m, const MfxSampleParams *p, double *texture, float *rgba)
 {
     if (!m || !p) return fail(MFX_ERR_INVALID_ARGUMENT, "null argument");
     if (p->spp <= 0) return fail(MFX_ERR_INVALID_ARGUMENT, "spp must be positive, got %d", p->spp);
     if (p->world > 1) return fail(MFX_ERR_INVALID_ARGUMENT, "mfx_multi_sample shards the frame itself: pass world <= 1");
-    const auto t0 = std::chrono::steady_clock::now();
-    {
-        std::lock_guard<std::mutex> lk(m->mu);
-        m->params = *p; m->texture = texture; m->rgba = rgba;
-        m->pending = (int)m->devices.size();
-        m->job++;
-    }
+    std::lock_guard<std::mutex> lk(m->mu);
+    if (m->pending != 0) return fail(MFX_ERR_INVALID_ARGUMENT, "a frame is still in flight on this handle: call mfx_multi_wait first");
+    m->t_post = std::chrono::steady_clock::now();
+    m->params = *p; m->texture = texture; m->rgba = rgba;
+    m->pending = (int)m->devices.size();
+    m->posted = true;
+    m->job++;
     m->cv_job.notify_all();
+    return MFX_OK;
+}
+
+static int multi_wait(MfxMulti *m)
+{
+    if (!m) return fail(MFX_ERR_INVALID_ARGUMENT, "null argument");
     {
         std::unique_lock<std::mutex> lk(m->mu);
+        if (!m->posted) return MFX_OK;
         m->cv_done.wait(lk, [&] { return m->pending == 0; });
+        m->posted = false;
     }
-    m->ms_call = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    m->ms_call = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - m->t_post).count();
     for (size_t i = 0; i < m->devices.size(); i++)
         if (m->rc[i] != MFX_OK) return fail(m->rc[i], "device %d: %s", m->devices[i], m->err[i].c_str());
     return MFX_OK;
@@ -205,14 +219,25 @@ static int multi_run(MfxMulti *m, const MfxSampleParams *p, double *texture, flo
 extern "C" int mfx_multi_sample(MfxMulti *m, const MfxSampleParams *p, double *texture)
 {
     if (!texture) return fail(MFX_ERR_INVALID_ARGUMENT, "null texture");
-    return multi_run(m, p, texture, nullptr);
+    MFX_TRY(multi_post(m, p, texture, nullptr));
+    return multi_wait(m);
 }
 
 extern "C" int mfx_multi_sample_f32(MfxMulti *m, const MfxSampleParams *p, float *rgba)
 {
     if (!rgba) return fail(MFX_ERR_INVALID_ARGUMENT, "null output");
-    return multi_run(m, p, nullptr, rgba);
+    MFX_TRY(multi_post(m, p, nullptr, rgba));
+    return multi_wait(m);
 }
+
+// Sample without the wait: the workers render and download while the caller goes on (e.g. builds the next frame's scene).
+extern "C" int mfx_multi_sample_async(MfxMulti *m, const MfxSampleParams *p, double *texture)
+{
+    if (!texture) return fail(MFX_ERR_INVALID_ARGUMENT, "null texture");
+    return multi_post(m, p, texture, nullptr);
+}
+
+extern "C" int mfx_multi_wait(MfxMulti *m) { return multi_wait(m); }
 
 // total: rays / paths / launches summed over the devices, times = the slowest device (they run side by side);
 // per_device (n_devices entries, may be NULL): each device's own MfxStats.

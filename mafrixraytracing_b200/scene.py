@@ -426,6 +426,15 @@ class MultiGpuPixelIntegrator:
         self._after()
         return tex
 
+    def SampleAsync(self, n, out, first_sample=0, flags=0):
+        """Posts Sample(n) to the device workers and returns; Wait() completes it (one frame in flight per handle)."""
+        p = _lib.MfxSampleParams(self.precision, int(n), self.seed, int(first_sample), 0, 0, 1, int(flags))
+        _lib.check(_lib.load().mfx_multi_sample_async(self._h, C.byref(p), _lib.ptr(out)))
+
+    def Wait(self):
+        _lib.check(_lib.load().mfx_multi_wait(self._h))
+        self._after()
+
     def SampleF32(self, n, first_sample=0, flags=0):
         img = np.zeros((self.height, self.width, 4), dtype=np.float32)
         p = _lib.MfxSampleParams(self.precision, int(n), self.seed, int(first_sample), 0, 0, 1, int(flags))

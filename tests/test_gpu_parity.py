@@ -255,24 +255,33 @@ def test_direct_sampler_converges_to_the_rejection_sampler(name, kw, mode):
     assert abs(c(da).mean() / c(ra).mean() - 1) < 5e-3, f"{name}: mean radiance {c(da).mean():.5e} vs {c(ra).mean():.5e}"
 
 
-@pytest.mark.parametrize("name,kw", [("c3_renault", dict(width=160, height=90)), ("spheres", dict(width=160, height=90, grid=24))])
-def test_fast_sample_mode_b_is_statistically_equal(name, kw):
-    """NewPathTracer scenes have specular chains and 1/|cos| weights: single paths diverge between
-    f32 and f64, so the bar is statistical -- the fast frame must sit inside the exact renderer's
-    own seed-to-seed noise and agree in mean radiance."""
+@pytest.mark.parametrize("name,kw,tol64,tol256", [("c3_renault", dict(width=160, height=90), 0.40, 0.20),
+                                                  ("spheres", dict(width=160, height=90, grid=24), 0.19, 0.095)])
+def test_fast_sample_mode_b_stated_tolerance(name, kw, tol64, tol256):
+    """NewPathTracer scenes have specular chains and 1/|cos| weights: single paths diverge between f32 and f64, so the
+    bar is on converged images at matched spp (north_star).  STATED TOLERANCE, 99th-percentile-clipped radiance:
+      relative RMSE of the fast frame against the exact frame  <= tol64 at 64 spp, <= tol256 at 256 spp
+        (measured 0.34 / 0.17 on Renault, 0.15 / 0.075 on the spheres: it halves per 4x spp -- both renderers converge to
+         the same image -- and stays BELOW the exact renderer's own seed-to-seed RMSE, 0.40 / 0.20 and 0.19 / 0.093);
+      relative luminance (Rec. 709) of the whole frame within 5e-3 at 64 spp and 2e-3 at 256 spp (measured <= 3.2e-3 / 8e-4)."""
     desc = _desc(name, **kw)
     s = Scene(desc)
-    spp = 64
-    ea = CudaPixelIntegrator(s, precision=EXACT_F64, seed=5).Sample(spp).copy()[:, :, :3]
-    eb = CudaPixelIntegrator(s, precision=EXACT_F64, seed=6).Sample(spp).copy()[:, :, :3]
-    fa = CudaPixelIntegrator(s, precision=FAST_F32, seed=5).Sample(spp).copy()[:, :, :3]
-    # robust statistics: heavy-tailed fireflies make plain RMSE meaningless here
-    clip = np.percentile(ea, 99.0)
-    c = lambda x: np.clip(x, -clip, clip)
-    noise = np.sqrt(((c(ea) - c(eb)) ** 2).mean())
-    err = np.sqrt(((c(fa) - c(ea)) ** 2).mean())
-    assert err <= noise, f"{name}: fast-vs-exact {err:.3e} exceeds the seed-to-seed noise {noise:.3e}"
-    assert abs(c(fa).mean() / c(ea).mean() - 1) < 2e-2
+    rel = {}
+    for spp, tol, ltol in ((64, tol64, 5e-3), (256, tol256, 2e-3)):
+        ea = CudaPixelIntegrator(s, precision=EXACT_F64, seed=5).Sample(spp).copy()[:, :, :3]
+        eb = CudaPixelIntegrator(s, precision=EXACT_F64, seed=6).Sample(spp).copy()[:, :, :3]
+        fa = CudaPixelIntegrator(s, precision=FAST_F32, seed=5).Sample(spp).copy()[:, :, :3]
+        # robust statistics: heavy-tailed fireflies make plain RMSE meaningless here
+        clip = np.percentile(ea, 99.0)
+        c = lambda x: np.clip(x, -clip, clip)
+        lum = lambda x: (c(x) * [0.2126, 0.7152, 0.0722]).sum(-1).mean()
+        mean = np.abs(c(ea)).mean()
+        noise = np.sqrt(((c(ea) - c(eb)) ** 2).mean()) / mean
+        rel[spp] = np.sqrt(((c(fa) - c(ea)) ** 2).mean()) / mean
+        assert rel[spp] <= tol, f"{name} {spp} spp: relative RMSE {rel[spp]:.3f} above the stated {tol}"
+        assert rel[spp] <= noise, f"{name} {spp} spp: fast-vs-exact {rel[spp]:.3f} exceeds the seed-to-seed noise {noise:.3f}"
+        assert abs(lum(fa) / lum(ea) - 1) < ltol, f"{name} {spp} spp: relative luminance off by {lum(fa) / lum(ea) - 1:+.2e}"
+    assert rel[256] <= 0.6 * rel[64]                     # Monte-Carlo convergence towards the SAME image (ideal: 0.5)
 
 
 def test_sample_is_deterministic_and_progressive():
@@ -366,9 +375,16 @@ def test_multi_gpu_api_on_the_devices_present():
             _lib.check(_lib.load().mfx_host_register(_lib.ptr(tex), tex.nbytes))
             try:
                 got = m.Sample(4, out=tex)
+                assert np.array_equal(got, want)
+                tex[:] = -1.0
+                m.SampleAsync(4, tex)                                 # the same call without the wait
+                with pytest.raises(MafrixError):
+                    m.SampleAsync(4, tex)                             # one frame in flight per handle
+                m.Wait()
+                assert np.array_equal(tex, want)
+                m.Wait()                                              # nothing in flight: no-op
             finally:
                 _lib.load().mfx_host_unregister(_lib.ptr(tex))
-            assert np.array_equal(got, want)
             assert np.array_equal(m.SampleF32(4), want32)                 # pageable destination
             st = m.stats
             assert st["paths"] == desc.width * desc.height * 4 and len(st["per_device"]) == len(devs)
