@@ -1175,7 +1175,7 @@ static void launch_trace_variant(const LaunchCfg &c, const SceneF &sc, const Wav
             else launch_trace6b<ANY, false, 16, 10, 2, 1, 1, true>(c, sc, w, bounce, ctr);
             return;
         }
-        switch (c.variant) {    // tuning knobs kept for A/B runs (tools/kb2.py); the default is the measured best (profiles/)
+        switch (c.variant) {    // tuning knobs kept for A/B runs (tools/ab_env.py MFX_TRACE_VARIANT ...); the default is the measured best (profiles/)
         case 61: launch_trace6<ANY, 8, 12, 2, 2>(c, sc, w, bounce); break;      // two parked leaves
         case 62: launch_trace6<ANY, 12, 16, 1, 2>(c, sc, w, bounce); break;     // one node step per iteration
         case 65: launch_trace6<ANY, 8, 12, 2, 1>(c, sc, w, bounce); break;
