@@ -1181,6 +1181,8 @@ static void launch_trace_variant(const LaunchCfg &c, const SceneF &sc, const Wav
         case 65: launch_trace6<ANY, 8, 12, 2, 1>(c, sc, w, bounce); break;
         case 84: launch_trace6<ANY, 12, 12, 2, 1>(c, sc, w, bounce); break;
         case 85: launch_trace6<ANY, 16, 8, 2, 1>(c, sc, w, bounce); break;
+        // refill batches of 20 / 24 / 28 / 32 lanes (more sector sharing near the root, more idle lanes) measured -3 / -10 /
+        // -18 / -30 % on C2 in round 2: 16 stays
         default: launch_trace6<ANY, 16, 10, 2, 1, 8>(c, sc, w, bounce); break;    // 8 blocks/SM: 64 registers
         }
         return;
