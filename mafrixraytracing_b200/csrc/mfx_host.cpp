@@ -177,6 +177,8 @@ struct MfxScene {
     int sm_count = 148;
     cudaStream_t stream = nullptr;
     cudaStream_t stream2 = nullptr;          // shadow queries of bounce b run beside the closest hits of bounce b+1 (run_sample)
+    float4 *sh2[3] = { nullptr, nullptr, nullptr };   // second shadow queue (sh_o, sh_d, sh_c) of the two-stream mode
+    int sh2_P = 0;
     std::vector<MfxPrim> prims;
     std::vector<MfxMaterial> mats;
     std::vector<MfxBvhNode> nodes;
@@ -1259,15 +1261,25 @@ static int launch_sample(MfxScene *s, const MfxSampleParams *p, double *d_color_
     // Two streams (fast precision, light-sampling integrators): the shadow queries of bounce b touch sh_* and rad only,
     // the closest hits of bounce b+1 the ray queue and hit[] only -- side by side, the head of one persistent grid fills
     // the SMs the tail of the other one leaves idle.  shade(b+1) rewrites sh_*: it waits for shadow(b).
-    // Measured (C2 / C3): +1.5 % / +3.8 % on frames of 16 M paths (what one of eight GPUs renders), +0.2 % / +0.9 % on the
-    // full 133 M-path frame -- so it is used where launches are short and their tails weigh, and big frames keep one
+    // Measured (C2 / C3, two shadow queues deep): +2.7 % / +4.2 % on frames of 16 M paths (what one of eight GPUs renders),
+    // +0.4 % / +1.0 % on the full 133 M-path frame -- so it is used where launches are short and their tails weigh, and big frames keep one
     // stream (and per-kernel event times that do not overlap).  MFX_TWO_STREAMS = 0 / 1 forces either.
     const long two_env = env_long("MFX_TWO_STREAMS", -1);
     const bool two = !exact && !sky && !ctr && (two_env >= 0 ? two_env != 0 : (size_t)tm.n_pix * (size_t)p->spp <= ((size_t)48 << 20));
     if (two && !s->stream2) CUDA_TRY(cudaStreamCreateWithFlags(&s->stream2, cudaStreamNonBlocking));
     cudaStream_t st2 = two ? s->stream2 : st;
     LaunchCfg cfg2 = cfg; cfg2.stream = st2;
-    cudaEvent_t e_shadow_done = nullptr;
+    // ... and with a second shadow queue shade(b+1) does not wait for shadow(b) either: the shadow launches trail the
+    // extend / shade chain on their own stream, two queues deep (shade(b) waits for shadow(b-2), which used its queue)
+    if (two && s->sh2_P != s->wf.P) {
+        CUDA_TRY(cudaStreamSynchronize(st));
+        for (int k = 0; k < 3; k++) { dev_free_one(s, s->sh2[k]); s->sh2[k] = nullptr; }
+        for (int k = 0; k < 3; k++) MFX_TRY(dev_alloc_t(s, &s->sh2[k], (size_t)s->wf.P));
+        s->sh2_P = s->wf.P;
+    }
+    WaveF wf_alt = s->wf;
+    if (two) { wf_alt.sh_o = s->sh2[0]; wf_alt.sh_d = s->sh2[1]; wf_alt.sh_c = s->sh2[2]; }
+    cudaEvent_t e_shadow_done[2] = { nullptr, nullptr };
 
     const int P = exact ? s->wx.P : s->wf.P;
     const int D = s->max_depth;
@@ -1319,9 +1331,10 @@ static int launch_sample(MfxScene *s, const MfxSampleParams *p, double *d_color_
                     }
                     continue;
                 }
-                if (two && e_shadow_done) CUDA_TRY(cudaStreamWaitEvent(st, e_shadow_done, 0));      // shade(b) rewrites the shadow queue
+                const WaveF &wq = (two && (b & 1)) ? wf_alt : s->wf;           // the shadow queue of this bounce
+                if (two && e_shadow_done[b & 1]) CUDA_TRY(cudaStreamWaitEvent(st, e_shadow_done[b & 1], 0));   // shade(b) rewrites the queue shadow(b-2) read
                 if (exact) mfx_x_shade(cfg, s->sx, s->wx, tm, pix0, np, sabs, b, p->seed);
-                else mfx_f_shade(cfg, *sfp, s->wf, tm, pix0, np, sabs, b, p->seed);
+                else mfx_f_shade(cfg, *sfp, wq, tm, pix0, np, sabs, b, p->seed);
                 if (two) {
                     cudaEvent_t e_shaded;
                     MFX_TRY(get_event(job, ev++, &e_shaded));
@@ -1329,15 +1342,16 @@ static int launch_sample(MfxScene *s, const MfxSampleParams *p, double *d_color_
                     CUDA_TRY(cudaStreamWaitEvent(st2, e_shaded, 0));
                 }
                 MFX_TRY(timed(1, st2));
-                if (exact) mfx_x_shadow(cfg, s->sx, s->wx, b, ctr); else mfx_f_shadow(cfg2, *sfp, s->wf, b, ctr);
+                if (exact) mfx_x_shadow(cfg, s->sx, s->wx, b, ctr); else mfx_f_shadow(cfg2, *sfp, wq, b, ctr);
                 MFX_TRY(timed_end(st2));
                 if (two) {
-                    MFX_TRY(get_event(job, ev++, &e_shadow_done));
-                    CUDA_TRY(cudaEventRecord(e_shadow_done, st2));
+                    MFX_TRY(get_event(job, ev++, &e_shadow_done[b & 1]));
+                    CUDA_TRY(cudaEventRecord(e_shadow_done[b & 1], st2));
                 }
                 launches += 3; l_ext++; l_sh++;
             }
-            if (two && e_shadow_done) { CUDA_TRY(cudaStreamWaitEvent(st, e_shadow_done, 0)); e_shadow_done = nullptr; }   // resolve reads rad
+            for (int k = 0; k < 2; k++)                                          // resolve reads rad: every shadow launch is in
+                if (two && e_shadow_done[k]) { CUDA_TRY(cudaStreamWaitEvent(st, e_shadow_done[k], 0)); e_shadow_done[k] = nullptr; }
             if (exact) mfx_x_resolve(cfg, s->sx, s->wx, tm, pix0, np, S, s->d_pixsum);
             else mfx_f_resolve(cfg, *sfp, s->wf, tm, pix0, np, S, s->d_pixsum);
             // rays traced: exact: closest = counts[0..D], shadow = counts[1..D+1];
