@@ -159,6 +159,7 @@ extern "C" int mfx_camera_lens(const double lookfrom[3], const double lookat[3],
 struct Span { size_t a, b; int cls; };
 struct FrameJob {
     bool active = false;
+    int device = 0;
     std::vector<cudaEvent_t> events;         // timing + dependency events of this job (grown on demand, reused)
     std::vector<Span> spans;
     size_t e_begin = 0, e_end = 1;
@@ -308,6 +309,8 @@ long mfx_env_long(const char *name, long dflt)
     return atol(v);
 }
 
+static int stream_get(int device, cudaStream_t *out);
+
 // A caller-supplied Bvh (nodes + indices) is indexed by the flatteners and by the kernels: reject anything that is not
 // a permutation / a well-formed heap-indexed tree instead of reading out of bounds.
 static int validate_tree(const std::vector<MfxBvhNode> &nodes, const std::vector<int32_t> &indices)
@@ -409,7 +412,7 @@ extern "C" int mfx_scene_create(const MfxSceneDesc *d, MfxScene **out)
         memcpy(s->indices.data(), d->indices, sizeof(int32_t) * (size_t)d->n_prims);
     } else rc = mfx_bvh_build(s->prims.data(), d->n_prims, s->nodes.data(), n_slots, s->indices.data());
     if (rc != MFX_OK) { delete s; return rc; }
-    if (cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking) != cudaSuccess) { delete s; return fail(MFX_ERR_CUDA, "cudaStreamCreate failed"); }
+    if (stream_get(s->device, &s->stream) != MFX_OK) { delete s; return fail(MFX_ERR_CUDA, "cudaStreamCreate failed"); }
     memset(&s->stats, 0, sizeof(s->stats));
     *out = s;
     return MFX_OK;
@@ -417,21 +420,59 @@ extern "C" int mfx_scene_create(const MfxSceneDesc *d, MfxScene **out)
 
 static void stat_block_put(void *p);
 
+// Streams and events are recycled per device for the life of the process, like the device buffers: a host that re-creates
+// its Scene every frame (and the eight replicas of a multi-GPU handle) would otherwise issue ~150 driver calls per scene
+// for them, contending for the driver with the worker threads that are launching the previous frame's kernels.
+static std::map<int, std::vector<cudaStream_t>> g_streams;
+static std::map<std::pair<int, int>, std::vector<cudaEvent_t>> g_events;      // (device, timing?) -> free events
+static int stream_get(int device, cudaStream_t *out)
+{
+    {
+        std::lock_guard<std::mutex> g(g_pool_mu);
+        auto &v = g_streams[device];
+        if (!v.empty()) { *out = v.back(); v.pop_back(); return MFX_OK; }
+    }
+    CUDA_TRY(cudaStreamCreateWithFlags(out, cudaStreamNonBlocking));
+    return MFX_OK;
+}
+static void stream_put(int device, cudaStream_t st)       // the caller has synchronised it
+{
+    if (!st) return;
+    std::lock_guard<std::mutex> g(g_pool_mu);
+    g_streams[device].push_back(st);
+}
+static int event_get(int device, bool timing, cudaEvent_t *out)
+{
+    {
+        std::lock_guard<std::mutex> g(g_pool_mu);
+        auto &v = g_events[{ device, timing ? 1 : 0 }];
+        if (!v.empty()) { *out = v.back(); v.pop_back(); return MFX_OK; }
+    }
+    CUDA_TRY(cudaEventCreateWithFlags(out, timing ? cudaEventDefault : cudaEventDisableTiming));
+    return MFX_OK;
+}
+static void event_put(int device, bool timing, cudaEvent_t e)
+{
+    if (!e) return;
+    std::lock_guard<std::mutex> g(g_pool_mu);
+    g_events[{ device, timing ? 1 : 0 }].push_back(e);
+}
+
 extern "C" int mfx_scene_destroy(MfxScene *s)
 {
     if (!s) return MFX_OK;
     cudaSetDevice(s->device);
     if (s->stream) cudaStreamSynchronize(s->stream);
-    if (s->copy_stream) { cudaStreamSynchronize(s->copy_stream); cudaStreamDestroy(s->copy_stream); }
+    if (s->copy_stream) { cudaStreamSynchronize(s->copy_stream); stream_put(s->device, s->copy_stream); }
     for (auto &a : s->allocs) dev_release(s->device, a.first, a.second);
     for (FrameJob &j : s->jobs) {
-        for (cudaEvent_t e : j.events) cudaEventDestroy(e);
-        if (j.done) cudaEventDestroy(j.done);
-        if (j.copied) cudaEventDestroy(j.copied);
+        for (cudaEvent_t e : j.events) event_put(s->device, true, e);
+        event_put(s->device, false, j.done);
+        event_put(s->device, false, j.copied);
         stat_block_put(j.h_totals);
     }
-    if (s->stream2) { cudaStreamSynchronize(s->stream2); cudaStreamDestroy(s->stream2); }
-    if (s->stream) cudaStreamDestroy(s->stream);
+    if (s->stream2) { cudaStreamSynchronize(s->stream2); stream_put(s->device, s->stream2); }
+    if (s->stream) stream_put(s->device, s->stream);
     delete s;
     return MFX_OK;
 }
@@ -1146,7 +1187,7 @@ static int get_event(FrameJob &j, size_t idx, cudaEvent_t *e)
 {
     while (j.events.size() <= idx) {
         cudaEvent_t ev;
-        CUDA_TRY(cudaEventCreate(&ev));
+        MFX_TRY(event_get(j.device, true, &ev));
         j.events.push_back(ev);
     }
     *e = j.events[idx];
@@ -1182,8 +1223,9 @@ static int ensure_job(MfxScene *s, FrameJob &j)
         j.h_totals = (unsigned long long *)blk;
         j.h_ctr = (TravCounters *)((char *)blk + 128);
     }
-    if (!j.done) CUDA_TRY(cudaEventCreateWithFlags(&j.done, cudaEventDisableTiming));
-    if (!j.copied) CUDA_TRY(cudaEventCreateWithFlags(&j.copied, cudaEventDisableTiming));
+    j.device = s->device;
+    if (!j.done) MFX_TRY(event_get(s->device, false, &j.done));
+    if (!j.copied) MFX_TRY(event_get(s->device, false, &j.copied));
     return MFX_OK;
 }
 
@@ -1266,7 +1308,7 @@ static int launch_sample(MfxScene *s, const MfxSampleParams *p, double *d_color_
     // stream (and per-kernel event times that do not overlap).  MFX_TWO_STREAMS = 0 / 1 forces either.
     const long two_env = env_long("MFX_TWO_STREAMS", -1);
     const bool two = !exact && !sky && !ctr && (two_env >= 0 ? two_env != 0 : (size_t)tm.n_pix * (size_t)p->spp <= ((size_t)48 << 20));
-    if (two && !s->stream2) CUDA_TRY(cudaStreamCreateWithFlags(&s->stream2, cudaStreamNonBlocking));
+    if (two && !s->stream2) MFX_TRY(stream_get(s->device, &s->stream2));
     cudaStream_t st2 = two ? s->stream2 : st;
     LaunchCfg cfg2 = cfg; cfg2.stream = st2;
     // ... and with a second shadow queue shade(b+1) does not wait for shadow(b) either: the shadow launches trail the
@@ -1485,7 +1527,7 @@ extern "C" int mfx_pixel_integrator_sample_async(MfxScene *s, const MfxSamplePar
     const int slot = (s->job_head + s->job_count) % 2;
     const size_t bytes = (size_t)s->width * s->height * 4 * sizeof(double);
     if (!s->d_color_async[slot]) MFX_TRY(dev_alloc(s, (void **)&s->d_color_async[slot], bytes));
-    if (!s->copy_stream) CUDA_TRY(cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking));
+    if (!s->copy_stream) MFX_TRY(stream_get(s->device, &s->copy_stream));
     FrameJob &job = s->jobs[slot];
     MFX_TRY(launch_sample(s, p, s->d_color_async[slot], nullptr, job));
     CUDA_TRY(cudaStreamWaitEvent(s->copy_stream, job.done, 0));
