@@ -430,7 +430,7 @@ def main():
             own_bc = 128.0 * rec[0] + 48.0 * tri[0] + 16.0 * sph[0]
             own_bs = 128.0 * rec[1] + 48.0 * tri[1] + 16.0 * sph[1]
             ach = ext_rays * own_bc / (ext_ms * 1e-3) / 1e9
-            cp = cache_peaks() if world == 1 else None
+            cp = cache_peaks()          # rank 0's GPU; the other ranks wait at the next barrier
             roof.update({"records_per_ray": rec, "tris_per_ray": tri, "spheres_per_ray": sph,
                          "bytes_per_ray_closest": own_bc, "bytes_per_ray_shadow": own_bs,
                          "algorithmic_bytes_per_launch": ext_rays * own_bc / max(ext_launches, 1),
@@ -446,7 +446,7 @@ def main():
                              "cache_peaks": cp})
             else:
                 roof.update({"bound": "l1", "peak": None, "frac": None,
-                             "peak_source": "tools/peaks_cache not run (N > 1 or binary missing): see the N = 1 line"})
+                             "peak_source": "tools/peaks_cache binary missing (run __graft_entry__.build())"})
         else:
             roof.update({"bound": "hbm", "achieved": hbm_def["achieved"], "peak": hbm_peak, "unit": "GB/s", "frac": hbm_def["frac"], "peak_source": how})
         roof["traffic"] = traffic.get("extend_dram_bytes_per_launch")
