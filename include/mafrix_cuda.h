@@ -228,6 +228,9 @@ MFX_API int mfx_stripe_map(int32_t width, int32_t height, int32_t stripe, int32_
 /* ---- scene: replaces `new Scene(state)`'s Bvh + PathIntegrator + PixelIntegrator ------------ */
 MFX_API int mfx_scene_create(const MfxSceneDesc *desc, MfxScene **out);
 MFX_API int mfx_scene_destroy(MfxScene *scene);
+/* Builds the device layouts a Sample of this MfxPrecision uses now, not inside the first Sample (a host that pipelines
+ * frames calls it while the previous frame renders). */
+MFX_API int mfx_scene_prepare(MfxScene *scene, int32_t precision);
 /* Copies out the tree the scene traverses (as built or as supplied). */
 MFX_API int mfx_scene_get_bvh(const MfxScene *scene, MfxBvhNode *nodes_out, int32_t *indices_out);
 /* Bytes of the flattened scene resident in HBM for each precision. */
@@ -293,6 +296,8 @@ MFX_API int mfx_multi_sample(MfxMulti *multi, const MfxSampleParams *params, dou
  * on; mfx_multi_wait completes it.  texture must stay untouched until then. */
 MFX_API int mfx_multi_sample_async(MfxMulti *multi, const MfxSampleParams *params, double *texture);
 MFX_API int mfx_multi_wait(MfxMulti *multi);
+/* mfx_scene_prepare on every replica, side by side. */
+MFX_API int mfx_multi_prepare(MfxMulti *multi, int32_t precision);
 /* Same, float RGBA row-major. */
 MFX_API int mfx_multi_sample_f32(MfxMulti *multi, const MfxSampleParams *params, float *rgba);
 /* total: rays / paths / launches summed over the devices, ms_* of the slowest one; per_device: n entries or NULL. */

@@ -81,6 +81,7 @@ SYMBOLS = {
     "mfx_stripe_map": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, C.POINTER(C.c_int32)]),
     "mfx_scene_create": (C.c_int, [C.POINTER(MfxSceneDesc), C.POINTER(_P)]),
     "mfx_scene_destroy": (C.c_int, [_P]),
+    "mfx_scene_prepare": (C.c_int, [_P, C.c_int32]),
     "mfx_scene_get_bvh": (C.c_int, [_P, _P, _P]),
     "mfx_scene_device_bytes": (C.c_int, [_P, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "mfx_bvh_hit": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int64, _P, _P, C.c_double, C.c_double, _P, _P, _P]),
@@ -100,6 +101,7 @@ SYMBOLS = {
     "mfx_multi_sample": (C.c_int, [_P, C.POINTER(MfxSampleParams), _P]),
     "mfx_multi_sample_async": (C.c_int, [_P, C.POINTER(MfxSampleParams), _P]),
     "mfx_multi_wait": (C.c_int, [_P]),
+    "mfx_multi_prepare": (C.c_int, [_P, C.c_int32]),
     "mfx_multi_sample_f32": (C.c_int, [_P, C.POINTER(MfxSampleParams), _P]),
     "mfx_multi_get_stats": (C.c_int, [_P, C.POINTER(MfxStats), _P]),
     "mfx_film_create": (C.c_int, [_P, C.POINTER(_P)]),

@@ -1009,6 +1009,27 @@ static int ensure_wave_hybrid(MfxScene *s)
     return MFX_OK;
 }
 
+static bool use_hybrid(int flags);
+static int ensure_frame_buffers(MfxScene *s);
+
+// Builds the device layouts a Sample of this precision will use (exact: reference tree + f64 primitives; fast: own SAH tree,
+// f32 slots and the id-exact tables) now instead of inside the first Sample: a host that pipelines frames does it while the
+// previous frame renders.
+extern "C" int mfx_scene_prepare(MfxScene *s, int32_t precision)
+{
+    if (!s) return fail(MFX_ERR_INVALID_ARGUMENT, "null scene");
+    if (precision != MFX_EXACT_F64 && precision != MFX_FAST_F32) return fail(MFX_ERR_INVALID_ARGUMENT, "unknown precision %d", precision);
+    MFX_TRY(bind_device(s->device));
+    if (precision == MFX_EXACT_F64) MFX_TRY(flatten_exact(s));
+    else {
+        MFX_TRY(flatten_fast(s));
+        if (use_hybrid(0)) MFX_TRY(flatten_hybrid(s));
+    }
+    MFX_TRY(ensure_frame_buffers(s));
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    return MFX_OK;
+}
+
 extern "C" int mfx_scene_device_bytes(const MfxScene *sc, uint64_t *exact_bytes, uint64_t *fast_bytes)
 {
     if (!sc) return fail(MFX_ERR_INVALID_ARGUMENT, "null scene");

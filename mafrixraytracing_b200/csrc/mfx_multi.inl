@@ -33,6 +33,7 @@ struct MfxMulti {
     std::vector<double> ms_wall;    // per device: run_sample + its D2H, host clock
     double ms_call = 0.;
     bool posted = false;            // a job was handed to the workers and not yet waited for
+    bool prepare_only = false;      // ... and it is mfx_multi_prepare's (layouts only)
     std::chrono::steady_clock::time_point t_post;
 };
 
@@ -83,6 +84,14 @@ static void multi_worker(MfxMulti *m, int i)
         p.rank = i; p.world = (int)m->devices.size(); p.tile_size = m->stripe;
         p.flags |= MFX_SAMPLE_STRIPES | MFX_SAMPLE_NO_CLEAR;
         int rc = ensure_frame_buffers(s);
+        if (m->prepare_only) {      // mfx_multi_prepare: the layouts of this precision, no frame
+            if (rc == MFX_OK) rc = mfx_scene_prepare(s, m->params.precision);
+            m->rc[(size_t)i] = rc;
+            if (rc != MFX_OK) m->err[(size_t)i] = g_err;
+            std::lock_guard<std::mutex> lk(m->mu);
+            if (--m->pending == 0) m->cv_done.notify_all();
+            continue;
+        }
         if (rc == MFX_OK) rc = run_sample(s, &p, m->texture ? s->d_color_wh : nullptr, m->texture ? nullptr : s->d_rgba);
         const auto t1 = std::chrono::steady_clock::now();
         if (rc == MFX_OK) rc = multi_copy_out(m, i);
@@ -194,6 +203,7 @@ static int multi_post(MfxMulti *m, const MfxSampleParams *p, double *texture, fl
     if (m->pending != 0) return fail(MFX_ERR_INVALID_ARGUMENT, "a frame is still in flight on this handle: call mfx_multi_wait first");
     m->t_post = std::chrono::steady_clock::now();
     m->params = *p; m->texture = texture; m->rgba = rgba;
+    m->prepare_only = (texture == nullptr && rgba == nullptr);
     m->pending = (int)m->devices.size();
     m->posted = true;
     m->job++;
@@ -238,6 +248,16 @@ extern "C" int mfx_multi_sample_async(MfxMulti *m, const MfxSampleParams *p, dou
 }
 
 extern "C" int mfx_multi_wait(MfxMulti *m) { return multi_wait(m); }
+
+// Every replica builds the device layouts of this precision now (side by side) instead of inside its first Sample: a host
+// that pipelines frames calls it while the previous frame renders.
+extern "C" int mfx_multi_prepare(MfxMulti *m, int32_t precision)
+{
+    MfxSampleParams p; memset(&p, 0, sizeof(p));
+    p.precision = precision; p.spp = 1; p.world = 1;
+    MFX_TRY(multi_post(m, &p, nullptr, nullptr));
+    return multi_wait(m);
+}
 
 // total: rays / paths / launches summed over the devices, times = the slowest device (they run side by side);
 // per_device (n_devices entries, may be NULL): each device's own MfxStats.

@@ -280,6 +280,10 @@ class Scene:
         except Exception:
             pass
 
+    def Prepare(self, precision=FAST_F32):
+        """Builds the device layouts of `precision` now instead of inside the first Sample."""
+        _lib.check(_lib.load().mfx_scene_prepare(self._h, int(precision)))
+
     def bvh(self):
         n = len(self.desc.prims)
         nodes = np.zeros(2 * n - 1, dtype=NODE_DTYPE)
@@ -425,6 +429,10 @@ class MultiGpuPixelIntegrator:
         _lib.check(_lib.load().mfx_multi_sample(self._h, C.byref(p), _lib.ptr(tex)))
         self._after()
         return tex
+
+    def Prepare(self):
+        """Builds every replica's device layouts now instead of inside the first Sample."""
+        _lib.check(_lib.load().mfx_multi_prepare(self._h, self.precision))
 
     def SampleAsync(self, n, out, first_sample=0, flags=0):
         """Posts Sample(n) to the device workers and returns; Wait() completes it (one frame in flight per handle)."""

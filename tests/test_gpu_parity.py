@@ -329,7 +329,7 @@ def test_tile_sharding_sums_to_the_whole_frame(world):
         assert np.array_equal(acc, full)          # RNG keyed on absolute pixel/sample: bit-identical for any world
 
 
-@pytest.mark.parametrize("world,w,h", [(2, 200, 136), (3, 70, 33), (8, 300, 64), (5, 50, 7)])
+@pytest.mark.parametrize("world,w,h", [(2, 200, 136), (3, 70, 33), (8, 300, 64), (5, 50, 7), (8, 20, 16)])     # the last: six ranks own nothing
 def test_stripe_sharding_assembles_the_whole_frame(world, w, h):
     """Column stripes (MFX_SAMPLE_STRIPES, arithmetic ownership in the kernels -- no pixel table): the ranks' frames are
     disjoint, cover the frame and sum to the one-GPU frame bit for bit; with MFX_SAMPLE_NO_CLEAR a rank touches only its
@@ -363,7 +363,8 @@ def test_multi_gpu_api_on_the_devices_present():
     gpurun --gpus N) the assembled Color[w,h] and the float frame equal the single-GPU frame bit for bit."""
     from mafrixraytracing_b200 import MultiGpuPixelIntegrator
     n = _lib.load().mfx_device_count()
-    for name, kw in (("c1_cube", dict(width=333, height=120)), ("c2_spot", dict(width=480, height=270))):
+    for name, kw in (("c1_cube", dict(width=333, height=120)), ("c2_spot", dict(width=480, height=270)), ("cornell", dict(width=24, height=40)),
+                     ("random_scene", dict(width=200, height=100))):      # 24 columns: devices beyond the second own nothing; the sphere sample
         desc = _desc(name, **kw)
         single = CudaPixelIntegrator(Scene(desc), precision=FAST_F32, seed=3)
         want = single.Sample(4).copy()
@@ -371,6 +372,7 @@ def test_multi_gpu_api_on_the_devices_present():
         for devs in ([0], list(range(n))) if n > 1 else ([0],):
             m = MultiGpuPixelIntegrator(desc, devices=devs, precision=FAST_F32, seed=3)
             assert m.n_devices == len(devs)
+            m.Prepare()                                               # layouts uploaded now, not inside the first Sample
             tex = np.full((desc.width, desc.height, 4), -1.0)
             _lib.check(_lib.load().mfx_host_register(_lib.ptr(tex), tex.nbytes))
             try:
@@ -419,6 +421,7 @@ def test_async_sample_pipelines_frames_and_equals_the_blocking_call():
     texture equal to the blocking call's, statistics of the frame each wait completes, pageable textures refused."""
     desc = _desc("c2_spot", width=480, height=270)
     s = Scene(desc)
+    s.Prepare(FAST_F32)                                                # mfx_scene_prepare: layouts before the first Sample
     integ = CudaPixelIntegrator(s, precision=FAST_F32, seed=4)
     want = [integ.Sample(2, first_sample=2 * k).copy() for k in range(5)]
     rays = integ.stats["closest_rays"]
