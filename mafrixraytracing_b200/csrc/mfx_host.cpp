@@ -1067,10 +1067,12 @@ static int ensure_wave_exact(MfxScene *s)
 // 1080p) costs 25 % against 32-64 Mi because every persistent launch pays its ramp-up and its tail (profiles/), so
 // the wave is sized for the call at hand -- pixels x spp -- up to MFX_WAVE_PATHS (default 128 Mi paths = 24.6 GB of
 // the 180 GB) and only ever grows.
-static int ensure_wave_fast(MfxScene *s, size_t want)
+static int ensure_wave_fast(MfxScene *s, size_t want, bool at_least = false)
 {
-    const size_t cap = (size_t)std::max(1024L, env_long("MFX_WAVE_PATHS", 1L << 27));
+    // at_least: the caller needs room for `want` entries whatever the cap says (the exact wavefront borrows these queues)
+    const size_t cap = at_least ? want : (size_t)std::max(1024L, env_long("MFX_WAVE_PATHS", 1L << 27));
     size_t P = std::min(cap, std::max(want, (size_t)1 << 16));
+    if (at_least) P = std::max(want, (size_t)1 << 16);
     if (s->wf_ready && (size_t)s->wf.P >= P) return MFX_OK;
     WaveF &w = s->wf;
     if (s->wf_ready) {
@@ -1290,6 +1292,17 @@ static int launch_sample(MfxScene *s, const MfxSampleParams *p, double *d_color_
     // bounce 0 of the throughput path is traced id-exactly (mfx_hybrid.cu) unless the caller opts out
     const bool hyb = !exact && sfp->own_tree && !counting && use_hybrid(p->flags);
     if (hyb) { MFX_TRY(flatten_hybrid(s)); MFX_TRY(ensure_wave_hybrid(s)); }
+    // ... and the exact precision sends ITS closest-hit queries through the same kernel (same answers as bvh_hit_x, bit for
+    // bit, on the own tree instead of ~50 f64 box tests per ray on the reference's); MFX_EXACT_WALK=1 keeps the plain walk
+    const bool hyb_x = exact && !counting && env_long("MFX_EXACT_WALK", 0) == 0;
+    if (hyb_x) {
+        MFX_TRY(flatten_hybrid(s));
+        MFX_TRY(ensure_wave_fast(s, (size_t)s->wx.P, true));
+        if (s->wf.P < s->wx.P) return fail(MFX_ERR_OUT_OF_MEMORY, "no room for the exact wavefront's closest-hit queue");
+        MFX_TRY(ensure_wave_hybrid(s));
+        s->wf.cam_origin = 0;
+        CUDA_TRY(cudaMemsetAsync(s->wf.counts, 0, MFX_COUNTS_LEN * sizeof(int), s->stream));
+    }
     MFX_TRY(ensure_job(s, job));
     TravCounters *ctr = counting ? job.d_ctr : nullptr;
     const bool sky = (s->integrator == MFX_SKY_TRACER);
@@ -1369,7 +1382,13 @@ static int launch_sample(MfxScene *s, const MfxSampleParams *p, double *d_color_
             launches++;
             for (int b = 0; b <= D; b++) {
                 MFX_TRY(timed(0, st));
-                if (exact) mfx_x_extend(cfg, s->sx, s->wx, b, ctr);
+                if (exact && hyb_x) {
+                    const HybQuery q{ sky ? MFX_SKY_TMIN : 1e-6, sky ? MFX_SKY_TMAX : 99999999., sky ? 1 : 0 };
+                    mfx_h_extend_x(cfg, s->sf, s->sx, s->sh, s->wx, s->wf, s->wh, b, q);
+                    mfx_h_accum_fixups(st, s->wh, job.d_totals + 4);
+                    mfx_h_guard(st, s->wf, job.d_totals);
+                    launches += 6;
+                } else if (exact) mfx_x_extend(cfg, s->sx, s->wx, b, ctr);
                 else if (hyb && b == 0) {
                     const HybQuery q{ sky ? MFX_SKY_TMIN : 1e-6, sky ? MFX_SKY_TMAX : 99999999., sky ? 1 : 0 };   // Integrators.fs:108 / RayTracing.fs:368
                     mfx_h_extend(cfg, *sfp, s->sx, s->sh, s->wf, s->wh, 0, q, 0);

@@ -398,6 +398,42 @@ __global__ void __launch_bounds__(256) k_h_seam_read(SceneX sx, WaveH wh, int n,
     }
 }
 
+// MFX_EXACT_F64 frames through the same kernel: the closest-hit queries of the exact wavefront (WaveX: f64 SoA by path id,
+// queues of path ids) are gathered into the hybrid's queue, traced, and scattered back.  bvh_hit_x and k_h_trace return
+// the same (slot, sub, t) by construction, so the frames stay bit-identical -- at a fraction of the f64 box tests.
+__global__ void __launch_bounds__(256) k_h_gather_x(WaveX wx, WaveF w, WaveH wh, int bounce)
+{
+    const int n = wx.counts[bounce];
+    const int *q = wx.queue[bounce & 1];
+    const size_t P = (size_t)wx.P;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int pid = q[i];
+        double *op = wh.org64 + 3 * (size_t)i, *dp = wh.dir64 + 3 * (size_t)i;
+        op[0] = wx.ray_o[pid]; op[1] = wx.ray_o[P + pid]; op[2] = wx.ray_o[2 * P + pid];
+        dp[0] = wx.ray_d[pid]; dp[1] = wx.ray_d[P + pid]; dp[2] = wx.ray_d[2 * P + pid];
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) { w.counts[0] = n; w.counts[CUR_EXT(0)] = 0; }
+}
+
+__global__ void __launch_bounds__(256) k_h_scatter_x(WaveX wx, WaveH wh, int bounce)
+{
+    const int n = wx.counts[bounce];
+    const int *q = wx.queue[bounce & 1];
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int pid = q[i];
+        const int ref = wh.ref[i];
+        wx.hit_t[pid] = wh.t[i];
+        wx.hit_slot[pid] = ref;                     // -1 miss, else exact slot | sub << 30: WaveX's own convention
+    }
+}
+
+// the exact wavefront keeps its own counts: the hybrid kernel's watchdog / debug-check flags live in WaveF.counts
+__global__ void k_h_guard(int *counts, unsigned long long *totals)
+{
+    totals[3] += (unsigned)counts[MFX_COUNTS_LEN - 1]; totals[5] += (unsigned)counts[MFX_DBG_SLOT];
+    counts[MFX_COUNTS_LEN - 1] = 0; counts[MFX_DBG_SLOT] = 0;
+}
+
 __global__ void k_h_accum(const int *fix_n, unsigned long long *total) { *total += (unsigned)*fix_n; }
 
 // ---------------------------------------------------------------- launchers
@@ -437,6 +473,13 @@ void mfx_h_extend(const LaunchCfg &c, const SceneF &sc, const SceneX &sx, const 
     }
     k_h_fixup<<<c.blocks * 4, 128, 0, c.stream>>>(sx, sh, w, wh, bounce, q, w.cam_origin, seam);
 }
+void mfx_h_extend_x(const LaunchCfg &c, const SceneF &sc, const SceneX &sx, const SceneH &sh, const WaveX &wx, const WaveF &w, const WaveH &wh, int bounce, HybQuery q)
+{
+    k_h_gather_x<<<persistent_blocks(k_h_gather_x, 256, c.blocks), 256, 0, c.stream>>>(wx, w, wh, bounce);
+    mfx_h_extend(c, sc, sx, sh, w, wh, 0, q, 1);
+    k_h_scatter_x<<<persistent_blocks(k_h_scatter_x, 256, c.blocks), 256, 0, c.stream>>>(wx, wh, bounce);
+}
+void mfx_h_guard(cudaStream_t st, const WaveF &w, unsigned long long *totals) { k_h_guard<<<1, 1, 0, st>>>(w.counts, totals); }
 void mfx_h_seam_read(const LaunchCfg &c, const SceneX &sx, const WaveH &wh, int n, long long first, int *prim, int *sub, double *t)
 {
     k_h_seam_read<<<persistent_blocks(k_h_seam_read, 256, c.blocks), 256, 0, c.stream>>>(sx, wh, n, first, prim, sub, t);

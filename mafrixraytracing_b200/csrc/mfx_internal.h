@@ -283,6 +283,9 @@ void mfx_h_seam_setup(const LaunchCfg &, const SceneX &, const WaveF &, const Wa
 void mfx_h_extend(const LaunchCfg &, const SceneF &, const SceneX &, const SceneH &, const WaveF &, const WaveH &, int bounce, HybQuery q, int seam);
 void mfx_h_seam_read(const LaunchCfg &, const SceneX &, const WaveH &, int n, long long first, int *prim, int *sub, double *t);
 void mfx_h_accum_fixups(cudaStream_t, const WaveH &, unsigned long long *total);
+// the closest-hit queries of an MFX_EXACT_F64 wave (queue `bounce` of WaveX) through the hybrid kernel
+void mfx_h_guard(cudaStream_t, const WaveF &, unsigned long long *totals);
+void mfx_h_extend_x(const LaunchCfg &, const SceneF &, const SceneX &, const SceneH &, const WaveX &, const WaveF &, const WaveH &, int bounce, HybQuery q);
 
 // misc (mfx_fast.cu)
 // totals[0] += sum counts[ext_lo..+ext_n), totals[1] += sum counts[sh_lo..+sh_n), totals[2] += counts[0]
