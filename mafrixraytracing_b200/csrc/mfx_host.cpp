@@ -1300,6 +1300,7 @@ static int launch_sample(MfxScene *s, const MfxSampleParams *p, double *d_color_
         MFX_TRY(ensure_wave_fast(s, (size_t)s->wx.P, true));
         if (s->wf.P < s->wx.P) return fail(MFX_ERR_OUT_OF_MEMORY, "no room for the exact wavefront's closest-hit queue");
         MFX_TRY(ensure_wave_hybrid(s));
+        if (s->integrator != MFX_SKY_TRACER) MFX_TRY(flatten_fast_ref(s));                  // the f32 copy of the reference tree: the exact shadow walk
         s->wf.cam_origin = 0;
         CUDA_TRY(cudaMemsetAsync(s->wf.counts, 0, MFX_COUNTS_LEN * sizeof(int), s->stream));
     }
@@ -1424,7 +1425,9 @@ static int launch_sample(MfxScene *s, const MfxSampleParams *p, double *d_color_
                     CUDA_TRY(cudaStreamWaitEvent(st2, e_shaded, 0));
                 }
                 MFX_TRY(timed(1, st2));
-                if (exact) mfx_x_shadow(cfg, s->sx, s->wx, b, ctr); else mfx_f_shadow(cfg2, *sfp, wq, b, ctr);
+                if (exact && hyb_x) mfx_h_shadow_x(cfg, s->sx, s->sf_ref, s->sh, s->wx, b);
+                else if (exact) mfx_x_shadow(cfg, s->sx, s->wx, b, ctr);
+                else mfx_f_shadow(cfg2, *sfp, wq, b, ctr);
                 MFX_TRY(timed_end(st2));
                 if (two) {
                     MFX_TRY(get_event(job, ev++, &e_shadow_done[b & 1]));

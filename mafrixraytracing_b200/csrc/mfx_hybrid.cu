@@ -427,6 +427,91 @@ __global__ void __launch_bounds__(256) k_h_scatter_x(WaveX wx, WaveH wh, int bou
     }
 }
 
+// ---------------------------------------------------------------- exact shadow queries without ~46 f64 box tests per ray
+// SingleDirectLightIntegrator.Eval asks `bvh.Hit(shadowRay, 1e-6, dist - 1e-6).hit` (Integrators.fs:44).  CheckHit's answer
+// is "some leaf the walk reaches yields a hit record": a leaf is reached iff AABB.hit passes for it and its ancestors -- and,
+// boxes nesting exactly and the slab test being monotone in the box, iff it passes for the LEAF's own box (fixed tMin, tMax);
+// its record is Array.minBy (hit ? t : tMax) over its <= 3 primitives (BvhNode.fs:76-80: tMax-blind triangles, quirk Q2,
+// included).  So the walk over the interior nodes only has to VISIT A SUPERSET of the reachable leaves: it runs on the f32
+// copy of the reference tree (PairF: both children of a heap node in 64 bytes, boxes rounded outward) with the per-ray pad
+// of k_h_trace, and every visited leaf is then decided exactly -- AABB.hit verbatim on its f64 box, prim_hit_x on its
+// primitives in index order.  Two f64 box tests per ray instead of forty-six.  A direction with a zero component (the
+// 0/0 family of AABB.hit, where monotonicity fails) or a window that ends at or before the origin (a light sample closer
+// than 1e-6: the f32 test clips the near side at 0) takes bvh_hit_x.
+__device__ __noinline__ bool shadow_leaf_x(const NodeX *nodes, const PrimX *prims, int node0, D3 o, D3 d, double tMin, double tMax)
+{
+    const NodeX nd = nodes[node0];
+    double e;
+    if (!aabb_hit_x(nd, o, d, tMin, tMax, e)) return false;             // the reference's walk does not reach this leaf
+    bool have = false, recHit = false; double bestKey = 0.;
+    for (int k = 0; k < nd.count; k++) {
+        const PrimX p = prims[nd.first + k];
+        double t; int sub;
+        const bool h = prim_hit_x(p, o, d, tMin, tMax, t, sub);
+        const double key = h ? t : tMax;
+        if (!have || key < bestKey) { have = true; bestKey = key; recHit = h; }
+    }
+    return recHit;
+}
+
+__global__ void __launch_bounds__(128) k_h_shadow_x(SceneX sx, const PairF *pairs, float3 root_lo, float3 root_hi, int root_meta,
+                                                    WaveX w, int bounce, float max_abs, float pad_factor)
+{
+    const int n = w.counts[bounce + 1];                 // the paths shaded at vertex `bounce` (k_x_shadow's convention)
+    const int *q = w.queue[(bounce + 1) & 1];
+    const size_t P = (size_t)w.P;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int pid = q[i];
+        const D3 o = mk3<double>(w.ray_o[pid], w.ray_o[P + pid], w.ray_o[2 * P + pid]);   // hit.point
+        const D3 d = mk3<double>(w.sh_d[pid], w.sh_d[P + pid], w.sh_d[2 * P + pid]);
+        const double tMin = 1e-6, tMax = w.sh_dist[pid] - 1e-6;
+        bool occluded;
+        if (d.x == 0. || d.y == 0. || d.z == 0. || !(tMax > 0.)) occluded = bvh_hit_x<true, false>(sx, o, d, tMin, tMax, nullptr).slot >= 0;
+        else {
+            occluded = false;
+            const F3 of = f3((float)o.x, (float)o.y, (float)o.z), df = f3((float)d.x, (float)d.y, (float)d.z);
+            const RayF r = make_ray_fast(of, df, HYB_TMIN_BOX, -1);
+            const float pad = pad_factor * (max_abs + fmaxf(fabsf(of.x), fmaxf(fabsf(of.y), fabsf(of.z))));
+            const F3 pt = f3(pad * fabsf(r.idir.x), pad * fabsf(r.idir.y), pad * fabsf(r.idir.z));
+            const F3 on = r.ood + pt, ofar = r.ood - pt;
+            const bool px = r.idir.x >= 0.f, py = r.idir.y >= 0.f, pz = r.idir.z >= 0.f;
+            const float lim = __double2float_ru(tMax) * 1.000001f + 1e-30f;
+#define HS_BOX(lx, ly, lz, hx, hy, hz)                                                                                  \
+            (fmaxf(fmaxf(fmaf(px ? (lx) : (hx), r.idir.x, -on.x), fmaf(py ? (ly) : (hy), r.idir.y, -on.y)),                 \
+                   fmaxf(fmaf(pz ? (lz) : (hz), r.idir.z, -on.z), 0.f)) <=                                                  \
+             fminf(fminf(fmaf(px ? (hx) : (lx), r.idir.x, -ofar.x), fmaf(py ? (hy) : (ly), r.idir.y, -ofar.y)),             \
+                   fminf(fmaf(pz ? (hz) : (lz), r.idir.z, -ofar.z), lim)))
+            if (HS_BOX(root_lo.x, root_lo.y, root_lo.z, root_hi.x, root_hi.y, root_hi.z)) {
+                if (root_meta >= 0) occluded = shadow_leaf_x(sx.nodes, sx.prims, 0, o, d, tMin, tMax);
+                else {
+                    unsigned stack[40];
+                    int sp = 0;
+                    unsigned h = 1u;                                    // 1-based heap index of the interior node to expand
+                    for (int guard = 0; guard < (1 << 24); guard++) {
+                        const PairF *pp = pairs + h;
+                        const float4 q0 = ldg4(&pp->q0), q1 = ldg4(&pp->q1), q2 = ldg4(&pp->q2), q3 = ldg4(&pp->q3);
+                        const bool hitL = HS_BOX(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y), hitR = HS_BOX(q1.z, q1.w, q2.x, q2.y, q2.z, q2.w);
+                        const bool leafL = __float_as_int(q3.x) >= 0, leafR = __float_as_int(q3.y) >= 0;
+                        if (hitL && leafL && shadow_leaf_x(sx.nodes, sx.prims, (int)(2u * h) - 1, o, d, tMin, tMax)) { occluded = true; break; }
+                        if (hitR && leafR && shadow_leaf_x(sx.nodes, sx.prims, (int)(2u * h), o, d, tMin, tMax)) { occluded = true; break; }
+                        const bool inL = hitL && !leafL, inR = hitR && !leafR;
+                        if (inL && inR) { if (sp < 40) stack[sp++] = 2u * h + 1u; h = 2u * h; }
+                        else if (inL) h = 2u * h;
+                        else if (inR) h = 2u * h + 1u;
+                        else if (sp > 0) h = stack[--sp];
+                        else break;
+                    }
+                }
+            }
+#undef HS_BOX
+        }
+        if (occluded) {
+            const size_t vb = (size_t)bounce * 3 * P;
+            w.v_l[vb + pid] = 0.; w.v_l[vb + P + pid] = 0.; w.v_l[vb + 2 * P + pid] = 0.;
+        }
+    }
+}
+
 // the exact wavefront keeps its own counts: the hybrid kernel's watchdog / debug-check flags live in WaveF.counts
 __global__ void k_h_guard(int *counts, unsigned long long *totals)
 {
@@ -478,6 +563,13 @@ void mfx_h_extend_x(const LaunchCfg &c, const SceneF &sc, const SceneX &sx, cons
     k_h_gather_x<<<persistent_blocks(k_h_gather_x, 256, c.blocks), 256, 0, c.stream>>>(wx, w, wh, bounce);
     mfx_h_extend(c, sc, sx, sh, w, wh, 0, q, 1);
     k_h_scatter_x<<<persistent_blocks(k_h_scatter_x, 256, c.blocks), 256, 0, c.stream>>>(wx, wh, bounce);
+}
+void mfx_h_shadow_x(const LaunchCfg &c, const SceneX &sx, const SceneF &ref_layout, const SceneH &sh, const WaveX &wx, int bounce)
+{
+    const float3 lo = make_float3(ref_layout.root_min[0], ref_layout.root_min[1], ref_layout.root_min[2]);
+    const float3 hi = make_float3(ref_layout.root_max[0], ref_layout.root_max[1], ref_layout.root_max[2]);
+    k_h_shadow_x<<<persistent_blocks(k_h_shadow_x, 128, c.blocks), 128, 0, c.stream>>>(sx, ref_layout.pairs, lo, hi, ref_layout.root_meta, wx, bounce,
+                                                                                       sh.max_abs, sh.pad_factor);
 }
 void mfx_h_guard(cudaStream_t st, const WaveF &w, unsigned long long *totals) { k_h_guard<<<1, 1, 0, st>>>(w.counts, totals); }
 void mfx_h_seam_read(const LaunchCfg &c, const SceneX &sx, const WaveH &wh, int n, long long first, int *prim, int *sub, double *t)

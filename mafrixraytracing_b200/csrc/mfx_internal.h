@@ -285,6 +285,8 @@ void mfx_h_seam_read(const LaunchCfg &, const SceneX &, const WaveH &, int n, lo
 void mfx_h_accum_fixups(cudaStream_t, const WaveH &, unsigned long long *total);
 // the closest-hit queries of an MFX_EXACT_F64 wave (queue `bounce` of WaveX) through the hybrid kernel
 void mfx_h_guard(cudaStream_t, const WaveF &, unsigned long long *totals);
+// the shadow queries of an MFX_EXACT_F64 wave: f32 walk of the reference tree's copy, exact decision at every visited leaf
+void mfx_h_shadow_x(const LaunchCfg &, const SceneX &, const SceneF &ref_layout, const SceneH &, const WaveX &, int bounce);
 void mfx_h_extend_x(const LaunchCfg &, const SceneF &, const SceneX &, const SceneH &, const WaveX &, const WaveF &, const WaveH &, int bounce, HybQuery q);
 
 // misc (mfx_fast.cu)
