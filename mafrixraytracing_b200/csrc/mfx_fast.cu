@@ -461,7 +461,12 @@ __global__ void __launch_bounds__(FAST_BLOCK) k_f_trace5(SceneF sc, WaveF w, int
 // 8-byte entries (sort key, record that holds the child) in shared memory [entry][thread]; trees deeper than the
 // shared-memory budget overflow into a per-thread global column.  A pop re-reads the child link (one 4-byte load
 // from a record the lane fetched a few steps earlier) instead of carrying it through the sorting network.
-template <bool ANY, bool BIG, int REFILL_T, int LEAF_T, int NSTEP, int NLEAF, int MINB, bool COUNT>
+// CMP: the 64-byte records (QuadC) -- two sectors per node step instead of four.  A plane's distance is
+// (o + q*s - ray.o) / d = q*S + C with S = s/d, C = (o - ray.o)/d; the byte q becomes a float by being dropped into the
+// mantissa of 2^23 (one PRMT, which also picks the near or the far word by the octant and the child's byte), and the
+// 2^23 goes into the constant: t = (2^23 + q)*S + (C - 2^23*S), one fma.  The constant is rounded at the magnitude of
+// 2^23*S, i.e. to within half a step: the builder moved every plane outward by that much (compress_quads).
+template <bool ANY, bool BIG, int REFILL_T, int LEAF_T, int NSTEP, int NLEAF, int MINB, bool COUNT, bool CMP = false>
 __global__ void __launch_bounds__(FAST_BLOCK, MINB) k_f_trace6(SceneF sc, WaveF w, int bounce, TravCounters *ctr)
 {
     extern __shared__ uint2 s_stack[];              // [stack_smem][FAST_BLOCK]
@@ -504,6 +509,10 @@ __global__ void __launch_bounds__(FAST_BLOCK, MINB) k_f_trace6(SceneF sc, WaveF 
                     if (!cam0) o = ro[pid];
                     const float4 d = rd[pid];
                     r = make_ray_fast(f3(o.x, o.y, o.z), f3(d.x, d.y, d.z), w.tmin, __float_as_int(o.w));
+                    if (CMP) {      // 2^23 * step / d must stay finite
+                        r.idir = f3(fminf(fmaxf(r.idir.x, -1e24f), 1e24f), fminf(fmaxf(r.idir.y, -1e24f), 1e24f), fminf(fmaxf(r.idir.z, -1e24f), 1e24f));
+                        r.ood = f3(r.o.x * r.idir.x, r.o.y * r.idir.y, r.o.z * r.idir.z);
+                    }
                     best_t = ANY ? d.w - 1e-6f : w.tmax;                // shadow: dist - 1e-6 (Integrators.fs:44); closest: tMax (:108)
                     best_slot = -1; sp = 0; leafA = leafB = -1; node = 0; needPop = false;
                 }
@@ -515,11 +524,35 @@ __global__ void __launch_bounds__(FAST_BLOCK, MINB) k_f_trace6(SceneF sc, WaveF 
 #pragma unroll
         for (int rep = 0; rep < NSTEP; rep++)
         if (pid >= 0 && leafA < 0 && !needPop) {
-            const QuadF *qp = sc.quads + node;
             if (COUNT) local[0]++;
             float4 lox, hix, loy, hiy, loz, hiz, m4, pad4;
-            ldg8(&qp->lox, lox, hix); ldg8(&qp->loy, loy, hiy); ldg8(&qp->loz, loz, hiz); ldg8(&qp->meta, m4, pad4);
             unsigned key[4];
+            if (CMP) {
+                const float4 *qc = reinterpret_cast<const float4 *>(sc.cquads + node);
+                ldg8(qc, lox, hix); ldg8(qc + 2, loy, m4);                      // (o, sx | sy, sz, lox, loy) (loz, hix, hiy, hiz | meta)
+                const float Sx = lox.w * r.idir.x, Sy = hix.x * r.idir.y, Sz = hix.y * r.idir.z;
+                const float Cx = fmaf(-8388608.f, Sx, fmaf(lox.x, r.idir.x, -r.ood.x));
+                const float Cy = fmaf(-8388608.f, Sy, fmaf(lox.y, r.idir.y, -r.ood.y));
+                const float Cz = fmaf(-8388608.f, Sz, fmaf(lox.z, r.idir.z, -r.ood.z));
+                const bool px = r.idir.x >= 0.f, py = r.idir.y >= 0.f, pz = r.idir.z >= 0.f;
+                const unsigned wlx = __float_as_uint(hix.z), wly = __float_as_uint(hix.w), wlz = __float_as_uint(loy.x);
+                const unsigned whx = __float_as_uint(loy.y), why = __float_as_uint(loy.z), whz = __float_as_uint(loy.w);
+                const unsigned nx = px ? wlx : whx, fx = px ? whx : wlx, ny = py ? wly : why, fy = py ? why : wly, nz = pz ? wlz : whz, fz = pz ? whz : wlz;
+#define CQ_PLANE(W, S_, SC, CC) fmaf(__uint_as_float(__byte_perm((W), 0x4B000000u, 0x7440u | (unsigned)(S_))), (SC), (CC))
+#define CQUAD_SLOT(S_, C)                                                                                            \
+                {                                                                                                    \
+                    const float tn = fmaxf(fmaxf(CQ_PLANE(nx, S_, Sx, Cx), CQ_PLANE(ny, S_, Sy, Cy)), fmaxf(CQ_PLANE(nz, S_, Sz, Cz), r.tmin));   \
+                    const float tf = fminf(fminf(CQ_PLANE(fx, S_, Sx, Cx), CQ_PLANE(fy, S_, Sy, Cy)), fminf(CQ_PLANE(fz, S_, Sz, Cz), best_t));   \
+                    const int mt = __float_as_int(m4.C);                                                             \
+                    const unsigned ord = ANY ? (0x7f7ffff8u - (__float_as_uint(tn) & ~7u)) : (__float_as_uint(tn) & ~7u);   \
+                    key[S_] = (tn <= tf && mt != MFX_QUAD_EMPTY) ? (ord | (mt >= 0 ? 4u : 0u) | (unsigned)S_) : KEY_INF;   \
+                }
+                CQUAD_SLOT(0, x) CQUAD_SLOT(1, y) CQUAD_SLOT(2, z) CQUAD_SLOT(3, w)
+#undef CQUAD_SLOT
+#undef CQ_PLANE
+            } else {
+            const QuadF *qp = sc.quads + node;
+            ldg8(&qp->lox, lox, hix); ldg8(&qp->loy, loy, hiy); ldg8(&qp->loz, loz, hiz); ldg8(&qp->meta, m4, pad4);
 #define QUAD_SLOT(S_, C)                                                                                             \
             {                                                                                                        \
                 const float x0 = fmaf(lox.C, r.idir.x, -r.ood.x), x1 = fmaf(hix.C, r.idir.x, -r.ood.x);              \
@@ -537,6 +570,7 @@ __global__ void __launch_bounds__(FAST_BLOCK, MINB) k_f_trace6(SceneF sc, WaveF 
             }
             QUAD_SLOT(0, x) QUAD_SLOT(1, y) QUAD_SLOT(2, z) QUAD_SLOT(3, w)
 #undef QUAD_SLOT
+            }
             // sorting network (0,1)(2,3)(0,2)(1,3)(1,2)
             unsigned a0 = umin_(key[0], key[1]), a1 = umax_(key[0], key[1]);
             unsigned a2 = umin_(key[2], key[3]), a3 = umax_(key[2], key[3]);
@@ -586,7 +620,7 @@ __global__ void __launch_bounds__(FAST_BLOCK, MINB) k_f_trace6(SceneF sc, WaveF 
                 --sp;
                 const uint2 e = (sp < S) ? my_stack[(size_t)sp * FAST_BLOCK] : my_spill[(size_t)(sp - S) * spill_stride];
                 if (ANY || __uint_as_float(e.x & ~7u) <= best_t) {
-                    const int link = __ldg(reinterpret_cast<const int *>(&sc.quads[e.y].meta) + (e.x & 3u));
+                    const int link = CMP ? __ldg(&sc.cquads[e.y].meta[e.x & 3u]) : __ldg(reinterpret_cast<const int *>(&sc.quads[e.y].meta) + (e.x & 3u));
                     if (e.x & 4u) { leafA = link; leafB = -1; }
                     else { node = ~link; needPop = false; }
                     DBG_CHECK(e.y < (unsigned)sc.n_quads && ((e.x & 4u) ? (link >= 0 && (link >> 3) + (link & 7) <= sc.n_slots) : (unsigned)~link < (unsigned)sc.n_quads), w.counts);
@@ -1150,32 +1184,39 @@ static void launch_trace5(const LaunchCfg &c, const SceneF &sc, const WaveF &w, 
     if (sc.has_big_sphere) launch_trace5b<ANY, true, RT, LT, NS>(c, sc, w, bounce);
     else launch_trace5b<ANY, false, RT, LT, NS>(c, sc, w, bounce);
 }
-template <bool ANY, bool BIG, int RT, int LT, int NS, int NL, int MB, bool CNT = false>
+template <bool ANY, bool BIG, int RT, int LT, int NS, int NL, int MB, bool CNT = false, bool CMP = false>
 static void launch_trace6b(const LaunchCfg &c, const SceneF &sc, const WaveF &w, int bounce, TravCounters *ctr = nullptr)
 {
     const size_t smem = (size_t)sc.stack_smem * FAST_BLOCK * sizeof(uint2);
     // the spill columns were sized for spill_threads: never launch more threads than that
-    int blocks = persistent_blocks(k_f_trace6<ANY, BIG, RT, LT, NS, NL, MB, CNT>, FAST_BLOCK, c.blocks, smem);
+    int blocks = persistent_blocks(k_f_trace6<ANY, BIG, RT, LT, NS, NL, MB, CNT, CMP>, FAST_BLOCK, c.blocks, smem);
     if (sc.stack_spill && blocks * FAST_BLOCK > sc.spill_threads) blocks = sc.spill_threads / FAST_BLOCK;
     if (c.max_items > 0) blocks = std::max(1, std::min(blocks, (c.max_items + FAST_BLOCK - 1) / FAST_BLOCK));
-    k_f_trace6<ANY, BIG, RT, LT, NS, NL, MB, CNT><<<blocks, FAST_BLOCK, smem, c.stream>>>(sc, w, bounce, ctr);
+    k_f_trace6<ANY, BIG, RT, LT, NS, NL, MB, CNT, CMP><<<blocks, FAST_BLOCK, smem, c.stream>>>(sc, w, bounce, ctr);
 }
-template <bool ANY, int RT, int LT, int NS, int NL = 2, int MB = 1>
+template <bool ANY, int RT, int LT, int NS, int NL = 2, int MB = 1, bool CMP = false>
 static void launch_trace6(const LaunchCfg &c, const SceneF &sc, const WaveF &w, int bounce)
 {
-    if (sc.has_big_sphere) launch_trace6b<ANY, true, RT, LT, NS, NL, MB>(c, sc, w, bounce);
-    else launch_trace6b<ANY, false, RT, LT, NS, NL, MB>(c, sc, w, bounce);
+    if (sc.has_big_sphere) launch_trace6b<ANY, true, RT, LT, NS, NL, MB, false, CMP>(c, sc, w, bounce);
+    else launch_trace6b<ANY, false, RT, LT, NS, NL, MB, false, CMP>(c, sc, w, bounce);
 }
 template <bool ANY>
 static void launch_trace_variant(const LaunchCfg &c, const SceneF &sc, const WaveF &w, int bounce, TravCounters *ctr)
 {
     if (sc.own_tree) {          // the library's SAH tree (default); the host passes the reference-tree layout for the others
         if (ctr) {              // MFX_SAMPLE_COUNT_OWN_TREE: the shipped configuration, instrumented
+            if (c.variant == 7 || c.variant == 71) {
+                if (sc.has_big_sphere) launch_trace6b<ANY, true, 16, 10, 2, 1, 1, true, true>(c, sc, w, bounce, ctr);
+                else launch_trace6b<ANY, false, 16, 10, 2, 1, 1, true, true>(c, sc, w, bounce, ctr);
+                return;
+            }
             if (sc.has_big_sphere) launch_trace6b<ANY, true, 16, 10, 2, 1, 1, true>(c, sc, w, bounce, ctr);
             else launch_trace6b<ANY, false, 16, 10, 2, 1, 1, true>(c, sc, w, bounce, ctr);
             return;
         }
-        switch (c.variant) {    // tuning knobs kept for A/B runs (tools/ab_env.py MFX_TRACE_VARIANT ...); the default is the measured best (profiles/)
+        switch (c.variant) {
+        case 7: launch_trace6<ANY, 16, 10, 2, 1, 8, true>(c, sc, w, bounce); break;      // 64-byte records (QuadC)
+        case 71: launch_trace6<ANY, 16, 10, 2, 1, 6, true>(c, sc, w, bounce); break;    // tuning knobs kept for A/B runs (tools/ab_env.py MFX_TRACE_VARIANT ...); the default is the measured best (profiles/)
         case 61: launch_trace6<ANY, 8, 12, 2, 2>(c, sc, w, bounce); break;      // two parked leaves
         case 62: launch_trace6<ANY, 12, 16, 1, 2>(c, sc, w, bounce); break;     // one node step per iteration
         case 65: launch_trace6<ANY, 8, 12, 2, 1>(c, sc, w, bounce); break;

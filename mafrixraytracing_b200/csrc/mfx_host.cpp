@@ -173,6 +173,7 @@ struct FrameJob {
     bool has_copy = false;
 };
 
+struct OwnTreeHost;
 struct MfxScene {
     int device = 0;
     int sm_count = 148;
@@ -200,6 +201,7 @@ struct MfxScene {
     uint64_t x_bytes = 0, f_bytes = 0, fr_bytes = 0, h_bytes = 0;
     bool h_ready = false, wh_ready = false;  // hybrid (id-exact closest hit on the own tree): tables, f64 ray queue
     SceneH sh; WaveH wh; int wh_P = 0;
+    std::shared_ptr<OwnTreeHost> own_host;   // the cached host half of the own tree this scene was flattened from
     std::vector<int> f_slot_prim;            // own-tree fast slot -> caller's primitive index, bit 30 = second half of a Rect
     MatF *d_matf = nullptr;
     float *d_perlin_rf = nullptr; int *d_perlin_perm = nullptr;
@@ -791,11 +793,12 @@ static int flatten_fast_ref(MfxScene *s)
 // key the cache; a handful of entries, bounded in bytes, least recently used goes first.
 struct OwnTreeHost {
     std::vector<QuadF> quads;
+    std::vector<QuadC> cquads;          // the same records on 8-bit grids (QuadC)
     std::vector<SlotF> slots;
     std::vector<float4> nrm;
     std::vector<int> slot_prim;         // own-tree fast slot -> primitive index, bit 30 = second triangle of a Rect
     int depth = 0, has_big = 0;
-    size_t bytes() const { return quads.size() * sizeof(QuadF) + slots.size() * sizeof(SlotF) + nrm.size() * 16 + slot_prim.size() * 4; }
+    size_t bytes() const { return quads.size() * sizeof(QuadF) + cquads.size() * sizeof(QuadC) + slots.size() * sizeof(SlotF) + nrm.size() * 16 + slot_prim.size() * 4; }
 };
 struct TreeKey {
     uint64_t h1, h2; size_t n; long max_leaf, trav, collapse;
@@ -909,6 +912,7 @@ static int flatten_fast(MfxScene *s)
     memset(&sf, 0, sizeof(sf));
     SlotF *dslots; float4 *dnrm; QuadF *dquads;
     MFX_TRY(upload(s, &dquads, quads)); MFX_TRY(upload(s, &dslots, host->slots)); MFX_TRY(upload(s, &dnrm, host->nrm));
+    s->own_host = host;
     s->f_bytes = quads.size() * sizeof(QuadF) + host->slots.size() * sizeof(SlotF) + host->nrm.size() * 16 + s->mats.size() * sizeof(MatF);
     sf.quads = dquads; sf.slots = dslots; sf.slot_nrm = dnrm;
     sf.ref_id = nullptr;                                        // b.w already holds the caller's primitive index
@@ -936,6 +940,16 @@ static int fast_layout(MfxScene *s, bool counting, int variant, const SceneF **o
     const bool ref = counting || variant == 4 || variant == 5 || variant == 51 || variant == 52;
     if (ref) { MFX_TRY(flatten_fast_ref(s)); *out = &s->sf_ref; }
     else { MFX_TRY(flatten_fast(s)); *out = &s->sf; }
+    if (!ref && (variant == 7 || variant == 71) && !s->sf.cquads) {       // the 64-byte records: an experiment, built on demand
+        {
+            std::lock_guard<std::mutex> g(g_tree_mu);
+            if (s->own_host->cquads.empty()) mfx_compress_quads(s->own_host->quads, s->own_host->cquads);
+        }
+        QuadC *dc;
+        MFX_TRY(upload(s, &dc, s->own_host->cquads));
+        s->sf.cquads = dc;
+        s->f_bytes += s->own_host->cquads.size() * sizeof(QuadC);
+    }
     return MFX_OK;
 }
 

@@ -122,9 +122,17 @@ struct LightF {
 };
 struct CamF { float pos[3], topleft[3], right[3], down[3]; };
 
+// The own tree again, 64 bytes per record (two 32-byte sectors instead of four): child planes as 8-bit offsets on a
+// per-record grid, origin o and power-of-two step s per axis -- plane = o + q*s, the min planes rounded down and the
+// max planes up by half a step more than the quantisation needs (the kernel folds the int->float conversion into one
+// fma whose constant carries up to half a step of rounding: mfx_fast.cu, k_f_trace6<CMP>).  Byte c of each word
+// belongs to child c; meta as in QuadF.
+struct __align__(32) QuadC { float ox, oy, oz, sx, sy, sz; unsigned lox, loy, loz, hix, hiy, hiz; int meta[4]; };
+
 struct SceneF {
     const PairF *pairs;     // indexed by the interior node's 1-based heap index h (siblings share a 128 B line)
     const QuadF *quads;     // compact, even-depth interior nodes (see QuadF)
+    const QuadC *cquads;    // own tree only: the same records in 64 bytes (null unless built)
     const SlotF *slots;     // leaf order (rects split in two)
     const int   *slot_prim; // slot -> leaf-order primitive (exact slot) ; sub in bit 30
     const int   *ref_id;    // exact slot -> original primitive index

@@ -724,10 +724,11 @@ def test_cpp_host_driver_matches_python_host(tmp_path):
     assert np.array_equal(img, want)
 
 
-@pytest.mark.parametrize("variant", ["4", "5", "51", "61", "62"])
+@pytest.mark.parametrize("variant", ["4", "5", "51", "61", "62", "7"])
 def test_every_traversal_kernel_variant_gives_the_same_hits(monkeypatch, variant):
     """The shipped kernel (default: own SAH tree, k_f_trace6), the reference-tree kernels (MFX_TRACE_VARIANT=4 binary --
-    also the instrumented counting kernel -- and 5 heap-indexed quads) and other refill/vote thresholds must find the
+    also the instrumented counting kernel -- and 5 heap-indexed quads), other refill/vote thresholds and the 64-byte
+    quantised records (7: boxes only ever grow) must find the
     same closest hits and frames: a nearest-hit query has one answer whichever tree finds it."""
     desc = _desc("c3_renault", width=200, height=112)
     s = Scene(desc)

@@ -28,11 +28,12 @@ for spp in spps:
             st = integ.stats
             if best is None or st["ms_total"] < best["ms_total"]:
                 best = dict(st)
-        same = None
+        same, ndiff = None, None
         if spp in ref:
             same = bool(np.array_equal(ref[spp], img))
+            ndiff = int((np.abs(ref[spp] - img).max(axis=-1) > 0).sum())
         else:
             ref[spp] = img.copy()
         rays = best["closest_rays"] + best["shadow_rays"]
         print(json.dumps({"workload": name, "spp": spp, var: v, "ms_total": round(best["ms_total"], 3), "mrays_s": round(rays / best["ms_total"] / 1e3, 1),
-                          "ms_extend": round(best["ms_extend"], 3), "ms_shadow": round(best["ms_shadow"], 3), "same_frame_as_first": same}), flush=True)
+                          "ms_extend": round(best["ms_extend"], 3), "ms_shadow": round(best["ms_shadow"], 3), "same_frame_as_first": same, "pixels_differing": ndiff}), flush=True)
