@@ -352,18 +352,21 @@ def main():
                 creates the replicas of frame k+1 and posts it (mfx_multi_sample_async / mfx_multi_wait).  (Measured on 4 GPUs:
                 uploading frame k+1's layouts with mfx_multi_prepare during frame k and posting it only once frame k is complete
                 is slower -- 18.9 against 16.5 ms per frame: the uploads do not proceed beside the running persistent grids.)"""
-                rays, prev = 0.0, None
+                rays, prev, stamps = 0.0, None, [time.perf_counter()]
                 for k in range(n_steps):
                     m = MultiGpuPixelIntegrator(desc, devices=list(range(world)), bvh=bvh, precision=prec, seed=1)
                     m.SampleAsync(args.spp, texs[k % 2])
                     if prev is not None:
                         prev.Wait()
+                        stamps.append(time.perf_counter())
                         rays += prev.stats["closest_rays"] + prev.stats["shadow_rays"]
                         prev.close()
                     prev = m
                 prev.Wait()
+                stamps.append(time.perf_counter())
                 rays += prev.stats["closest_rays"] + prev.stats["shadow_rays"]
                 prev.close()
+                dbg("pipelined_multi frame completion intervals, ms: " + " ".join(f"{1e3 * (b - a):.1f}" for a, b in zip(stamps[:-1], stamps[1:])))
                 return rays
             one_blocking(); pipelined_multi(2)                       # untimed: contexts, path state of two frames in flight
             torch.cuda.synchronize()

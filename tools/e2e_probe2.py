@@ -6,7 +6,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 from mafrixraytracing_b200 import scenes, Scene, CudaPixelIntegrator, Bvh, FAST_F32, _lib
 desc = scenes.c2_spot(); bvh = Bvh.Build(desc.prims)
-spp, K = 64, 10
+spp, K = (int(sys.argv[1]) if len(sys.argv) > 1 else 64), (int(sys.argv[2]) if len(sys.argv) > 2 else 10)
 lib = _lib.load()
 texs = [np.zeros((desc.width, desc.height, 4)) for _ in range(2)]
 for t in texs:

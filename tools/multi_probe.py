@@ -26,9 +26,10 @@ for k in range(4):
 texs = [tex, np.zeros_like(tex)]
 _lib.check(_lib.load().mfx_host_register(_lib.ptr(texs[1]), texs[1].nbytes))
 acc = {"create": 0.0, "post": 0.0, "wait": 0.0, "close": 0.0}
-K = 12
+K = 30
+stamps = []
 prev = None
-t_all = time.perf_counter()
+t_all = t_all0 = time.perf_counter()
 for k in range(K):
     t0 = time.perf_counter()
     m = MultiGpuPixelIntegrator(desc, devices=list(range(n)), bvh=bvh, precision=FAST_F32, seed=1)
@@ -41,8 +42,12 @@ for k in range(K):
         prev.close()
         t4 = time.perf_counter()
         acc["wait"] += t3 - t2; acc["close"] += t4 - t3
+        stamps.append(t3)
     acc["create"] += t1 - t0; acc["post"] += t2 - t1
     prev = m
 prev.Wait(); prev.close()
 t_all = time.perf_counter() - t_all
+print("frame completion intervals, ms:", " ".join(f"{1e3 * (b - a):.1f}" for a, b in zip([t_all0] + stamps[:-1], stamps)))
+steady = (stamps[-1] - stamps[4]) / (len(stamps) - 5)
+print(f"pipelined, steady state (frames 5..{K - 1}): {1e3 * steady:.2f} ms per frame")
 print(f"pipelined x{K}: {1e3 * t_all / K:.2f} ms per frame; host thread per frame: " + ", ".join(f"{k} {1e3 * v / K:.2f}" for k, v in acc.items()), flush=True)
