@@ -349,9 +349,8 @@ def main():
 
             def pipelined_multi(n_steps):
                 """n_steps frames, each through its own mfx_multi_create: frame k renders and downloads while the host thread
-                creates the replicas of frame k+1 and posts it (mfx_multi_sample_async / mfx_multi_wait).  (Measured on 4 GPUs:
-                uploading frame k+1's layouts with mfx_multi_prepare during frame k and posting it only once frame k is complete
-                is slower -- 18.9 against 16.5 ms per frame: the uploads do not proceed beside the running persistent grids.)"""
+                creates the replicas of frame k+1 and posts it (mfx_multi_sample_async / mfx_multi_wait); on every device the
+                kernels of frame k+1 are ordered behind those of frame k by an event, everything else overlaps."""
                 rays, prev, stamps = 0.0, None, [time.perf_counter()]
                 for k in range(n_steps):
                     m = MultiGpuPixelIntegrator(desc, devices=list(range(world)), bvh=bvh, precision=prec, seed=1)
@@ -368,7 +367,7 @@ def main():
                 prev.close()
                 dbg("pipelined_multi frame completion intervals, ms: " + " ".join(f"{1e3 * (b - a):.1f}" for a, b in zip(stamps[:-1], stamps[1:])))
                 return rays
-            one_blocking(); pipelined_multi(2)                       # untimed: contexts, path state of two frames in flight
+            one_blocking(); pipelined_multi(3)                       # untimed: contexts, path state of two frames in flight
             torch.cuda.synchronize()
             t0 = time.perf_counter()
             rays_e2e = pipelined_multi(args.steps)
