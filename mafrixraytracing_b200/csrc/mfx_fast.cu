@@ -461,13 +461,26 @@ __global__ void __launch_bounds__(FAST_BLOCK) k_f_trace5(SceneF sc, WaveF w, int
 // 8-byte entries (sort key, record that holds the child) in shared memory [entry][thread]; trees deeper than the
 // shared-memory budget overflow into a per-thread global column.  A pop re-reads the child link (one 4-byte load
 // from a record the lane fetched a few steps earlier) instead of carrying it through the sorting network.
+// MFX_SKY_TRACER, late bounces (TAIL): the lane that finishes a closest-hit query shades it on the spot (one level of
+// GetColor: sky_scatter_f, the function k_f_shade_sky calls too -- NOINLINE, so both run the same machine code and a
+// frame does not depend on which of them shaded a vertex) and carries the scattered ray on until the path ends.  One
+// launch takes every path still alive after bounce `MFX_SKY_TAIL` to the depth limit of 50 instead of two launches
+// per bounce whose cost is launch latency (profiles/: ~30 us per bounce for a handful of rays), and the host never
+// looks at a queue size in the middle of a Sample.
+struct SkyCtx {
+    const SlotF *slots; const float4 *slot_nrm; const MatF *mats; const float *perlin_rf; const int *perlin_perm;
+    TileMap tm; int width, pix0, npix, s0; uint32_t k0, k1;
+};
+template <bool DIRECT>
+__device__ bool sky_scatter_f(const SkyCtx &c, int k, int pid, int fs, float t, F3 o, F3 d, float4 &thr, float4 &st_o, float4 &st_d);
+
 // CMP: the 64-byte records (QuadC) -- two sectors per node step instead of four.  A plane's distance is
 // (o + q*s - ray.o) / d = q*S + C with S = s/d, C = (o - ray.o)/d; the byte q becomes a float by being dropped into the
 // mantissa of 2^23 (one PRMT, which also picks the near or the far word by the octant and the child's byte), and the
 // 2^23 goes into the constant: t = (2^23 + q)*S + (C - 2^23*S), one fma.  The constant is rounded at the magnitude of
 // 2^23*S, i.e. to within half a step: the builder moved every plane outward by that much (compress_quads).
-template <bool ANY, bool BIG, int REFILL_T, int LEAF_T, int NSTEP, int NLEAF, int MINB, bool COUNT, bool CMP = false>
-__global__ void __launch_bounds__(FAST_BLOCK, MINB) k_f_trace6(SceneF sc, WaveF w, int bounce, TravCounters *ctr)
+template <bool ANY, bool BIG, int REFILL_T, int LEAF_T, int NSTEP, int NLEAF, int MINB, bool COUNT, bool CMP = false, bool TAIL = false>
+__global__ void __launch_bounds__(FAST_BLOCK, MINB) k_f_trace6(SceneF sc, WaveF w, int bounce, TravCounters *ctr, SkyCtx sky)
 {
     extern __shared__ uint2 s_stack[];              // [stack_smem][FAST_BLOCK]
     uint2 *my_stack = s_stack + threadIdx.x;
@@ -490,11 +503,13 @@ __global__ void __launch_bounds__(FAST_BLOCK, MINB) k_f_trace6(SceneF sc, WaveF 
     bool exhausted = false;
     unsigned iters = 0u;
     unsigned long long local[3] = { 0ull, 0ull, 0ull };   // COUNT: 128 B records fetched, triangle tests, sphere tests
+    int path = -1, bnc = bounce, traced_on = 0;     // TAIL: path id, current bounce of the lane's path, rays traced beyond the queue's own
+    float4 thr = make_float4(1.f, 1.f, 1.f, 0.f);   // TAIL: product of the attenuations so far
 
     for (;;) {
         const unsigned idle = __ballot_sync(FULL, pid < 0);
         unsigned idle_now = idle;
-        if (++iters > (1u << 22)) { if (lane == 0) atomicAdd(&w.counts[MFX_COUNTS_LEN - 1], 1); break; }   // watchdog
+        if (++iters > (TAIL ? (1u << 26) : (1u << 22))) { if (lane == 0) atomicAdd(&w.counts[MFX_COUNTS_LEN - 1], 1); break; }   // watchdog
         if (!exhausted && __popc(idle) >= REFILL_T) {
             const int nidle = __popc(idle);
             int base = 0;
@@ -515,6 +530,7 @@ __global__ void __launch_bounds__(FAST_BLOCK, MINB) k_f_trace6(SceneF sc, WaveF 
                     }
                     best_t = ANY ? d.w - 1e-6f : w.tmax;                // shadow: dist - 1e-6 (Integrators.fs:44); closest: tMax (:108)
                     best_slot = -1; sp = 0; leafA = leafB = -1; node = 0; needPop = false;
+                    if (TAIL) { path = __float_as_int(d.w); bnc = bounce; thr = w.thr[bounce & 1][pid]; }
                 }
             }
             idle_now = __ballot_sync(FULL, pid < 0);
@@ -628,6 +644,28 @@ __global__ void __launch_bounds__(FAST_BLOCK, MINB) k_f_trace6(SceneF sc, WaveF 
                 }
             }
         }
+        if (TAIL && finished) {
+            // GetColor's next level, here and now (RayTracing.fs:367-382): a miss ends the path with T * sky, a hit at the
+            // depth limit or a failed scatter ends it black, anything else scatters and the lane traces on
+            DBG_CHECK(path >= 0 && path < w.P && best_slot < sc.n_slots, w.counts);
+            bool again = false;
+            if (best_slot < 0) {
+                const float ty = 0.5f * (r.d.y + 1.0f);
+                w.rad[path] = make_float4(thr.x * ((1.f - ty) + ty * 0.5f), thr.y * ((1.f - ty) + ty * 0.7f), thr.z * ((1.f - ty) + ty), 0.f);
+            } else if (bnc < sc.max_depth) {
+                float4 so, sd;
+                if (sky_scatter_f<true>(sky, bnc, path, best_slot, best_t, r.o, r.d, thr, so, sd)) {
+                    r = make_ray_fast(f3(so.x, so.y, so.z), f3(sd.x, sd.y, sd.z), w.tmin, __float_as_int(so.w));
+                    if (CMP) {
+                        r.idir = f3(fminf(fmaxf(r.idir.x, -1e24f), 1e24f), fminf(fmaxf(r.idir.y, -1e24f), 1e24f), fminf(fmaxf(r.idir.z, -1e24f), 1e24f));
+                        r.ood = f3(r.o.x * r.idir.x, r.o.y * r.idir.y, r.o.z * r.idir.z);
+                    }
+                    best_t = w.tmax; best_slot = -1; sp = 0; leafA = leafB = -1; node = 0; needPop = false;
+                    bnc++; traced_on++; again = true;
+                }
+            }
+            if (!again) pid = -1;
+        } else
         if (finished) {
             DBG_CHECK(pid >= 0 && pid < w.P && best_slot < sc.n_slots, w.counts);
             if (!ANY) w.hit[pid] = make_float2(best_t, __int_as_float(best_slot));
@@ -640,6 +678,7 @@ __global__ void __launch_bounds__(FAST_BLOCK, MINB) k_f_trace6(SceneF sc, WaveF 
         }
     }
     if (COUNT) { for (int j = 0; j < 3; j++) if (local[j]) atomicAdd(&ctr->v[ANY ? 1 : 0][j], local[j]); }
+    if (TAIL && traced_on) atomicAdd(&w.counts[bounce + 1], traced_on);     // the ray total sums counts[0..D]: the later bounces' rays land here
 }
 
 struct RngF { uint32_t pixel, sample, k0, k1; };
@@ -881,6 +920,87 @@ __device__ __forceinline__ F3 random_in_unit_ball_f(const RngF &g, uint32_t dim)
     return f3(0.f, 0.f, 0.f);
 }
 
+// One level of GetColor for a ray (o, d) that hit fast slot fs at distance t: scatter (Lambertian :282-290, Metal :291-299,
+// Dielectric :300-325), attenuation into thr; true if the path goes on (st_o / st_d: its next ray, source primitive and
+// path id in the w fields).  NOINLINE on purpose: see SkyCtx.
+template <bool DIRECT>
+__device__ __noinline__ bool sky_scatter_f(const SkyCtx &c, int k, int pid, int fs, float t, F3 o, F3 d, float4 &thr, float4 &st_o, float4 &st_d)
+{
+    const F3 point = o + d * t;
+    const float4 sa = ldg4(&c.slots[fs].a);
+    const float4 sb = ldg4(&c.slots[fs].b);
+    const int prim = __float_as_int(sb.w) & 0x3fffffff;
+    F3 normal;                                                         // (p - center) / radius, :198
+    if (__float_as_int(sa.w) == 3) {                                   // big sphere: f64 centre (see leaf_f3)
+        const float4 sc4 = ldg4(&c.slots[fs].c);
+        const double cx = __hiloint2double(__float_as_int(sb.y), __float_as_int(sb.x));
+        const double cy = __hiloint2double(__float_as_int(sc4.y), __float_as_int(sc4.x));
+        const double cz = __hiloint2double(__float_as_int(sc4.w), __float_as_int(sc4.z));
+        normal = normalize_f(f3((float)((double)point.x - cx), (float)((double)point.y - cy), (float)((double)point.z - cz)));
+    } else normal = normalize_f(point - f3(sa.x, sa.y, sa.z));
+    const MatF m = c.mats[__float_as_int(ldg4(&c.slot_nrm[fs]).w)];
+    const int sl = pid / c.npix, pl = pid - sl * c.npix;
+    int pix, px, py;
+    pixel_of(c.tm, c.width, c.pix0 + pl, pix, px, py);
+    RngF g; g.pixel = (uint32_t)pix; g.sample = (uint32_t)(c.s0 + sl); g.k0 = c.k0; g.k1 = c.k1;
+    uint32_t dz[4] = { 0u, 0u, 0u, 0u };
+    if (DIRECT) philox4x32_10(g.pixel, g.sample, MFX_DIM_BSDF(k), MFX_ITER_DIRECT, g.k0, g.k1, dz);
+    F3 wi, att;
+    bool ok = true;
+    if (m.kind == 3) {                                                 // Dielectric
+        const float dn = dot(d, normal);
+        const F3 reflected = d - normal * (2.f * dn);
+        const F3 outward = dn > 0.f ? -normal : normal;
+        const float nint = dn > 0.f ? m.ei : 1.f / m.ei;
+        const float cosine = dn > 0.f ? m.ei * dn : -dn;
+        const float dt = dot(d, outward);
+        const float disc = 1.f - nint * nint * (1.f - dt * dt);
+        float reflect_prob = 1.f;
+        F3 ref_dir = reflected;
+        if (disc > 0.f) {
+            ref_dir = (d - outward * dt) * nint - outward * sqrtf(disc);
+            const float r0 = (1.f - m.ei) / (1.f + m.ei), r1 = r0 * r0;
+            const float x = 1.f - cosine, x2 = x * x;
+            reflect_prob = r1 + (1.f - r1) * (x2 * x2 * x);
+        }
+        uint32_t coin = dz[3];
+        if (!DIRECT) { uint32_t c4[4]; philox4x32_10(g.pixel, g.sample, MFX_DIM_LIGHT(k), 0, g.k0, g.k1, c4); coin = c4[0]; }
+        // the coin uses the full 32-bit value like the f64 stream's `NextDouble() < reflect_prob`
+        wi = normalize_f(((double)coin * (1.0 / 4294967296.0) < (double)reflect_prob) ? reflected : ref_dir);
+        att = f3(1.f, 1.f, 1.f);
+    } else {
+        F3 ball;
+        if (DIRECT) {
+            const float z = 1.f - 2.f * u32_to_unit_f32(dz[0]);
+            const float r = sqrtf(fmaxf(0.f, 1.f - z * z));
+            float sn, cs;
+            __sincosf(6.283185307179586477f * u32_to_unit_f32(dz[1]), &sn, &cs);
+            ball = f3(r * cs, r * sn, z) * cbrtf(u32_to_unit_f32(dz[2]));
+        } else ball = random_in_unit_ball_f(g, MFX_DIM_BSDF(k));
+        if (m.kind == 1) {                                             // Metal
+            const float fuzz = fminf(m.fuzz, 1.f);
+            wi = normalize_f(d - normal * (2.f * dot(d, normal)) + ball * fuzz);
+            att = f3(m.albedo[0], m.albedo[1], m.albedo[2]);
+            ok = dot(wi, normal) > 0.f;
+        } else {                                                       // Lambertian over a texture (:50-61, :86-99)
+            wi = normalize_f(normal + ball);
+            att = f3(m.albedo[0], m.albedo[1], m.albedo[2]);
+            if (m.kind == 4) {
+                if (sinf(10.f * point.x) * sinf(10.f * point.y) * sinf(10.f * point.z) < 0.f) att = f3(m.fuzz, m.ei, m.et);
+            } else if (m.kind == 5) {
+                const int ia = (int)(4.f * point.x) & 255, ib = (int)(4.f * point.y) & 255, ic = (int)(4.f * point.z) & 255;
+                const float nz = __ldg(&c.perlin_rf[__ldg(&c.perlin_perm[ia]) ^ __ldg(&c.perlin_perm[256 + ib]) ^ __ldg(&c.perlin_perm[512 + ic])]);
+                att = f3(nz, nz, nz);
+            }
+        }
+    }
+    thr.x *= att.x; thr.y *= att.y; thr.z *= att.z;
+    const bool cont = ok && ((thr.x != 0.f) || (thr.y != 0.f) || (thr.z != 0.f));
+    st_o = make_float4(point.x, point.y, point.z, __int_as_float(prim));
+    st_d = make_float4(wi.x, wi.y, wi.z, __int_as_float(pid));
+    return cont;
+}
+
 template <bool DIRECT>
 __global__ void __launch_bounds__(SHADE_BLOCK, 4) k_f_shade_sky(SceneF sc, WaveF w, TileMap tm, int pix0, int npix, int s0, int bounce, uint64_t seed)
 {
@@ -892,6 +1012,7 @@ __global__ void __launch_bounds__(SHADE_BLOCK, 4) k_f_shade_sky(SceneF sc, WaveF
     const bool last = (bounce >= sc.max_depth);          // `depth < 50`, :373
     const int nblock_iters = (n + SHADE_BLOCK - 1) / SHADE_BLOCK;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const SkyCtx ctx{ sc.slots, sc.slot_nrm, sc.mats, sc.perlin_rf, sc.perlin_perm, tm, sc.width, pix0, npix, s0, (uint32_t)seed, (uint32_t)(seed >> 32) };
     int par = 0;
     for (int it = blockIdx.x; it < nblock_iters; it += gridDim.x, par ^= 1) {
         const int i = it * SHADE_BLOCK + threadIdx.x;
@@ -911,78 +1032,7 @@ __global__ void __launch_bounds__(SHADE_BLOCK, 4) k_f_shade_sky(SceneF sc, WaveF
             } else if (!last) {
                 float4 o4 = make_float4(sc.cam.pos[0], sc.cam.pos[1], sc.cam.pos[2], __int_as_float(-1));
                 if (!(bounce == 0 && w.cam_origin)) o4 = w.ray_o[cur][i];
-                const F3 point = f3(o4.x, o4.y, o4.z) + d * hr.x;
-                const float4 sa = ldg4(&sc.slots[fs].a);
-                const float4 sb = ldg4(&sc.slots[fs].b);
-                const int prim = __float_as_int(sb.w) & 0x3fffffff;
-                F3 normal;                                                         // (p - center) / radius, :198
-                if (__float_as_int(sa.w) == 3) {                                   // big sphere: f64 centre (see leaf_f3)
-                    const float4 sc4 = ldg4(&sc.slots[fs].c);
-                    const double cx = __hiloint2double(__float_as_int(sb.y), __float_as_int(sb.x));
-                    const double cy = __hiloint2double(__float_as_int(sc4.y), __float_as_int(sc4.x));
-                    const double cz = __hiloint2double(__float_as_int(sc4.w), __float_as_int(sc4.z));
-                    normal = normalize_f(f3((float)((double)point.x - cx), (float)((double)point.y - cy), (float)((double)point.z - cz)));
-                } else normal = normalize_f(point - f3(sa.x, sa.y, sa.z));
-                const MatF m = sc.mats[__float_as_int(ldg4(&sc.slot_nrm[fs]).w)];
-                const int sl = pid / npix, pl = pid - sl * npix;
-                int pix, px, py;
-                pixel_of(tm, sc.width, pix0 + pl, pix, px, py);
-                RngF g; g.pixel = (uint32_t)pix; g.sample = (uint32_t)(s0 + sl); g.k0 = (uint32_t)seed; g.k1 = (uint32_t)(seed >> 32);
-                uint32_t dz[4] = { 0u, 0u, 0u, 0u };
-                if (DIRECT) philox4x32_10(g.pixel, g.sample, MFX_DIM_BSDF(k), MFX_ITER_DIRECT, g.k0, g.k1, dz);
-                F3 wi, att;
-                bool ok = true;
-                if (m.kind == 3) {                                                 // Dielectric
-                    const float dn = dot(d, normal);
-                    const F3 reflected = d - normal * (2.f * dn);
-                    const F3 outward = dn > 0.f ? -normal : normal;
-                    const float nint = dn > 0.f ? m.ei : 1.f / m.ei;
-                    const float cosine = dn > 0.f ? m.ei * dn : -dn;
-                    const float dt = dot(d, outward);
-                    const float disc = 1.f - nint * nint * (1.f - dt * dt);
-                    float reflect_prob = 1.f;
-                    F3 ref_dir = reflected;
-                    if (disc > 0.f) {
-                        ref_dir = (d - outward * dt) * nint - outward * sqrtf(disc);
-                        const float r0 = (1.f - m.ei) / (1.f + m.ei), r1 = r0 * r0;
-                        const float x = 1.f - cosine, x2 = x * x;
-                        reflect_prob = r1 + (1.f - r1) * (x2 * x2 * x);
-                    }
-                    uint32_t coin = dz[3];
-                    if (!DIRECT) { uint32_t c4[4]; philox4x32_10(g.pixel, g.sample, MFX_DIM_LIGHT(k), 0, g.k0, g.k1, c4); coin = c4[0]; }
-                    // the coin uses the full 32-bit value like the f64 stream's `NextDouble() < reflect_prob`
-                    wi = normalize_f(((double)coin * (1.0 / 4294967296.0) < (double)reflect_prob) ? reflected : ref_dir);
-                    att = f3(1.f, 1.f, 1.f);
-                } else {
-                    F3 ball;
-                    if (DIRECT) {
-                        const float z = 1.f - 2.f * u32_to_unit_f32(dz[0]);
-                        const float r = sqrtf(fmaxf(0.f, 1.f - z * z));
-                        float sn, cs;
-                        __sincosf(6.283185307179586477f * u32_to_unit_f32(dz[1]), &sn, &cs);
-                        ball = f3(r * cs, r * sn, z) * cbrtf(u32_to_unit_f32(dz[2]));
-                    } else ball = random_in_unit_ball_f(g, MFX_DIM_BSDF(k));
-                    if (m.kind == 1) {                                             // Metal
-                        const float fuzz = fminf(m.fuzz, 1.f);
-                        wi = normalize_f(d - normal * (2.f * dot(d, normal)) + ball * fuzz);
-                        att = f3(m.albedo[0], m.albedo[1], m.albedo[2]);
-                        ok = dot(wi, normal) > 0.f;
-                    } else {                                                       // Lambertian over a texture (:50-61, :86-99)
-                        wi = normalize_f(normal + ball);
-                        att = f3(m.albedo[0], m.albedo[1], m.albedo[2]);
-                        if (m.kind == 4) {
-                            if (sinf(10.f * point.x) * sinf(10.f * point.y) * sinf(10.f * point.z) < 0.f) att = f3(m.fuzz, m.ei, m.et);
-                        } else if (m.kind == 5) {
-                            const int a = (int)(4.f * point.x) & 255, b = (int)(4.f * point.y) & 255, c = (int)(4.f * point.z) & 255;
-                            const float nz = __ldg(&sc.perlin_rf[__ldg(&sc.perlin_perm[a]) ^ __ldg(&sc.perlin_perm[256 + b]) ^ __ldg(&sc.perlin_perm[512 + c])]);
-                            att = f3(nz, nz, nz);
-                        }
-                    }
-                }
-                thr.x *= att.x; thr.y *= att.y; thr.z *= att.z;
-                cont = ok && ((thr.x != 0.f) || (thr.y != 0.f) || (thr.z != 0.f));
-                st_o = make_float4(point.x, point.y, point.z, __int_as_float(prim));
-                st_d = make_float4(wi.x, wi.y, wi.z, __int_as_float(pid));
+                cont = sky_scatter_f<DIRECT>(ctx, k, pid, fs, hr.x, f3(o4.x, o4.y, o4.z), d, thr, st_o, st_d);
                 st_thr = thr;
             }
         }
@@ -1184,15 +1234,15 @@ static void launch_trace5(const LaunchCfg &c, const SceneF &sc, const WaveF &w, 
     if (sc.has_big_sphere) launch_trace5b<ANY, true, RT, LT, NS>(c, sc, w, bounce);
     else launch_trace5b<ANY, false, RT, LT, NS>(c, sc, w, bounce);
 }
-template <bool ANY, bool BIG, int RT, int LT, int NS, int NL, int MB, bool CNT = false, bool CMP = false>
-static void launch_trace6b(const LaunchCfg &c, const SceneF &sc, const WaveF &w, int bounce, TravCounters *ctr = nullptr)
+template <bool ANY, bool BIG, int RT, int LT, int NS, int NL, int MB, bool CNT = false, bool CMP = false, bool TAIL = false>
+static void launch_trace6b(const LaunchCfg &c, const SceneF &sc, const WaveF &w, int bounce, TravCounters *ctr = nullptr, const SkyCtx &sky = SkyCtx{})
 {
     const size_t smem = (size_t)sc.stack_smem * FAST_BLOCK * sizeof(uint2);
     // the spill columns were sized for spill_threads: never launch more threads than that
-    int blocks = persistent_blocks(k_f_trace6<ANY, BIG, RT, LT, NS, NL, MB, CNT, CMP>, FAST_BLOCK, c.blocks, smem);
+    int blocks = persistent_blocks(k_f_trace6<ANY, BIG, RT, LT, NS, NL, MB, CNT, CMP, TAIL>, FAST_BLOCK, c.blocks, smem);
     if (sc.stack_spill && blocks * FAST_BLOCK > sc.spill_threads) blocks = sc.spill_threads / FAST_BLOCK;
     if (c.max_items > 0) blocks = std::max(1, std::min(blocks, (c.max_items + FAST_BLOCK - 1) / FAST_BLOCK));
-    k_f_trace6<ANY, BIG, RT, LT, NS, NL, MB, CNT, CMP><<<blocks, FAST_BLOCK, smem, c.stream>>>(sc, w, bounce, ctr);
+    k_f_trace6<ANY, BIG, RT, LT, NS, NL, MB, CNT, CMP, TAIL><<<blocks, FAST_BLOCK, smem, c.stream>>>(sc, w, bounce, ctr, sky);
 }
 template <bool ANY, int RT, int LT, int NS, int NL = 2, int MB = 1, bool CMP = false>
 static void launch_trace6(const LaunchCfg &c, const SceneF &sc, const WaveF &w, int bounce)
@@ -1238,6 +1288,13 @@ static void launch_trace_variant(const LaunchCfg &c, const SceneF &sc, const Wav
 void mfx_f_extend(const LaunchCfg &c, const SceneF &sc, const WaveF &w, int bounce, TravCounters *ctr)
 {
     launch_trace_variant<false>(c, sc, w, bounce, ctr);
+}
+// MFX_SKY_TRACER: every path in the extend queue of `bounce` traced AND shaded to its end in one launch (k_f_trace6<TAIL>)
+void mfx_f_sky_tail(const LaunchCfg &c, const SceneF &sc, const WaveF &w, TileMap tm, int pix0, int npix, int s0, int bounce, uint64_t seed)
+{
+    const SkyCtx sky{ sc.slots, sc.slot_nrm, sc.mats, sc.perlin_rf, sc.perlin_perm, tm, sc.width, pix0, npix, s0, (uint32_t)seed, (uint32_t)(seed >> 32) };
+    if (sc.has_big_sphere) launch_trace6b<false, true, 16, 10, 2, 1, 4, false, false, true>(c, sc, w, bounce, nullptr, sky);
+    else launch_trace6b<false, false, 16, 10, 2, 1, 4, false, false, true>(c, sc, w, bounce, nullptr, sky);
 }
 void mfx_f_shade(const LaunchCfg &c, const SceneF &sc, const WaveF &w, TileMap tm, int pix0, int npix, int s0, int bounce, uint64_t seed)
 {

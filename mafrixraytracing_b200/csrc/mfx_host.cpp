@@ -1394,6 +1394,8 @@ static int launch_sample(MfxScene *s, const MfxSampleParams *p, double *d_color_
 
     const int P = exact ? s->wx.P : s->wf.P;
     const int D = s->max_depth;
+    // (own tree, default sampler and uncounted runs only: the instrumented and reference-stream runs keep one launch pair per bounce)
+    const int sky_tail = (sky && !exact && !counting && sfp->own_tree && !(p->flags & MFX_SAMPLE_REFERENCE_STREAM)) ? (int)env_long("MFX_SKY_TAIL", 8) : 0;
     const int npix_total = tm.n_pix;
     const int pix_chunk = std::min(npix_total, P);
     const int S_wave = std::max(1, std::min(p->spp, P / std::max(1, pix_chunk)));
@@ -1435,6 +1437,16 @@ static int launch_sample(MfxScene *s, const MfxSampleParams *p, double *d_color_
                     if (exact) mfx_x_shade_sky(cfg, s->sx, s->wx, tm, pix0, np, sabs, b, p->seed);
                     else mfx_f_shade_sky(cfg, *sfp, s->wf, tm, pix0, np, sabs, b, p->seed);
                     launches += 2; l_ext++;
+                    // the throughput path hands whatever is still alive after bounce MFX_SKY_TAIL (default 8) to ONE launch
+                    // that traces and shades every such path to its end (k_f_trace6<TAIL>): the late bounces hold a few
+                    // rays at most and cost launch latency, and the host no longer looks at a queue size inside a Sample
+                    if (sky_tail > 0 && b == sky_tail && b < D) {
+                        MFX_TRY(timed(0, st));
+                        mfx_f_sky_tail(cfg, *sfp, s->wf, tm, pix0, np, sabs, b + 1, p->seed);
+                        MFX_TRY(timed_end(st));
+                        launches++; l_ext++;
+                        break;
+                    }
                     // `depth < 50`: the late bounces hold a few rays at most (paths caught inside glass spheres), and a
                     // full persistent grid that finds a tiny queue still costs ~30 us per bounce (profiles/).  A queue
                     // never grows from one bounce to the next, so the host looks at the device-side count now and then

@@ -172,3 +172,25 @@ def test_exact_matches_the_committed_sky_goldens_and_display_transform(name):
     assert np.array_equal(disp, oracle.sky_display_rgba8(tex))
     assert np.array_equal(np.frombuffer(hashlib.sha256(disp.tobytes()).digest(), dtype=np.uint8), g[f"image/{name}/display_sha"])
     film.close()
+
+
+@pytest.mark.parametrize("make", [lambda: scenes.random_scene(width=320, height=160), lambda: mixed(width=240, height=160)])
+def test_late_bounces_in_one_launch_give_the_same_frame(monkeypatch, make):
+    """From bounce MFX_SKY_TAIL (default 8) on the fast path traces AND shades every surviving path to the depth limit
+    in one launch (k_f_trace6<TAIL>); the wavefront loop (MFX_SKY_TAIL=0: two launches per bounce up to depth 50) must
+    give the same frame bit for bit -- both call the one sky_scatter_f -- and count the same rays, with a fraction of
+    the launches.  A tail that starts right after the camera rays (MFX_SKY_TAIL=1) must agree too."""
+    desc = make()
+    s = Scene(desc)
+    integ = CudaPixelIntegrator(s, precision=FAST_F32, seed=4)
+    monkeypatch.setenv("MFX_SKY_TAIL", "0")
+    ref = integ.Sample(4).copy()
+    st0 = dict(integ.stats)
+    for tail in ("8", "1", "3"):
+        monkeypatch.setenv("MFX_SKY_TAIL", tail)
+        img = integ.Sample(4).copy()
+        st = dict(integ.stats)
+        assert np.array_equal(img, ref), tail
+        assert st["closest_rays"] == st0["closest_rays"], (tail, st["closest_rays"], st0["closest_rays"])
+        assert st["launches"] < st0["launches"] // 2
+    assert np.isfinite(ref).all() and ref[..., :3].mean() > 0.05
