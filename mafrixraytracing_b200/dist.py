@@ -74,7 +74,11 @@ class StripeGather:
         self.per = -(-self.n_stripes // world)
         self.view = frame.view(self.n_stripes, -1)                     # one row per stripe (contiguous in x-major)
         self.send = torch.zeros((self.per, self.view.shape[1]), dtype=frame.dtype, device=frame.device)
-        self.recv = [torch.empty_like(self.send) for _ in range(world)] if rank == dst else None
+        # one receive buffer: rank r's packed stripes are row r, so when the stripes divide evenly the destination puts
+        # them all back with ONE strided copy (stripe k*world + r <- recv[r, k]) instead of one copy per rank
+        self.recv_all = torch.empty((world,) + tuple(self.send.shape), dtype=frame.dtype, device=frame.device) if rank == dst else None
+        self.recv = [self.recv_all[r] for r in range(world)] if rank == dst else None
+        self.even = (self.n_stripes % world == 0)
 
     def __call__(self):
         import torch.distributed as dist
@@ -83,7 +87,9 @@ class StripeGather:
         mine = self.view[self.rank::self.world]
         self.send[:mine.shape[0]].copy_(mine)
         dist.gather(self.send, self.recv, dst=self.dst)
-        if self.rank == self.dst:
+        if self.rank == self.dst and self.even:
+            self.view.view(self.per, self.world, -1).copy_(self.recv_all.transpose(0, 1))     # (its own row holds its own stripes)
+        elif self.rank == self.dst:
             for r in range(self.world):
                 if r == self.dst:
                     continue
