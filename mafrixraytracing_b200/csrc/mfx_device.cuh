@@ -91,6 +91,22 @@ __device__ __forceinline__ void pixel_of(const TileMap &tm, int width, int pl, i
     px = pix - py * width;
 }
 
+// Path id of a wave <-> (sample, pixel): blocks of 2^sshift samples of one pixel are neighbours, pixels follow in
+// pixel_of's order, then the next block of samples.  With 8-pixel stripe rows and sshift = 2 the 32 rays a warp picks up
+// together are 4 samples each of 8 adjacent pixels -- the coherence of primary rays lasts into their shadow rays and
+// the first bounce.  (Which path carries which sample never shows in a frame: the RNG is keyed on pixel and sample.)
+__device__ __forceinline__ void path_split(const TileMap &tm, long long pid, int npix, int &sl, int &pl)
+{
+    const long long q = pid >> tm.sshift;
+    const int slb = (int)(q / npix);
+    pl = (int)(q - (long long)slb * npix);
+    sl = (slb << tm.sshift) | (int)(pid & ((1 << tm.sshift) - 1));
+}
+__device__ __forceinline__ size_t path_join(const TileMap &tm, int sl, int pl, int npix)
+{
+    return ((((size_t)(sl >> tm.sshift)) * (size_t)npix + (size_t)pl) << tm.sshift) | (size_t)(sl & ((1 << tm.sshift) - 1));
+}
+
 // Persistent grids: SM count x resident blocks per SM for this kernel (cached per kernel, dynamic shared memory and
 // device; guarded: distinct handles may launch from distinct host threads, one per GPU).
 #include <map>

@@ -123,7 +123,8 @@ __global__ void __launch_bounds__(256) k_f_raygen(SceneF sc, WaveF w, TileMap tm
 {
     const long long total = (long long)npix * S;
     for (long long pid = (long long)blockIdx.x * blockDim.x + threadIdx.x; pid < total; pid += (long long)gridDim.x * blockDim.x) {
-        const int sl = (int)(pid / npix), pl = (int)(pid - (long long)sl * npix);
+        int sl, pl;
+        path_split(tm, pid, npix, sl, pl);
         int pix, px, py;
         pixel_of(tm, sc.width, pix0 + pl, pix, px, py);
         uint32_t o4[4];
@@ -794,7 +795,8 @@ __global__ void __launch_bounds__(SHADE_BLOCK, 4) k_f_shade(SceneF sc, WaveF w, 
                 }
                 DBG_CHECK(fs < sc.n_slots && pid >= 0 && pid < w.P && (unsigned)__float_as_int(nm4.w) < (unsigned)sc.n_mats, w.counts);
                 const MatF m = sc.mats[__float_as_int(nm4.w)];
-                const int sl = pid / npix, pl = pid - sl * npix;
+                int sl, pl;
+                path_split(tm, pid, npix, sl, pl);
                 int pix, px, py;
                 pixel_of(tm, sc.width, pix0 + pl, pix, px, py);
                 DBG_CHECK(pix >= 0 && pix < sc.width * sc.height, w.counts);
@@ -939,7 +941,8 @@ __device__ __noinline__ bool sky_scatter_f(const SkyCtx &c, int k, int pid, int 
         normal = normalize_f(f3((float)((double)point.x - cx), (float)((double)point.y - cy), (float)((double)point.z - cz)));
     } else normal = normalize_f(point - f3(sa.x, sa.y, sa.z));
     const MatF m = c.mats[__float_as_int(ldg4(&c.slot_nrm[fs]).w)];
-    const int sl = pid / c.npix, pl = pid - sl * c.npix;
+    int sl, pl;
+    path_split(c.tm, pid, c.npix, sl, pl);
     int pix, px, py;
     pixel_of(c.tm, c.width, c.pix0 + pl, pix, px, py);
     RngF g; g.pixel = (uint32_t)pix; g.sample = (uint32_t)(c.s0 + sl); g.k0 = c.k0; g.k1 = c.k1;
@@ -1062,7 +1065,7 @@ __global__ void __launch_bounds__(256) k_f_resolve(SceneF sc, WaveF w, TileMap t
         double *p = pixsum + 4 * (size_t)pix;
         double r = p[0], g = p[1], b = p[2];
         for (int sl = 0; sl < S; sl++) {
-            const float4 a = w.rad[(size_t)sl * npix + pl];
+            const float4 a = w.rad[path_join(tm, sl, pl, npix)];
             r += (double)a.x; g += (double)a.y; b += (double)a.z;
         }
         p[0] = r; p[1] = g; p[2] = b; p[3] = 1.0;

@@ -1201,7 +1201,14 @@ static int get_tilemap(MfxScene *s, int tile, int rank, int world, bool stripes,
 {
     memset(tm, 0, sizeof(*tm));
     tm->height = s->height;
-    if (world <= 1 || tile <= 0) { tm->pix = nullptr; tm->n_pix = s->width * s->height; return MFX_OK; }
+    if (world <= 1 || tile <= 0) {
+        // one device, whole frame: path ids walk the frame in column stripes of MFX_PIXEL_STRIPE pixels (rows of 8 inside a
+        // stripe), so the 32 rays a warp picks up together come from an 8 x 4 block of pixels instead of a 32 x 1 run
+        const long ps = env_long("MFX_PIXEL_STRIPE", 8);
+        tm->pix = nullptr; tm->n_pix = s->width * s->height;
+        if (ps > 0) { tm->stripe = (int)ps; tm->rank = 0; tm->world = 1; }
+        return MFX_OK;
+    }
     if (stripes) {
         tm->stripe = tile; tm->rank = rank; tm->world = world;
         tm->n_pix = stripe_pixels(s->width, s->height, tile, rank, world);
@@ -1406,6 +1413,8 @@ static int launch_sample(MfxScene *s, const MfxSampleParams *p, double *d_color_
         for (int s0 = 0; s0 < p->spp; s0 += S_wave) {
             const int S = std::min(S_wave, p->spp - s0);
             const int sabs = p->first_sample + s0;
+            tm.sshift = 0;                                       // (the exact kernels keep sample-major path ids)
+            if (!exact) for (long want = env_long("MFX_SAMPLE_BLOCK_LOG2", 4); tm.sshift < want && S % (2 << tm.sshift) == 0; tm.sshift++) {}
             CUDA_TRY(cudaMemsetAsync(counts, 0, MFX_COUNTS_LEN * sizeof(int), st));
 #ifdef MFX_DEBUG_CHECKS
             // (MFX_DEBUG_FAULT=1 leaves the previous call's stamps in place: the next call's shadow rays then look like

@@ -337,7 +337,8 @@ __global__ void __launch_bounds__(256) k_h_raygen(SceneF sc, SceneX sx, WaveF w,
 {
     const long long total = (long long)npix * S;
     for (long long pid = (long long)blockIdx.x * blockDim.x + threadIdx.x; pid < total; pid += (long long)gridDim.x * blockDim.x) {
-        const int sl = (int)(pid / npix), pl = (int)(pid - (long long)sl * npix);
+        int sl, pl;
+        path_split(tm, pid, npix, sl, pl);
         int pix, px, py;
         pixel_of(tm, sx.width, pix0 + pl, pix, px, py);
         RngX g; g.pixel = (uint32_t)pix; g.sample = (uint32_t)(s0 + sl); g.k0 = (uint32_t)seed; g.k1 = (uint32_t)(seed >> 32);

@@ -243,6 +243,7 @@ struct TileMap {
     const int *pix;
     int  n_pix;
     int  stripe, rank, world, height;
+    int  sshift;            // fast wavefront: path ids keep 2^sshift samples of one pixel next to each other (path_split)
 };
 
 // ------------------------------------------------------------------ launchers (defined in the .cu TUs)
