@@ -598,6 +598,31 @@ def test_wave_grows_with_the_call_and_frames_do_not_depend_on_it():
     assert (p >= 0).all() and np.isfinite(t).all()
 
 
+@pytest.mark.parametrize("name,width,height,spp", [("cornell", 50, 37, 6), ("c1_cube", 97, 33, 5), ("c2_spot", 200, 112, 48), ("spheres", 64, 48, 16)])
+def test_frames_do_not_depend_on_the_order_of_the_path_ids(monkeypatch, name, width, height, spp):
+    """Path ids walk the frame in 8-pixel column stripes with blocks of 16 samples of a pixel next to each other
+    (path_split / pixel_of: coherence for the warps).  The RNG is keyed on pixel and sample, so the frame
+    must be the one the row-major, sample-major order of round 1 gives -- for widths that are no multiple of the stripe,
+    sample counts that are no multiple of the block, and frames cut into several waves of pixels or of samples."""
+    desc = _desc(name, width=width, height=height)
+    s = Scene(desc)
+    integ = CudaPixelIntegrator(s, precision=FAST_F32, seed=9)
+    monkeypatch.setenv("MFX_PIXEL_STRIPE", "0"); monkeypatch.setenv("MFX_SAMPLE_BLOCK_LOG2", "0")
+    ref = integ.Sample(spp).copy()
+    rays = integ.stats["closest_rays"] + integ.stats["shadow_rays"]
+    for stripe, blk, wave in (("8", "4", None), ("4", "6", None), ("16", "2", None), ("8", "4", str(width * height * 2 + 7)), ("8", "4", str(width * 3))):
+        monkeypatch.setenv("MFX_PIXEL_STRIPE", stripe); monkeypatch.setenv("MFX_SAMPLE_BLOCK_LOG2", blk)
+        if wave:
+            monkeypatch.setenv("MFX_WAVE_PATHS", wave)
+        sc = Scene(desc)                                     # a fresh scene: the wave is sized under the new cap
+        it = CudaPixelIntegrator(sc, precision=FAST_F32, seed=9)
+        img = it.Sample(spp).copy()
+        assert np.array_equal(img, ref), (stripe, blk, wave)
+        assert it.stats["closest_rays"] + it.stats["shadow_rays"] == rays
+        sc.close()
+        monkeypatch.delenv("MFX_WAVE_PATHS", raising=False)
+
+
 def test_wave_shrinks_when_the_gpu_is_nearly_full():
     """Another tenant holds almost all HBM: the path-state wave (6.5 GB wanted here) must fall back to a smaller one
     -- more launches, same frame -- instead of failing."""
