@@ -1460,7 +1460,7 @@ static int launch_sample(MfxScene *s, const MfxSampleParams *p, double *d_color_
                     // full persistent grid that finds a tiny queue still costs ~30 us per bounce (profiles/).  A queue
                     // never grows from one bounce to the next, so the host looks at the device-side count now and then
                     // and sizes the following grids for it -- or leaves the loop when nothing is left.
-                    if (b >= 8 && (b % 6) == 2 && b < D) {
+                    if (sky_tail == 0 && b >= 8 && (b % 6) == 2 && b < D) {      // (per-bounce mode only: exact precision, instrumented and reference-stream runs)
                         int next_n = 0;
                         CUDA_TRY(cudaMemcpyAsync(&next_n, counts + b + 1, sizeof(int), cudaMemcpyDeviceToHost, st));
                         CUDA_TRY(cudaStreamSynchronize(st));
