@@ -555,6 +555,10 @@ void mfx_h_extend(const LaunchCfg &c, const SceneF &sc, const SceneX &sx, const 
     case 4: launch_h_trace<16, 10, 2, 6>(c, sc, sx, sh, w, wh, bounce, q, seam); break;
     case 5: launch_h_trace<16, 10, 1, 5>(c, sc, sx, sh, w, wh, bounce, q, seam); break;
     case 6: launch_h_trace<8, 10, 2, 5>(c, sc, sx, sh, w, wh, bounce, q, seam); break;
+    case 7: launch_h_trace<24, 16, 2, 5>(c, sc, sx, sh, w, wh, bounce, q, seam); break;     // (7..10: thresholds for the coherent warps the path-id order gives)
+    case 8: launch_h_trace<16, 16, 2, 5>(c, sc, sx, sh, w, wh, bounce, q, seam); break;
+    case 9: launch_h_trace<24, 10, 2, 5>(c, sc, sx, sh, w, wh, bounce, q, seam); break;
+    case 10: launch_h_trace<28, 20, 2, 5>(c, sc, sx, sh, w, wh, bounce, q, seam); break;
     default: launch_h_trace<16, 10, 2, 5>(c, sc, sx, sh, w, wh, bounce, q, seam); break;
     }
     k_h_fixup<<<c.blocks * 4, 128, 0, c.stream>>>(sx, sh, w, wh, bounce, q, w.cam_origin, seam);

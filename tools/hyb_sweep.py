@@ -10,7 +10,7 @@ for name in names:
     desc.max_depth = 0
     s = Scene(desc)
     integ = CudaPixelIntegrator(s, precision=FAST_F32, seed=1)
-    for v in [0, 1, 2, 3, 4, 5, 6]:
+    for v in [0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10]:
         os.environ["MFX_HYB_VARIANT"] = str(v)
         best = None
         for _ in range(3):
