@@ -292,6 +292,96 @@ static void sah_build(SahCtx &c, int root, int par_depth)
     for (auto &f : spawned) f.get();
 }
 
+// Insertion-based optimisation of the binary tree (after Bittner, Hapala, Havran 2013): take a subtree out, let its sibling
+// move up, and put it back where the sum of the interior nodes' areas grows least -- found by branch and bound from the
+// root (induced cost = what the ancestors of a candidate grow by; a subtree can never cost less than its own area).
+// The best position includes the old one, so the SAH cost never rises; primitives and leaves are untouched.  Sequential
+// (every move changes the boxes the next search reads); `passes` sweeps over all nodes, largest area first.
+static void sah_reinsert(SahNode *nodes, int nn, int passes)
+{
+    std::vector<int> parent(nn, -1), cand;
+    {
+        std::vector<int> st{ 0 };
+        while (!st.empty()) {
+            const int i = st.back(); st.pop_back();
+            if (nodes[i].count == 0) { parent[nodes[i].left] = i; parent[nodes[i].right] = i; st.push_back(nodes[i].left); st.push_back(nodes[i].right); }
+            if (i != 0) cand.push_back(i);
+        }
+    }
+    auto refit = [&](int i) {           // from node i up to the root
+        for (; i >= 0; i = parent[i]) {
+            SahNode &n = nodes[i];
+            if (n.count > 0) continue;
+            const SahNode &l = nodes[n.left], &r = nodes[n.right];
+            float lo[3], hi[3];
+            for (int a = 0; a < 3; a++) { lo[a] = std::min(l.lo[a], r.lo[a]); hi[a] = std::max(l.hi[a], r.hi[a]); }
+            bool same = true;
+            for (int a = 0; a < 3; a++) same = same && lo[a] == n.lo[a] && hi[a] == n.hi[a];
+            if (same) break;
+            for (int a = 0; a < 3; a++) { n.lo[a] = lo[a]; n.hi[a] = hi[a]; }
+        }
+    };
+    auto union_area = [&](const SahNode &x, const SahNode &y) {
+        float lo[3], hi[3];
+        for (int a = 0; a < 3; a++) { lo[a] = std::min(x.lo[a], y.lo[a]); hi[a] = std::max(x.hi[a], y.hi[a]); }
+        return half_area(lo, hi);
+    };
+    struct Item { float ind; int node; bool operator<(const Item &o) const { return ind > o.ind; } };
+    std::vector<Item> heap;
+    for (int pass = 0; pass < passes; pass++) {
+        std::sort(cand.begin(), cand.end(), [&](int x, int y) {
+            const float ax = half_area(nodes[x].lo, nodes[x].hi), ay = half_area(nodes[y].lo, nodes[y].hi);
+            return ax > ay || (ax == ay && x < y);
+        });
+        for (int N : cand) {
+            const int P = parent[N];
+            if (P <= 0) continue;                                   // children of the root stay (the root keeps index 0)
+            const int G = parent[P];
+            const int S = nodes[P].left == N ? nodes[P].right : nodes[P].left;
+            // take N (and its parent P) out: S moves up
+            (nodes[G].left == P ? nodes[G].left : nodes[G].right) = S;
+            parent[S] = G;
+            refit(G);
+            // branch and bound for the cheapest new sibling X
+            const float aN = half_area(nodes[N].lo, nodes[N].hi);
+            float best = SAH_INF; int bestX = S;
+            heap.clear(); heap.push_back({ 0.f, 0 });
+            while (!heap.empty()) {
+                std::pop_heap(heap.begin(), heap.end()); const Item it = heap.back(); heap.pop_back();
+                if (it.ind + aN >= best) break;
+                const SahNode &X = nodes[it.node];
+                const float direct = union_area(X, nodes[N]);
+                const float total = it.ind + direct;
+                if (total < best) { best = total; bestX = it.node; }
+                const float child_ind = total - half_area(X.lo, X.hi);
+                if (X.count == 0 && child_ind + aN < best) {
+                    heap.push_back({ child_ind, X.left }); std::push_heap(heap.begin(), heap.end());
+                    heap.push_back({ child_ind, X.right }); std::push_heap(heap.begin(), heap.end());
+                }
+            }
+            // put P (with children bestX and N) where bestX was
+            const int X = bestX, XP = parent[X];
+            if (XP < 0) {                                            // new sibling is the root: the root record must stay node 0
+                // swap roles: node 0 keeps being the root, P takes over the old root's content
+                nodes[P] = nodes[0];
+                if (nodes[P].count == 0) { parent[nodes[P].left] = P; parent[nodes[P].right] = P; }
+                nodes[0].count = 0; nodes[0].left = P; nodes[0].right = N; nodes[0].first = 0;
+                parent[P] = 0; parent[N] = 0;
+                refit(0);
+                // force a full refit of the new root
+                for (int a = 0; a < 3; a++) { nodes[0].lo[a] = std::min(nodes[P].lo[a], nodes[N].lo[a]); nodes[0].hi[a] = std::max(nodes[P].hi[a], nodes[N].hi[a]); }
+                continue;
+            }
+            (nodes[XP].left == X ? nodes[XP].left : nodes[XP].right) = P;
+            parent[P] = XP;
+            nodes[P].left = X; nodes[P].right = N; nodes[P].count = 0;
+            parent[X] = P; parent[N] = P;
+            for (int a = 0; a < 3; a++) { nodes[P].lo[a] = std::min(nodes[X].lo[a], nodes[N].lo[a]); nodes[P].hi[a] = std::max(nodes[X].hi[a], nodes[N].hi[a]); }
+            refit(XP);
+        }
+    }
+}
+
 void mfx_build_own_tree(const float *lo, const float *hi, int ns, int max_leaf, float trav_cost, int par_depth, MfxOwnTree &out)
 {
     std::vector<int> idx(ns);
@@ -306,6 +396,12 @@ void mfx_build_own_tree(const float *lo, const float *hi, int ns, int max_leaf, 
     nodes[0].first = 0; nodes[0].count = ns; nodes[0].left = nodes[0].right = -1;
     sah_bound(c, nodes[0]);
     sah_build(c, 0, par_depth);
+    // MFX_TREE_OPT = reinsertion passes over the binary tree before it is collapsed (0: off); scenes above
+    // MFX_TREE_OPT_MAX primitives skip it (the pass is sequential)
+    {
+        const int passes = (int)env_long("MFX_TREE_OPT", 2);
+        if (passes > 0 && nodes[0].count == 0 && ns <= env_long("MFX_TREE_OPT_MAX", 1000000)) sah_reinsert(nodes.data(), c.next.load(), passes);
+    }
 
     // MFX_COLLAPSE_DP = cost of one record step in percent of one primitive test (default 100; 0 = the greedy
     // largest-area-first collapse of round 1; measured on B200: +1.0 % C2, +1.0 % C3, +0.5 % C4, same build time):
@@ -401,7 +497,14 @@ void mfx_build_own_tree(const float *lo, const float *hi, int ns, int max_leaf, 
             const int cnt = slot_prims(kids[k]);
             if (cnt > 0) {
                 meta[k] = ((int)order.size() << 3) | cnt;
-                for (int j = 0; j < cnt; j++) order.push_back(idx[nd.first + j]);
+                // (a binary subtree merged into one leaf: its primitives are gathered leaf by leaf -- after the reinsertion
+                //  pass they are no longer one range of idx)
+                int st[16], sp = 0; st[sp++] = kids[k];
+                while (sp > 0) {
+                    const SahNode &g = nodes[st[--sp]];
+                    if (g.count > 0) { for (int j = 0; j < g.count; j++) order.push_back(idx[g.first + j]); }
+                    else { st[sp++] = g.right; st[sp++] = g.left; }
+                }
             }
         }
         q.lox = make_float4(lo[0][0], lo[0][1], lo[0][2], lo[0][3]); q.hix = make_float4(hi[0][0], hi[0][1], hi[0][2], hi[0][3]);

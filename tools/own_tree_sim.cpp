@@ -18,6 +18,7 @@
 #include "mfx_build.h"
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -161,6 +162,7 @@ int main(int argc, char **argv)
         hi[3 * (size_t)i + a] = std::nextafterf((float)std::max(v0, std::max(v1, v2)), INFINITY);
     }
     MfxOwnTree tree;
+    const auto tb0 = std::chrono::steady_clock::now();
     mfx_build_own_tree(lo.data(), hi.data(), n, (int)mfx_env_long("MFX_SAH_MAX_LEAF", 4), (float)mfx_env_long("MFX_SAH_TRAV_COST_PCT", 100) * 0.01f, 3, tree);
     g_quant = (int)mfx_env_long("SIM_QUANT", 0);
     std::vector<QuadC> cq;
@@ -189,6 +191,7 @@ int main(int argc, char **argv)
         }
         printf("8-bit grids: mean surface-area ratio of a child box, interior %.4f, leaf %.4f\n", infl[0] / cnt[0], infl[1] / cnt[1]);
     }
+    printf("own tree built in %.2f ms\n", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tb0).count());
     Sim sim; sim.t = &tree; sim.cq = &cq; sim.tri.resize(n);
     for (int k = 0; k < n; k++) {
         const double *p = &raw[9 * (size_t)tree.order[k]];
