@@ -817,7 +817,7 @@ static TreeKey tree_key(const std::vector<MfxPrim> &prims, long max_leaf, long t
         a = (a ^ w[i]) * 0x100000001B3ull; a ^= a >> 29;
         b = (b + w[i]) * 0xFF51AFD7ED558CCDull; b ^= b >> 32;
     }
-    return TreeKey{ a, b, prims.size(), max_leaf, trav, env_long("MFX_COLLAPSE_DP", 100) };
+    return TreeKey{ a, b, prims.size(), max_leaf, trav, env_long("MFX_COLLAPSE_DP", 100) * 1000 + env_long("MFX_TREE_OPT", 2) };     // (every builder knob that shapes the tree)
 }
 
 static std::shared_ptr<OwnTreeHost> build_own_tree_host(MfxScene *s, long max_leaf, long trav)
