@@ -296,8 +296,8 @@ static void sah_build(SahCtx &c, int root, int par_depth)
 // move up, and put it back where the sum of the interior nodes' areas grows least -- found by branch and bound from the
 // root (induced cost = what the ancestors of a candidate grow by; a subtree can never cost less than its own area).
 // The best position includes the old one, so the SAH cost never rises; primitives and leaves are untouched.  Sequential
-// (every move changes the boxes the next search reads); `passes` sweeps over all nodes, largest area first.
-static void sah_reinsert(SahNode *nodes, int nn, int passes)
+// (every move changes the boxes the next search reads); `passes` sweeps over the `max_cand` largest nodes, largest first.
+static void sah_reinsert(SahNode *nodes, int nn, int passes, size_t max_cand)
 {
     std::vector<int> parent(nn, -1), cand;
     {
@@ -333,7 +333,9 @@ static void sah_reinsert(SahNode *nodes, int nn, int passes)
             const float ax = half_area(nodes[x].lo, nodes[x].hi), ay = half_area(nodes[y].lo, nodes[y].hi);
             return ax > ay || (ax == ay && x < y);
         });
-        for (int N : cand) {
+        // the largest subtrees matter most (every ray meets them) and the cost of a pass is bounded by their number
+        for (size_t ci = 0; ci < cand.size() && ci < max_cand; ci++) {
+            const int N = cand[ci];
             const int P = parent[N];
             if (P <= 0) continue;                                   // children of the root stay (the root keeps index 0)
             const int G = parent[P];
@@ -396,11 +398,12 @@ void mfx_build_own_tree(const float *lo, const float *hi, int ns, int max_leaf, 
     nodes[0].first = 0; nodes[0].count = ns; nodes[0].left = nodes[0].right = -1;
     sah_bound(c, nodes[0]);
     sah_build(c, 0, par_depth);
-    // MFX_TREE_OPT = reinsertion passes over the binary tree before it is collapsed (0: off); scenes above
-    // MFX_TREE_OPT_MAX primitives skip it (the pass is sequential)
+    // MFX_TREE_OPT = reinsertion passes over the binary tree before it is collapsed (0: off), each over the
+    // MFX_TREE_OPT_NODES largest subtrees; scenes above MFX_TREE_OPT_MAX primitives skip it (the pass is sequential)
     {
         const int passes = (int)env_long("MFX_TREE_OPT", 2);
-        if (passes > 0 && nodes[0].count == 0 && ns <= env_long("MFX_TREE_OPT_MAX", 1000000)) sah_reinsert(nodes.data(), c.next.load(), passes);
+        if (passes > 0 && nodes[0].count == 0 && ns <= env_long("MFX_TREE_OPT_MAX", 500000))
+            sah_reinsert(nodes.data(), c.next.load(), passes, (size_t)std::max(1L, env_long("MFX_TREE_OPT_NODES", 32768)));
     }
 
     // MFX_COLLAPSE_DP = cost of one record step in percent of one primitive test (default 100; 0 = the greedy
