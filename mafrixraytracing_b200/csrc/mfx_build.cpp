@@ -346,7 +346,11 @@ static void sah_reinsert(SahNode *nodes, int nn, int passes, size_t max_cand)
             refit(G);
             // branch and bound for the cheapest new sibling X
             const float aN = half_area(nodes[N].lo, nodes[N].hi);
-            float best = SAH_INF; int bestX = S;
+            // the position it came from is the one to beat, STRICTLY: among equal costs (coincident boxes) nothing moves,
+            // or every subtree would end up beside the root and the tree would degenerate into a chain
+            float best, ind0 = 0.f; int bestX = S;
+            for (int A = G; A >= 0; A = parent[A]) ind0 += union_area(nodes[A], nodes[N]) - half_area(nodes[A].lo, nodes[A].hi);
+            best = ind0 + union_area(nodes[S], nodes[N]);
             heap.clear(); heap.push_back({ 0.f, 0 });
             while (!heap.empty()) {
                 std::pop_heap(heap.begin(), heap.end()); const Item it = heap.back(); heap.pop_back();
@@ -354,7 +358,7 @@ static void sah_reinsert(SahNode *nodes, int nn, int passes, size_t max_cand)
                 const SahNode &X = nodes[it.node];
                 const float direct = union_area(X, nodes[N]);
                 const float total = it.ind + direct;
-                if (total < best) { best = total; bestX = it.node; }
+                if (total < best * 0.99999f) { best = total; bestX = it.node; }
                 const float child_ind = total - half_area(X.lo, X.hi);
                 if (X.count == 0 && child_ind + aN < best) {
                     heap.push_back({ child_ind, X.left }); std::push_heap(heap.begin(), heap.end());

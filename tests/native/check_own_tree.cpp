@@ -79,7 +79,22 @@ int main(int argc, char **argv)
     REQUIRE(visited == t.quads.size());
     REQUIRE(leaf_slots == n);
     REQUIRE(depth == t.depth);
-    printf("ok n=%d mode=%d records=%zu depth=%d\n", n, mode, t.quads.size(), t.depth);
+    // SAH cost of the records: every record costs one step per unit of its area, every leaf child one test per slot
+    double cost = 0.;
+    for (const QuadF &q : t.quads) {
+        const float *L[3] = { &q.lox.x, &q.loy.x, &q.loz.x }, *H[3] = { &q.hix.x, &q.hiy.x, &q.hiz.x };
+        double rlo[3] = { 3e38, 3e38, 3e38 }, rhi[3] = { -3e38, -3e38, -3e38 };
+        for (int s = 0; s < 4; s++) {
+            const int link = as_int((&q.meta.x)[s]);
+            if (link == MFX_QUAD_EMPTY) continue;
+            const double x = (double)H[0][s] - L[0][s], y = (double)H[1][s] - L[1][s], z = (double)H[2][s] - L[2][s];
+            if (link >= 0) cost += (x * y + y * z + z * x) * (link & 7);
+            for (int a = 0; a < 3; a++) { rlo[a] = std::min(rlo[a], (double)L[a][s]); rhi[a] = std::max(rhi[a], (double)H[a][s]); }
+        }
+        const double x = rhi[0] - rlo[0], y = rhi[1] - rlo[1], z = rhi[2] - rlo[2];
+        cost += x * y + y * z + z * x;
+    }
+    printf("ok n=%d mode=%d records=%zu depth=%d cost=%.6g\n", n, mode, t.quads.size(), t.depth, cost);
     if (mode == 3) {
         long kids[5] = { 0, 0, 0, 0, 0 }, leafsz[8] = { 0, 0, 0, 0, 0, 0, 0, 0 }, leaves = 0, inner = 0;
         for (const QuadF &q : t.quads) {

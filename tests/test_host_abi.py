@@ -65,6 +65,20 @@ def test_own_tree_builder_is_a_valid_bvh(tmp_path):
     for n, mode in [(1, 0), (2, 0), (3, 0), (5, 0), (17, 0), (1000, 0), (150000, 0), (3000, 1), (5000, 2)]:
         out = subprocess.check_output([exe, str(n), str(mode)], text=True)
         assert out.startswith(f"ok n={n} mode={mode}"), out
+    # the reinsertion pass (sah_reinsert: default 2 passes over the 32768 largest subtrees) moves whole subtrees: valid
+    # trees for any number of passes and any bound on the subtrees moved, and a SAH cost that does not rise
+    def cost(n, mode, **env):
+        out = subprocess.check_output([exe, str(n), str(mode)], text=True, env=dict(os.environ, **env))
+        assert out.startswith(f"ok n={n} mode={mode}"), (env, out)
+        return float(out.split("cost=")[1])
+    for n, mode in [(5, 0), (17, 0), (1000, 0), (40000, 0), (3000, 1), (5000, 2)]:
+        base = cost(n, mode, MFX_TREE_OPT="0")
+        for env in (dict(MFX_TREE_OPT="1"), dict(MFX_TREE_OPT="4"), dict(MFX_TREE_OPT="2", MFX_TREE_OPT_NODES="50"), dict(MFX_TREE_OPT="2", MFX_TREE_OPT_MAX="10")):
+            assert cost(n, mode, **env) <= base * 1.02, (n, mode, env)
+    assert cost(5000, 2, MFX_TREE_OPT="2") < 0.97 * cost(5000, 2, MFX_TREE_OPT="0")         # a few huge boxes among small ones: the pass pays
+    # coincident boxes: every position costs the same -- nothing may move (a non-strict rule chains the tree: depth 341)
+    out = subprocess.check_output([exe, "3000", "1"], text=True, env=dict(os.environ, MFX_TREE_OPT="3"))
+    assert int(out.split("depth=")[1].split()[0]) <= 8, out
     # the greedy collapse of round 1 (MFX_COLLAPSE_DP=0) and another record cost must give valid trees too
     for dp in ("0", "250"):
         for n, mode in [(1, 0), (3, 0), (5, 0), (17, 0), (1000, 0), (40000, 0), (3000, 1), (5000, 2)]:
